@@ -1,0 +1,839 @@
+"""CPU ORACLE — test infrastructure only, never shipped, never on the product path.
+
+A float64 CPU restatement (torch-CPU / numpy) of the reference's algorithm for the
+temporally-parallel state-space GP path of EEA-sensors/parallel-gps.  Only ``tests/``,
+``__graft_entry__.smoke()`` and ``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may
+import this module.  The product package (``parallel-gps_b200``) must never import it.
+
+Every function cites the reference ``file:line`` it follows (paths relative to the reference
+repository root).  The reference's heavy arithmetic lives in third-party packages that are not
+installable here (tensorflow==2.6.0, tensorflow-probability==0.13.0, gpflow==2.2.1,
+numba==0.53.1 — ``requirements.txt:26,58,96,98``); their published algorithms are restated:
+
+* ``tf.linalg.expm``            -> ``torch.linalg.matrix_exp`` (same Higham scaling-and-squaring
+                                   Pade family; cross-checked against scipy.linalg.expm in tests)
+* ``tf.linalg.solve``           -> ``torch.linalg.solve`` (partial-pivot LU, LAPACK getrf/getrs)
+* ``tf.linalg.cholesky[_solve]``-> ``torch.linalg.cholesky`` / ``torch.cholesky_solve``
+* ``tfp.math.scan_associative`` -> :func:`scan_associative` below: recursive odd/even
+                                   work-efficient inclusive scan, operator called on batched
+                                   slices ``fn(elems[0:-1:2], elems[1::2])``, earlier element first
+* ``MultivariateNormalTriL.log_prob`` -> closed form for a 1x1 (scalar) observation covariance
+* TF autodiff                   -> torch autograd through this restatement (same computation
+                                   graph op for op, so the gradient is the gradient of the
+                                   *parallel* computation like the reference's)
+* gpflow ``positive()``          -> softplus; gpflow stationary kernels -> closed forms below
+
+PARITY PINNING: the restatement is pinned against every golden vector the reference's own tests
+hold for this path (``tests/test_rbf.py:27-47``, ``tests/test_periodic.py:32-61``) and against the
+reference's GP-equivalence contract (``tests/test_gp_vs_kfs.py:45-99``: state-space log-likelihood,
+gradient and posterior equal the dense GP within the per-kernel tolerances).  Outputs of the real
+TF reference cannot be produced in this image (TF/TFP/GPflow absent, no network), so parity at the
+1e-9 level against *TF outputs* is unpinned; see DESIGN.md.
+"""
+import math
+from collections import namedtuple
+from functools import reduce
+
+import numpy as np
+import torch
+from scipy.special import binom, comb, factorial
+
+DTYPE = torch.float64
+
+# pssgp/kalman/base.py:3
+LGSSM = namedtuple("LGSSM", ["P0", "Fs", "Qs", "H", "R"])
+# pssgp/kernels/base.py:15
+ContinuousDiscreteModel = namedtuple("ContinuousDiscreteModel", ["P0", "F", "L", "H", "Q"])
+
+# pssgp/config.py:6
+NUMBER_OF_BALANCING_STEPS = 10
+
+
+def _t(x, dtype=DTYPE):
+    if isinstance(x, torch.Tensor):
+        return x.to(dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype)
+
+
+def mv(A, x):
+    return (A @ x.unsqueeze(-1)).squeeze(-1)
+
+
+def tr(A):
+    return A.transpose(-1, -2)
+
+
+# --------------------------------------------------------------------------------------------
+# gpflow.Parameter(transform=positive()) == softplus
+# --------------------------------------------------------------------------------------------
+def softplus_inv(x):
+    x = float(x)
+    return x + math.log(-math.expm1(-x))
+
+
+class Parameter:
+    """Unconstrained leaf + softplus, like gpflow.Parameter(transform=positive())."""
+
+    def __init__(self, value, dtype=DTYPE, trainable=True):
+        self.unconstrained = torch.tensor(softplus_inv(value), dtype=dtype, requires_grad=trainable)
+        self.trainable = trainable
+
+    @property
+    def value(self):
+        return torch.nn.functional.softplus(self.unconstrained)
+
+
+# --------------------------------------------------------------------------------------------
+# pssgp/kernels/math_utils.py
+# --------------------------------------------------------------------------------------------
+def _balance_ss_d(F, n_iter):
+    """pssgp/kernels/math_utils.py:10-29 (_numba_balance_ss): returns the scaling d only."""
+    F = np.array(F, dtype=np.float64, copy=True)
+    dim = F.shape[0]
+    d = np.ones((dim,), dtype=F.dtype)
+    for _ in range(n_iter):
+        for i in range(dim):
+            tmp = np.copy(F[:, i])
+            tmp[i] = 0.
+            c = np.linalg.norm(tmp, 2)
+            tmp2 = np.copy(F[i, :])
+            tmp2[i] = 0.
+            r = np.linalg.norm(tmp2, 2)
+            with np.errstate(divide="ignore", invalid="ignore"):
+                f = np.sqrt(r / c)
+            d[i] *= f
+            F[:, i] *= f
+            F[i, :] /= f
+    return d
+
+
+def balance_ss(F, L, H, q, n_iter=5):
+    """pssgp/kernels/math_utils.py:32-81.  ``d`` is a constant w.r.t. autodiff (it crosses
+    tf.numpy_function at :68)."""
+    d = torch.as_tensor(_balance_ss_d(F.detach().cpu().numpy(), n_iter), dtype=F.dtype)
+    F = F * d[None, :] / d[:, None]
+    L = L / d[:, None]
+    H = H * d[None, :]
+    tmp3 = torch.max(torch.abs(L))
+    L = L / tmp3
+    q = (tmp3 ** 2) * q
+    tmp4 = torch.max(torch.abs(H))
+    H = H / tmp4
+    q = (tmp4 ** 2) * q
+    return F, L, H, q
+
+
+def solve_lyap_vec(F, L, Q):
+    """pssgp/kernels/math_utils.py:84-120:  F P + P F' + L Q L' = 0 via the d^2 x d^2 Kronecker system."""
+    dim = F.shape[0]
+    eye = torch.eye(dim, dtype=F.dtype)
+    F1 = torch.kron(eye, F)
+    F2 = torch.kron(F, eye)
+    Fk = F1 + F2
+    Qm = L @ (Q @ tr(L))
+    Pinf = torch.linalg.solve(Fk, Qm.reshape(-1, 1)).reshape(dim, dim)
+    Pinf = -0.5 * (Pinf + tr(Pinf))
+    return Pinf
+
+
+# --------------------------------------------------------------------------------------------
+# pssgp/kernels/base.py
+# --------------------------------------------------------------------------------------------
+def get_ssm(sde, ts, R, t0=0.):
+    """pssgp/kernels/base.py:29-47 (_get_ssm): Fs = expm(dt F); Qs by matrix-fraction decomposition."""
+    dtype = sde.F.dtype
+    n = sde.F.shape[0]
+    ts = _t(ts, dtype).reshape(-1, 1)
+    t0 = torch.as_tensor(t0, dtype=dtype).reshape(1, 1)
+    ts = torch.cat([t0, ts], dim=0)
+    dts = (ts[1:] - ts[:-1]).reshape(-1, 1, 1)
+    Fs = torch.linalg.matrix_exp(dts * sde.F.unsqueeze(0))
+    zeros = torch.zeros_like(sde.F)
+    Phi = torch.cat([torch.cat([sde.F, sde.L @ (sde.Q @ tr(sde.L))], dim=1),
+                     torch.cat([zeros, -tr(sde.F)], dim=1)], dim=0)
+    AB = torch.linalg.matrix_exp(dts * Phi.unsqueeze(0))
+    AB = AB @ torch.cat([zeros, torch.eye(n, dtype=dtype)], dim=0)
+    Qs = AB[:, :n, :] @ tr(Fs)
+    return LGSSM(sde.P0, Fs, Qs, sde.H, R)
+
+
+def get_ssm_stationary(sde, ts, R, t0=0.):
+    """North-star variant of _get_ssm: same Fs, but Q_k = Pinf - A_k Pinf A_k' (valid because
+    P0 = Pinf solves the Lyapunov equation).  Used to bound the difference between the two forms."""
+    dtype = sde.F.dtype
+    ts = _t(ts, dtype).reshape(-1, 1)
+    t0 = torch.as_tensor(t0, dtype=dtype).reshape(1, 1)
+    ts = torch.cat([t0, ts], dim=0)
+    dts = (ts[1:] - ts[:-1]).reshape(-1, 1, 1)
+    Fs = torch.linalg.matrix_exp(dts * sde.F.unsqueeze(0))
+    Qs = sde.P0.unsqueeze(0) - Fs @ sde.P0.unsqueeze(0) @ tr(Fs)
+    Qs = 0.5 * (Qs + tr(Qs))
+    return LGSSM(sde.P0, Fs, Qs, sde.H, R)
+
+
+class SDEKernel:
+    """pssgp/kernels/base.py:50-107 (SDEKernelMixin) plus the dense covariance the gpflow parent provides."""
+
+    def get_sde(self):
+        raise NotImplementedError
+
+    def K(self, X, X2=None):
+        raise NotImplementedError
+
+    @property
+    def trainable_variables(self):
+        raise NotImplementedError
+
+    def get_ssm(self, ts, R, t0=0.):
+        # pssgp/kernels/base.py:73-93
+        return get_ssm(self.get_sde(), ts, R, t0)
+
+    def __add__(self, other):
+        return SDESum([self, other])  # pssgp/kernels/base.py:95-96
+
+    def __mul__(self, other):
+        return SDEProduct([self, other])  # pssgp/kernels/base.py:98-99
+
+
+def _absdiff(X, X2):
+    X = _t(X).reshape(-1)
+    X2 = X if X2 is None else _t(X2).reshape(-1)
+    return torch.abs(X[:, None] - X2[None, :])
+
+
+# pssgp/kernels/matern/common.py:10-52
+def _matern_transition(lamda, d, dtype):
+    F = torch.diag(torch.ones(d - 1, dtype=dtype), diagonal=1)
+    binomial_coeffs = torch.as_tensor(binom(d, np.arange(0, d, dtype=int)).astype(np.float64), dtype=dtype)
+    lambda_powers = lamda ** torch.arange(d, 0, -1, dtype=dtype)
+    last = -(lambda_powers * binomial_coeffs)
+    return torch.cat([F[:-1], last.reshape(1, d)], dim=0) if d > 1 else last.reshape(1, 1)
+
+
+def get_matern_sde(variance, lengthscales, d, dtype=DTYPE):
+    lamda = math.sqrt(2 * d - 1) / lengthscales
+    F = _matern_transition(lamda, d, dtype)
+    L = torch.zeros(d, 1, dtype=dtype)
+    L[d - 1, 0] = 1.
+    H = torch.zeros(1, d, dtype=dtype)
+    H[0, 0] = 1.
+    q = (2 * lamda) ** (2 * d - 1) * variance * math.factorial(d - 1) ** 2 / math.factorial(2 * d - 2)
+    Q = q * torch.eye(1, dtype=dtype)
+    return F, L, H, Q
+
+
+class _Stationary(SDEKernel):
+    def __init__(self, variance=1.0, lengthscales=1.0):
+        self.variance_p = Parameter(variance)
+        self.lengthscales_p = Parameter(lengthscales)
+
+    @property
+    def variance(self):
+        return self.variance_p.value
+
+    @property
+    def lengthscales(self):
+        return self.lengthscales_p.value
+
+    @property
+    def trainable_variables(self):
+        # gpflow orders module variables by attribute name: lengthscales before variance
+        return [self.lengthscales_p.unconstrained, self.variance_p.unconstrained]
+
+
+class Matern12(_Stationary):
+    def K(self, X, X2=None):
+        return self.variance * torch.exp(-_absdiff(X, X2) / self.lengthscales)
+
+    def get_sde(self):
+        # pssgp/kernels/matern/matern12.py:18-23
+        F, L, H, Q = get_matern_sde(self.variance, self.lengthscales, 1)
+        P_infty = self.variance.reshape(1, 1)
+        return ContinuousDiscreteModel(P_infty, F, L, H, Q)
+
+
+class Matern32(_Stationary):
+    def K(self, X, X2=None):
+        r = _absdiff(X, X2) / self.lengthscales
+        s3 = math.sqrt(3.)
+        return self.variance * (1. + s3 * r) * torch.exp(-s3 * r)
+
+    def get_sde(self):
+        # pssgp/kernels/matern/matern32.py:20-28
+        F, L, H, Q = get_matern_sde(self.variance, self.lengthscales, 2)
+        lamda = math.sqrt(3) / self.lengthscales
+        P_infty = torch.diag(torch.stack([self.variance, lamda ** 2 * self.variance]))
+        return ContinuousDiscreteModel(P_infty, F, L, H, Q)
+
+
+class Matern52(_Stationary):
+    def __init__(self, variance=1.0, lengthscales=1.0, balancing_iter=None):
+        super().__init__(variance, lengthscales)
+        self._balancing_iter = NUMBER_OF_BALANCING_STEPS if balancing_iter is None else balancing_iter
+
+    def K(self, X, X2=None):
+        r = _absdiff(X, X2) / self.lengthscales
+        s5 = math.sqrt(5.)
+        return self.variance * (1. + s5 * r + 5. / 3. * r ** 2) * torch.exp(-s5 * r)
+
+    def get_sde(self):
+        # pssgp/kernels/matern/matern52.py:21-25
+        F, L, H, q = get_matern_sde(self.variance, self.lengthscales, 3)
+        Fb, Lb, Hb, Qb = balance_ss(F, L, H, q.reshape(1, 1), n_iter=self._balancing_iter)
+        Pinf = solve_lyap_vec(Fb, Lb, Qb)
+        return ContinuousDiscreteModel(Pinf, Fb, Lb, Hb, Qb)
+
+
+def _get_unscaled_rbf_sde(order=6):
+    """pssgp/kernels/rbf.py:14-61."""
+    B = math.sqrt(2 * math.pi)
+    A = np.zeros((2 * order + 1,), dtype=np.float64)
+    i = 0
+    for k in range(order, -1, -1):
+        A[i] = 0.5 ** k / math.factorial(k)
+        i = i + 2
+    q = B / np.polyval(A, 0)
+    LA = np.real(A / (1j ** np.arange(A.size - 1, -1, -1, dtype=np.float64)))
+    AR = np.roots(LA)
+    GB = 1
+    GA = np.poly(AR[np.real(AR) < 0])
+    GA = GA / GA[-1]
+    GB = GB / GA[0]
+    GA = GA / GA[0]
+    GA = np.real(GA)
+    F = np.zeros((GA.size - 1, GA.size - 1), dtype=np.float64)
+    F[-1, :] = -GA[:0:-1]
+    F[:-1, 1:] = np.eye(GA.size - 2, dtype=np.float64)
+    L = np.zeros((GA.size - 1, 1), dtype=np.float64)
+    L[-1, 0] = 1
+    H = np.zeros((1, GA.size - 1), dtype=np.float64)
+    H[0, 0] = np.real(GB)
+    return F, L, H, q
+
+
+class RBF(_Stationary):
+    def __init__(self, variance=1.0, lengthscales=1.0, order=3, balancing_iter=None):
+        super().__init__(variance, lengthscales)
+        self._order = order
+        self._balancing_iter = NUMBER_OF_BALANCING_STEPS if balancing_iter is None else balancing_iter
+
+    def K(self, X, X2=None):
+        r = _absdiff(X, X2) / self.lengthscales
+        return self.variance * torch.exp(-0.5 * r ** 2)
+
+    def get_sde(self):
+        # pssgp/kernels/rbf.py:78-101
+        F_, L_, H_, q_ = _get_unscaled_rbf_sde(self._order)
+        F = _t(F_)
+        L = _t(L_)
+        H = _t(H_)
+        q = _t(q_)
+        dim = F.shape[0]
+        ell_vec = self.lengthscales ** torch.arange(dim, 0, -1, dtype=DTYPE)
+        F = torch.cat([F[:-1], (F[-1, :] / ell_vec).reshape(1, dim)], dim=0)
+        H = H / (self.lengthscales ** dim)
+        Q = self.variance * self.lengthscales * q.reshape(1, 1)
+        Fb, Lb, Hb, Qb = balance_ss(F, L, H, Q, n_iter=self._balancing_iter)
+        Pinf = solve_lyap_vec(Fb, Lb, Qb)
+        Q = Qb.reshape(1, 1)
+        return ContinuousDiscreteModel(Pinf, Fb, Lb, Hb, Q)
+
+
+def _get_offline_coeffs(N):
+    """pssgp/kernels/periodic.py:18-38."""
+    r = np.arange(0, N + 1)
+    J, K = np.meshgrid(r, r)
+    div_facto_K = 1 / factorial(K)
+    b = 2 * comb(K, np.floor((K - J) / 2) * (J <= K)) / \
+        (1 + (J == 0)) * (J <= K) * (np.mod(K - J, 2) == 0)
+    return b, K, div_facto_K
+
+
+class SquaredExponential(_Stationary):
+    """gpflow.kernels.SquaredExponential stand-in (only carries parameters for Periodic)."""
+
+    def K(self, X, X2=None):
+        r = _absdiff(X, X2) / self.lengthscales
+        return self.variance * torch.exp(-0.5 * r ** 2)
+
+
+class Periodic(SDEKernel):
+    def __init__(self, base_kernel, period=1.0, order=6):
+        assert isinstance(base_kernel, SquaredExponential)
+        self.base_kernel = base_kernel
+        self.period_p = Parameter(period)
+        self._order = order
+
+    @property
+    def period(self):
+        return self.period_p.value
+
+    @property
+    def trainable_variables(self):
+        # gpflow order: base_kernel.(lengthscales, variance), period
+        return self.base_kernel.trainable_variables + [self.period_p.unconstrained]
+
+    def K(self, X, X2=None):
+        # gpflow.kernels.Periodic: base.K_r2( sum_d (sin(pi (x-x')/p) / ell)^2 )
+        r = math.pi * _absdiff(X, X2) / self.period
+        scaled = torch.sin(r) / self.base_kernel.lengthscales
+        return self.base_kernel.variance * torch.exp(-0.5 * scaled ** 2)
+
+    def get_sde(self):
+        # pssgp/kernels/periodic.py:53-81
+        N = self._order
+        w0 = 2 * math.pi / self.period
+        lengthscales = self.base_kernel.lengthscales * 2.
+        b, K, div_facto_K = _get_offline_coeffs(N)
+        b = _t(b)
+        K = _t(K)
+        div_facto_K = _t(div_facto_K)
+        zero = torch.zeros((), dtype=DTYPE)
+        op_F = torch.stack([torch.stack([zero, -w0]), torch.stack([w0, zero])])
+        op_diag = torch.diag(torch.arange(0, N + 1, dtype=DTYPE))
+        F = torch.kron(op_diag, op_F)
+        L = torch.eye(2 * (N + 1), dtype=DTYPE)
+        Q = torch.zeros((2 * (N + 1), 2 * (N + 1)), dtype=DTYPE)
+        q2 = b * lengthscales ** (-2 * K) * div_facto_K * torch.exp(-lengthscales ** (-2)) * \
+            2 ** (-K) * self.base_kernel.variance
+        q2 = torch.diag(torch.sum(q2, dim=0))
+        Pinf = torch.kron(q2, torch.eye(2, dtype=DTYPE))
+        H = torch.kron(torch.ones((1, N + 1), dtype=DTYPE), torch.tensor([[1., 0.]], dtype=DTYPE))
+        return ContinuousDiscreteModel(Pinf, F, L, H, Q)
+
+
+def block_diag(arrs):
+    return torch.block_diag(*arrs)
+
+
+class SDESum(SDEKernel):
+    def __init__(self, kernels):
+        self.kernels = list(kernels)
+
+    @property
+    def trainable_variables(self):
+        return sum((k.trainable_variables for k in self.kernels), [])
+
+    def K(self, X, X2=None):
+        return reduce(lambda a, b: a + b, [k.K(X, X2) for k in self.kernels])
+
+    def get_sde(self):
+        # pssgp/kernels/base.py:151-183
+        P0s, Fs, Ls, Hs, Qs = zip(*[k.get_sde() for k in self.kernels])
+        Fsum = block_diag(Fs)
+        Lsum = block_diag(Ls)
+        Hsum = torch.cat(Hs, dim=1)
+        Qsum = block_diag(Qs)
+        Fb, Lb, Hb, Qb = balance_ss(Fsum, Lsum, Hsum, Qsum, NUMBER_OF_BALANCING_STEPS)
+        Pinf = solve_lyap_vec(Fb, Lb, Qb)
+        return ContinuousDiscreteModel(Pinf, Fb, Lb, Hb, Qb)
+
+
+class SDEProduct(SDEKernel):
+    def __init__(self, kernels):
+        self.kernels = list(kernels)
+
+    @property
+    def trainable_variables(self):
+        return sum((k.trainable_variables for k in self.kernels), [])
+
+    def K(self, X, X2=None):
+        return reduce(lambda a, b: a * b, [k.K(X, X2) for k in self.kernels])
+
+    @staticmethod
+    def _combine_F(op1, op2):
+        # pssgp/kernels/base.py:199-207
+        I1 = torch.eye(op1.shape[0], dtype=op1.dtype)
+        I2 = torch.eye(op2.shape[0], dtype=op2.dtype)
+        return torch.kron(op1, I2) + torch.kron(I1, op2)
+
+    @staticmethod
+    def _combine_Q(sde1, sde2):
+        # pssgp/kernels/base.py:209-220
+        gamma1 = sde1.L @ sde1.Q @ tr(sde1.L)
+        gamma2 = sde2.L @ sde2.Q @ tr(sde2.L)
+        return torch.kron(gamma1, sde2.P0) + torch.kron(sde1.P0, gamma2)
+
+    def get_sde(self):
+        # pssgp/kernels/base.py:222-244
+        sdes = [k.get_sde() for k in self.kernels]
+        F = reduce(self._combine_F, [s.F for s in sdes])
+        Q = reduce(self._combine_Q, sdes)
+        H = reduce(torch.kron, [s.H for s in sdes])
+        L = torch.eye(Q.shape[0], dtype=DTYPE)
+        Fb, Lb, Hb, Qb = balance_ss(F, L, H, Q, NUMBER_OF_BALANCING_STEPS)
+        Pinf = solve_lyap_vec(Fb, Lb, Qb)
+        return ContinuousDiscreteModel(Pinf, Fb, Lb, Hb, Qb)
+
+
+# --------------------------------------------------------------------------------------------
+# tfp.math.scan_associative (TFP 0.13.0) — restated published algorithm
+# --------------------------------------------------------------------------------------------
+def scan_associative(fn, elems, max_num_levels=48):
+    """Inclusive prefix scan, recursive odd/even (work-efficient) order, as in
+    tensorflow_probability/python/math/scan_associative.py (0.13.0): pairs are reduced with
+    ``fn(elems[0:-1:2], elems[1::2])`` (earlier element first), the reduced sequence is scanned
+    recursively, and the even positions are filled with ``fn(odd[:-1], elems[2::2])``."""
+    elems = tuple(elems)
+    n = elems[0].shape[0]
+
+    def _interleave(a, b):
+        # a has len(b) or len(b)+1 rows
+        na, nb = a.shape[0], b.shape[0]
+        out = torch.empty((na + nb,) + tuple(a.shape[1:]), dtype=a.dtype)
+        out[0::2] = a
+        out[1::2] = b
+        return out
+
+    def _scan(level, es):
+        num = es[0].shape[0]
+        if num < 2:
+            return es
+        if level > max_num_levels:
+            raise ValueError("max_num_levels exceeded")
+        reduced = fn(tuple(e[0:-1:2] for e in es), tuple(e[1::2] for e in es))
+        odd = _scan(level + 1, tuple(reduced))
+        if num % 2 == 0:
+            even = fn(tuple(e[:-1] for e in odd), tuple(e[2::2] for e in es))
+        else:
+            even = fn(tuple(odd), tuple(e[2::2] for e in es))
+        even = tuple(torch.cat([e[0:1], r], dim=0) for e, r in zip(es, even))
+        return tuple(_interleave(e, o) for e, o in zip(even, odd))
+
+    if n < 2:
+        return elems
+    return _scan(0, elems)
+
+
+# --------------------------------------------------------------------------------------------
+# pssgp/kalman/parallel.py
+# --------------------------------------------------------------------------------------------
+def first_filtering_element(m0, P0, F, Q, H, R, y):
+    """pssgp/kalman/parallel.py:13-43."""
+    if bool(torch.isnan(y).any()):
+        return torch.zeros_like(F), m0, P0, torch.zeros_like(F), torch.zeros_like(m0)
+    S1 = H @ P0 @ tr(H) + R
+    S1_chol = torch.linalg.cholesky(S1)
+    K1t = torch.cholesky_solve(H @ P0, S1_chol)
+    A = torch.zeros_like(F)
+    b = m0 + mv(tr(K1t), y - mv(H, m0))
+    C = P0 - tr(K1t) @ S1 @ K1t
+    S = H @ Q @ tr(H) + R
+    chol = torch.linalg.cholesky(S)
+    HF = H @ F
+    eta = mv(tr(HF), torch.cholesky_solve(y.unsqueeze(1), chol).squeeze(1))
+    J = tr(HF) @ torch.cholesky_solve(H @ F, chol)
+    return A, b, C, J, eta
+
+
+def _generic_filtering_element_nan(F, Q):
+    """pssgp/kalman/parallel.py:46-53."""
+    b = torch.zeros(F.shape[:2], dtype=F.dtype)
+    return F, b, Q, torch.zeros_like(F), torch.zeros(F.shape[:2], dtype=F.dtype)
+
+
+def _generic_filtering_element(F, Q, H, R, y):
+    """pssgp/kalman/parallel.py:56-72."""
+    S = H @ Q @ tr(H) + R.unsqueeze(0)
+    chol = torch.linalg.cholesky(S)
+    Kt = torch.cholesky_solve(H @ Q, chol)
+    A = F - (tr(Kt) @ H) @ F
+    b = mv(tr(Kt), y)
+    C = Q - (tr(Kt) @ H) @ Q
+    HF = H @ F
+    eta = mv(tr(HF), torch.cholesky_solve(y.unsqueeze(-1), chol).squeeze(-1))
+    J = tr(HF) @ torch.cholesky_solve(HF, chol)
+    return A, b, C, J, eta
+
+
+def make_associative_filtering_elements(m0, P0, Fs, Qs, H, R, observations):
+    """pssgp/kalman/parallel.py:83-97."""
+    init_res = first_filtering_element(m0, P0, Fs[0], Qs[0], H, R, observations[0])
+    nan_ys = torch.isnan(observations).reshape(-1)
+    nan_res = _generic_filtering_element_nan(Fs, Qs)
+    safe_obs = torch.where(torch.isnan(observations), torch.zeros_like(observations), observations)
+    # TF computes the "ok" branch on the NaN rows as well and discards it with tf.where; the value
+    # is irrelevant, but torch autograd would propagate NaN * 0, so the discarded rows get y = 0.
+    ok_res = _generic_filtering_element(Fs, Qs, H, R, safe_obs)
+    gen_res = []
+    for nan_elem, ok_elem in zip(nan_res, ok_res):
+        ndim = nan_elem.dim()
+        gen_res.append(torch.where(nan_ys.reshape((-1,) + (1,) * (ndim - 1)), nan_elem, ok_elem))
+    return tuple(torch.cat([first_e.unsqueeze(0), gen_es[1:]], dim=0)
+                 for first_e, gen_es in zip(init_res, gen_res))
+
+
+def filtering_operator(elem1, elem2):
+    """pssgp/kalman/parallel.py:100-118."""
+    A1, b1, C1, J1, eta1 = elem1
+    A2, b2, C2, J2, eta2 = elem2
+    n, dim = A1.shape[0], A1.shape[1]
+    I = torch.eye(dim, dtype=A1.dtype).expand(n, dim, dim)
+    # tf.linalg.solve(M, rhs, adjoint=True) solves M^H x = rhs
+    temp = torch.linalg.solve(tr(I + C1 @ J2), tr(A2))
+    A = tr(temp) @ A1
+    b = mv(tr(temp), b1 + mv(C1, eta2)) + b2
+    C = tr(temp) @ (C1 @ tr(A2)) + C2
+    temp = torch.linalg.solve(tr(I + J2 @ C1), A1)
+    eta = mv(tr(temp), eta2 - mv(J2, b1)) + eta1
+    J = tr(temp) @ (J2 @ A1) + J1
+    C = 0.5 * (C + tr(C))
+    J = 0.5 * (J + tr(J))
+    return A, b, C, J, eta
+
+
+def pkf(lgssm, observations, return_loglikelihood=False, max_parallel=10000):
+    """pssgp/kalman/parallel.py:121-152."""
+    P0, Fs, Qs, H, R = lgssm
+    dtype = P0.dtype
+    observations = _t(observations, dtype)
+    m0 = torch.zeros(P0.shape[0], dtype=dtype)
+    max_num_levels = math.ceil(math.log2(max_parallel))
+    initial_elements = make_associative_filtering_elements(m0, P0, Fs, Qs, H, R, observations)
+    final_elements = scan_associative(filtering_operator, initial_elements, max_num_levels=max_num_levels)
+    if return_loglikelihood:
+        filtered_means = torch.cat([m0.unsqueeze(0), final_elements[1][:-1]], dim=0)
+        filtered_cov = torch.cat([P0.unsqueeze(0), final_elements[2][:-1]], dim=0)
+        predicted_means = mv(Fs, filtered_means)
+        predicted_covs = Fs @ (filtered_cov @ tr(Fs)) + Qs
+        obs_means = mv(H, predicted_means)
+        obs_covs = H @ (predicted_covs @ tr(H)) + R.unsqueeze(0)
+        # MultivariateNormalTriL(obs_means, chol(obs_covs)).log_prob(observations), 1x1 case
+        nan_ys = torch.isnan(observations)
+        safe_obs = torch.where(nan_ys, obs_means.detach(), observations)
+        S = obs_covs[:, 0, 0]
+        r = (safe_obs - obs_means)[:, 0]
+        logprobs = -0.5 * (r * r / S) - 0.5 * torch.log(S) - 0.5 * math.log(2 * math.pi)
+        logprobs_without_nans = torch.where(nan_ys[:, 0], torch.zeros_like(logprobs), logprobs)
+        total_log_prob = torch.sum(logprobs_without_nans)
+        return final_elements[1], final_elements[2], total_log_prob
+    return final_elements[1], final_elements[2]
+
+
+def generic_smoothing_element(F, Q, m, P):
+    """pssgp/kalman/parallel.py:159-166."""
+    Pp = F @ (P @ tr(F)) + Q
+    chol = torch.linalg.cholesky(Pp)
+    E = tr(torch.cholesky_solve(F @ P, chol))
+    g = m - mv(E @ F, m)
+    L = P - E @ (Pp @ tr(E))
+    L = 0.5 * (L + tr(L))
+    return E, g, L
+
+
+def make_associative_smoothing_elements(Fs, Qs, filtering_means, filtering_covariances):
+    """pssgp/kalman/parallel.py:155-156,169-173."""
+    last_elems = (torch.zeros_like(filtering_covariances[-1]), filtering_means[-1], filtering_covariances[-1])
+    if Fs.shape[0] == 1:
+        return tuple(e.unsqueeze(0) for e in last_elems)
+    generic_elems = generic_smoothing_element(Fs[1:], Qs[1:], filtering_means[:-1], filtering_covariances[:-1])
+    return tuple(torch.cat([gen_es, last_e.unsqueeze(0)], dim=0)
+                 for gen_es, last_e in zip(generic_elems, last_elems))
+
+
+def smoothing_operator(elem1, elem2):
+    """pssgp/kalman/parallel.py:176-184."""
+    E1, g1, L1 = elem1
+    E2, g2, L2 = elem2
+    E = E2 @ E1
+    g = mv(E2, g1) + g2
+    L = E2 @ (L1 @ tr(E2)) + L2
+    return E, g, L
+
+
+def pks(lgssm, ms, Ps, max_parallel=10000):
+    """pssgp/kalman/parallel.py:187-196."""
+    max_num_levels = math.ceil(math.log2(max_parallel))
+    _, Fs, Qs, *_ = lgssm
+    initial_elements = make_associative_smoothing_elements(Fs, Qs, ms, Ps)
+    reversed_elements = tuple(torch.flip(e, dims=[0]) for e in initial_elements)
+    final_elements = scan_associative(smoothing_operator, reversed_elements, max_num_levels=max_num_levels)
+    return torch.flip(final_elements[1], dims=[0]), torch.flip(final_elements[2], dims=[0])
+
+
+def pkfs(model, observations, max_parallel=10000):
+    """pssgp/kalman/parallel.py:199-201."""
+    fms, fPs = pkf(model, observations, False, max_parallel)
+    return pks(model, fms, fPs, max_parallel)
+
+
+# --------------------------------------------------------------------------------------------
+# pssgp/kalman/sequential.py
+# --------------------------------------------------------------------------------------------
+def kf(lgssm, observations, return_loglikelihood=False, return_predicted=False):
+    """pssgp/kalman/sequential.py:11-47 (tf.scan -> python loop)."""
+    P0, Fs, Qs, H, R = lgssm
+    dtype = P0.dtype
+    observations = _t(observations, dtype)
+    m = torch.zeros(P0.shape[0], dtype=dtype)
+    P = P0
+    ell = torch.zeros((), dtype=dtype)
+    fms, fPs, mps, Pps = [], [], [], []
+    for k in range(Fs.shape[0]):
+        y, F, Q = observations[k], Fs[k], Qs[k]
+        mp = mv(F, m)
+        Pp = F @ (P @ tr(F)) + Q
+        Pp = 0.5 * (Pp + tr(Pp))
+        if not bool(torch.isnan(y).any()):
+            S = H @ (Pp @ tr(H)) + R
+            yp = mv(H, mp)
+            chol = torch.linalg.cholesky(S)
+            r = (y - yp)[0]
+            ell_t = -0.5 * r * r / S[0, 0] - torch.log(chol[0, 0]) - 0.5 * math.log(2 * math.pi)
+            Kt = torch.cholesky_solve(H @ Pp, chol)
+            m = mp + mv(tr(Kt), y - yp)
+            P = Pp - tr(Kt) @ S @ Kt
+            ell = ell + ell_t
+        else:
+            m, P = mp, Pp
+        P = 0.5 * (P + tr(P))
+        fms.append(m)
+        fPs.append(P)
+        mps.append(mp)
+        Pps.append(Pp)
+    out = (torch.stack(fms), torch.stack(fPs))
+    if return_loglikelihood:
+        out = out + (ell,)
+    if return_predicted:
+        out = out + (torch.stack(mps), torch.stack(Pps))
+    return out
+
+
+def ks(lgssm, ms, Ps, mps, Pps):
+    """pssgp/kalman/sequential.py:50-68."""
+    _, Fs, Qs, *_ = lgssm
+    T = Fs.shape[0]
+    sm, sP = ms[-1], Ps[-1]
+    sms, sPs = [sm], [sP]
+    for k in range(T - 2, -1, -1):
+        F, m, P, mp, Pp = Fs[k + 1], ms[k], Ps[k], mps[k + 1], Pps[k + 1]
+        chol = torch.linalg.cholesky(Pp)
+        Ct = torch.cholesky_solve(F @ P, chol)
+        sm = m + mv(tr(Ct), sm - mp)
+        sP = P + tr(Ct) @ (sP - Pp) @ Ct
+        sP = 0.5 * (sP + tr(sP))
+        sms.append(sm)
+        sPs.append(sP)
+    return torch.stack(sms[::-1]), torch.stack(sPs[::-1])
+
+
+def kfs(model, observations):
+    """pssgp/kalman/sequential.py:71-73."""
+    fms, fPs, mps, Pps = kf(model, observations, return_predicted=True)
+    return ks(model, fms, fPs, mps, Pps)
+
+
+# --------------------------------------------------------------------------------------------
+# pssgp/model.py
+# --------------------------------------------------------------------------------------------
+def merge_sorted(a, b, *args):
+    """pssgp/model.py:15-55 restated with searchsorted (side='left', like tf.searchsorted default)."""
+    a = _t(a)
+    b = _t(b)
+    if a.shape[0] < b.shape[0]:
+        a, b = b, a
+        args = tuple((j, i) for i, j in args)
+    na, nb = a.shape[0], b.shape[0]
+    b_indices = torch.arange(nb) + torch.searchsorted(a, b)
+    a_flags = torch.ones(na + nb, dtype=torch.bool)
+    a_flags[b_indices] = False
+    a_mask = torch.arange(na + nb)[a_flags]
+
+    def _inner(u, v):
+        c = torch.cat([u, v], 0).clone()
+        c[b_indices] = v
+        c[a_mask] = u
+        return c
+
+    return (_inner(a, b),) + tuple(_inner(i, j) for i, j in args)
+
+
+class StateSpaceGP:
+    """pssgp/model.py:58-117."""
+
+    def __init__(self, data, kernel, noise_variance=1.0, parallel=False, max_parallel=10000):
+        self.noise_variance_p = Parameter(noise_variance)
+        ts, ys = data
+        self.data = (_t(ts).reshape(-1, 1), _t(ys).reshape(-1, 1))
+        self.kernel = kernel
+        self.parallel = parallel
+        self.max_parallel = max_parallel
+
+    @property
+    def noise_variance(self):
+        return self.noise_variance_p.value
+
+    def _make_model(self, ts):
+        R = self.noise_variance.reshape(1, 1)
+        return self.kernel.get_ssm(ts, R)
+
+    def predict_f(self, Xnew):
+        ts, ys = self.data
+        Xnew = _t(Xnew).reshape(-1, 1)
+        sq_ts, sq_X = ts.reshape(-1), Xnew.reshape(-1)
+        float_ys = float("nan") * torch.ones((Xnew.shape[0], ys.shape[1]), dtype=ys.dtype)
+        all_ts, all_ys, all_flags = merge_sorted(sq_ts, sq_X, (ys, float_ys),
+                                                 (torch.zeros_like(sq_ts, dtype=torch.bool),
+                                                  torch.ones_like(sq_X, dtype=torch.bool)))
+        ssm = self._make_model(all_ts[:, None])
+        if self.parallel:
+            sms, sPs = pkfs(ssm, all_ys, max_parallel=self.max_parallel)
+        else:
+            sms, sPs = kfs(ssm, all_ys)
+        rm, rP = sms[all_flags], sPs[all_flags]
+        return mv(ssm.H, rm), torch.diagonal(ssm.H @ (rP @ tr(ssm.H)), dim1=-2, dim2=-1)
+
+    def maximum_log_likelihood_objective(self):
+        ts, Y = self.data
+        ssm = self._make_model(ts)
+        if self.parallel:
+            _, _, ll = pkf(ssm, Y, return_loglikelihood=True, max_parallel=max(ts.shape[0], 2))
+        else:
+            _, _, ll = kf(ssm, Y, return_loglikelihood=True)
+        return ll
+
+
+class GPR:
+    """gpflow.models.GPR (zero mean): the comparator of tests/test_gp_vs_kfs.py."""
+
+    def __init__(self, data, kernel, noise_variance=1.0):
+        ts, ys = data
+        self.data = (_t(ts).reshape(-1, 1), _t(ys).reshape(-1, 1))
+        self.kernel = kernel
+        self.noise_variance_p = Parameter(noise_variance)
+
+    def maximum_log_likelihood_objective(self):
+        X, Y = self.data
+        n = X.shape[0]
+        K = self.kernel.K(X) + self.noise_variance_p.value * torch.eye(n, dtype=DTYPE)
+        Lc = torch.linalg.cholesky(K)
+        alpha = torch.linalg.solve_triangular(Lc, Y, upper=False)
+        return (-0.5 * torch.sum(alpha ** 2) - torch.sum(torch.log(torch.diagonal(Lc)))
+                - 0.5 * n * math.log(2 * math.pi))
+
+    def predict_f(self, Xnew):
+        X, Y = self.data
+        n = X.shape[0]
+        Xnew = _t(Xnew).reshape(-1, 1)
+        Kmm = self.kernel.K(X) + self.noise_variance_p.value * torch.eye(n, dtype=DTYPE)
+        Kmn = self.kernel.K(X, Xnew)
+        knn = torch.diagonal(self.kernel.K(Xnew))
+        Lc = torch.linalg.cholesky(Kmm)
+        A = torch.linalg.solve_triangular(Lc, Kmn, upper=False)
+        V = torch.linalg.solve_triangular(Lc, Y, upper=False)
+        return tr(A) @ V, (knn - torch.sum(A ** 2, dim=0)).reshape(-1, 1)
+
+
+# --------------------------------------------------------------------------------------------
+# pssgp/toymodels/data_funcs.py (pure numpy in the reference; restated so the GPU box needs no
+# /root/reference)
+# --------------------------------------------------------------------------------------------
+def sinu(t):
+    """pssgp/toymodels/data_funcs.py:10-23."""
+    return np.sin(np.pi * t) + np.sin(2 * np.pi * t) + np.cos(3 * np.pi * t)
+
+
+def obs_noise(x, r, seed=None):
+    """pssgp/toymodels/data_funcs.py:75-97 (the noise is drawn with MEAN x — reference quirk kept)."""
+    rng = np.random.RandomState(seed)
+    return x + np.sqrt(r) * rng.normal(x, math.sqrt(r), (x.shape[0],)).astype(x.dtype)
