@@ -1,0 +1,90 @@
+"""Host<->device plumbing: torch is used only for device memory, pinned staging and streams."""
+import numpy as np
+import torch
+
+from . import _lib
+
+_DT = {torch.float64: _lib.PSSGP_F64, torch.float32: _lib.PSSGP_F32}
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise RuntimeError("pssgp_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+
+
+def dtype_code(t):
+    try:
+        return _DT[t.dtype]
+    except KeyError:
+        raise TypeError(f"pssgp_b200 supports float64/float32, got {t.dtype}")
+
+
+def torch_dtype(x):
+    if isinstance(x, torch.Tensor):
+        return x.dtype
+    dt = np.asarray(x).dtype
+    return torch.float32 if dt == np.float32 else torch.float64
+
+
+class _Staging:
+    """Reusable pinned host buffers so numpy callers do not pay cudaHostAlloc on every call."""
+
+    def __init__(self):
+        self._bufs = {}
+
+    def get(self, key, nbytes):
+        buf = self._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+            self._bufs[key] = buf
+        return buf
+
+
+_staging = _Staging()
+
+
+def is_device_tensor(x):
+    return isinstance(x, torch.Tensor) and x.is_cuda
+
+
+def pick_device(*xs):
+    for x in xs:
+        if is_device_tensor(x):
+            return x.device
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def to_device(x, dtype, device, key=None):
+    """Returns a contiguous CUDA tensor of `dtype` on `device` (async H2D from pinned memory for host data)."""
+    if isinstance(x, torch.Tensor):
+        if x.is_cuda:
+            return x.detach().to(device=device, dtype=dtype).contiguous()
+        src = x.detach().to(dtype).contiguous()
+    else:
+        src = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float64 if dtype == torch.float64 else np.float32))
+    if src.numel() == 0:
+        return torch.empty(src.shape, dtype=dtype, device=device)
+    if not src.is_pinned():
+        nbytes = src.numel() * src.element_size()
+        stage = _staging.get(key if key is not None else id(x), nbytes)[:nbytes].view(dtype).view(src.shape)
+        stage.copy_(src)
+        src = stage
+    return src.to(device, non_blocking=True)
+
+
+def to_host(t, out=None):
+    """Device->host read of a result (into pinned memory), returned as numpy."""
+    nbytes = t.numel() * t.element_size()
+    stage = _staging.get(("out", out if out is not None else t.shape, t.dtype), nbytes)[:nbytes].view(t.dtype).view(t.shape)
+    stage.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return stage.numpy().copy()
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
