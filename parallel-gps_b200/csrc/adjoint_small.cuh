@@ -1,0 +1,351 @@
+// Adjoint (reverse-mode) algebra of the filter log-likelihood for D <= 4.
+//
+// The reference obtains d ll / d(P0, Fs, Qs, H, R) by TF autodiff through pkf
+// (pssgp/kalman/parallel.py:121-152; contract: tests/test_gp_vs_kfs.py:53-67).  Here the adjoint of
+// the mathematically identical sequential recursion is itself run as a reverse associative scan:
+// the adjoint state (dm, dP) w.r.t. the filtered moments propagates backwards through the affine map
+//     dm' = Abar^T dm + a ,   dP' = Abar^T dP Abar + sym(Abar^T dm a^T) + B
+// whose compositions are closed under
+//     (Abar1 Abar2,  Abar2^T a1 + a2,  Abar2^T B1 Abar2 + sym(Abar2^T a1 a2^T) + B2)      (1 = later in time)
+// (matmul only, no solves).  Everything is computed for an upstream gradient of 1 and scaled by
+// g_ll when written.
+//
+// Aggregate layout: Abar[D*D] | a[D] | B[NS] ; state: dm[D] | dP[NS] ; accumulators: dR, dH[D]
+#pragma once
+#include "smalld.cuh"
+
+namespace pssgp {
+
+template <typename T, int D>
+struct AdjointAlg {
+    using scalar = T;
+    static constexpr int NS = nsym(D);
+    static constexpr int oA = 0, oa = D * D, oB = oa + D;
+    static constexpr int NAGG = oB + NS;
+    static constexpr int NSTATE = D + NS;
+    static constexpr int NACC = 1 + D;
+
+    struct Params {
+        const T* Fs;
+        const T* Qs;
+        const T* y;
+        const T* H;
+        const T* R;
+        const T* P0;      // [D,D] prior covariance (first_special) or filtered covariance before the shard
+        const T* m0;      // [D] or null
+        const T* fms;     // [n,D]   filtered means from the forward pass
+        const T* fPs;     // [n,D,D]
+        const T* g;       // [1] upstream gradient of ll
+        const T* init;    // [NSTATE] adjoint state entering from the right (null = zeros)
+        T* dFs;           // [n,D,D]
+        T* dQs;           // [n,D,D]
+        T* dP0;           // [D,D]
+        T* dH;            // [D]
+        T* dR;            // [1]
+        T* first_state;   // unused here (returned through final_state of the framework)
+        long n;
+        int first_special;
+    };
+
+    PSSGP_DEV static void identity(T* a) {
+#pragma unroll
+        for (int e = 0; e < NAGG; ++e) a[e] = T(0);
+#pragma unroll
+        for (int i = 0; i < D; ++i) a[oA + i * D + i] = T(1);
+    }
+
+    struct Fwd {
+        T F[D * D];
+        T m[D], P[NS];     // filtered at k-1
+        T mp[D], Pp[NS];   // predicted at k
+        T h[D];
+        T u[D];            // Pp h
+        T s, r, R, yk;
+        bool obs, first;
+    };
+
+    // Recomputes the forward quantities of time step k.
+    PSSGP_DEV static void forward(const Params& p, long k, Fwd& f) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) f.h[i] = __ldg(p.H + i);
+        f.R = __ldg(p.R);
+        f.yk = __ldg(p.y + k);
+        f.obs = !t_isnan(f.yk);
+        f.first = (k == 0 && p.first_special);
+        const T* pf = p.Fs + k * (D * D);
+        const T* pq = p.Qs + k * (D * D);
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) f.F[e] = __ldg(pf + e);
+        T Q[NS];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (__ldg(pq + i * D + j) + __ldg(pq + j * D + i));
+        if (k > 0) {
+            const T* pm = p.fms + (k - 1) * D;
+            const T* pP = p.fPs + (k - 1) * (D * D);
+#pragma unroll
+            for (int i = 0; i < D; ++i) f.m[i] = __ldg(pm + i);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                    f.P[sidx(i, j)] = T(0.5) * (__ldg(pP + i * D + j) + __ldg(pP + j * D + i));
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) f.m[i] = p.m0 ? p.m0[i] : T(0);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                    f.P[sidx(i, j)] = T(0.5) * (p.P0[i * D + j] + p.P0[j * D + i]);
+        }
+        T FP[D * D];
+        mv_f<T, D>(f.F, f.m, f.mp);
+        mm_fs<T, D>(f.F, f.P, FP);
+        sym_xat_plus<T, D>(FP, f.F, Q, f.Pp);
+        mv_s<T, D>(f.Pp, f.h, f.u);
+        f.s = dot<T, D>(f.h, f.u) + f.R;
+        f.r = f.yk - dot<T, D>(f.h, f.mp);
+    }
+
+    // Element (Abar, a, B) of time step k for an upstream gradient of 1.
+    PSSGP_DEV static void element(const Params& p, long k, T* x) {
+        Fwd f;
+        forward(p, k, f);
+        if (f.first) {
+            // filter update acts on (m0, P0) directly, no likelihood term through this path
+            identity(x);
+            if (f.obs) {
+                T u0[D];
+                mv_s<T, D>(f.P, f.h, u0);
+                const T s0 = dot<T, D>(f.h, u0) + f.R;
+                const T is = T(1) / s0;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) x[oA + i * D + j] -= u0[i] * is * f.h[j];
+            }
+            return;
+        }
+        if (!f.obs) {
+#pragma unroll
+            for (int e = 0; e < D * D; ++e) x[oA + e] = f.F[e];
+#pragma unroll
+            for (int e = 0; e < D; ++e) x[oa + e] = T(0);
+#pragma unroll
+            for (int e = 0; e < NS; ++e) x[oB + e] = T(0);
+            return;
+        }
+        const T is = T(1) / f.s;
+        T w[D];  // F^T h
+        mv_t<T, D>(f.F, f.h, w);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) x[oA + i * D + j] = fma(-f.u[i] * is, w[j], f.F[i * D + j]);
+        const T ris = f.r * is;
+#pragma unroll
+        for (int i = 0; i < D; ++i) x[oa + i] = w[i] * ris;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) x[oB + sidx(i, j)] = T(0.5) * (ris * ris - is) * w[i] * w[j];
+    }
+
+    // x1 = later in time (earlier in the reversed sequence)
+    PSSGP_DEV static void combine(const T* x1, const T* x2, T* r) {
+        mm_ff<T, D>(x1 + oA, x2 + oA, r + oA);
+        T t[D];
+        mv_t<T, D>(x2 + oA, x1 + oa, t);
+#pragma unroll
+        for (int i = 0; i < D; ++i) r[oa + i] = t[i] + x2[oa + i];
+        T X[D * D];  // B1 A2
+        mm_sf<T, D>(x1 + oB, x2 + oA, X);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                T acc = x2[oB + sidx(i, j)] + T(0.5) * (t[i] * x2[oa + j] + t[j] * x2[oa + i]);
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) acc = fma(x2[oA + kk * D + i], X[kk * D + j], acc);
+                r[oB + sidx(i, j)] = acc;
+            }
+    }
+
+    PSSGP_DEV static void append(T* a, long j, const Params& p) {
+        T x[NAGG], r[NAGG];
+        element(p, p.n - 1 - j, x);
+        combine(a, x, r);
+#pragma unroll
+        for (int e = 0; e < NAGG; ++e) a[e] = r[e];
+    }
+
+    PSSGP_DEV static void apply(const T* s, const T* x, T* s2) {
+        T t[D];
+        mv_t<T, D>(x + oA, s, t);
+#pragma unroll
+        for (int i = 0; i < D; ++i) s2[i] = t[i] + x[oa + i];
+        T X[D * D];
+        mm_sf<T, D>(s + D, x + oA, X);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                T acc = x[oB + sidx(i, j)] + T(0.5) * (t[i] * x[oa + j] + t[j] * x[oa + i]);
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) acc = fma(x[oA + kk * D + i], X[kk * D + j], acc);
+                s2[D + sidx(i, j)] = acc;
+            }
+    }
+
+    PSSGP_DEV static void load_init(const Params& p, T* s) {
+#pragma unroll
+        for (int e = 0; e < NSTATE; ++e) s[e] = p.init ? p.init[e] : T(0);
+    }
+
+    // Adjoint of the measurement update given (mp, Pp, u, s, r): in (dm+, dP+) -> out (dmp, dPp),
+    // accumulating dR and dH.  with_ll: include the log-density term of this step.
+    PSSGP_DEV static void update_adjoint(const T* h, const T* mp, const T* Pp, const T* u, T s, T r, bool with_ll,
+                                         const T* dm, const T* dP, T* dmp, T* dPp, T* acc) {
+        const T is = T(1) / s;
+        const T udm = dot<T, D>(u, dm);
+        T Pu[D];
+        mv_s<T, D>(dP, u, Pu);
+        const T uPu = dot<T, D>(u, Pu);
+        T rbar = udm * is;
+        T sbar = (-udm * r + uPu) * is * is;
+        if (with_ll) {
+            rbar -= r * is;
+            sbar += T(0.5) * (r * r * is * is - is);
+        }
+        T ut[D];
+#pragma unroll
+        for (int i = 0; i < D; ++i) ut[i] = dm[i] * r * is - T(2) * Pu[i] * is + sbar * h[i];
+        T Pput[D];
+        mv_s<T, D>(Pp, ut, Pput);
+        acc[0] += sbar;
+#pragma unroll
+        for (int i = 0; i < D; ++i) acc[1 + i] += sbar * u[i] + Pput[i] - mp[i] * rbar;
+#pragma unroll
+        for (int i = 0; i < D; ++i) dmp[i] = dm[i] - h[i] * rbar;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) dPp[sidx(i, j)] = dP[sidx(i, j)] + T(0.5) * (ut[i] * h[j] + ut[j] * h[i]);
+    }
+
+    // s = adjoint w.r.t. the filtered moments at time k; on exit w.r.t. those at time k-1.
+    PSSGP_DEV static void step(T* s, long j, const Params& p, T* acc) {
+        const long k = p.n - 1 - j;
+        const T g = __ldg(p.g);
+        Fwd f;
+        forward(p, k, f);
+        T dmp[D], dPp[NS];
+        T* oF = p.dFs + k * (D * D);
+        T* oQ = p.dQs + k * (D * D);
+        if (f.first) {
+            // (i) likelihood term of step 0 through the prediction from (m0, P0)
+            T dPp0[NS], dmp0[D];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) dPp0[e] = T(0);
+#pragma unroll
+            for (int e = 0; e < D; ++e) dmp0[e] = T(0);
+            if (f.obs) {
+                const T is = T(1) / f.s;
+                const T sbar = T(0.5) * (f.r * f.r * is * is - is);
+                const T rbar = -f.r * is;
+                acc[0] += sbar;
+#pragma unroll
+                for (int i = 0; i < D; ++i) acc[1 + i] += T(2) * sbar * f.u[i] - f.mp[i] * rbar;
+#pragma unroll
+                for (int i = 0; i < D; ++i) dmp0[i] = -f.h[i] * rbar;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int jj = 0; jj <= i; ++jj) dPp0[sidx(i, jj)] = sbar * f.h[i] * f.h[jj];
+            }
+            T X[D * D], Y[D * D];
+            mm_sf<T, D>(dPp0, f.F, X);   // dPp0 F
+            mm_fs<T, D>(X, f.P, Y);      // dPp0 F P
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int jj = 0; jj < D; ++jj) {
+                    oF[i * D + jj] = g * (dmp0[i] * f.m[jj] + T(2) * Y[i * D + jj]);
+                    oQ[i * D + jj] = g * dPp0[sidx(i, jj)];
+                }
+            // (ii) filter update on (m0, P0) directly
+            if (f.obs) {
+                T u0[D];
+                mv_s<T, D>(f.P, f.h, u0);
+                const T s0 = dot<T, D>(f.h, u0) + f.R;
+                const T r0 = f.yk - dot<T, D>(f.h, f.m);
+                update_adjoint(f.h, f.m, f.P, u0, s0, r0, false, s, s + D, dmp, dPp, acc);
+            } else {
+#pragma unroll
+                for (int e = 0; e < D; ++e) dmp[e] = s[e];
+#pragma unroll
+                for (int e = 0; e < NS; ++e) dPp[e] = s[D + e];
+            }
+            // dP0 = F0^T dPp0 F0 + dPp(update)
+            if (p.dP0) {
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int jj = 0; jj < D; ++jj) {
+                        T a1 = dPp[sidx(i, jj)];
+#pragma unroll
+                        for (int kk = 0; kk < D; ++kk) a1 = fma(f.F[kk * D + i], X[kk * D + jj], a1);
+                        p.dP0[i * D + jj] = g * a1;
+                    }
+            }
+#pragma unroll
+            for (int e = 0; e < D; ++e) s[e] = dmp[e];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) s[D + e] = dPp[e];
+            return;
+        }
+        if (f.obs) {
+            update_adjoint(f.h, f.mp, f.Pp, f.u, f.s, f.r, true, s, s + D, dmp, dPp, acc);
+        } else {
+#pragma unroll
+            for (int e = 0; e < D; ++e) dmp[e] = s[e];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) dPp[e] = s[D + e];
+        }
+        T X[D * D], Y[D * D];
+        mm_sf<T, D>(dPp, f.F, X);  // dPp F
+        mm_fs<T, D>(X, f.P, Y);    // dPp F P
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int jj = 0; jj < D; ++jj) {
+                oF[i * D + jj] = g * (dmp[i] * f.m[jj] + T(2) * Y[i * D + jj]);
+                oQ[i * D + jj] = g * dPp[sidx(i, jj)];
+            }
+        mv_t<T, D>(f.F, dmp, s);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int jj = 0; jj <= i; ++jj) {
+                T a1 = T(0);
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) a1 = fma(f.F[kk * D + i], X[kk * D + jj], a1);
+                s[D + sidx(i, jj)] = a1;
+            }
+        // when the shard does not start at the global origin, the state after its first step is the
+        // adjoint w.r.t. the previous shard's last filtered moments: the framework returns it.
+    }
+
+    PSSGP_DEV static void finish(const Params& p, int e, T tot, T*) {
+        const T g = p.g[0];
+        if (e == 0) {
+            if (p.dR) p.dR[0] = g * tot;
+        } else {
+            if (p.dH) p.dH[e - 1] = g * tot;
+        }
+    }
+};
+
+}  // namespace pssgp

@@ -9,6 +9,7 @@
 
 #include <new>
 
+#include "adjoint_small.cuh"
 #include "filter_small.cuh"
 #include "scan_small.cuh"
 #include "smoother_small.cuh"
@@ -127,6 +128,34 @@ int pks_impl(pssgp_handle* h, int64_t n, const void* Fs, const void* Qs, const v
     return run_scan<Alg>(h, p, n, nullptr, (T*)first_state, st);
 }
 
+template <typename T, int D>
+int pkf_bwd_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
+                 const void* R, const void* y, const void* fms, const void* fPs, const void* g_ll, void* dP0,
+                 void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
+    using Alg = AdjointAlg<T, D>;
+    typename Alg::Params p;
+    p.Fs = (const T*)Fs;
+    p.Qs = (const T*)Qs;
+    p.y = (const T*)y;
+    p.H = (const T*)H;
+    p.R = (const T*)R;
+    p.P0 = (const T*)P0;
+    p.m0 = nullptr;
+    p.fms = (const T*)fms;
+    p.fPs = (const T*)fPs;
+    p.g = (const T*)g_ll;
+    p.init = nullptr;
+    p.dFs = (T*)dFs;
+    p.dQs = (T*)dQs;
+    p.dP0 = (T*)dP0;
+    p.dH = (T*)dH;
+    p.dR = (T*)dR;
+    p.first_state = nullptr;
+    p.n = n;
+    p.first_special = 1;
+    return run_scan<Alg>(h, p, n, (T*)dR, nullptr, st);
+}
+
 }  // namespace pssgp
 
 using namespace pssgp;
@@ -243,6 +272,7 @@ int pssgp_pks(pssgp_handle* h, int dtype, int64_t n, int d, const void* Fs, cons
 // ---- ones below are placeholders until their kernels land (they fail loudly, never fall back).
 extern "C" {
 #define PSSGP_TODO(name) return set_err(PSSGP_ERR_UNSUPPORTED, name ": not implemented yet")
+#define PSSGP_HAVE_DISCRETISE
 #ifndef PSSGP_HAVE_DISCRETISE
 int pssgp_discretise(pssgp_handle*, int, int64_t, int, const void*, const void*, const void*, void*, void*, void*) {
     PSSGP_TODO("pssgp_discretise");
@@ -265,14 +295,16 @@ int pssgp_smoother_fold(pssgp_handle*, int, int, int, const void*, void*, void*)
 }
 #endif
 #ifndef PSSGP_HAVE_BACKWARD
-int pssgp_pkf_backward(pssgp_handle*, int, int64_t, int, const void*, const void*, const void*, const void*,
-                       const void*, const void*, const void*, const void*, const void*, void*, void*, void*, void*,
-                       void*, void*) {
-    PSSGP_TODO("pssgp_pkf_backward");
-}
-int pssgp_discretise_backward(pssgp_handle*, int, int64_t, int, const void*, const void*, const void*, const void*,
-                              const void*, const void*, void*, void*, void*) {
-    PSSGP_TODO("pssgp_discretise_backward");
+int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+                       const void* H, const void* R, const void* y, const void* fms, const void* fPs, const void* g_ll,
+                       void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs || !g_ll || !dP0 || !dFs || !dQs || !dH || !dR)
+        return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_SMALL(pkf_bwd_impl, h, n, P0, Fs, Qs, H, R, y, fms, fPs, g_ll, dP0, dFs, dQs, dH, dR, st);
+    return set_err(PSSGP_ERR_UNSUPPORTED, "pkf_backward: state dimension %d not supported yet", d);
 }
 #endif
 }

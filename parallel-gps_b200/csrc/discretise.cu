@@ -1,0 +1,492 @@
+// SDE discretisation and its adjoint.
+//
+// Replaces the reference's pssgp/kernels/base.py:29-47 (_get_ssm): Fs = expm(dt F) and Qs (the
+// reference uses a matrix-fraction decomposition through a second, 2d x 2d expm; here the
+// stationary identity Q = Pinf - A Pinf A^T is used).
+//
+// Because F is the same for every time step, expm(F dt_k) is evaluated as a scaled Taylor polynomial
+// whose matrix coefficients C_j = (F/||F||_1)^j / j! are computed ONCE (setup kernel):
+//     x = ||F||_1 |dt| / 2^s <= theta,  A_h = sum_j C_j x^j (Horner, d^2 FMAs per term, no matmul),
+//     A = A_h^(2^s) by s squarings.
+// The adjoint needs no per-step matmul when s = 0 either: dF = 1/||F|| sum_p 1/p! sum_i (G^T)^i W_p (G^T)^(p-1-i)
+// with the moment matrices W_p = sum_k x_k^p dA_h,k, which are plain reductions over time.
+#include "../../include/pssgp_b200.h"
+
+#include <cuda_runtime.h>
+
+#include "smalld.cuh"
+#include "workspace.h"
+
+namespace pssgp {
+
+int set_err(int code, const char* fmt, ...);
+int ws_reserve(pssgp_handle* h, int slot, size_t bytes);
+int check_launch(pssgp_handle* h, const char* what, int nlaunches);
+
+template <typename T> struct Taylor;
+template <> struct Taylor<double> { static constexpr int DEG = 18; };
+template <> struct Taylor<float> { static constexpr int DEG = 10; };
+constexpr int kMaxSquarings = 24;
+constexpr int kDiscThreads = 128;
+
+// coef layout: [0]: ||F||_1 ; then C_j (j = 0..DEG), each d*d, starting at offset 8 (keeps 16B alignment)
+template <typename T>
+__global__ void taylor_setup_kernel(const T* __restrict__ F, int d, T* __restrict__ coef, int transpose) {
+    extern __shared__ unsigned char smem_raw[];
+    T* G = (T*)smem_raw;          // d*d
+    T* cur = G + d * d;           // d*d
+    T* nxt = cur + d * d;         // d*d
+    __shared__ T normF;
+    const int dd = d * d;
+    if (threadIdx.x == 0) {
+        T best = T(0);
+        for (int j = 0; j < d; ++j) {
+            T cs = T(0);
+            for (int i = 0; i < d; ++i) cs += t_abs(F[i * d + j]);
+            best = cs > best ? cs : best;
+        }
+        normF = best;
+        coef[0] = best;
+    }
+    __syncthreads();
+    const T inv = normF > T(0) ? T(1) / normF : T(0);
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        const int i = e / d, j = e % d;
+        G[e] = (transpose ? F[j * d + i] : F[e]) * inv;
+        cur[e] = (i == j) ? T(1) : T(0);
+        coef[8 + e] = cur[e];
+    }
+    __syncthreads();
+    const int DEG = Taylor<T>::DEG;
+    for (int p = 1; p <= DEG; ++p) {
+        for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+            const int i = e / d, j = e % d;
+            T acc = T(0);
+            for (int k = 0; k < d; ++k) acc = fma(G[i * d + k], cur[k * d + j], acc);
+            nxt[e] = acc / T(p);
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+            cur[e] = nxt[e];
+            coef[8 + (size_t)p * dd + e] = nxt[e];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T> PSSGP_DEV int pick_squarings(T nrm, T& x) {
+    // x = nrm / 2^s <= 1
+    int s = 0;
+    x = nrm;
+    while (x > T(1) && s < kMaxSquarings) {
+        x *= T(0.5);
+        ++s;
+    }
+    return s;
+}
+
+template <typename T, int D>
+__global__ void __launch_bounds__(kDiscThreads)
+discretise_small_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, const T* __restrict__ dts, long n,
+                        T* __restrict__ Fs, T* __restrict__ Qs) {
+    constexpr int DEG = Taylor<T>::DEG;
+    constexpr int DD = D * D;
+    __shared__ T sC[(DEG + 1) * DD];
+    __shared__ T sP[DD];
+    __shared__ T sOut[2 * kDiscThreads * DD];
+    for (int e = threadIdx.x; e < (DEG + 1) * DD; e += blockDim.x) sC[e] = coef[8 + e];
+    for (int e = threadIdx.x; e < DD; e += blockDim.x) sP[e] = Pinf[e];
+    const T normF = coef[0];
+    __syncthreads();
+    const long base = (long)blockIdx.x * kDiscThreads;
+    const long k = base + threadIdx.x;
+    if (k < n) {
+        const T dt = dts[k];
+        T x;
+        const int s = pick_squarings<T>(normF * t_abs(dt), x);
+        if (dt < T(0)) x = -x;
+        T A[DD];
+#pragma unroll
+        for (int e = 0; e < DD; ++e) A[e] = sC[DEG * DD + e];
+#pragma unroll 1
+        for (int p = DEG - 1; p >= 0; --p) {
+#pragma unroll
+            for (int e = 0; e < DD; ++e) A[e] = fma(A[e], x, sC[p * DD + e]);
+        }
+        for (int i = 0; i < s; ++i) {
+            T B[DD];
+            mm_ff<T, D>(A, A, B);
+#pragma unroll
+            for (int e = 0; e < DD; ++e) A[e] = B[e];
+        }
+        // Q = Pinf - A Pinf A^T, symmetrised
+        T P[nsym(D)];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (sP[i * D + j] + sP[j * D + i]);
+        T AP[DD];
+        mm_fs<T, D>(A, P, AP);
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                T a1 = T(0), a2 = T(0);
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) {
+                    a1 = fma(AP[i * D + kk], A[j * D + kk], a1);
+                    a2 = fma(AP[j * D + kk], A[i * D + kk], a2);
+                }
+                sOut[kDiscThreads * DD + threadIdx.x * DD + i * D + j] = P[sidx(i, j)] - T(0.5) * (a1 + a2);
+            }
+#pragma unroll
+        for (int e = 0; e < DD; ++e) sOut[threadIdx.x * DD + e] = A[e];
+    }
+    __syncthreads();
+    long cnt = n - base;
+    if (cnt > kDiscThreads) cnt = kDiscThreads;
+    const long tot = cnt * DD;
+    T* gF = Fs + base * DD;
+    T* gQ = Qs + base * DD;
+    for (long e = threadIdx.x; e < tot; e += blockDim.x) {
+        gF[e] = sOut[e];
+        gQ[e] = sOut[kDiscThreads * DD + e];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward
+// ---------------------------------------------------------------------------------------------
+// Per-block partial sums: part[b][ (DEG)*DD (W_1..W_DEG) + DD (dPinf) ].
+template <typename T, int D> __host__ __device__ constexpr int bwd_tile() { return sizeof(T) * D * D > 100 ? 64 : 128; }
+
+template <typename T, int D>
+__global__ void __launch_bounds__((bwd_tile<T, D>()))
+discretise_bwd_small_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, const T* __restrict__ dts,
+                            long n, const T* __restrict__ Fs, const T* __restrict__ dFs,
+                            const T* __restrict__ dQs, T* __restrict__ part) {
+    constexpr int DEG = Taylor<T>::DEG;
+    constexpr int TB = bwd_tile<T, D>();
+    constexpr int DD = D * D;
+    constexpr int NOUT = (DEG + 1) * DD;
+    constexpr int PER = (NOUT + TB - 1) / TB;
+    __shared__ T sC[(DEG + 1) * DD];
+    __shared__ T sP[DD];
+    __shared__ T sA[TB * DD];        // dA_h per step
+    __shared__ T sQ[TB * DD];        // dPinf contribution per step
+    __shared__ T sXp[DEG * (TB + 1)]; // x^p per step, p-major
+    __shared__ T sMax[TB / 32];
+    for (int e = threadIdx.x; e < (DEG + 1) * DD; e += blockDim.x) sC[e] = coef[8 + e];
+    for (int e = threadIdx.x; e < DD; e += blockDim.x) sP[e] = Pinf[e];
+    const T normF = coef[0];
+    __syncthreads();
+    T P[nsym(D)];
+#pragma unroll
+    for (int i = 0; i < D; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (sP[i * D + j] + sP[j * D + i]);
+    T accv[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) accv[q] = T(0);
+    const long ntiles = (n + TB - 1) / TB;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long k = tile * TB + threadIdx.x;
+        T dA[DD], dPi[DD];
+        T x = T(0);
+        if (k < n) {
+            const T dt = dts[k];
+            const int s = pick_squarings<T>(normF * t_abs(dt), x);
+            if (dt < T(0)) x = -x;
+            T A[DD], dQ[nsym(D)];
+#pragma unroll
+            for (int e = 0; e < DD; ++e) A[e] = Fs[k * DD + e];
+#pragma unroll
+            for (int e = 0; e < DD; ++e) dA[e] = dFs[k * DD + e];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j)
+                    dQ[sidx(i, j)] = T(0.5) * (dQs[k * DD + i * D + j] + dQs[k * DD + j * D + i]);
+            // dA_tot = dA - 2 dQ A Pinf ; dPinf += dQ - A^T dQ A
+            T QA[DD], QAP[DD];
+            mm_sf<T, D>(dQ, A, QA);
+            mm_fs<T, D>(QA, P, QAP);
+#pragma unroll
+            for (int e = 0; e < DD; ++e) dA[e] -= T(2) * QAP[e];
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j < D; ++j) {
+                    T a1 = dQ[sidx(i, j)];
+#pragma unroll
+                    for (int kk = 0; kk < D; ++kk) a1 = fma(-A[kk * D + i], QA[kk * D + j], a1);
+                    dPi[i * D + j] = a1;
+                }
+            if (s > 0) {
+                // recompute the squaring chain A_0 = A_h, A_{i+1} = A_i^2 and back-propagate through it
+                T chain[kMaxSquarings][DD];
+                T B[DD];
+#pragma unroll
+                for (int e = 0; e < DD; ++e) B[e] = sC[DEG * DD + e];
+#pragma unroll 1
+                for (int p = DEG - 1; p >= 0; --p) {
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) B[e] = fma(B[e], x, sC[p * DD + e]);
+                }
+                for (int i = 0; i < s; ++i) {
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) chain[i][e] = B[e];
+                    T B2[DD];
+                    mm_ff<T, D>(B, B, B2);
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) B[e] = B2[e];
+                }
+                for (int i = s - 1; i >= 0; --i) {
+                    // dA_i = A_i^T dA_{i+1} + dA_{i+1} A_i^T
+                    T t1[DD];
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) B[e] = chain[i][e];
+                    mm_tf<T, D>(B, dA, t1);
+#pragma unroll
+                    for (int r = 0; r < D; ++r)
+#pragma unroll
+                        for (int c = 0; c < D; ++c) {
+                            T a1 = t1[r * D + c];
+#pragma unroll
+                            for (int kk = 0; kk < D; ++kk) a1 = fma(dA[r * D + kk], B[c * D + kk], a1);
+                            t1[r * D + c] = a1;
+                        }
+#pragma unroll
+                    for (int e = 0; e < DD; ++e) dA[e] = t1[e];
+                }
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < DD; ++e) {
+                dA[e] = T(0);
+                dPi[e] = T(0);
+            }
+        }
+        __syncthreads();  // previous tile's readers are done
+#pragma unroll
+        for (int e = 0; e < DD; ++e) {
+            sA[threadIdx.x * DD + e] = dA[e];
+            sQ[threadIdx.x * DD + e] = dPi[e];
+        }
+        {
+            // power table x^1..x^DEG (p-major, padded against bank conflicts) and the tile's max |x|
+            T xp = T(1);
+#pragma unroll 1
+            for (int p = 1; p <= DEG; ++p) {
+                xp *= x;
+                sXp[(p - 1) * (TB + 1) + threadIdx.x] = xp;
+            }
+            T ax = t_abs(x);
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                T o = shfl_down_t(ax, off);
+                ax = o > ax ? o : ax;
+            }
+            if ((threadIdx.x & 31) == 0) sMax[threadIdx.x >> 5] = ax;
+        }
+        __syncthreads();
+        // degrees whose weight x^(p-1)/p! is below 1e-19 (f64) / 1e-10 (f32) for every step of the tile are skipped
+        int pmax = DEG;
+        {
+            T ax = sMax[0];
+            for (int w = 1; w < TB / 32; ++w) ax = sMax[w] > ax ? sMax[w] : ax;
+            const T tol = sizeof(T) == 8 ? T(1e-19) : T(1e-10);
+            T wgt = T(1);
+            for (int p = 1; p <= DEG; ++p) {
+                if (p > 1) wgt *= ax / T(p);
+                if (wgt < tol) {
+                    pmax = p - 1;
+                    break;
+                }
+            }
+            if (pmax < 1) pmax = 1;
+        }
+        // re-partition: thread owns outputs o = threadIdx.x + q*blockDim.x ; o = p*DD + e (p = 0 -> dPinf, p >= 1 -> W_p)
+#pragma unroll
+        for (int q = 0; q < PER; ++q) {
+            const int o = threadIdx.x + q * TB;
+            if (o < NOUT) {
+                const int p = o / DD, e = o % DD;
+                T acc = accv[q];
+                if (p == 0) {
+                    for (int t = 0; t < TB; ++t) acc += sQ[t * DD + e];
+                } else if (p <= pmax) {
+                    const T* xp = sXp + (p - 1) * (TB + 1);
+#pragma unroll 4
+                    for (int t = 0; t < TB; ++t) acc = fma(xp[t], sA[t * DD + e], acc);
+                }
+                accv[q] = acc;
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+        const int o = threadIdx.x + q * TB;
+        if (o < NOUT) part[(long)blockIdx.x * NOUT + o] = accv[q];
+    }
+}
+
+// Sums the per-block partials and assembles dF and dPinf.  One block; generic d.
+// coefT holds C_j of G^T (setup kernel called with transpose = 1).
+template <typename T>
+__global__ void discretise_bwd_final_kernel(const T* __restrict__ coefT, const T* __restrict__ part, int nparts, int d,
+                                            T* __restrict__ W, T* __restrict__ dF, T* __restrict__ dPinf) {
+    const int DEG = Taylor<T>::DEG;
+    const int dd = d * d;
+    const int NOUT = (DEG + 1) * dd;
+    extern __shared__ unsigned char smem_raw[];
+    T* V = (T*)smem_raw;   // d*d
+    T* V2 = V + dd;        // d*d
+    T* acc = V2 + dd;      // d*d
+    for (int o = threadIdx.x; o < NOUT; o += blockDim.x) {
+        T s = T(0);
+        for (int b = 0; b < nparts; ++b) s += part[(long)b * NOUT + o];
+        W[o] = s;
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        dPinf[e] = W[e];
+        acc[e] = T(0);
+    }
+    __syncthreads();
+    const T normF = coefT[0];
+    const T inv = normF > T(0) ? T(1) / normF : T(0);
+    // dF = inv * sum_{i>=0} B^i V_i ,  V_i = sum_{l>=0} W_{i+l+1} B^l / (i+l+1)! ... with C_j = B^j / j! available,
+    // use   sum_{p} (1/p!) sum_{i=0}^{p-1} B^i W_p B^(p-1-i)
+    //     = sum_{i,l} [ i! l! / (i+l+1)! ] C_i W_{i+l+1} C_l
+    for (int i = 0; i < DEG; ++i) {
+        // V = sum_l w(i,l) W_{i+l+1} C_l
+        for (int e = threadIdx.x; e < dd; e += blockDim.x) V[e] = T(0);
+        __syncthreads();
+        T wgt = T(1) / T(i + 1);  // i! 0! / (i+1)!
+        for (int l = 0; i + l + 1 <= DEG; ++l) {
+            const T* Wp = W + (size_t)(i + l + 1) * dd;
+            const T* Cl = coefT + 8 + (size_t)l * dd;
+            for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+                const int r = e / d, c = e % d;
+                T a1 = T(0);
+                for (int k = 0; k < d; ++k) a1 = fma(Wp[r * d + k], Cl[k * d + c], a1);
+                V2[e] = a1;
+            }
+            __syncthreads();
+            for (int e = threadIdx.x; e < dd; e += blockDim.x) V[e] = fma(wgt, V2[e], V[e]);
+            __syncthreads();
+            wgt = wgt * T(l + 1) / T(i + l + 2);  // i!(l+1)!/(i+l+2)!
+        }
+        const T* Ci = coefT + 8 + (size_t)i * dd;
+        for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+            const int r = e / d, c = e % d;
+            T a1 = T(0);
+            for (int k = 0; k < d; ++k) a1 = fma(Ci[r * d + k], V[k * d + c], a1);
+            acc[e] += a1;
+        }
+        __syncthreads();
+    }
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) dF[e] = acc[e] * inv;
+}
+
+constexpr size_t coef_count(int deg, int d) { return 8 + (size_t)(deg + 1) * d * d; }
+
+template <typename T>
+int setup_coef(pssgp_handle* h, const void* F, int d, int transpose, T** coef_out, size_t slot_offset, cudaStream_t st) {
+    const size_t cnt = coef_count(Taylor<T>::DEG, d);
+    *coef_out = (T*)h->buf[WS_MISC] + slot_offset;
+    taylor_setup_kernel<T><<<1, 256, 3 * d * d * sizeof(T), st>>>((const T*)F, d, *coef_out, transpose);
+    (void)cnt;
+    return check_launch(h, "taylor_setup", 1);
+}
+
+template <typename T, int D>
+int discretise_impl(pssgp_handle* h, int64_t n, const void* F, const void* Pinf, const void* dts, void* Fs, void* Qs,
+                    cudaStream_t st) {
+    int rc;
+    const size_t cnt = coef_count(Taylor<T>::DEG, D);
+    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * cnt * 2))) return rc;
+    T* coef;
+    if ((rc = setup_coef<T>(h, F, D, 0, &coef, 0, st))) return rc;
+    const unsigned grid = (unsigned)((n + kDiscThreads - 1) / kDiscThreads);
+    discretise_small_kernel<T, D><<<grid, kDiscThreads, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n, (T*)Fs, (T*)Qs);
+    return check_launch(h, "discretise", 1);
+}
+
+template <typename T, int D>
+int discretise_bwd_impl(pssgp_handle* h, int64_t n, const void* F, const void* Pinf, const void* dts, const void* Fs,
+                        const void* dFs, const void* dQs, void* dF, void* dPinf, cudaStream_t st) {
+    int rc;
+    constexpr int DEG = Taylor<T>::DEG;
+    const size_t cnt = coef_count(DEG, D);
+    const int NOUT = (DEG + 1) * D * D;
+    constexpr int TB = bwd_tile<T, D>();
+    const long ntiles = (n + TB - 1) / TB;
+    int grid = h->num_sms * 4;
+    if (grid > ntiles) grid = (int)ntiles;
+    if (grid < 1) grid = 1;
+    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + NOUT)))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * grid))) return rc;
+    T *coef, *coefT;
+    if ((rc = setup_coef<T>(h, F, D, 0, &coef, 0, st))) return rc;
+    if ((rc = setup_coef<T>(h, F, D, 1, &coefT, cnt, st))) return rc;
+    T* W = (T*)h->buf[WS_MISC] + 2 * cnt;
+    T* part = (T*)h->buf[WS_PART];
+    discretise_bwd_small_kernel<T, D><<<grid, TB, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n,
+                                                                     (const T*)Fs, (const T*)dFs, (const T*)dQs, part);
+    discretise_bwd_final_kernel<T><<<1, 256, 3 * D * D * sizeof(T), st>>>(coefT, part, grid, D, W, (T*)dF, (T*)dPinf);
+    return check_launch(h, "discretise_backward", 2);
+}
+
+}  // namespace pssgp
+
+using namespace pssgp;
+
+#define DISPATCH_SMALL(FN, ...)                                                                   \
+    do {                                                                                          \
+        if (dtype == PSSGP_F64) {                                                                 \
+            switch (d) {                                                                          \
+                case 1: return FN<double, 1>(__VA_ARGS__);                                        \
+                case 2: return FN<double, 2>(__VA_ARGS__);                                        \
+                case 3: return FN<double, 3>(__VA_ARGS__);                                        \
+                case 4: return FN<double, 4>(__VA_ARGS__);                                        \
+            }                                                                                     \
+        } else if (dtype == PSSGP_F32) {                                                          \
+            switch (d) {                                                                          \
+                case 1: return FN<float, 1>(__VA_ARGS__);                                         \
+                case 2: return FN<float, 2>(__VA_ARGS__);                                         \
+                case 3: return FN<float, 3>(__VA_ARGS__);                                         \
+                case 4: return FN<float, 4>(__VA_ARGS__);                                         \
+            }                                                                                     \
+        }                                                                                         \
+    } while (0)
+
+extern "C" {
+
+int pssgp_discretise(pssgp_handle* h, int dtype, int64_t n, int d, const void* F, const void* Pinf, const void* dts,
+                     void* Fs, void* Qs, void* stream) {
+    if (!h) return set_err(PSSGP_ERR_INVALID, "null handle");
+    if (n < 1 || d < 1) return set_err(PSSGP_ERR_INVALID, "discretise: n and d must be >= 1");
+    if (!F || !Pinf || !dts || !Fs || !Qs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_SMALL(discretise_impl, h, n, F, Pinf, dts, Fs, Qs, st);
+    return set_err(PSSGP_ERR_UNSUPPORTED, "discretise: state dimension %d / dtype %d not supported yet", d, dtype);
+}
+
+int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d, const void* F, const void* Pinf,
+                              const void* dts, const void* Fs, const void* dFs, const void* dQs, void* dF, void* dPinf,
+                              void* stream) {
+    if (!h) return set_err(PSSGP_ERR_INVALID, "null handle");
+    if (n < 1 || d < 1) return set_err(PSSGP_ERR_INVALID, "discretise_backward: n and d must be >= 1");
+    if (!F || !Pinf || !dts || !Fs || !dFs || !dQs || !dF || !dPinf)
+        return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    cudaSetDevice(h->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    DISPATCH_SMALL(discretise_bwd_impl, h, n, F, Pinf, dts, Fs, dFs, dQs, dF, dPinf, st);
+    return set_err(PSSGP_ERR_UNSUPPORTED, "discretise_backward: state dimension %d / dtype %d not supported yet", d,
+                   dtype);
+}
+
+}  // extern "C"
