@@ -1,0 +1,349 @@
+#!/usr/bin/env python
+"""bench.py — filter + smoother + log-likelihood-gradient throughput of the temporally-parallel
+state-space GP path (BASELINE.json metric), on synthetic data.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]; SURVEY.md §8d "Config 2"): Matern52(variance 1, lengthscale 1),
+noise 0.1, FP64, N = 1e6 irregular time steps per GPU: dt_k = 0.004 * U(0.5, 1.5) (RandomState
+31415926), y = obs_noise(sinu(t), 0.1, seed 0), 1 % of the observations set to NaN.
+
+* ``value``: time-steps/s of ONE device-resident step = pkf (+log-likelihood) + pks + pkf_backward
+  (gradient w.r.t. the LGSSM fields) through the C ABI, LGSSM (Fs, Qs, y, P0, H, R) already in HBM.
+* ``e2e``: the same metric through the reference-facing model API with HOST buffers, per step:
+  H2D of (t, y) from pinned memory -> StateSpaceGP.maximum_log_likelihood_objective() + gradient
+  w.r.t. the unconstrained hyper-parameters (discretisation + filter + adjoint scans) ->
+  predict_f at N query times (merge + discretise + filter + smoother) -> D2H of ll, gradient,
+  posterior mean and variance.
+* ``roofline``: dominant kernel of the device-resident step, timed with CUDA events on its stream
+  inside the timed region (library option "timing"); algorithmic bytes per DESIGN.md.
+* ``cpu_baseline``: the CPU oracle (restated reference: pkf + autograd gradient + pks in TFP's
+  scan order, torch-CPU on all host cores) on the same workload (rank 0, N = 1 only).
+* ``--impl reference``: only the CPU arm (the reference's TF stack is not installable here; the
+  oracle port is the stand-in), same metric/config.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_PER_GPU = 1_000_000
+NOISE = 0.1
+METRIC = "filter+smoother+grad timesteps/s"
+UNIT = "timesteps/s"
+
+
+def sinu(t):
+    return np.sin(np.pi * t) + np.sin(2 * np.pi * t) + np.cos(3 * np.pi * t)
+
+
+def make_series(n, seed_offset=0):
+    """fixed-rate irregular sampling, 1 % missing observations."""
+    rng = np.random.RandomState(31415926 + seed_offset)
+    t = np.cumsum(0.004 * rng.uniform(0.5, 1.5, size=n))
+    x = sinu(t)
+    rng_y = np.random.RandomState(0 + seed_offset)
+    y = x + np.sqrt(NOISE) * rng_y.normal(x, math.sqrt(NOISE), (n,))  # obs_noise quirk: noise drawn with mean x
+    miss = np.random.RandomState(7 + seed_offset).choice(n, size=n // 100, replace=False)
+    y[miss] = np.nan
+    return t, y
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_step(O, torch, ssm, y, n):
+    """One CPU step of the restated reference: pkf + gradient (autograd through the parallel scan) + pks."""
+    P0, Fs, Qs, H, R = [x.clone().requires_grad_(True) for x in ssm]
+    fm, fP, ll = O.pkf((P0, Fs, Qs, H, R), y[:, None], True, max_parallel=max(n, 2))
+    grads = torch.autograd.grad(ll, (P0, Fs, Qs, H, R))
+    with torch.no_grad():
+        sm, sP = O.pks(ssm, fm.detach(), fP.detach(), max_parallel=max(n, 2))
+    return float(ll), grads, sm, sP
+
+
+def cpu_reference_arm(steps, warmup, sample_n):
+    """Times the CPU restatement of the reference path (oracle port) with all host threads."""
+    import torch
+    import __graft_entry__ as entry
+    O = entry.import_oracle()
+    t, y = make_series(sample_n)
+    cov = O.Matern52(1.0, 1.0)
+    with torch.no_grad():
+        ssm = cov.get_ssm(t[:, None], torch.tensor([[NOISE]], dtype=torch.float64))
+    for _ in range(warmup):
+        oracle_step(O, torch, ssm, y, sample_n)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oracle_step(O, torch, ssm, y, sample_n)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return sample_n / dt, dt, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_n = 250_000
+    val, dt, cores = cpu_reference_arm(args.steps, max(args.warmup, 1), sample_n)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "Matern52 single series N=1e6 per GPU, FP64, log-lik + gradient + RTS smoother "
+                               "(configs[1]); each step a bounded sample of 250,000 steps of it",
+                   "sample_steps": sample_n},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "first 250,000 time steps of the workload per step; oracle port (torch-CPU "
+                                   "restatement of pkf + autograd gradient + pks); the TF reference is not installable"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n", type=int, default=N_PER_GPU, help="time steps per GPU (default: the BASELINE workload)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import __graft_entry__ as entry
+    entry.import_package()
+    from pssgp_b200 import _lib, kernels, ops
+    from pssgp_b200.model import StateSpaceGP
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.n
+    d = 3
+    W = max(args.warmup, 3)
+    K = args.steps
+
+    # ---- synthetic workload -------------------------------------------------------------------------
+    from pssgp_b200 import dist as pdist
+    t_host, y_host = make_series(n * world)  # one long series, time-sharded across ranks
+    lo, hi = rank * n, (rank + 1) * n
+    cov = kernels.Matern52(1.0, 1.0)
+    with torch.no_grad():
+        sde = cov.get_sde()
+    F = sde.F.to(dev).contiguous()
+    Pinf = sde.P0.to(dev).contiguous()
+    H = sde.H.to(dev).reshape(-1).contiguous()
+    R = torch.tensor([NOISE], dtype=torch.float64, device=dev)
+    t_dev = torch.as_tensor(t_host[lo:hi]).to(dev)
+    t_prev = 0.0 if lo == 0 else float(t_host[lo - 1])
+    dts = t_dev - torch.cat([torch.tensor([t_prev], dtype=torch.float64, device=dev), t_dev[:-1]])
+    y_dev = torch.as_tensor(y_host[lo:hi]).to(dev)
+    Fs, Qs = ops.discretise(F, Pinf, dts)
+    g_ll = torch.ones(1, dtype=torch.float64, device=dev)
+    shard = pdist.TimeShard(rank, world, dist) if world > 1 else None
+    h = _lib.handle(local_rank)
+
+    def device_step():
+        if shard is None:
+            fms, fPs, ll, _ = ops.pkf(Pinf, Fs, Qs, H, R, y_dev)
+            sms, sPs, _ = ops.pks(Fs, Qs, fms, fPs)
+            grads = ops.pkf_backward(Pinf, Fs, Qs, H, R, y_dev, fms, fPs, g_ll)
+            return ll, sms, sPs, grads
+        return shard.filter_smoother_grad(Pinf, Fs, Qs, H, R, y_dev, g_ll)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ---------------------------------------------------------------------
+    for _ in range(W):
+        out = device_step()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    h.set_option("timing", 1)
+    h.timing_report()
+    launches0 = h.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        out = device_step()
+    e1.record()
+    barrier()
+    ms_dev = e0.elapsed_time(e1) / K
+    launches = (h.launch_count() - launches0) // max(K, 1)
+    ktimes = h.timing_report()
+    h.set_option("timing", 0)
+    clock_info = clocks.stop() if rank == 0 else None
+    if dist is not None:
+        tt = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev = float(tt)
+    value = n * world / (ms_dev * 1e-3)
+
+    # ---- end-to-end through the model API with host buffers --------------------------------------------
+    e2e = None
+    if world == 1:
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        t_pin, y_pin = pin(t_host[:, None]), pin(y_host[:, None])
+        q_host = t_host + 0.002  # N query times interleaved with the training grid
+        q_pin = pin(q_host[:, None])
+        model = StateSpaceGP((t_pin, y_pin), kernels.Matern52(1.0, 1.0), noise_variance=NOISE, parallel=True,
+                             max_parallel=2 * n)
+
+        def e2e_step():
+            model.data = (t_pin, y_pin)  # H2D of this step's inputs from pinned memory
+            ll = model.maximum_log_likelihood_objective()
+            grads = torch.autograd.grad(ll, model.trainable_variables)
+            mean, var = model.predict_f(q_pin.numpy())  # numpy in -> numpy out (D2H of the result)
+            return float(ll), [float(g) for g in grads], mean, var
+
+        for _ in range(W):
+            r = e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            r = e2e_step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / K
+        e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * 2 * n + 8 * n),
+               "d2h_bytes_per_step": int(8 * 2 * n + 8 * 4), "ms_per_step": dt * 1e3,
+               "api": "StateSpaceGP.data= ; maximum_log_likelihood_objective + autograd.grad ; predict_f(N queries)"}
+    else:
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+               "note": "model-level e2e is measured at n_gpus=1"}
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    s = 8
+    alg_bytes = {  # algorithmic bytes per time step of each kernel
+        "pkf_reduce": s * (2 * d * d + 1), "pkf_apply": s * (3 * d * d + d + 1), "pkf_mid": 0,
+        "pks_reduce": s * (3 * d * d + d), "pks_apply": s * (4 * d * d + 2 * d), "pks_mid": 0,
+        "pkf_bwd_reduce": s * (3 * d * d + d + 1), "pkf_bwd_apply": s * (5 * d * d + d + 1), "pkf_bwd_mid": 0,
+    }
+    per_kernel = {k: {"launches": c, "avg_us": 1e3 * ms / max(c, 1)} for k, (c, ms) in ktimes.items()}
+    dom = max(ktimes.items(), key=lambda kv: kv[1][1])[0] if ktimes else None
+    roofline = None
+    if dom is not None:
+        avg_s = ktimes[dom][1] / max(ktimes[dom][0], 1) * 1e-3
+        achieved = alg_bytes.get(dom, 0) * n / avg_s / 1e9
+        roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "share_of_step": ktimes[dom][1] / sum(v[1] for v in ktimes.values())}
+    stage_bytes = s * (12 * d * d + 4 * d + 2)
+    step_roof = {"alg_bytes_per_timestep": stage_bytes, "achieved_gbs": stage_bytes * n * world / (ms_dev * 1e-3) / 1e9,
+                 "frac_of_hbm_peak": stage_bytes * n * world / (ms_dev * 1e-3) / 1e9 / (hbm_peak * world)}
+
+    # ---- CPU baseline (oracle port) on the host cores ------------------------------------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        sample_n = min(n, 1_000_000)
+        val, dt, cores = cpu_reference_arm(1, 1, sample_n)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"the full workload once ({sample_n} time steps, {dt:.1f} s): oracle port = torch-CPU "
+                         f"restatement of the reference's pkf + autograd gradient + pks; TF reference not installable"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "Matern52 single series N=1e6 per GPU (one series of n_gpus*1e6 steps, time-sharded), "
+                               "FP64, log-lik + gradient + RTS smoother (configs[1])",
+                   "n_per_gpu": n, "state_dim": d, "l2_policy": "inputs larger than L2 (Fs+Qs+y = 152 MB, "
+                   "plus 96+96+144 MB of outputs per step; L2 = 126 MB)",
+                   "parallelism": "time-sharded x%d" % world if world > 1 else "single GPU"},
+        "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "step_roofline": step_roof,
+        "kernels": per_kernel, "cpu_baseline": cpu, "clocks": clock_info,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -39,10 +39,21 @@ const char* pssgp_last_error(void);
 /* A handle owns the reusable device workspace (chunk aggregates, warp totals, partial sums). */
 int pssgp_create(pssgp_handle** out, int device);
 int pssgp_destroy(pssgp_handle* h);
-/* Tuning knobs: "chunk" = time steps per thread-chunk (0 = heuristic). */
+/* Options: "chunk" = time steps per thread-chunk (0 = heuristic); "timing" = 1 brackets every
+ * kernel launch with CUDA events on its stream (read back with pssgp_timing_report). */
 int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t pssgp_launch_count(const pssgp_handle* h);
+/* Writes "name count total_ms\n" per kernel name for the launches recorded since the last report
+ * (synchronises the device) into buf (host, buflen bytes) and clears the records. */
+int pssgp_timing_report(pssgp_handle* h, char* buf, int64_t buflen);
+
+/*
+ * HOST routine (host pointers, float64): diagonal balancing of the SDE drift matrix.  Replaces the
+ * reference's only natively compiled function, _numba_balance_ss (pssgp/kernels/math_utils.py:10-29).
+ * F [d,d] row-major; d_out [d] receives the scaling (F_balanced = D^-1 F D).
+ */
+int pssgp_balance_ss(const void* F, int d, int n_iter, void* d_out);
 
 /*
  * Discretisation of the LTI SDE.  Replaces pssgp/kernels/base.py:29-47 (_get_ssm):
@@ -60,8 +71,8 @@ int pssgp_discretise(pssgp_handle* h, int dtype, int64_t n, int d,
  * missing); m0 [d] or NULL (zeros, as the reference).  first_special != 0: step 0 is the global first
  * step (update on (m0,P0) without prediction, parallel.py:24-30); 0: (m0,P0) is the filtered state
  * just before this shard (time-sharded multi-GPU use).
- * Outputs: fms [n,d], fPs [n,d,d], ll [1] or NULL, final_state [d + d(d+1)/2] or NULL
- * (filtered mean | packed lower-triangular covariance after the last step).
+ * Outputs: fms [n,d], fPs [n,d,d], ll [1] or NULL, final_state [d + d*d] or NULL (filtered mean |
+ * full covariance after the last step: usable as (m0, P0 = m0 + d) of the next shard).
  */
 int pssgp_pkf(pssgp_handle* h, int dtype, int64_t n, int d,
               const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,
@@ -71,7 +82,8 @@ int pssgp_pkf(pssgp_handle* h, int dtype, int64_t n, int d,
 /*
  * Parallel RTS smoother.  Replaces pssgp/kalman/parallel.py:187-196 (pks) incl. :155-184.
  * last_special != 0: time n-1 is the global last step.  Otherwise Fnext/Qnext [d,d] are F, Q of
- * time n (first step of the next shard) and init [d + d(d+1)/2] is the smoothed state at time n.
+ * time n (first step of the next shard) and init [d + d(d+1)/2] is the smoothed state at time n
+ * (mean | packed lower-triangular covariance).
  * Outputs sms [n,d], sPs [n,d,d], first_state (smoothed state at time 0, packed) or NULL.
  */
 int pssgp_pks(pssgp_handle* h, int dtype, int64_t n, int d,
@@ -80,10 +92,30 @@ int pssgp_pks(pssgp_handle* h, int dtype, int64_t n, int d,
               void* sms, void* sPs, void* first_state, void* stream);
 
 /*
- * Time-sharded scans (one shard per GPU).  *_summary runs the local reduce and writes the shard's
- * aggregate element ((A,b,C,J,eta) packed: d*d + 2d + d(d+1) values; (E,g,L) packed: d*d + d +
- * d(d+1)/2 values) so that ranks can all-gather them; pssgp_filter_fold / pssgp_smoother_fold turn
- * the gathered summaries of the preceding (following) shards into the state entering this shard.
+ * Gradient of the log-likelihood w.r.t. the LGSSM fields (hand-written adjoint scan; replaces TF
+ * autodiff through pkf, cf. tests/test_gp_vs_kfs.py:53-67).  g_ll [1] is the upstream gradient;
+ * fms/fPs are pkf's outputs.  (P0, m0, first_special) as in pssgp_pkf.  adj_init [d + d(d+1)/2] or
+ * NULL: adjoint w.r.t. the filtered moments of this shard's last step coming from the next shard.
+ * Outputs: dP0 [d,d] (written only when first_special; may be NULL otherwise), dFs [n,d,d],
+ * dQs [n,d,d], dH [d], dR [1] (this shard's contributions), adj_first [d + d(d+1)/2] or NULL
+ * (adjoint w.r.t. the filtered moments entering this shard).
+ */
+int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d,
+                       const void* P0, const void* m0, const void* Fs, const void* Qs, const void* H,
+                       const void* R, const void* y, const void* fms, const void* fPs, const void* g_ll,
+                       int first_special, const void* adj_init,
+                       void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* adj_first, void* stream);
+
+/*
+ * Time-sharded scans (one contiguous shard of the time axis per GPU).  *_summary runs the local
+ * reduce and writes the shard's aggregate element so that ranks can all-gather them:
+ *   filter   (A,b,C,J,eta): d*d + 2d + d(d+1) values      smoother (E,g,L): d*d + d + d(d+1)/2
+ *   adjoint  (Abar,a,B):    d*d + d + d(d+1)/2
+ * The chunk aggregates stay in the handle's workspace: the matching full call (same arrays) that
+ * follows skips its reduce kernel.  *_fold turns gathered summaries into the state entering this
+ * shard: pssgp_filter_fold folds the `nshards_before` summaries (rank order) onto (m0, P0) and writes
+ * m [d] | P [d,d]; pssgp_smoother_fold / pssgp_adjoint_fold fold the `nshards_after` summaries of the
+ * following shards (given in rank order, applied last-to-first) and write the packed state.
  */
 int pssgp_pkf_summary(pssgp_handle* h, int dtype, int64_t n, int d,
                       const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,
@@ -97,16 +129,12 @@ int pssgp_pks_summary(pssgp_handle* h, int dtype, int64_t n, int d,
                       void* summary, void* stream);
 int pssgp_smoother_fold(pssgp_handle* h, int dtype, int d, int nshards_after,
                         const void* summaries, void* state_out, void* stream);
-
-/*
- * Gradient of the log-likelihood w.r.t. the LGSSM fields (hand-written adjoint scan; replaces TF
- * autodiff through pkf, cf. tests/test_gp_vs_kfs.py:53-67).  g_ll [1] is the upstream gradient.
- * Outputs: dP0 [d,d], dFs [n,d,d], dQs [n,d,d], dH [d], dR [1].
- */
-int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d,
-                       const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,
-                       const void* y, const void* fms, const void* fPs, const void* g_ll,
-                       void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream);
+int pssgp_pkf_backward_summary(pssgp_handle* h, int dtype, int64_t n, int d,
+                               const void* P0, const void* m0, const void* Fs, const void* Qs, const void* H,
+                               const void* R, const void* y, const void* fms, const void* fPs,
+                               int first_special, void* summary, void* stream);
+int pssgp_adjoint_fold(pssgp_handle* h, int dtype, int d, int nshards_after,
+                       const void* summaries, void* state_out, void* stream);
 
 /*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].

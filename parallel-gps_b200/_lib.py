@@ -25,6 +25,8 @@ SIGNATURES = {
     "pssgp_destroy": (_int, [_vp]),
     "pssgp_set_option": (_int, [_vp, ctypes.c_char_p, _i64]),
     "pssgp_launch_count": (_i64, [_vp]),
+    "pssgp_timing_report": (_int, [_vp, ctypes.c_char_p, _i64]),
+    "pssgp_balance_ss": (_int, [_vp, _int, _int, _vp]),
     "pssgp_discretise": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_pkf": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_pks": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
@@ -32,8 +34,11 @@ SIGNATURES = {
     "pssgp_filter_fold": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_pks_summary": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
     "pssgp_smoother_fold": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp]),
-    "pssgp_pkf_backward": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
-                                  _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pssgp_pkf_backward": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
+                                  _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pssgp_pkf_backward_summary": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
+                                          _vp, _vp]),
+    "pssgp_adjoint_fold": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp]),
     "pssgp_discretise_backward": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
@@ -92,6 +97,16 @@ class Handle:
     def launch_count(self):
         return int(lib().pssgp_launch_count(self._h))
 
+    def timing_report(self):
+        """{kernel name: (launch count, total ms)} since the last report (option "timing" must be 1)."""
+        buf = ctypes.create_string_buffer(1 << 16)
+        check(lib().pssgp_timing_report(self._h, buf, len(buf)))
+        out = {}
+        for line in buf.value.decode().splitlines():
+            name, cnt, ms = line.split()
+            out[name] = (int(cnt), float(ms))
+        return out
+
     def close(self):
         if self._h:
             lib().pssgp_destroy(self._h)
@@ -108,9 +123,10 @@ _handles = {}
 
 
 def handle(device):
-    device = int(device)
-    h = _handles.get(device)
+    """One handle (device workspace) per (device, host thread): handles are not shared between threads."""
+    key = (int(device), threading.get_ident())
+    h = _handles.get(key)
     if h is None:
-        h = Handle(device)
-        _handles[device] = h
+        h = Handle(int(device))
+        _handles[key] = h
     return h

@@ -13,12 +13,17 @@
 // Aggregate layout: Abar[D*D] | a[D] | B[NS] ; state: dm[D] | dP[NS] ; accumulators: dR, dH[D]
 #pragma once
 #include "smalld.cuh"
+#include "workspace.h"
 
 namespace pssgp {
 
 template <typename T, int D>
 struct AdjointAlg {
     using scalar = T;
+    static constexpr int KIND = KIND_ADJOINT;
+    static const char* name_reduce() { return "pkf_bwd_reduce"; }
+    static const char* name_mid() { return "pkf_bwd_mid"; }
+    static const char* name_apply() { return "pkf_bwd_apply"; }
     static constexpr int NS = nsym(D);
     static constexpr int oA = 0, oa = D * D, oB = oa + D;
     static constexpr int NAGG = oB + NS;
@@ -336,6 +341,11 @@ struct AdjointAlg {
             }
         // when the shard does not start at the global origin, the state after its first step is the
         // adjoint w.r.t. the previous shard's last filtered moments: the framework returns it.
+    }
+
+    PSSGP_DEV static void expand_state(const T* s, T* out) {
+#pragma unroll
+        for (int e = 0; e < NSTATE; ++e) out[e] = s[e];
     }
 
     PSSGP_DEV static void finish(const Params& p, int e, T tot, T*) {

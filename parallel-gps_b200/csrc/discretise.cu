@@ -19,9 +19,6 @@
 
 namespace pssgp {
 
-int set_err(int code, const char* fmt, ...);
-int ws_reserve(pssgp_handle* h, int slot, size_t bytes);
-int check_launch(pssgp_handle* h, const char* what, int nlaunches);
 
 template <typename T> struct Taylor;
 template <> struct Taylor<double> { static constexpr int DEG = 18; };
@@ -396,9 +393,10 @@ template <typename T>
 int setup_coef(pssgp_handle* h, const void* F, int d, int transpose, T** coef_out, size_t slot_offset, cudaStream_t st) {
     const size_t cnt = coef_count(Taylor<T>::DEG, d);
     *coef_out = (T*)h->buf[WS_MISC] + slot_offset;
-    taylor_setup_kernel<T><<<1, 256, 3 * d * d * sizeof(T), st>>>((const T*)F, d, *coef_out, transpose);
+    PSSGP_LAUNCH(h, "taylor_setup", st,
+                 (taylor_setup_kernel<T><<<1, 256, 3 * d * d * sizeof(T), st>>>((const T*)F, d, *coef_out, transpose)));
     (void)cnt;
-    return check_launch(h, "taylor_setup", 1);
+    return check_launch(h, "taylor_setup", 0);
 }
 
 template <typename T, int D>
@@ -410,8 +408,10 @@ int discretise_impl(pssgp_handle* h, int64_t n, const void* F, const void* Pinf,
     T* coef;
     if ((rc = setup_coef<T>(h, F, D, 0, &coef, 0, st))) return rc;
     const unsigned grid = (unsigned)((n + kDiscThreads - 1) / kDiscThreads);
-    discretise_small_kernel<T, D><<<grid, kDiscThreads, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n, (T*)Fs, (T*)Qs);
-    return check_launch(h, "discretise", 1);
+    PSSGP_LAUNCH(h, "discretise", st,
+                 (discretise_small_kernel<T, D><<<grid, kDiscThreads, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n,
+                                                                              (T*)Fs, (T*)Qs)));
+    return check_launch(h, "discretise", 2);
 }
 
 template <typename T, int D>
@@ -433,10 +433,13 @@ int discretise_bwd_impl(pssgp_handle* h, int64_t n, const void* F, const void* P
     if ((rc = setup_coef<T>(h, F, D, 1, &coefT, cnt, st))) return rc;
     T* W = (T*)h->buf[WS_MISC] + 2 * cnt;
     T* part = (T*)h->buf[WS_PART];
-    discretise_bwd_small_kernel<T, D><<<grid, TB, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n,
-                                                                     (const T*)Fs, (const T*)dFs, (const T*)dQs, part);
-    discretise_bwd_final_kernel<T><<<1, 256, 3 * D * D * sizeof(T), st>>>(coefT, part, grid, D, W, (T*)dF, (T*)dPinf);
-    return check_launch(h, "discretise_backward", 2);
+    PSSGP_LAUNCH(h, "discretise_bwd", st,
+                 (discretise_bwd_small_kernel<T, D><<<grid, TB, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n,
+                                                                        (const T*)Fs, (const T*)dFs, (const T*)dQs, part)));
+    PSSGP_LAUNCH(h, "discretise_bwd_final", st,
+                 (discretise_bwd_final_kernel<T><<<1, 256, 3 * D * D * sizeof(T), st>>>(coefT, part, grid, D, W, (T*)dF,
+                                                                                       (T*)dPinf)));
+    return check_launch(h, "discretise_backward", 4);
 }
 
 }  // namespace pssgp

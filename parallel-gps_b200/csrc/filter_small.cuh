@@ -10,12 +10,17 @@
 // State layout: m[D] | P[NS]
 #pragma once
 #include "smalld.cuh"
+#include "workspace.h"
 
 namespace pssgp {
 
 template <typename T, int D>
 struct FilterAlg {
     using scalar = T;
+    static constexpr int KIND = KIND_FILTER;
+    static const char* name_reduce() { return "pkf_reduce"; }
+    static const char* name_mid() { return "pkf_mid"; }
+    static const char* name_apply() { return "pkf_apply"; }
     static constexpr int NS = nsym(D);
     static constexpr int oA = 0, ob = D * D, oC = ob + D, oJ = oC + NS, oE = oJ + NS;
     static constexpr int NAGG = oE + D;
@@ -274,6 +279,16 @@ struct FilterAlg {
         for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int j = 0; j < D; ++j) oP[i * D + j] = s[D + sidx(i, j)];
+    }
+
+    // fold output: m[D] | P full [D,D]  (so that the caller can pass m0 = out, P0 = out + D to pssgp_pkf)
+    PSSGP_DEV static void expand_state(const T* s, T* out) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) out[i] = s[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) out[D + i * D + j] = s[D + sidx(i, j)];
     }
 
     PSSGP_DEV static void finish(const Params&, int, T tot, T* acc_out) {

@@ -1,0 +1,112 @@
+// Host-side launcher of the three-kernel chunked scan (scan_small.cuh) + (dtype, d) dispatch helpers.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/pssgp_b200.h"
+#include "scan_small.cuh"
+#include "workspace.h"
+
+namespace pssgp {
+
+int pick_chunk(const pssgp_handle* h, int64_t n);
+int check_common(pssgp_handle* h, int dtype, int64_t n, int d);
+
+// generic state dimension (warp-cooperative path, generic.cu); summary != nullptr selects summary mode
+int pkf_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+                const void* H, const void* R, const void* y, const void* m0, int first_special, void* fms, void* fPs,
+                void* ll, void* final_state, void* summary, cudaStream_t st);
+int filter_fold_generic(pssgp_handle* h, int dtype, int d, int count, const void* P0, const void* m0,
+                        const void* summaries, void* state_out, cudaStream_t st);
+int pks_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* Fs, const void* Qs, const void* fms,
+                const void* fPs, int last_special, const void* Fnext, const void* Qnext, const void* init, void* sms,
+                void* sPs, void* first_state, void* summary, cudaStream_t st);
+int smoother_fold_generic(pssgp_handle* h, int dtype, int d, int count, const void* summaries, void* state_out,
+                          cudaStream_t st);
+int pkf_bwd_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* m0, const void* Fs,
+                    const void* Qs, const void* H, const void* R, const void* y, const void* fms, const void* fPs,
+                    const void* g_ll, int first_special, const void* adj_init, void* dP0, void* dFs, void* dQs,
+                    void* dH, void* dR, void* adj_first, void* summary, cudaStream_t st);
+int adjoint_fold_generic(pssgp_handle* h, int dtype, int d, int count, const void* summaries, void* state_out,
+                         cudaStream_t st);
+
+enum ScanMode { SCAN_FULL = 0, SCAN_SUMMARY = 1 };
+
+// Runs K1/K2/K3 for an algebra.  SCAN_SUMMARY: K1 + total only (shard summary for time sharding); the
+// chunk aggregates stay in the workspace and the next SCAN_FULL call with the same key skips K1.
+template <typename Alg>
+int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::scalar* acc_out,
+             typename Alg::scalar* final_state, cudaStream_t st, int mode = SCAN_FULL,
+             typename Alg::scalar* summary = nullptr, const void* key = nullptr) {
+    using T = typename Alg::scalar;
+    const int L = pick_chunk(h, n);
+    const int64_t nChunks = (n + L - 1) / L;
+    const int64_t nBlocks = (nChunks + kReduceThreads - 1) / kReduceThreads;
+    const int64_t nW = nBlocks;  // one aggregate per CTA of K1
+    const int64_t nChunksPad = nBlocks * kReduceThreads;
+    constexpr int kind = Alg::KIND;
+    const bool reuse = (mode == SCAN_FULL && key != nullptr && h->pending_key[kind] == key &&
+                        h->pending_n[kind] == n && h->pending_L[kind] == L);
+    h->pending_key[kind] = nullptr;
+    int rc;
+    if (!reuse) {
+        if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * Alg::NAGG * (size_t)nChunksPad))) return rc;
+        if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * Alg::NAGG * (size_t)nW))) return rc;
+    }
+    if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * Alg::NSTATE * (size_t)nW))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (Alg::NACC > 0 ? Alg::NACC : 1) * (size_t)nBlocks))) return rc;
+    T* lane = (T*)h->buf[WS_LANE + kind];
+    T* wagg = (T*)h->buf[WS_WAGG + kind];
+    T* wstate = (T*)h->buf[WS_WSTATE];
+    T* part = (T*)h->buf[WS_PART];
+    int nl = 0;
+    if (!reuse) {
+        PSSGP_LAUNCH(h, Alg::name_reduce(), st,
+                     (scan_reduce_kernel<Alg><<<(unsigned)nBlocks, kReduceThreads, 0, st>>>(p, n, L, nChunksPad, lane,
+                                                                                           wagg, nW)));
+        ++nl;
+    }
+    int midThreads = kMidThreads;
+    if (nW < kMidThreads) midThreads = (int)(((nW + 31) / 32) * 32);
+    if (midThreads < 32) midThreads = 32;
+    if (mode == SCAN_SUMMARY) {
+        PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_total_kernel<Alg><<<1, midThreads, 0, st>>>(wagg, nW, summary)));
+        h->pending_key[kind] = key;
+        h->pending_n[kind] = n;
+        h->pending_L[kind] = L;
+        return check_launch(h, "scan summary", nl + 1);
+    }
+    PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_mid_kernel<Alg><<<1, midThreads, 0, st>>>(p, wagg, nW, wstate, final_state)));
+    PSSGP_LAUNCH(h, Alg::name_apply(), st,
+                 (scan_apply_kernel<Alg><<<(unsigned)nBlocks, kReduceThreads, 0, st>>>(p, n, L, nChunksPad, lane, wstate,
+                                                                                      nW, part, h->ticket, acc_out)));
+    return check_launch(h, "scan", nl + 2);
+}
+
+template <typename Alg>
+int run_fold(pssgp_handle* h, typename Alg::Params p, const typename Alg::scalar* summaries, int count, long stride,
+             typename Alg::scalar* out, cudaStream_t st) {
+    PSSGP_LAUNCH(h, "fold", st, (scan_fold_kernel<Alg><<<1, 32, 0, st>>>(p, summaries, count, stride, out)));
+    return check_launch(h, "fold", 1);
+}
+
+}  // namespace pssgp
+
+#define DISPATCH_SMALL(FN, ...)                                                                   \
+    do {                                                                                          \
+        if (dtype == PSSGP_F64) {                                                                 \
+            switch (d) {                                                                          \
+                case 1: return FN<double, 1>(__VA_ARGS__);                                        \
+                case 2: return FN<double, 2>(__VA_ARGS__);                                        \
+                case 3: return FN<double, 3>(__VA_ARGS__);                                        \
+                case 4: return FN<double, 4>(__VA_ARGS__);                                        \
+            }                                                                                     \
+        } else if (dtype == PSSGP_F32) {                                                          \
+            switch (d) {                                                                          \
+                case 1: return FN<float, 1>(__VA_ARGS__);                                         \
+                case 2: return FN<float, 2>(__VA_ARGS__);                                         \
+                case 3: return FN<float, 3>(__VA_ARGS__);                                         \
+                case 4: return FN<float, 4>(__VA_ARGS__);                                         \
+            }                                                                                     \
+        }                                                                                         \
+    } while (0)
+

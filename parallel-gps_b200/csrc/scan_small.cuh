@@ -219,14 +219,8 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
         for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
     }
     // the thread that owns the last warp total holds the final state
-    if (final_state != nullptr && i1 == nW && i0 < nW) {
-#pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) final_state[e] = s[e];
-    }
-    if (final_state != nullptr && nW == 0 && tid == 0) {
-#pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) final_state[e] = s[e];
-    }
+    if (final_state != nullptr && i1 == nW && i0 < nW) Alg::expand_state(s, final_state);
+    if (final_state != nullptr && nW == 0 && tid == 0) Alg::expand_state(s, final_state);
 }
 
 template <typename Alg>
@@ -304,6 +298,80 @@ scan_apply_kernel(typename Alg::Params p, long n, int L, long nChunksPad,
             if (threadIdx.x == 0) *ticket = 0u;
         }
     }
+}
+
+// Single CTA: out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding).
+template <typename Alg>
+__global__ void __launch_bounds__(kMidThreads)
+scan_total_kernel(const typename Alg::scalar* __restrict__ wagg, long nW, typename Alg::scalar* __restrict__ out) {
+    using T = typename Alg::scalar;
+    __shared__ T sh[(kMidThreads / 32) * Alg::NAGG];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int nthreads = blockDim.x;
+    const long per = (nW + nthreads - 1) / nthreads;
+    long i0 = (long)tid * per, i1 = i0 + per;
+    if (i0 > nW) i0 = nW;
+    if (i1 > nW) i1 = nW;
+    T a[Alg::NAGG];
+    Alg::identity(a);
+    for (long i = i0; i < i1; ++i) {
+        T b[Alg::NAGG], r[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) b[e] = wagg[(long)e * nW + i];
+        Alg::combine(a, b, r);
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
+    }
+    // ordered tree reduction inside the warp: lane l <- a[l] o a[l+off]
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        T o[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_down_t(a[e], off);
+        if ((lane & (2 * off - 1)) == 0) {
+            T r[Alg::NAGG];
+            Alg::combine(a, o, r);
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) sh[wid * Alg::NAGG + e] = a[e];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const int nwarps = nthreads >> 5;
+        for (int w = 1; w < nwarps; ++w) {
+            T b[Alg::NAGG], r[Alg::NAGG];
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) b[e] = sh[w * Alg::NAGG + e];
+            Alg::combine(a, b, r);
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
+        }
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) out[e] = a[e];
+    }
+}
+
+// One thread: s = init; for i in 0..count-1: s = s o summaries[i*stride ...]; out = Alg::expand(s).
+template <typename Alg>
+__global__ void scan_fold_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__ summaries,
+                                 int count, long stride, typename Alg::scalar* __restrict__ out) {
+    using T = typename Alg::scalar;
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    T s[Alg::NSTATE];
+    Alg::load_init(p, s);
+    for (int i = 0; i < count; ++i) {
+        T b[Alg::NAGG], s2[Alg::NSTATE];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) b[e] = summaries[(long)i * stride + e];
+        Alg::apply(s, b, s2);
+#pragma unroll
+        for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
+    }
+    Alg::expand_state(s, out);
 }
 
 }  // namespace pssgp

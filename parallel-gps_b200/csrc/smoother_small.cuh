@@ -10,12 +10,17 @@
 // Aggregate layout: E[D*D] | g[D] | L[NS] ; state: sm[D] | sP[NS]
 #pragma once
 #include "smalld.cuh"
+#include "workspace.h"
 
 namespace pssgp {
 
 template <typename T, int D>
 struct SmootherAlg {
     using scalar = T;
+    static constexpr int KIND = KIND_SMOOTHER;
+    static const char* name_reduce() { return "pks_reduce"; }
+    static const char* name_mid() { return "pks_mid"; }
+    static const char* name_apply() { return "pks_apply"; }
     static constexpr int NS = nsym(D);
     static constexpr int oE = 0, og = D * D, oL = og + D;
     static constexpr int NAGG = oL + NS;
@@ -186,6 +191,11 @@ struct SmootherAlg {
         for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int jj = 0; jj < D; ++jj) oP[i * D + jj] = s[D + sidx(i, jj)];
+    }
+
+    PSSGP_DEV static void expand_state(const T* s, T* out) {
+#pragma unroll
+        for (int e = 0; e < NSTATE; ++e) out[e] = s[e];
     }
 
     PSSGP_DEV static void finish(const Params&, int, T, T*) {}

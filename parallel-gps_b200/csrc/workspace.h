@@ -3,7 +3,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
-enum { WS_LANE = 0, WS_WAGG, WS_WSTATE, WS_PART, WS_MISC, WS_COUNT };
+// chunk-aggregate slots exist once per scan kind (filter / smoother / adjoint) so that several
+// *_summary calls can be pending at the same time.
+enum { WS_LANE = 0, WS_WAGG = 3, WS_WSTATE = 6, WS_PART, WS_MISC, WS_GEN0, WS_GEN1, WS_GEN2, WS_GEN3, WS_COUNT };
+enum { KIND_FILTER = 0, KIND_SMOOTHER = 1, KIND_ADJOINT = 2 };
 
 struct pssgp_handle {
     int device;
@@ -13,4 +16,34 @@ struct pssgp_handle {
     unsigned int* ticket;
     int64_t chunk_opt;
     int64_t launches;
+    // chunk aggregates left in the workspace by a *_summary call (time sharding)
+    const void* pending_key[3];
+    int64_t pending_n[3];
+    int pending_L[3];
+    // optional per-kernel CUDA-event timing (option "timing" = 1)
+    int timing;
+    int n_rec, cap_rec;
+    struct pssgp_timing_rec* recs;
 };
+
+struct pssgp_timing_rec {
+    const char* name;
+    void* ev0;
+    void* ev1;
+};
+
+namespace pssgp {
+int set_err(int code, const char* fmt, ...);
+int ws_reserve(pssgp_handle* h, int slot, size_t bytes);
+int check_launch(pssgp_handle* h, const char* what, int nlaunches);
+void timing_begin(pssgp_handle* h, const char* name, void* stream);
+void timing_end(pssgp_handle* h, void* stream);
+}  // namespace pssgp
+
+// Launch wrapper: PSSGP_LAUNCH(h, "name", stream, kernel<<<grid, block, smem, stream>>>(args...));
+#define PSSGP_LAUNCH(h, name, st, ...)                  \
+    do {                                                \
+        if ((h)->timing) pssgp::timing_begin((h), (name), (void*)(st)); \
+        __VA_ARGS__;                                    \
+        if ((h)->timing) pssgp::timing_end((h), (void*)(st));           \
+    } while (0)

@@ -1,0 +1,117 @@
+"""Time-sharded scans: the time axis is cut into `world` contiguous shards, one per GPU (one process
+per GPU, torch.distributed / NCCL over NVLink for the plumbing).
+
+Per scan each rank reduces its shard to ONE aggregate element (a few hundred bytes), the aggregates
+are all-gathered, every rank folds the aggregates of the shards before (filter) or after (smoother,
+adjoint) it into the state entering its shard, and finishes locally.  The messages are latency-bound;
+three collectives per filter+smoother+gradient step:
+
+  1. all_gather [filter summary | F, Q of the shard's first step (halo for the smoother)]
+  2. all_gather [smoother summary | adjoint summary]
+  3. all_reduce [ll | dH | dR | dP0]
+
+The reference has no multi-device code; this is the §8(e) design.  ``backend`` is the
+object providing the per-shard operations (default: pssgp_b200.ops = CUDA); tests substitute a CPU
+implementation to exercise the exchange logic under gloo.
+"""
+import torch
+
+
+class TimeShard:
+    def __init__(self, rank, world, dist=None, backend=None, group=None):
+        self.rank, self.world, self.dist, self.group = int(rank), int(world), dist, group
+        if backend is None:
+            from . import ops as backend
+        self.ops = backend
+        self._state_in = None   # m | P entering this shard (from the filter phase)
+        self._halo = None       # (Fnext, Qnext)
+
+    # ---- collectives ---------------------------------------------------------------------------------
+    def _all_gather(self, vec):
+        if self.world == 1:
+            return vec.reshape(1, -1)
+        out = torch.empty((self.world * vec.numel(),), dtype=vec.dtype, device=vec.device)
+        self.dist.all_gather_into_tensor(out, vec.contiguous().reshape(-1), group=self.group)
+        return out.reshape(self.world, vec.numel())
+
+    def _all_reduce(self, vec):
+        if self.world > 1:
+            self.dist.all_reduce(vec, group=self.group)
+        return vec
+
+    @property
+    def first(self):
+        return self.rank == 0
+
+    @property
+    def last(self):
+        return self.rank == self.world - 1
+
+    # ---- filter --------------------------------------------------------------------------------------
+    def filter(self, P0, Fs, Qs, H, R, y, reduce_ll=True):
+        d = Fs.shape[1]
+        summ = self.ops.pkf_summary(P0, Fs, Qs, H, R, y, self.first)
+        msg = torch.cat([summ, Fs[0].reshape(-1), Qs[0].reshape(-1)])
+        gathered = self._all_gather(msg)
+        na = summ.numel()
+        if not self.last:
+            nxt = gathered[self.rank + 1]
+            self._halo = (nxt[na:na + d * d].reshape(d, d).contiguous(), nxt[na + d * d:].reshape(d, d).contiguous())
+        else:
+            self._halo = (None, None)
+        if self.first:
+            m_in, P_in = None, P0
+        else:
+            st = self.ops.filter_fold(P0, None, gathered[:, :na].contiguous(), self.rank)
+            m_in, P_in = st[:d].contiguous(), st[d:].reshape(d, d).contiguous()
+        self._state_in = (m_in, P_in)
+        fms, fPs, ll, fin = self.ops.pkf(P_in, Fs, Qs, H, R, y, m0=m_in, first_special=self.first, want_ll=True,
+                                         want_final=False)
+        if reduce_ll:
+            ll = self._all_reduce(ll)
+        return fms, fPs, ll
+
+    # ---- smoother + adjoint (their summaries travel in one message) ------------------------------------
+    def smoother_and_grad(self, P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=None, want_smoother=True, want_grad=True):
+        d = Fs.shape[1]
+        m_in, P_in = self._state_in
+        Fn, Qn = self._halo
+        parts = []
+        if want_smoother:
+            s_sm = self.ops.pks_summary(Fs, Qs, fms, fPs, self.last, Fn, Qn)
+            parts.append(s_sm)
+        if want_grad:
+            s_ad = self.ops.pkf_backward_summary(P_in, m_in, Fs, Qs, H, R, y, fms, fPs, self.first)
+            parts.append(s_ad)
+        gathered = self._all_gather(torch.cat(parts))
+        after = self.world - 1 - self.rank
+        out = {}
+        off = 0
+        if want_smoother:
+            na = s_sm.numel()
+            init = None
+            if after > 0:
+                init = self.ops.smoother_fold(gathered[self.rank + 1:, off:off + na].contiguous(), after, d)
+            sms, sPs, _ = self.ops.pks(Fs, Qs, fms, fPs, last_special=self.last, Fnext=Fn, Qnext=Qn, init=init)
+            out["sms"], out["sPs"] = sms, sPs
+            off += na
+        if want_grad:
+            na = s_ad.numel()
+            adj = None
+            if after > 0:
+                adj = self.ops.adjoint_fold(gathered[self.rank + 1:, off:off + na].contiguous(), after, d)
+            dP0, dFs, dQs, dH, dR = self.ops.pkf_backward(P_in, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=m_in,
+                                                          first_special=self.first, adj_init=adj)
+            red = torch.cat([dH.reshape(-1), dR.reshape(-1), dP0.reshape(-1)] + ([ll.reshape(-1)] if ll is not None else []))
+            red = self._all_reduce(red)
+            out["dH"], out["dR"], out["dP0"] = red[:d], red[d:d + 1], red[d + 1:d + 1 + d * d].reshape(d, d)
+            if ll is not None:
+                out["ll"] = red[d + 1 + d * d:]
+            out["dFs"], out["dQs"] = dFs, dQs
+        return out
+
+    def filter_smoother_grad(self, P0, Fs, Qs, H, R, y, g_ll):
+        """One full step: returns (ll, sms, sPs, (dP0, dFs, dQs, dH, dR)); ll and the small gradients are global."""
+        fms, fPs, ll = self.filter(P0, Fs, Qs, H, R, y, reduce_ll=False)
+        o = self.smoother_and_grad(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=ll)
+        return o["ll"], o["sms"], o["sPs"], (o["dP0"], o["dFs"], o["dQs"], o["dH"], o["dR"])

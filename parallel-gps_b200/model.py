@@ -1,0 +1,150 @@
+"""Mirror of the reference's pssgp/model.py: ``StateSpaceGP(data, kernel, noise_variance, parallel,
+max_parallel)`` with ``maximum_log_likelihood_objective()`` (:113-117) and ``predict_f(Xnew)`` (:92-111).
+
+The log-likelihood is a torch autograd node whose forward is  discretise -> pkf  and whose backward is
+the hand-written adjoint scan + discretisation adjoint (C ABI ``pssgp_pkf_backward`` /
+``pssgp_discretise_backward``), i.e. the role tf.custom_gradient plays in a TF binding
+(INTEGRATION.md).  Gradients then flow through the d x d SDE construction to the kernel's
+unconstrained variables exactly as in the reference's test (tests/test_gp_vs_kfs.py:53-67).
+"""
+import numpy as np
+import torch
+
+from . import _arrays as A
+from . import config as pssgp_config
+from . import ops
+from .kernels.base import time_steps
+from .params import Parameter
+
+
+class _LogLikelihood(torch.autograd.Function):
+    """ll(F, Pinf, H, R; dts, y) with P0 = Pinf (kernels/base.py:47)."""
+
+    @staticmethod
+    def forward(ctx, F, Pinf, H, R, dts, y):
+        device, dtype = dts.device, dts.dtype
+        Fd = F.detach().to(device=device, dtype=dtype).contiguous()
+        Pd = Pinf.detach().to(device=device, dtype=dtype).contiguous()
+        Hd = H.detach().to(device=device, dtype=dtype).reshape(-1).contiguous()
+        Rd = R.detach().to(device=device, dtype=dtype).reshape(-1).contiguous()
+        Fs, Qs = ops.discretise(Fd, Pd, dts)
+        fms, fPs, ll, _ = ops.pkf(Pd, Fs, Qs, Hd, Rd, y)
+        ctx.save_for_backward(Fd, Pd, Hd, Rd, dts, y, Fs, Qs, fms, fPs)
+        ctx.host = (F.device, F.dtype, tuple(H.shape), tuple(R.shape))
+        return ll[0].to(device=F.device, dtype=F.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        Fd, Pd, Hd, Rd, dts, y, Fs, Qs, fms, fPs = ctx.saved_tensors
+        hdev, hdt, hshape, rshape = ctx.host
+        gd = g.detach().to(device=dts.device, dtype=dts.dtype).reshape(1).contiguous()
+        dP0, dFs, dQs, dH, dR = ops.pkf_backward(Pd, Fs, Qs, Hd, Rd, y, fms, fPs, gd)
+        dF, dPinf = ops.discretise_backward(Fd, Pd, dts, Fs, dFs, dQs)
+        back = lambda t, shape=None: (t.reshape(shape) if shape else t).to(device=hdev, dtype=hdt)
+        return back(dF), back(dPinf + dP0), back(dH, hshape), back(dR, rshape), None, None
+
+
+def _merge_sorted(a, b, *args):
+    """model.py:15-55: merge two sorted 1-d device tensors (and companion data) without a sort."""
+    if a.shape[0] < b.shape[0]:
+        a, b = b, a
+        args = tuple((j, i) for i, j in args)
+    na, nb = a.shape[0], b.shape[0]
+    b_idx = torch.arange(nb, device=a.device) + torch.searchsorted(a, b)
+    is_a = torch.ones(na + nb, dtype=torch.bool, device=a.device)
+    is_a[b_idx] = False
+    a_idx = torch.nonzero(is_a).reshape(-1)
+
+    def inner(u, v):
+        c = torch.empty((na + nb,) + tuple(u.shape[1:]), dtype=u.dtype, device=u.device)
+        c[b_idx] = v
+        c[a_idx] = u
+        return c
+
+    return (inner(a, b),) + tuple(inner(i, j) for i, j in args)
+
+
+class StateSpaceGP:
+    """model.py:58-117.  ``parallel=False`` selects the same CUDA kernels run as one sequential chunk."""
+
+    def __init__(self, data, kernel, noise_variance=1.0, parallel=False, max_parallel=10000, device=None):
+        A.require_cuda()
+        self.noise_variance = Parameter(noise_variance, name="noise_variance")
+        self.kernel = kernel
+        self.parallel = parallel
+        self.max_parallel = max_parallel
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.data = data
+
+    @property
+    def data(self):
+        return self._data
+
+    @data.setter
+    def data(self, data):
+        ts, ys = data
+        dtype = pssgp_config.default_float()
+        tsd = A.to_device(ts, dtype, self.device, "data_ts").reshape(-1, 1)
+        ysd = A.to_device(ys, dtype, self.device, "data_ys").reshape(-1, 1)
+        if ysd.shape[0] != tsd.shape[0]:
+            raise ValueError("ts and ys must have the same length")
+        self._data = (tsd, ysd)
+
+    # --- gpflow.Module stand-ins -------------------------------------------------------------
+    @property
+    def parameters(self):
+        return self.kernel.parameters + [self.noise_variance]
+
+    @property
+    def trainable_variables(self):
+        return [p.unconstrained_variable for p in self.parameters if p.trainable]
+
+    def log_prior_density(self):
+        out = torch.zeros((), dtype=torch.float64)
+        for p in self.parameters:
+            if p.trainable:
+                out = out + p.log_prior_density()
+        return out
+
+    def log_posterior_density(self):
+        return self.maximum_log_likelihood_objective() + self.log_prior_density()
+
+    def training_loss(self):
+        return -self.log_posterior_density()
+
+    # --- the path ----------------------------------------------------------------------------
+    def _make_model(self, ts):
+        """model.py:86-90."""
+        R = self.noise_variance.value.reshape(1, 1)
+        return self.kernel.get_ssm(ts, R)
+
+    def maximum_log_likelihood_objective(self):
+        """model.py:113-117; differentiable w.r.t. trainable_variables."""
+        ts, Y = self._data
+        sde = self.kernel.get_sde()
+        R = self.noise_variance.value.reshape(1, 1)
+        dts = time_steps(ts, 0., ts.dtype, ts.device)
+        return _LogLikelihood.apply(sde.F, sde.P0, sde.H, R, dts, Y.reshape(-1))
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+        """model.py:92-111: merge query times as NaN observations, filter + smooth, project with H.
+        Returns (mean[K,1], var[K,1]) — numpy for host inputs, CUDA tensors for device inputs."""
+        ts, ys = self._data
+        dtype, dev = ts.dtype, ts.device
+        Xd = A.to_device(Xnew, dtype, dev, "Xnew").reshape(-1)
+        K = Xd.shape[0]
+        nan_ys = torch.full((K, ys.shape[1]), float("nan"), dtype=dtype, device=dev)
+        all_ts, all_ys, all_flags = _merge_sorted(ts.reshape(-1), Xd, (ys, nan_ys),
+                                                  (torch.zeros(ts.shape[0], dtype=torch.bool, device=dev),
+                                                   torch.ones(K, dtype=torch.bool, device=dev)))
+        with torch.no_grad():
+            ssm = self._make_model(all_ts[:, None])
+            Hd, Rd = ssm.H.reshape(-1).contiguous(), ssm.R.reshape(-1).contiguous()
+            fms, fPs, _, _ = ops.pkf(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, all_ys.reshape(-1).contiguous(), want_ll=False)
+            sms, sPs, _ = ops.pks(ssm.Fs, ssm.Qs, fms, fPs)
+            rm, rP = sms[all_flags], sPs[all_flags]
+            mean = rm @ Hd.reshape(-1, 1)
+            var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)
+        if A.is_device_tensor(Xnew):
+            return mean, var
+        return A.to_host(mean, "pred_mean"), A.to_host(var, "pred_var")

@@ -39,12 +39,13 @@ def discretise_backward(F, Pinf, dts, Fs, dFs, dQs):
 
 
 def pkf(P0, Fs, Qs, H, R, y, m0=None, first_special=True, want_ll=True, want_final=False):
-    """C ABI: pssgp_pkf.  H[d], R[1], y[n] flat.  -> fms, fPs, ll(1-elem tensor or None), final_state or None."""
+    """C ABI: pssgp_pkf.  H[d], R[1], y[n] flat.  -> fms, fPs, ll(1-elem tensor or None), final_state or None
+    (final_state = m[d] | P[d,d])."""
     n, d = Fs.shape[0], Fs.shape[1]
     fms = torch.empty((n, d), dtype=Fs.dtype, device=Fs.device)
     fPs = torch.empty((n, d, d), dtype=Fs.dtype, device=Fs.device)
     ll = torch.empty((1,), dtype=Fs.dtype, device=Fs.device) if want_ll else None
-    fin = torch.empty((nstate(d),), dtype=Fs.dtype, device=Fs.device) if want_final else None
+    fin = torch.empty((d + d * d,), dtype=Fs.dtype, device=Fs.device) if want_final else None
     _lib.check(_lib.lib().pssgp_pkf(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs), A.ptr(H),
                                    A.ptr(R), A.ptr(y), A.ptr(m0), 1 if first_special else 0, A.ptr(fms), A.ptr(fPs),
                                    A.ptr(ll), A.ptr(fin), A.stream_ptr(Fs.device)))
@@ -63,17 +64,82 @@ def pks(Fs, Qs, fms, fPs, last_special=True, Fnext=None, Qnext=None, init=None, 
     return sms, sPs, first
 
 
-def pkf_backward(P0, Fs, Qs, H, R, y, fms, fPs, g_ll):
-    """C ABI: pssgp_pkf_backward. g_ll: 1-elem device tensor. -> dP0, dFs, dQs, dH, dR."""
+def pkf_backward(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=None, first_special=True, adj_init=None, want_first=False):
+    """C ABI: pssgp_pkf_backward. g_ll: 1-elem device tensor. -> dP0, dFs, dQs, dH, dR[, adj_first]."""
     n, d = Fs.shape[0], Fs.shape[1]
     kw = dict(dtype=Fs.dtype, device=Fs.device)
-    dP0 = torch.empty((d, d), **kw)
+    dP0 = torch.zeros((d, d), **kw)
     dFs = torch.empty((n, d, d), **kw)
     dQs = torch.empty((n, d, d), **kw)
     dH = torch.empty((d,), **kw)
     dR = torch.empty((1,), **kw)
-    _lib.check(_lib.lib().pssgp_pkf_backward(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs),
-                                            A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(fms), A.ptr(fPs), A.ptr(g_ll),
-                                            A.ptr(dP0), A.ptr(dFs), A.ptr(dQs), A.ptr(dH), A.ptr(dR),
+    first = torch.empty((nstate(d),), **kw) if want_first else None
+    _lib.check(_lib.lib().pssgp_pkf_backward(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(m0), A.ptr(Fs),
+                                            A.ptr(Qs), A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(fms), A.ptr(fPs),
+                                            A.ptr(g_ll), 1 if first_special else 0, A.ptr(adj_init), A.ptr(dP0),
+                                            A.ptr(dFs), A.ptr(dQs), A.ptr(dH), A.ptr(dR), A.ptr(first),
                                             A.stream_ptr(Fs.device)))
+    if want_first:
+        return dP0, dFs, dQs, dH, dR, first
     return dP0, dFs, dQs, dH, dR
+
+
+# ---- time sharding (one contiguous shard per GPU) --------------------------------------------------------
+def nagg_filter(d):
+    return d * d + 2 * d + d * (d + 1)
+
+
+def nagg_smoother(d):
+    return d * d + d + d * (d + 1) // 2
+
+
+def pkf_summary(P0, Fs, Qs, H, R, y, first_special):
+    n, d = Fs.shape[0], Fs.shape[1]
+    out = torch.empty((nagg_filter(d),), dtype=Fs.dtype, device=Fs.device)
+    _lib.check(_lib.lib().pssgp_pkf_summary(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs),
+                                           A.ptr(H), A.ptr(R), A.ptr(y), 1 if first_special else 0, A.ptr(out),
+                                           A.stream_ptr(Fs.device)))
+    return out
+
+
+def filter_fold(P0, m0, summaries, count):
+    """summaries: [>=count, NAGG] in rank order. -> m[d] | P[d,d]."""
+    d = P0.shape[0]
+    out = torch.empty((d + d * d,), dtype=P0.dtype, device=P0.device)
+    _lib.check(_lib.lib().pssgp_filter_fold(_h(P0).ptr, A.dtype_code(P0), d, int(count), A.ptr(P0), A.ptr(m0),
+                                           A.ptr(summaries), A.ptr(out), A.stream_ptr(P0.device)))
+    return out
+
+
+def pks_summary(Fs, Qs, fms, fPs, last_special, Fnext=None, Qnext=None):
+    n, d = Fs.shape[0], Fs.shape[1]
+    out = torch.empty((nagg_smoother(d),), dtype=Fs.dtype, device=Fs.device)
+    _lib.check(_lib.lib().pssgp_pks_summary(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(Fs), A.ptr(Qs), A.ptr(fms),
+                                           A.ptr(fPs), 1 if last_special else 0, A.ptr(Fnext), A.ptr(Qnext),
+                                           A.ptr(out), A.stream_ptr(Fs.device)))
+    return out
+
+
+def smoother_fold(summaries, count, d):
+    """summaries: [count, NAGG] of the FOLLOWING shards in rank order. -> packed state."""
+    out = torch.empty((nstate(d),), dtype=summaries.dtype, device=summaries.device)
+    _lib.check(_lib.lib().pssgp_smoother_fold(_h(summaries).ptr, A.dtype_code(summaries), d, int(count),
+                                             A.ptr(summaries), A.ptr(out), A.stream_ptr(summaries.device)))
+    return out
+
+
+def pkf_backward_summary(P0, m0, Fs, Qs, H, R, y, fms, fPs, first_special):
+    n, d = Fs.shape[0], Fs.shape[1]
+    out = torch.empty((nagg_smoother(d),), dtype=Fs.dtype, device=Fs.device)
+    _lib.check(_lib.lib().pssgp_pkf_backward_summary(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(m0),
+                                                    A.ptr(Fs), A.ptr(Qs), A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(fms),
+                                                    A.ptr(fPs), 1 if first_special else 0, A.ptr(out),
+                                                    A.stream_ptr(Fs.device)))
+    return out
+
+
+def adjoint_fold(summaries, count, d):
+    out = torch.empty((nstate(d),), dtype=summaries.dtype, device=summaries.device)
+    _lib.check(_lib.lib().pssgp_adjoint_fold(_h(summaries).ptr, A.dtype_code(summaries), d, int(count),
+                                            A.ptr(summaries), A.ptr(out), A.stream_ptr(summaries.device)))
+    return out

@@ -1,0 +1,94 @@
+"""GP-equivalence of the drop-in StateSpaceGP on the GPU — the reference's own test contract
+(tests/test_gp_vs_kfs.py:45-99): log-likelihood, its gradient w.r.t. the kernel's unconstrained
+variables, and predict_f equal the dense GP (here: the oracle's GPR) within the reference's
+per-kernel tolerances; and they equal the oracle's StateSpaceGP(parallel=True) to <= 1e-9 (FP64)."""
+import numpy as np
+import pytest
+import torch
+
+from util import O, pkg
+
+pytestmark = pytest.mark.gpu
+
+T, K = 200, 50
+
+
+def _data():
+    rng = np.random.RandomState(31415926)
+    t = np.sort(rng.rand(T))
+    y = O.obs_noise(O.sinu(t), 0.1, 1)
+    q = np.sort(rng.rand(K, 1), 0)
+    return t, y, q
+
+
+def _pairs():
+    pkg()
+    from pssgp_b200 import kernels as PK
+    out = []
+
+    def both(name, mk_o, mk_p, vt, gt):
+        out.append(pytest.param(mk_o, mk_p, vt, gt, id=name))
+
+    both("matern12", lambda: O.Matern12(1., .5), lambda: PK.Matern12(1., .5), 1e-6, 1e-2)
+    both("matern32", lambda: O.Matern32(1., .5), lambda: PK.Matern32(1., .5), 1e-6, 1e-2)
+    both("matern52", lambda: O.Matern52(1., .5), lambda: PK.Matern52(1., .5), 1e-6, 1e-2)
+    both("m32+m52", lambda: O.Matern32(1., .5) + O.Matern52(1., .5), lambda: PK.Matern32(1., .5) + PK.Matern52(1., .5),
+         1e-6, 1e-2)
+    both("m32xm32", lambda: O.Matern32(1., .5) * O.Matern32(.7, 1.3), lambda: PK.Matern32(1., .5) * PK.Matern32(.7, 1.3),
+         1e-6, 1e-1)
+    return out
+
+
+@pytest.mark.parametrize("mk_o,mk_p,val_tol,grad_tol", _pairs())
+def test_gp_equivalence(mk_o, mk_p, val_tol, grad_tol):
+    pkg()
+    from pssgp_b200.model import StateSpaceGP
+    t, y, q = _data()
+    ocov, pcov = mk_o(), mk_p()
+    # dense GP (oracle GPR), like gpflow.models.GPR in the reference test
+    gp = O.GPR((t, y), ocov, 0.1)
+    gp_ll = gp.maximum_log_likelihood_objective()
+    gp_grad = torch.autograd.grad(gp_ll, ocov.trainable_variables)
+    gp_mean, gp_var = gp.predict_f(q)
+    # oracle state-space model (parallel=True)
+    oss = O.StateSpaceGP((t, y), ocov, 0.1, parallel=True, max_parallel=T + K)
+    o_ll = oss.maximum_log_likelihood_objective()
+    o_grad = torch.autograd.grad(o_ll, ocov.trainable_variables)
+    o_mean, o_var = oss.predict_f(q)
+    # product
+    ss = StateSpaceGP(data=(t[:, None], y[:, None]), kernel=pcov, noise_variance=0.1, parallel=True,
+                      max_parallel=T + K)
+    ll = ss.maximum_log_likelihood_objective()
+    grads = torch.autograd.grad(ll, pcov.trainable_variables)
+    mean, var = ss.predict_f(q)
+    assert mean.shape == (K, 1) and var.shape == (K, 1)
+    # reference contract: vs dense GP at the reference's tolerances
+    np.testing.assert_allclose(float(ll), float(gp_ll), atol=val_tol, rtol=val_tol)
+    for a, b in zip(grads, gp_grad):
+        np.testing.assert_allclose(float(a), float(b), atol=grad_tol, rtol=grad_tol)
+    np.testing.assert_allclose(mean[:, 0], gp_mean.detach().numpy().reshape(-1), atol=val_tol, rtol=val_tol)
+    np.testing.assert_allclose(var[:, 0], gp_var.detach().numpy().reshape(-1), atol=val_tol, rtol=val_tol)
+    # parity with the restated reference at 1e-9 (relative to the largest magnitude)
+    assert abs(float(ll) - float(o_ll)) <= 1e-9 * max(1.0, abs(float(o_ll)))
+    gscale = max(abs(float(g)) for g in o_grad)
+    for a, b in zip(grads, o_grad):
+        assert abs(float(a) - float(b)) <= 1e-9 * gscale
+    assert np.max(np.abs(mean[:, 0] - o_mean.detach().numpy().reshape(-1))) <= 1e-9 * float(o_mean.abs().max())
+    assert np.max(np.abs(var[:, 0] - o_var.detach().numpy().reshape(-1))) <= 1e-9 * float(o_var.abs().max())
+
+
+def test_noise_variance_gradient_and_training_loss():
+    pkg()
+    from pssgp_b200 import kernels as PK
+    from pssgp_b200.model import StateSpaceGP
+    t, y, q = _data()
+    ocov = O.Matern52(1., .5)
+    oss = O.StateSpaceGP((t, y), ocov, 0.1, parallel=True, max_parallel=T)
+    o_ll = oss.maximum_log_likelihood_objective()
+    o_g = torch.autograd.grad(o_ll, [oss.noise_variance_p.unconstrained] + ocov.trainable_variables)
+    ss = StateSpaceGP((t[:, None], y[:, None]), PK.Matern52(1., .5), 0.1, parallel=True)
+    loss = ss.training_loss()
+    g = torch.autograd.grad(loss, [ss.noise_variance.unconstrained_variable] + ss.kernel.trainable_variables)
+    assert abs(float(loss) + float(o_ll)) <= 1e-9 * abs(float(o_ll))
+    for a, b in zip(g, o_g):
+        assert abs(float(a) + float(b)) <= 1e-9 * max(abs(float(x)) for x in o_g)

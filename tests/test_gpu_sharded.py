@@ -1,0 +1,129 @@
+"""Time-sharded filter / smoother / gradient: G simulated ranks (threads + an in-process fake of
+torch.distributed) on ONE GPU must reproduce the unsharded result; plus a real 2-process NCCL run
+when two GPUs are visible."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+import torch
+
+from util import O, ROOT, make_problem, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+
+
+class FakeDist:
+    """all_gather_into_tensor / all_reduce for threads of one process."""
+
+    def __init__(self, world):
+        self.world = world
+        self.barrier = threading.Barrier(world)
+        self.slots = [None] * world
+        self.local = threading.local()
+
+    def all_gather_into_tensor(self, out, vec, group=None):
+        r = self.local.rank
+        torch.cuda.synchronize()
+        self.slots[r] = vec.clone()
+        self.barrier.wait()
+        out.copy_(torch.cat([self.slots[i].reshape(-1) for i in range(self.world)]))
+        torch.cuda.synchronize()
+        self.barrier.wait()
+
+    def all_reduce(self, vec, group=None):
+        r = self.local.rank
+        torch.cuda.synchronize()
+        self.slots[r] = vec.clone()
+        self.barrier.wait()
+        tot = sum(self.slots[i] for i in range(self.world))
+        torch.cuda.synchronize()
+        self.barrier.wait()
+        vec.copy_(tot)
+
+
+@pytest.mark.parametrize("name,T,G", [("matern32", 1000, 2), ("matern52", 5003, 3), ("matern52", 40, 4),
+                                      ("m32xm32", 2000, 2), ("matern12", 513, 8)])
+def test_sharded_equals_unsharded(name, T, G):
+    pkg()
+    from pssgp_b200 import ops
+    from pssgp_b200.dist import TimeShard
+    t, y, cov, ssm = make_problem(name, T, seed=11)
+    d = ssm.P0.shape[0]
+    to = lambda x: x.detach().to(DEV).contiguous()
+    P0, Fs, Qs, H, R = to(ssm.P0), to(ssm.Fs), to(ssm.Qs), to(ssm.H).reshape(-1), to(ssm.R).reshape(-1)
+    yd = torch.as_tensor(y).to(DEV)
+    g = torch.tensor([1.3], dtype=torch.float64, device=DEV)
+    fms, fPs, ll, _ = ops.pkf(P0, Fs, Qs, H, R, yd)
+    sms, sPs, _ = ops.pks(Fs, Qs, fms, fPs)
+    dP0, dFs, dQs, dH, dR = ops.pkf_backward(P0, Fs, Qs, H, R, yd, fms, fPs, g)
+    bounds = np.linspace(0, T, G + 1).astype(int)
+    fake = FakeDist(G)
+    results = [None] * G
+    errors = []
+
+    def worker(r):
+        try:
+            torch.cuda.set_device(0)
+            fake.local.rank = r
+            lo, hi = bounds[r], bounds[r + 1]
+            sh = TimeShard(r, G, fake)
+            results[r] = sh.filter_smoother_grad(P0, Fs[lo:hi].contiguous(), Qs[lo:hi].contiguous(), H, R,
+                                                 yd[lo:hi].contiguous(), g)
+            torch.cuda.synchronize()
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+            fake.barrier.abort()
+
+    threads = [threading.Thread(target=worker, args=(r,)) for r in range(G)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    tol = 1e-9
+    cat = lambda i: torch.cat([results[r][i] for r in range(G)])
+    assert rel_err(cat(1).cpu(), sms.cpu()) < tol and rel_err(cat(2).cpu(), sPs.cpu()) < tol
+    for r in range(G):
+        assert abs(float(results[r][0]) - float(ll)) <= tol * abs(float(ll))
+        gP0, _, _, gH, gR = results[r][3]
+        assert rel_err(gP0.cpu(), dP0.cpu()) < tol
+        assert float((gH - dH).abs().max()) <= tol * float(dH.abs().max())
+        assert abs(float(gR) - float(dR)) <= tol * abs(float(dR))
+    gF = torch.cat([results[r][3][1] for r in range(G)])
+    gQ = torch.cat([results[r][3][2] for r in range(G)])
+    assert rel_err(gF.cpu(), dFs.cpu()) < tol and rel_err(gQ.cpu(), dQs.cpu()) < tol
+
+
+def test_world1_summary_reuse_path():
+    """world = 1 runs summary -> full on the same arrays: the reduce kernel is skipped (pending aggregates)."""
+    pkg()
+    from pssgp_b200 import _lib, ops
+    from pssgp_b200.dist import TimeShard
+    t, y, cov, ssm = make_problem("matern52", 3000, seed=2)
+    to = lambda x: x.detach().to(DEV).contiguous()
+    P0, Fs, Qs, H, R = to(ssm.P0), to(ssm.Fs), to(ssm.Qs), to(ssm.H).reshape(-1), to(ssm.R).reshape(-1)
+    yd = torch.as_tensor(y).to(DEV)
+    g = torch.ones(1, dtype=torch.float64, device=DEV)
+    fms, fPs, ll, _ = ops.pkf(P0, Fs, Qs, H, R, yd)
+    sms, sPs, _ = ops.pks(Fs, Qs, fms, fPs)
+    h = _lib.handle(0)
+    n0 = h.launch_count()
+    out = TimeShard(0, 1).filter_smoother_grad(P0, Fs, Qs, H, R, yd, g)
+    torch.cuda.synchronize()
+    # 3 scans x (reduce + total + mid + apply) = 12 launches; without reuse it would be 15
+    assert h.launch_count() - n0 == 12
+    assert rel_err(out[1].cpu(), sms.cpu()) < 1e-12 and rel_err(out[2].cpu(), sPs.cpu()) < 1e-12
+    assert abs(float(out[0]) - float(ll)) <= 1e-12 * abs(float(ll))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_process_nccl():
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "sharded_worker.py"), "nccl"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "SHARDED_OK" in out.stdout
