@@ -14,7 +14,7 @@
 
 #include <cuda_runtime.h>
 
-#include "smalld.cuh"
+#include "coop.cuh"
 #include "workspace.h"
 
 namespace pssgp {
@@ -442,6 +442,224 @@ int discretise_bwd_impl(pssgp_handle* h, int64_t n, const void* F, const void* P
     return check_launch(h, "discretise_backward", 4);
 }
 
+// ---------------------------------------------------------------------------------------------
+// generic state dimension: one CTA per time step (grid-stride), matrices in shared memory
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void discretise_generic_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, int d,
+                                          const T* __restrict__ dts, long n, T* __restrict__ Fs, T* __restrict__ Qs) {
+    constexpr int DEG = Taylor<T>::DEG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dd = d * d;
+    T* A = (T*)smem_raw;
+    T* B = A + dd;
+    T* P = B + dd;
+    Coop c{(int)threadIdx.x, (int)blockDim.x};
+    for (int idx = c.tid; idx < dd; idx += c.nt) {
+        const int i = idx / d, j = idx - i * d;
+        P[idx] = T(0.5) * (Pinf[idx] + Pinf[j * d + i]);
+    }
+    const T normF = coef[0];
+    const T* C = coef + 8;
+    c.sync();
+    for (long k = blockIdx.x; k < n; k += gridDim.x) {
+        const T dt = dts[k];
+        T x;
+        const int s = pick_squarings<T>(normF * t_abs(dt), x);
+        if (dt < T(0)) x = -x;
+        for (int idx = c.tid; idx < dd; idx += c.nt) {
+            T a = C[(size_t)DEG * dd + idx];
+            for (int p = DEG - 1; p >= 0; --p) a = fma(a, x, C[(size_t)p * dd + idx]);
+            A[idx] = a;
+        }
+        c.sync();
+        T* cur = A;
+        T* nxt = B;
+        for (int i = 0; i < s; ++i) {
+            co_mm(c, d, d, d, cur, d, 1, cur, d, 1, nxt, d, (const T*)nullptr, T(1));
+            c.sync();
+            T* t = cur;
+            cur = nxt;
+            nxt = t;
+        }
+        co_copy(c, dd, cur, Fs + k * dd);
+        co_mm(c, d, d, d, cur, d, 1, P, d, 1, nxt, d, (const T*)nullptr, T(1));  // A P
+        c.sync();
+        T* gq = Qs + k * dd;
+        for (int idx = c.tid; idx < dd; idx += c.nt) {
+            const int i = idx / d, j = idx - i * d;
+            T a1 = T(0), a2 = T(0);
+            for (int kk = 0; kk < d; ++kk) {
+                a1 = fma(nxt[i * d + kk], cur[j * d + kk], a1);
+                a2 = fma(nxt[j * d + kk], cur[i * d + kk], a2);
+            }
+            gq[idx] = P[idx] - T(0.5) * (a1 + a2);
+        }
+        c.sync();
+    }
+}
+
+// part[cta][p*dd + idx]: p = 0 -> dPinf, p >= 1 -> W_p.  Each CTA accumulates into its own slice.
+template <typename T>
+__global__ void discretise_bwd_generic_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, int d,
+                                              const T* __restrict__ dts, long n, const T* __restrict__ Fs,
+                                              const T* __restrict__ dFs, const T* __restrict__ dQs,
+                                              T* __restrict__ part) {
+    constexpr int DEG = Taylor<T>::DEG;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int dd = d * d;
+    T* A = (T*)smem_raw;   // A_k
+    T* dA = A + dd;
+    T* dQ = dA + dd;
+    T* T1 = dQ + dd;
+    T* T2 = T1 + dd;
+    T* P = T2 + dd;
+    T* Ah = P + dd;
+    Coop c{(int)threadIdx.x, (int)blockDim.x};
+    const int NOUT = (DEG + 1) * dd;
+    T* mine = part + (size_t)blockIdx.x * NOUT;
+    for (int o = c.tid; o < NOUT; o += c.nt) mine[o] = T(0);
+    for (int idx = c.tid; idx < dd; idx += c.nt) {
+        const int i = idx / d, j = idx - i * d;
+        P[idx] = T(0.5) * (Pinf[idx] + Pinf[j * d + i]);
+    }
+    const T normF = coef[0];
+    const T* C = coef + 8;
+    c.sync();
+    for (long k = blockIdx.x; k < n; k += gridDim.x) {
+        const T dt = dts[k];
+        T x;
+        const int s = pick_squarings<T>(normF * t_abs(dt), x);
+        if (dt < T(0)) x = -x;
+        for (int idx = c.tid; idx < dd; idx += c.nt) {
+            const int i = idx / d, j = idx - i * d;
+            A[idx] = Fs[k * dd + idx];
+            dA[idx] = dFs[k * dd + idx];
+            dQ[idx] = T(0.5) * (dQs[k * dd + idx] + dQs[k * dd + j * d + i]);
+        }
+        c.sync();
+        co_mm(c, d, d, d, dQ, d, 1, A, d, 1, T1, d, (const T*)nullptr, T(1));   // dQ A
+        c.sync();
+        co_mm(c, d, d, d, T1, d, 1, P, d, 1, dA, d, dA, T(-2));                 // dA -= 2 dQ A P
+        for (int idx = c.tid; idx < dd; idx += c.nt) {
+            const int i = idx / d, j = idx - i * d;
+            T a1 = dQ[idx];
+            for (int kk = 0; kk < d; ++kk) a1 = fma(-A[kk * d + i], T1[kk * d + j], a1);
+            mine[idx] += a1;                                                     // dPinf += dQ - A^T dQ A
+        }
+        c.sync();
+        if (s > 0) {
+            for (int idx = c.tid; idx < dd; idx += c.nt) {
+                T a = C[(size_t)DEG * dd + idx];
+                for (int p = DEG - 1; p >= 0; --p) a = fma(a, x, C[(size_t)p * dd + idx]);
+                Ah[idx] = a;
+            }
+            c.sync();
+            for (int i = s - 1; i >= 0; --i) {
+                // A_i = Ah^(2^i) by i squarings (recomputed: no per-level storage)
+                T* cur = T1;
+                T* nxt = T2;
+                co_copy(c, dd, Ah, cur);
+                c.sync();
+                for (int q = 0; q < i; ++q) {
+                    co_mm(c, d, d, d, cur, d, 1, cur, d, 1, nxt, d, (const T*)nullptr, T(1));
+                    c.sync();
+                    T* t = cur;
+                    cur = nxt;
+                    nxt = t;
+                }
+                // dA_i = A_i^T dA + dA A_i^T   (into nxt, then back to dA)
+                for (int idx = c.tid; idx < dd; idx += c.nt) {
+                    const int r = idx / d, cc = idx - r * d;
+                    T a1 = T(0);
+                    for (int kk = 0; kk < d; ++kk) {
+                        a1 = fma(cur[kk * d + r], dA[kk * d + cc], a1);
+                        a1 = fma(dA[r * d + kk], cur[cc * d + kk], a1);
+                    }
+                    nxt[idx] = a1;
+                }
+                c.sync();
+                co_copy(c, dd, nxt, dA);
+                c.sync();
+            }
+        }
+        // moments W_p += x^p dA_h, skipping degrees whose weight x^(p-1)/p! is negligible
+        {
+            const T ax = t_abs(x);
+            const T tol = sizeof(T) == 8 ? T(1e-19) : T(1e-10);
+            int pmax = DEG;
+            T wgt = T(1);
+            for (int p = 1; p <= DEG; ++p) {
+                if (p > 1) wgt *= ax / T(p);
+                if (wgt < tol) {
+                    pmax = p - 1;
+                    break;
+                }
+            }
+            if (pmax < 1) pmax = 1;
+            for (int idx = c.tid; idx < dd; idx += c.nt) {
+                const T v = dA[idx];
+                T xp = T(1);
+                for (int p = 1; p <= pmax; ++p) {
+                    xp *= x;
+                    mine[(size_t)p * dd + idx] = fma(xp, v, mine[(size_t)p * dd + idx]);
+                }
+            }
+        }
+        c.sync();
+    }
+}
+
+template <typename T>
+int discretise_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F, const void* Pinf, const void* dts,
+                            void* Fs, void* Qs, cudaStream_t st) {
+    int rc;
+    const size_t cnt = coef_count(Taylor<T>::DEG, d);
+    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * cnt * 2))) return rc;
+    T* coef;
+    if ((rc = setup_coef<T>(h, F, d, 0, &coef, 0, st))) return rc;
+    const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
+    long grid = (long)h->num_sms * 8;
+    if (grid > n) grid = n;
+    const size_t sm = sizeof(T) * 3 * d * d;
+    if (sm > 48 * 1024) cudaFuncSetAttribute(discretise_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    PSSGP_LAUNCH(h, "discretise", st,
+                 (discretise_generic_kernel<T><<<(unsigned)grid, nt, sm, st>>>(coef, (const T*)Pinf, d, (const T*)dts, n,
+                                                                              (T*)Fs, (T*)Qs)));
+    return check_launch(h, "discretise", 2);
+}
+
+template <typename T>
+int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F, const void* Pinf, const void* dts,
+                                const void* Fs, const void* dFs, const void* dQs, void* dF, void* dPinf,
+                                cudaStream_t st) {
+    int rc;
+    constexpr int DEG = Taylor<T>::DEG;
+    const size_t cnt = coef_count(DEG, d);
+    const int NOUT = (DEG + 1) * d * d;
+    long grid = (long)h->num_sms * 2;
+    if (grid > n) grid = n;
+    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + NOUT)))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * grid))) return rc;
+    T *coef, *coefT;
+    if ((rc = setup_coef<T>(h, F, d, 0, &coef, 0, st))) return rc;
+    if ((rc = setup_coef<T>(h, F, d, 1, &coefT, cnt, st))) return rc;
+    T* W = (T*)h->buf[WS_MISC] + 2 * cnt;
+    T* part = (T*)h->buf[WS_PART];
+    const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
+    const size_t sm = sizeof(T) * 7 * d * d;
+    if (sm > 48 * 1024)
+        cudaFuncSetAttribute(discretise_bwd_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    PSSGP_LAUNCH(h, "discretise_bwd", st,
+                 (discretise_bwd_generic_kernel<T><<<(unsigned)grid, nt, sm, st>>>(coef, (const T*)Pinf, d, (const T*)dts,
+                                                                                  n, (const T*)Fs, (const T*)dFs,
+                                                                                  (const T*)dQs, part)));
+    PSSGP_LAUNCH(h, "discretise_bwd_final", st,
+                 (discretise_bwd_final_kernel<T><<<1, 256, 3 * d * d * sizeof(T), st>>>(coefT, part, (int)grid, d, W,
+                                                                                       (T*)dF, (T*)dPinf)));
+    return check_launch(h, "discretise_backward", 4);
+}
+
 }  // namespace pssgp
 
 using namespace pssgp;
@@ -474,8 +692,11 @@ int pssgp_discretise(pssgp_handle* h, int dtype, int64_t n, int d, const void* F
     if (!F || !Pinf || !dts || !Fs || !Qs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != PSSGP_F64 && dtype != PSSGP_F32) return set_err(PSSGP_ERR_INVALID, "bad dtype %d", dtype);
     DISPATCH_SMALL(discretise_impl, h, n, F, Pinf, dts, Fs, Qs, st);
-    return set_err(PSSGP_ERR_UNSUPPORTED, "discretise: state dimension %d / dtype %d not supported yet", d, dtype);
+    if (d > 64) return set_err(PSSGP_ERR_UNSUPPORTED, "discretise: state dimension %d > 64", d);
+    if (dtype == PSSGP_F64) return discretise_generic_impl<double>(h, n, d, F, Pinf, dts, Fs, Qs, st);
+    return discretise_generic_impl<float>(h, n, d, F, Pinf, dts, Fs, Qs, st);
 }
 
 int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d, const void* F, const void* Pinf,
@@ -487,9 +708,11 @@ int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d, cons
         return set_err(PSSGP_ERR_INVALID, "null pointer argument");
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (dtype != PSSGP_F64 && dtype != PSSGP_F32) return set_err(PSSGP_ERR_INVALID, "bad dtype %d", dtype);
     DISPATCH_SMALL(discretise_bwd_impl, h, n, F, Pinf, dts, Fs, dFs, dQs, dF, dPinf, st);
-    return set_err(PSSGP_ERR_UNSUPPORTED, "discretise_backward: state dimension %d / dtype %d not supported yet", d,
-                   dtype);
+    if (d > 64) return set_err(PSSGP_ERR_UNSUPPORTED, "discretise_backward: state dimension %d > 64", d);
+    if (dtype == PSSGP_F64) return discretise_bwd_generic_impl<double>(h, n, d, F, Pinf, dts, Fs, dFs, dQs, dF, dPinf, st);
+    return discretise_bwd_generic_impl<float>(h, n, d, F, Pinf, dts, Fs, dFs, dQs, dF, dPinf, st);
 }
 
 }  // extern "C"

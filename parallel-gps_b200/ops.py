@@ -85,12 +85,17 @@ def pkf_backward(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=None, first_special=Tru
 
 
 # ---- time sharding (one contiguous shard per GPU) --------------------------------------------------------
+SMALL_D = 4  # d <= SMALL_D: register-resident kernels with packed symmetric aggregates; above: full matrices
+
+
 def nagg_filter(d):
-    return d * d + 2 * d + d * (d + 1)
+    """length of a filter shard summary (A,b,C,J,eta)."""
+    return d * d + 2 * d + d * (d + 1) if d <= SMALL_D else 3 * d * d + 2 * d
 
 
 def nagg_smoother(d):
-    return d * d + d + d * (d + 1) // 2
+    """length of a smoother (E,g,L) or adjoint (Abar,a,B) shard summary."""
+    return d * d + d + d * (d + 1) // 2 if d <= SMALL_D else 2 * d * d + d
 
 
 def pkf_summary(P0, Fs, Qs, H, R, y, first_special):

@@ -36,11 +36,23 @@ def _pairs():
          1e-6, 1e-2)
     both("m32xm32", lambda: O.Matern32(1., .5) * O.Matern32(.7, 1.3), lambda: PK.Matern32(1., .5) * PK.Matern32(.7, 1.3),
          1e-6, 1e-1)
+    both("m32xm52", lambda: O.Matern32(1., .5) * O.Matern52(1., .5), lambda: PK.Matern32(1., .5) * PK.Matern52(1., .5),
+         1e-6, 1e-1)
+    both("rbf15", lambda: O.RBF(1., .5, order=15, balancing_iter=10), lambda: PK.RBF(1., .5, order=15, balancing_iter=10),
+         1e-2, 1e-2)
+    both("periodic10", lambda: O.Periodic(O.SquaredExponential(1., .5), period=.5, order=10),
+         lambda: PK.Periodic(PK.SquaredExponential(1., .5), period=.5, order=10), 1e-3, 1e-3)
     return out
 
 
+# parity with the restated reference: 1e-9 for well-conditioned kernels; RBF-15 (d = 15, companion-form drift with
+# entries up to ~1e9) and Periodic-10 (d = 22, no process noise) are ill-conditioned: 1e-5
+PARITY_TOL = {"rbf15": 1e-5, "periodic10": 1e-5}
+
+
 @pytest.mark.parametrize("mk_o,mk_p,val_tol,grad_tol", _pairs())
-def test_gp_equivalence(mk_o, mk_p, val_tol, grad_tol):
+def test_gp_equivalence(mk_o, mk_p, val_tol, grad_tol, request):
+    ptol = PARITY_TOL.get(request.node.callspec.id, 1e-9)
     pkg()
     from pssgp_b200.model import StateSpaceGP
     t, y, q = _data()
@@ -69,12 +81,12 @@ def test_gp_equivalence(mk_o, mk_p, val_tol, grad_tol):
     np.testing.assert_allclose(mean[:, 0], gp_mean.detach().numpy().reshape(-1), atol=val_tol, rtol=val_tol)
     np.testing.assert_allclose(var[:, 0], gp_var.detach().numpy().reshape(-1), atol=val_tol, rtol=val_tol)
     # parity with the restated reference at 1e-9 (relative to the largest magnitude)
-    assert abs(float(ll) - float(o_ll)) <= 1e-9 * max(1.0, abs(float(o_ll)))
+    assert abs(float(ll) - float(o_ll)) <= ptol * max(1.0, abs(float(o_ll)))
     gscale = max(abs(float(g)) for g in o_grad)
     for a, b in zip(grads, o_grad):
-        assert abs(float(a) - float(b)) <= 1e-9 * gscale
-    assert np.max(np.abs(mean[:, 0] - o_mean.detach().numpy().reshape(-1))) <= 1e-9 * float(o_mean.abs().max())
-    assert np.max(np.abs(var[:, 0] - o_var.detach().numpy().reshape(-1))) <= 1e-9 * float(o_var.abs().max())
+        assert abs(float(a) - float(b)) <= ptol * gscale
+    assert np.max(np.abs(mean[:, 0] - o_mean.detach().numpy().reshape(-1))) <= ptol * float(o_mean.abs().max())
+    assert np.max(np.abs(var[:, 0] - o_var.detach().numpy().reshape(-1))) <= ptol * float(o_var.abs().max())
 
 
 def test_noise_variance_gradient_and_training_loss():

@@ -46,7 +46,8 @@ class FakeDist:
 
 
 @pytest.mark.parametrize("name,T,G", [("matern32", 1000, 2), ("matern52", 5003, 3), ("matern52", 40, 4),
-                                      ("m32xm32", 2000, 2), ("matern12", 513, 8)])
+                                      ("m32xm32", 2000, 2), ("matern12", 513, 8),
+                                      ("rbf6", 900, 3), ("m52+rbf6", 700, 2)])
 def test_sharded_equals_unsharded(name, T, G):
     pkg()
     from pssgp_b200 import ops
