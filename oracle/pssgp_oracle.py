@@ -10,8 +10,10 @@ repository root).  The reference's heavy arithmetic lives in third-party package
 installable here (tensorflow==2.6.0, tensorflow-probability==0.13.0, gpflow==2.2.1,
 numba==0.53.1 — ``requirements.txt:26,58,96,98``); their published algorithms are restated:
 
-* ``tf.linalg.expm``            -> ``torch.linalg.matrix_exp`` (same Higham scaling-and-squaring
-                                   Pade family; cross-checked against scipy.linalg.expm in tests)
+* ``tf.linalg.expm``            -> :func:`expm` below: Higham (2005) scaling-and-squaring with Pade
+                                   3/5/7/9/13 selected per matrix by its 1-norm, every order evaluated and
+                                   masked like TF does (torch.linalg.matrix_exp is NOT used: its low-degree
+                                   Taylor branches are only ~1e-12 accurate; checked against scipy/mpmath)
 * ``tf.linalg.solve``           -> ``torch.linalg.solve`` (partial-pivot LU, LAPACK getrf/getrs)
 * ``tf.linalg.cholesky[_solve]``-> ``torch.linalg.cholesky`` / ``torch.cholesky_solve``
 * ``tfp.math.scan_associative`` -> :func:`scan_associative` below: recursive odd/even
@@ -137,6 +139,78 @@ def solve_lyap_vec(F, L, Q):
 
 
 # --------------------------------------------------------------------------------------------
+# tf.linalg.expm (TF 2.6.0, python/ops/linalg/linalg_impl.py: matrix_exponential) — restated
+# --------------------------------------------------------------------------------------------
+_PADE = {
+    3: [120., 60., 12., 1.],
+    5: [30240., 15120., 3360., 420., 30., 1.],
+    7: [17297280., 8648640., 1995840., 277200., 25200., 1512., 56., 1.],
+    9: [17643225600., 8821612800., 2075673600., 302702400., 30270240., 2162160., 110880., 3960., 90., 1.],
+    13: [64764752532480000., 32382376266240000., 7771770303897600., 1187353796428800., 129060195264000.,
+         10559470521600., 670442572800., 33522128640., 1323241920., 40840800., 960960., 16380., 182., 1.],
+}
+
+
+def _pade_uv(A, order):
+    b = _PADE[order]
+    n = A.shape[-1]
+    ident = torch.eye(n, dtype=A.dtype).expand(A.shape)
+    A2 = A @ A
+    if order == 13:
+        A4 = A2 @ A2
+        A6 = A4 @ A2
+        tmp_u = A6 @ (b[13] * A6 + b[11] * A4 + b[9] * A2) + b[7] * A6 + b[5] * A4 + b[3] * A2 + b[1] * ident
+        tmp_v = A6 @ (b[12] * A6 + b[10] * A4 + b[8] * A2) + b[6] * A6 + b[4] * A4 + b[2] * A2 + b[0] * ident
+        return A @ tmp_u, tmp_v
+    powers = [ident, A2]
+    for _ in range(2, (order + 1) // 2):
+        powers.append(powers[-1] @ A2)
+    tmp_u = sum(b[2 * i + 1] * powers[i] for i in range((order + 1) // 2))
+    tmp_v = sum(b[2 * i] * powers[i] for i in range((order + 1) // 2))
+    return A @ tmp_u, tmp_v
+
+
+# TF 2.6 computes squarings = max(floor(log2(||A||_1 / theta_13)), 0) (recalled from upstream source, not
+# verifiable offline).  With floor the scaled norm lies in [theta_13, 2 theta_13) and Pade-13 is used beyond its
+# threshold: up to ~2e-9 absolute error in expm (measured here against mpmath for the quasi-periodic drift at
+# ||F dt||_1 ~ 10-20).  The oracle uses Higham's ceil so that it is accurate to ~1e-15 everywhere; set
+# EXPM_TF_FLOOR = True to reproduce the under-scaled variant (tests/test_cpu_oracle.py bounds the difference).
+EXPM_TF_FLOOR = False
+
+
+def expm(A):
+    """Batched matrix exponential, float64: Pade order by ||A||_1 thresholds 1.4956e-2 / 2.5394e-1 / 9.5042e-1 /
+    2.0978, else order 13 after scaling by 2^-s, s = ceil(log2(||A||_1 / 5.371920351148152)) (see EXPM_TF_FLOOR)."""
+    A = A.to(torch.float64)
+    batch = A.shape[:-2]
+    l1 = A.abs().sum(dim=-2).amax(dim=-1)
+    maxnorm = 5.371920351148152
+    rnd = torch.floor if EXPM_TF_FLOOR else torch.ceil
+    sq = torch.clamp(rnd(torch.log2(torch.clamp(l1, min=1e-300) / maxnorm)), min=0.)
+    scale = torch.pow(torch.tensor(2.0, dtype=A.dtype), sq).reshape(batch + (1, 1))
+    u3, v3 = _pade_uv(A, 3)
+    u5, v5 = _pade_uv(A, 5)
+    u7, v7 = _pade_uv(A, 7)
+    u9, v9 = _pade_uv(A, 9)
+    u13, v13 = _pade_uv(A / scale, 13)
+    conds = (1.495585217958292e-2, 2.539398330063230e-1, 9.504178996162932e-1, 2.097847961257068e0)
+    ln = l1.reshape(batch + (1, 1))
+
+    def nest(x3, x5, x7, x9, x13):
+        return torch.where(ln < conds[0], x3, torch.where(ln < conds[1], x5, torch.where(
+            ln < conds[2], x7, torch.where(ln < conds[3], x9, x13))))
+
+    u, v = nest(u3, u5, u7, u9, u13), nest(v3, v5, v7, v9, v13)
+    sq = torch.where(l1 < conds[3], torch.zeros_like(sq), sq)
+    result = torch.linalg.solve(-u + v, u + v)
+    max_sq = int(sq.max().item()) if sq.numel() else 0
+    for i in range(max_sq):
+        mask = (sq > i).reshape(batch + (1, 1))
+        result = torch.where(mask, result @ result, result)
+    return result
+
+
+# --------------------------------------------------------------------------------------------
 # pssgp/kernels/base.py
 # --------------------------------------------------------------------------------------------
 def get_ssm(sde, ts, R, t0=0.):
@@ -147,11 +221,11 @@ def get_ssm(sde, ts, R, t0=0.):
     t0 = torch.as_tensor(t0, dtype=dtype).reshape(1, 1)
     ts = torch.cat([t0, ts], dim=0)
     dts = (ts[1:] - ts[:-1]).reshape(-1, 1, 1)
-    Fs = torch.linalg.matrix_exp(dts * sde.F.unsqueeze(0))
+    Fs = expm(dts * sde.F.unsqueeze(0))
     zeros = torch.zeros_like(sde.F)
     Phi = torch.cat([torch.cat([sde.F, sde.L @ (sde.Q @ tr(sde.L))], dim=1),
                      torch.cat([zeros, -tr(sde.F)], dim=1)], dim=0)
-    AB = torch.linalg.matrix_exp(dts * Phi.unsqueeze(0))
+    AB = expm(dts * Phi.unsqueeze(0))
     AB = AB @ torch.cat([zeros, torch.eye(n, dtype=dtype)], dim=0)
     Qs = AB[:, :n, :] @ tr(Fs)
     return LGSSM(sde.P0, Fs, Qs, sde.H, R)
@@ -165,7 +239,7 @@ def get_ssm_stationary(sde, ts, R, t0=0.):
     t0 = torch.as_tensor(t0, dtype=dtype).reshape(1, 1)
     ts = torch.cat([t0, ts], dim=0)
     dts = (ts[1:] - ts[:-1]).reshape(-1, 1, 1)
-    Fs = torch.linalg.matrix_exp(dts * sde.F.unsqueeze(0))
+    Fs = expm(dts * sde.F.unsqueeze(0))
     Qs = sde.P0.unsqueeze(0) - Fs @ sde.P0.unsqueeze(0) @ tr(Fs)
     Qs = 0.5 * (Qs + tr(Qs))
     return LGSSM(sde.P0, Fs, Qs, sde.H, R)
