@@ -59,7 +59,9 @@ def to_device(x, dtype, device, key=None):
     """Returns a contiguous CUDA tensor of `dtype` on `device` (async H2D from pinned memory for host data)."""
     if isinstance(x, torch.Tensor):
         if x.is_cuda:
-            return x.detach().to(device=device, dtype=dtype).contiguous()
+            t = x.detach().to(device=device, dtype=dtype).contiguous()
+            # the streaming kernels move 16-byte pieces: a sliced view may start off a 16-byte boundary
+            return t if t.data_ptr() % 16 == 0 else t.clone()
         src = x.detach().to(dtype).contiguous()
     else:
         src = torch.from_numpy(np.ascontiguousarray(np.asarray(x), dtype=np.float64 if dtype == torch.float64 else np.float32))

@@ -29,6 +29,12 @@ struct AdjointAlg {
     static constexpr int NAGG = oB + NS;
     static constexpr int NSTATE = D + NS;
     static constexpr int NACC = 1 + D;
+    // streaming tables: inputs F, Q, y at row k and fms, fPs at row k-1 (one-row shift); outputs dFs, dQs
+    static constexpr bool REVERSE = true;
+    static constexpr int NIN = 5, NOUT = 2, WMAX = D * D;
+    __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? 1 : (a == 3 ? D : D * D); }
+    __host__ __device__ static constexpr int in_shift(int a) { return a >= 3 ? -1 : 0; }
+    __host__ __device__ static constexpr int out_w(int) { return D * D; }
 
     struct Params {
         const T* Fs;
@@ -69,33 +75,47 @@ struct AdjointAlg {
         bool obs, first;
     };
 
-    // Recomputes the forward quantities of time step k.
-    PSSGP_DEV static void forward(const Params& p, long k, Fwd& f) {
+    __host__ __device__ __forceinline__ static const T* in_ptr(const Params& p, int a) {
+        return a == 0 ? p.Fs : (a == 1 ? p.Qs : (a == 2 ? p.y : (a == 3 ? p.fms : p.fPs)));
+    }
+    __host__ __device__ __forceinline__ static T* out_ptr(const Params& p, int a) { return a == 0 ? p.dFs : p.dQs; }
+
+    struct Ctx {
+        T h[D];
+        T R, g;
+    };
+    PSSGP_DEV static void load_ctx(const Params& p, Ctx& c) {
 #pragma unroll
-        for (int i = 0; i < D; ++i) f.h[i] = __ldg(p.H + i);
-        f.R = __ldg(p.R);
-        f.yk = __ldg(p.y + k);
+        for (int i = 0; i < D; ++i) c.h[i] = __ldg(p.H + i);
+        c.R = __ldg(p.R);
+        c.g = p.g ? __ldg(p.g) : T(1);
+    }
+
+    // Recomputes the forward quantities of time step k (row r of the staged tile).
+    template <int LSW>
+    PSSGP_DEV static void forward(const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p, Fwd& f) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) f.h[i] = cx.h[i];
+        f.R = cx.R;
+        f.yk = in[2][r];
         f.obs = !t_isnan(f.yk);
         f.first = (k == 0 && p.first_special);
-        const T* pf = p.Fs + k * (D * D);
-        const T* pq = p.Qs + k * (D * D);
 #pragma unroll
-        for (int e = 0; e < D * D; ++e) f.F[e] = __ldg(pf + e);
+        for (int e = 0; e < D * D; ++e) f.F[e] = in[0][r * D * D + e];
         T Q[NS];
+        const T* qf = &in[1][r * D * D];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (__ldg(pq + i * D + j) + __ldg(pq + j * D + i));
+            for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (qf[i * D + j] + qf[j * D + i]);
         if (k > 0) {
-            const T* pm = p.fms + (k - 1) * D;
-            const T* pP = p.fPs + (k - 1) * (D * D);
+            const T* pf = &in[4][r * D * D];
 #pragma unroll
-            for (int i = 0; i < D; ++i) f.m[i] = __ldg(pm + i);
+            for (int i = 0; i < D; ++i) f.m[i] = in[3][r * D + i];
 #pragma unroll
             for (int i = 0; i < D; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j)
-                    f.P[sidx(i, j)] = T(0.5) * (__ldg(pP + i * D + j) + __ldg(pP + j * D + i));
+                for (int j = 0; j <= i; ++j) f.P[sidx(i, j)] = T(0.5) * (pf[i * D + j] + pf[j * D + i]);
         } else {
 #pragma unroll
             for (int i = 0; i < D; ++i) f.m[i] = p.m0 ? p.m0[i] : T(0);
@@ -115,9 +135,10 @@ struct AdjointAlg {
     }
 
     // Element (Abar, a, B) of time step k for an upstream gradient of 1.
-    PSSGP_DEV static void element(const Params& p, long k, T* x) {
+    template <int LSW>
+    PSSGP_DEV static void element(const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p, T* x) {
         Fwd f;
-        forward(p, k, f);
+        forward(cx, in, r, k, p, f);
         if (f.first) {
             // filter update acts on (m0, P0) directly, no likelihood term through this path
             identity(x);
@@ -178,12 +199,13 @@ struct AdjointAlg {
             }
     }
 
-    PSSGP_DEV static void append(T* a, long j, const Params& p) {
-        T x[NAGG], r[NAGG];
-        element(p, p.n - 1 - j, x);
-        combine(a, x, r);
+    template <int LSW>
+    PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p) {
+        T x[NAGG], rr[NAGG];
+        element(cx, in, r, k, p, x);
+        combine(a, x, rr);
 #pragma unroll
-        for (int e = 0; e < NAGG; ++e) a[e] = r[e];
+        for (int e = 0; e < NAGG; ++e) a[e] = rr[e];
     }
 
     PSSGP_DEV static void apply(const T* s, const T* x, T* s2) {
@@ -241,14 +263,15 @@ struct AdjointAlg {
     }
 
     // s = adjoint w.r.t. the filtered moments at time k; on exit w.r.t. those at time k-1.
-    PSSGP_DEV static void step(T* s, long j, const Params& p, T* acc) {
-        const long k = p.n - 1 - j;
-        const T g = __ldg(p.g);
+    template <int LSW>
+    PSSGP_DEV static void step_row(T* s, const Ctx& cx, const T (&in)[NIN][LSW], T (&out)[NOUT][LSW], int r, long k,
+                                   const Params& p, T* acc) {
+        const T g = cx.g;
         Fwd f;
-        forward(p, k, f);
+        forward(cx, in, r, k, p, f);
         T dmp[D], dPp[NS];
-        T* oF = p.dFs + k * (D * D);
-        T* oQ = p.dQs + k * (D * D);
+        T* oF = &out[0][r * D * D];
+        T* oQ = &out[1][r * D * D];
         if (f.first) {
             // (i) likelihood term of step 0 through the prediction from (m0, P0)
             T dPp0[NS], dmp0[D];

@@ -70,15 +70,20 @@ void timing_end(pssgp_handle* h, void* stream) {
     h->n_rec++;
 }
 
-int pick_chunk(const pssgp_handle* h, int64_t n) {
-    if (h->chunk_opt > 0) return (int)h->chunk_opt;
-    // enough chunks to give every SM ~16 warps, but never shorter than 8 steps (amortises the
-    // generic-operator warp scan) nor longer than 64.
-    int64_t target_chunks = (int64_t)h->num_sms * 16 * 32;
-    int64_t L = n / (target_chunks > 0 ? target_chunks : 1);
-    int c = 8;
-    while (c < 64 && c * 2 <= L) c *= 2;
-    return c;
+int pick_chunk(const pssgp_handle* h, int64_t n, int threads_per_cta, int ls) {
+    int64_t L;
+    if (h->chunk_opt > 0) {
+        L = h->chunk_opt;
+    } else {
+        // one CTA per SM, all resident at once: the grid is a single wave and every thread streams one chunk.
+        // Never shorter than 8 steps (amortises the generic-operator warp scan).
+        const int64_t threads = (int64_t)(h->num_sms > 0 ? h->num_sms : 1) * threads_per_cta;
+        L = (n + threads - 1) / threads;
+        if (L < 8) L = 8;
+    }
+    L = ((L + ls - 1) / ls) * ls;
+    if (L > (1 << 30)) L = 1 << 30;
+    return (int)L;
 }
 
 }  // namespace pssgp

@@ -26,6 +26,12 @@ struct FilterAlg {
     static constexpr int NAGG = oE + D;
     static constexpr int NSTATE = D + NS;
     static constexpr int NACC = 1;
+    // streaming tables (scan_stream.cuh): inputs F, Q, y at row k; outputs fms, fPs at row k
+    static constexpr bool REVERSE = false;
+    static constexpr int NIN = 3, NOUT = 2, WMAX = D * D;
+    __host__ __device__ static constexpr int in_w(int a) { return a < 2 ? D * D : 1; }
+    __host__ __device__ static constexpr int in_shift(int) { return 0; }
+    __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {
         const T* Fs;   // [n, D, D]
@@ -47,27 +53,35 @@ struct FilterAlg {
         for (int i = 0; i < D; ++i) a[oA + i * D + i] = T(1);
     }
 
-    PSSGP_DEV static void load_FQ(const Params& p, long k, T* F, T* Q) {
-        const T* f = p.Fs + k * (D * D);
-        const T* q = p.Qs + k * (D * D);
+    __host__ __device__ __forceinline__ static const T* in_ptr(const Params& p, int a) { return a == 0 ? p.Fs : (a == 1 ? p.Qs : p.y); }
+    __host__ __device__ __forceinline__ static T* out_ptr(const Params& p, int a) { return a == 0 ? p.fms : p.fPs; }
+
+    struct Ctx {
+        T h[D];
+        T R;
+    };
+    PSSGP_DEV static void load_ctx(const Params& p, Ctx& c) {
 #pragma unroll
-        for (int e = 0; e < D * D; ++e) F[e] = __ldg(f + e);
-        T qf[D * D];
-#pragma unroll
-        for (int e = 0; e < D * D; ++e) qf[e] = __ldg(q + e);
+        for (int i = 0; i < D; ++i) c.h[i] = __ldg(p.H + i);
+        c.R = __ldg(p.R);
+    }
+
+    // Q of one row, symmetrised and packed
+    PSSGP_DEV static void sym_pack(const T* qf, T* Q) {
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (qf[i * D + j] + qf[j * D + i]);
     }
 
-    // Append logical step k to the aggregate: conditional Kalman recursion given the chunk-entry state.
-    PSSGP_DEV static void append(T* a, long k, const Params& p) {
-        T h[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) h[i] = __ldg(p.H + i);
-        const T R = __ldg(p.R);
-        const T yk = __ldg(p.y + k);
+    // Append time step k (row r of the staged tile) to the aggregate: conditional Kalman recursion given
+    // the chunk-entry state.
+    template <int LSW>
+    PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p) {
+        const T* F = &in[0][r * D * D];
+        const T* h = cx.h;
+        const T R = cx.R;
+        const T yk = in[2][r];
         T Ap[D * D], bp[D], Cp[NS];
         if (k == 0 && p.first_special) {
             // no prediction at the global first step (parallel.py:24-30)
@@ -78,8 +92,8 @@ struct FilterAlg {
 #pragma unroll
             for (int e = 0; e < NS; ++e) Cp[e] = a[oC + e];
         } else {
-            T F[D * D], Q[NS], FC[D * D];
-            load_FQ(p, k, F, Q);
+            T Q[NS], FC[D * D];
+            sym_pack(&in[1][r * D * D], Q);
             mm_ff<T, D>(F, a + oA, Ap);
             mv_f<T, D>(F, a + ob, bp);
             mm_fs<T, D>(F, a + oC, FC);
@@ -229,15 +243,16 @@ struct FilterAlg {
             for (int j = 0; j <= i; ++j) s[D + sidx(i, j)] = T(0.5) * (p.P0[i * D + j] + p.P0[j * D + i]);
     }
 
-    // Seeded Kalman step k: s=(m,P) filtered at k-1 -> filtered at k; writes fms/fPs, accumulates ll.
-    PSSGP_DEV static void step(T* s, long k, const Params& p, T* acc) {
-        T h[D];
-#pragma unroll
-        for (int i = 0; i < D; ++i) h[i] = __ldg(p.H + i);
-        const T R = __ldg(p.R);
-        const T yk = __ldg(p.y + k);
-        T F[D * D], Q[NS], FP[D * D], mp[D], Pp[NS];
-        load_FQ(p, k, F, Q);
+    // Seeded Kalman step k: s=(m,P) filtered at k-1 -> filtered at k; emits fms/fPs, accumulates ll.
+    template <int LSW>
+    PSSGP_DEV static void step_row(T* s, const Ctx& cx, const T (&in)[NIN][LSW], T (&out)[NOUT][LSW], int r, long k,
+                                   const Params& p, T* acc) {
+        const T* F = &in[0][r * D * D];
+        const T* h = cx.h;
+        const T R = cx.R;
+        const T yk = in[2][r];
+        T Q[NS], FP[D * D], mp[D], Pp[NS];
+        sym_pack(&in[1][r * D * D], Q);
         mv_f<T, D>(F, s, mp);
         mm_fs<T, D>(F, s + D, FP);
         sym_xat_plus<T, D>(FP, F, Q, Pp);
@@ -271,14 +286,12 @@ struct FilterAlg {
 #pragma unroll
             for (int e = 0; e < NS; ++e) s[D + e] = Pp[e];
         }
-        T* om = p.fms + k * D;
-        T* oP = p.fPs + k * (D * D);
 #pragma unroll
-        for (int i = 0; i < D; ++i) om[i] = s[i];
+        for (int i = 0; i < D; ++i) out[0][r * D + i] = s[i];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int j = 0; j < D; ++j) oP[i * D + j] = s[D + sidx(i, j)];
+            for (int j = 0; j < D; ++j) out[1][r * D * D + i * D + j] = s[D + sidx(i, j)];
     }
 
     // fold output: m[D] | P full [D,D]  (so that the caller can pass m0 = out, P0 = out + D to pssgp_pkf)

@@ -1,14 +1,18 @@
-// Host-side launcher of the three-kernel chunked scan (scan_small.cuh) + (dtype, d) dispatch helpers.
+// Host-side launcher of the three-kernel chunked scan (scan_stream.cuh, scan_small.cuh) + (dtype, d) dispatch helpers.
 #pragma once
 #include <cuda_runtime.h>
 
 #include "../../include/pssgp_b200.h"
+#include <stdint.h>
+
 #include "scan_small.cuh"
+#include "scan_stream.cuh"
 #include "workspace.h"
 
 namespace pssgp {
 
-int pick_chunk(const pssgp_handle* h, int64_t n);
+// time steps per thread-chunk: one resident wave of CTAs (threads_per_cta each), multiple of `ls`
+int pick_chunk(const pssgp_handle* h, int64_t n, int threads_per_cta, int ls);
 int check_common(pssgp_handle* h, int dtype, int64_t n, int d);
 
 // generic state dimension (warp-cooperative path, generic.cu); summary != nullptr selects summary mode
@@ -31,6 +35,25 @@ int adjoint_fold_generic(pssgp_handle* h, int dtype, int d, int count, const voi
 
 enum ScanMode { SCAN_FULL = 0, SCAN_SUMMARY = 1 };
 
+// Opts the streaming kernels of an algebra into their (> 48 KB) dynamic shared memory, once per process.
+template <typename Alg>
+int stream_configure(int device) {
+    using Lay = StreamLayout<Alg>;
+    static unsigned long long done = 0ull;  // one bit per device (the attribute is per device)
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done & bit) return PSSGP_OK;
+    cudaError_t e = cudaFuncSetAttribute(stream_reduce_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Lay::NW * Lay::WARP_BYTES);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stream_apply_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Lay::NW * Lay::WARP_BYTES);
+    if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+    done |= bit;
+    return PSSGP_OK;
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
 // Runs K1/K2/K3 for an algebra.  SCAN_SUMMARY: K1 + total only (shard summary for time sharding); the
 // chunk aggregates stay in the workspace and the next SCAN_FULL call with the same key skips K1.
 template <typename Alg>
@@ -38,16 +61,25 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
              typename Alg::scalar* final_state, cudaStream_t st, int mode = SCAN_FULL,
              typename Alg::scalar* summary = nullptr, const void* key = nullptr) {
     using T = typename Alg::scalar;
-    const int L = pick_chunk(h, n);
+    using Lay = StreamLayout<Alg>;
+    constexpr int NW = Lay::NW;
+    int rc;
+    if ((rc = stream_configure<Alg>(h->device))) return rc;
+    for (int a = 0; a < Alg::NIN; ++a)
+        if (!aligned16(Alg::in_ptr(p, a))) return set_err(PSSGP_ERR_INVALID, "input array %d is not 16-byte aligned", a);
+    if (mode == SCAN_FULL)
+        for (int a = 0; a < Alg::NOUT; ++a)
+            if (!aligned16(Alg::out_ptr(p, a)))
+                return set_err(PSSGP_ERR_INVALID, "output array %d is not 16-byte aligned", a);
+    const int L = pick_chunk(h, n, NW * 32, Lay::LS);
     const int64_t nChunks = (n + L - 1) / L;
-    const int64_t nBlocks = (nChunks + kReduceThreads - 1) / kReduceThreads;
+    const int64_t nBlocks = (nChunks + NW * 32 - 1) / (NW * 32);
     const int64_t nW = nBlocks;  // one aggregate per CTA of K1
-    const int64_t nChunksPad = nBlocks * kReduceThreads;
+    const int64_t nChunksPad = nBlocks * NW * 32;
     constexpr int kind = Alg::KIND;
     const bool reuse = (mode == SCAN_FULL && key != nullptr && h->pending_key[kind] == key &&
                         h->pending_n[kind] == n && h->pending_L[kind] == L);
     h->pending_key[kind] = nullptr;
-    int rc;
     if (!reuse) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * Alg::NAGG * (size_t)nChunksPad))) return rc;
         if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * Alg::NAGG * (size_t)nW))) return rc;
@@ -61,8 +93,8 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     int nl = 0;
     if (!reuse) {
         PSSGP_LAUNCH(h, Alg::name_reduce(), st,
-                     (scan_reduce_kernel<Alg><<<(unsigned)nBlocks, kReduceThreads, 0, st>>>(p, n, L, nChunksPad, lane,
-                                                                                           wagg, nW)));
+                     (stream_reduce_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES, st>>>(
+                         p, n, L, nChunks, nChunksPad, lane, wagg, nW)));
         ++nl;
     }
     int midThreads = kMidThreads;
@@ -77,8 +109,8 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     }
     PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_mid_kernel<Alg><<<1, midThreads, 0, st>>>(p, wagg, nW, wstate, final_state)));
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
-                 (scan_apply_kernel<Alg><<<(unsigned)nBlocks, kReduceThreads, 0, st>>>(p, n, L, nChunksPad, lane, wstate,
-                                                                                      nW, part, h->ticket, acc_out)));
+                 (stream_apply_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES, st>>>(
+                     p, n, L, nChunks, nChunksPad, lane, wstate, nW, part, h->ticket, acc_out)));
     return check_launch(h, "scan", nl + 2);
 }
 

@@ -1,115 +1,14 @@
-// Three-kernel chunked scan for register-resident state dimensions (D <= 4).
-//
-//   K1 reduce : one thread per chunk of L consecutive time steps builds the chunk aggregate by
-//               sequential "append" (cheap conditional recursion, no generic operator), then a
-//               warp-level Kogge-Stone scan with the generic associative operator. It stores the
-//               lane-exclusive aggregate of every chunk and the total of every warp.
-//   K2 mid    : one CTA scans the warp totals and turns them into the *state* entering each warp
-//               (prefixes that start at the sequence origin collapse to a state: (m,P) for the
-//               filter, (ms,Ps) for the smoother, (dm,dP) for the adjoint).
-//   K3 apply  : every thread applies state o lane-exclusive-aggregate to get the state entering
-//               its chunk and re-runs the cheap seeded recursion over its L steps, writing outputs.
-//
-// An "Algebra" supplies: NAGG, NSTATE, NACC, Params, identity, append, combine, apply, step,
-// load_init, finish.  Direction (forward/reverse in time) is the Algebra's business: the framework
-// only sees logical indices 0..n-1.
+// Single-CTA kernels of the chunked scan for register-resident state dimensions (D <= 4): the scan
+// over CTA totals (K2 of scan_stream.cuh), the shard summary and the fold of gathered summaries (time
+// sharding).  The streaming kernels K1 / K3 live in scan_stream.cuh.
 #pragma once
 #include "smalld.cuh"
 
 namespace pssgp {
 
-constexpr int kReduceThreads = 128;
 constexpr int kMidThreads = 256;
 
-template <typename Alg>
-__global__ void __launch_bounds__(kReduceThreads)
-scan_reduce_kernel(typename Alg::Params p, long n, int L, long nChunksPad,
-                   typename Alg::scalar* __restrict__ lane_excl,
-                   typename Alg::scalar* __restrict__ wagg, long nW) {
-    using T = typename Alg::scalar;
-    const long chunk = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    long k0 = chunk * (long)L;
-    long k1 = k0 + L;
-    if (k1 > n) k1 = n;
-    T a[Alg::NAGG];
-    Alg::identity(a);
-    for (long k = k0; k < k1; ++k) Alg::append(a, k, p);
-    // warp inclusive scan (earlier lane is the left operand)
-#pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
-        T o[Alg::NAGG];
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(a[e], off);
-        if (lane >= off) {
-            T r[Alg::NAGG];
-            Alg::combine(o, a, r);
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
-        }
-    }
-    // block level: every warp folds the totals of the warps before it (<= 3 combines)
-    __shared__ T shw[(kReduceThreads / 32) * Alg::NAGG];
-    const int wid = threadIdx.x >> 5;
-    if (lane == 31) {
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) shw[wid * Alg::NAGG + e] = a[e];
-    }
-    T ex[Alg::NAGG];
-#pragma unroll
-    for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
-    if (lane == 0) Alg::identity(ex);
-    __syncthreads();
-    if (wid > 0) {
-        T wp[Alg::NAGG];
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) wp[e] = shw[e];
-#pragma unroll 1
-        for (int w = 1; w < wid; ++w) {
-            T b[Alg::NAGG], r[Alg::NAGG];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) b[e] = shw[w * Alg::NAGG + e];
-            Alg::combine(wp, b, r);
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) wp[e] = r[e];
-        }
-        T r[Alg::NAGG];
-        Alg::combine(wp, ex, r);
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) ex[e] = r[e];
-    }
-    if (threadIdx.x != 0 && k0 < n) {
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + chunk] = ex[e];
-    }
-    if (threadIdx.x == kReduceThreads - 1) {
-        // block total = exclusive prefix of the last thread o its own chunk aggregate... the last
-        // lane's inclusive warp aggregate `a` already covers its warp, so fold the warp prefix in.
-        T tot[Alg::NAGG];
-        if (wid > 0) {
-            T wp[Alg::NAGG];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) wp[e] = shw[e];
-#pragma unroll 1
-            for (int w = 1; w < wid; ++w) {
-                T b[Alg::NAGG], r[Alg::NAGG];
-#pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) b[e] = shw[w * Alg::NAGG + e];
-                Alg::combine(wp, b, r);
-#pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) wp[e] = r[e];
-            }
-            Alg::combine(wp, a, tot);
-        } else {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) tot[e] = a[e];
-        }
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nW + blockIdx.x] = tot[e];
-    }
-}
-
-// Single CTA.  wstate[s*nW + w] = state entering warp w.  final_state = state after everything.
+// Single CTA.  wstate[s*nW + w] = state entering CTA w of K1/K3.  final_state = state after everything.
 template <typename Alg>
 __global__ void __launch_bounds__(kMidThreads)
 scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__ wagg, long nW,
@@ -221,83 +120,6 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
     // the thread that owns the last warp total holds the final state
     if (final_state != nullptr && i1 == nW && i0 < nW) Alg::expand_state(s, final_state);
     if (final_state != nullptr && nW == 0 && tid == 0) Alg::expand_state(s, final_state);
-}
-
-template <typename Alg>
-__global__ void __launch_bounds__(kReduceThreads)
-scan_apply_kernel(typename Alg::Params p, long n, int L, long nChunksPad,
-                  const typename Alg::scalar* __restrict__ lane_excl,
-                  const typename Alg::scalar* __restrict__ wstate, long nW,
-                  typename Alg::scalar* __restrict__ acc_part, unsigned int* __restrict__ ticket,
-                  typename Alg::scalar* __restrict__ acc_out) {
-    using T = typename Alg::scalar;
-    const long chunk = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    long k0 = chunk * (long)L;
-    long k1 = k0 + L;
-    if (k1 > n) k1 = n;
-    T acc[Alg::NACC > 0 ? Alg::NACC : 1];
-#pragma unroll
-    for (int e = 0; e < (Alg::NACC > 0 ? Alg::NACC : 1); ++e) acc[e] = T(0);
-    if (k0 < n) {
-        T s[Alg::NSTATE];
-#pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) s[e] = wstate[(long)e * nW + blockIdx.x];
-        if (threadIdx.x != 0) {
-            T ex[Alg::NAGG], s2[Alg::NSTATE];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = lane_excl[(long)e * nChunksPad + chunk];
-            Alg::apply(s, ex, s2);
-#pragma unroll
-            for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
-        }
-        for (long k = k0; k < k1; ++k) Alg::step(s, k, p, acc);
-    }
-    if (Alg::NACC > 0) {
-        // deterministic grid reduction: warp shuffle -> smem -> per-block partial -> last block sums in order
-        __shared__ T red[(kReduceThreads / 32) * (Alg::NACC > 0 ? Alg::NACC : 1)];
-        __shared__ bool is_last;
-#pragma unroll
-        for (int e = 0; e < Alg::NACC; ++e) {
-            T v = acc[e];
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) v += shfl_down_t(v, off);
-            if (lane == 0) red[(threadIdx.x >> 5) * Alg::NACC + e] = v;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            for (int e = 0; e < Alg::NACC; ++e) {
-                T v = T(0);
-                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += red[w * Alg::NACC + e];
-                acc_part[(long)blockIdx.x * Alg::NACC + e] = v;
-            }
-            __threadfence();
-            unsigned int t = atomicAdd(ticket, 1u);
-            is_last = (t == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (is_last) {
-            __threadfence();
-            const int nb = gridDim.x;
-            for (int e = 0; e < Alg::NACC; ++e) {
-                // fixed-shape tree: thread t sums blocks t, t+128, ... then ordered smem tree
-                T v = T(0);
-                for (int b = threadIdx.x; b < nb; b += blockDim.x)
-                    v += ((volatile T*)acc_part)[(long)b * Alg::NACC + e];
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) v += shfl_down_t(v, off);
-                __syncthreads();
-                if (lane == 0) red[threadIdx.x >> 5] = v;
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    T tot = T(0);
-                    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
-                    Alg::finish(p, e, tot, acc_out);
-                }
-            }
-            if (threadIdx.x == 0) *ticket = 0u;
-        }
-    }
 }
 
 // Single CTA: out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding).

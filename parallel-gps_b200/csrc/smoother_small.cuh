@@ -1,5 +1,5 @@
-// RTS smoothing algebra for D <= 4 (one thread per chunk), reverse-time scan done by index
-// reversal (logical index j  <->  time k = n-1-j), never by physically reversing arrays.
+// RTS smoothing algebra for D <= 4 (one thread per chunk), reverse-time scan done by walking chunks
+// and rows in descending time (scan_stream.cuh), never by physically reversing arrays.
 //
 // Replaces, for the reference's pssgp/kalman/parallel.py:
 //   last_smoothing_element     :155-156
@@ -26,6 +26,12 @@ struct SmootherAlg {
     static constexpr int NAGG = oL + NS;
     static constexpr int NSTATE = D + NS;
     static constexpr int NACC = 0;
+    // streaming tables: inputs F, Q at row k+1 (one-row shift), fms, fPs at row k; outputs sms, sPs at row k
+    static constexpr bool REVERSE = true;
+    static constexpr int NIN = 4, NOUT = 2, WMAX = D * D;
+    __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? D : D * D; }
+    __host__ __device__ static constexpr int in_shift(int a) { return a < 2 ? 1 : 0; }
+    __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {
         const T* Fs;     // [n, D, D]
@@ -48,35 +54,25 @@ struct SmootherAlg {
         for (int i = 0; i < D; ++i) a[oE + i * D + i] = T(1);
     }
 
-    // element (E, g, L) of time k (parallel.py:159-166)
-    PSSGP_DEV static void element(const Params& p, long k, T* E, T* g, T* L) {
-        const T* f = (k + 1 < p.n) ? p.Fs + (k + 1) * (D * D) : p.Fnext;
-        const T* q = (k + 1 < p.n) ? p.Qs + (k + 1) * (D * D) : p.Qnext;
-        T F[D * D], Pp[NS], m[D], P[NS];
+    __host__ __device__ __forceinline__ static const T* in_ptr(const Params& p, int a) {
+        return a == 0 ? p.Fs : (a == 1 ? p.Qs : (a == 2 ? p.fms : p.fPs));
+    }
+    __host__ __device__ __forceinline__ static T* out_ptr(const Params& p, int a) { return a == 0 ? p.sms : p.sPs; }
+
+    struct Ctx {};
+    PSSGP_DEV static void load_ctx(const Params&, Ctx&) {}
+
+    PSSGP_DEV static void sym_pack(const T* qf, T* Q) {
 #pragma unroll
-        for (int e = 0; e < D * D; ++e) F[e] = __ldg(f + e);
-        {
-            T qf[D * D];
+        for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int e = 0; e < D * D; ++e) qf[e] = __ldg(q + e);
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) Pp[sidx(i, j)] = T(0.5) * (qf[i * D + j] + qf[j * D + i]);
-        }
-        {
-            const T* pm = p.fms + k * D;
-            const T* pP = p.fPs + k * (D * D);
-#pragma unroll
-            for (int i = 0; i < D; ++i) m[i] = __ldg(pm + i);
-            T pf[D * D];
-#pragma unroll
-            for (int e = 0; e < D * D; ++e) pf[e] = __ldg(pP + e);
-#pragma unroll
-            for (int i = 0; i < D; ++i)
-#pragma unroll
-                for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (pf[i * D + j] + pf[j * D + i]);
-        }
+            for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (qf[i * D + j] + qf[j * D + i]);
+    }
+
+    // element (E, g, L) of time k (parallel.py:159-166) from F_{k+1}, Q_{k+1} (full) and m_k, P_k (packed)
+    PSSGP_DEV static void element(const T* F, const T* Qf, const T* m, const T* P, T* E, T* g, T* L) {
+        T Pp[NS];
+        sym_pack(Qf, Pp);
         T FP[D * D];
         mm_fs<T, D>(F, P, FP);
         sym_xat_plus<T, D>(FP, F, Pp, Pp);  // Pp = FP F^T + Q
@@ -110,27 +106,39 @@ struct SmootherAlg {
             }
     }
 
-    PSSGP_DEV static void load_filtered(const Params& p, long k, T* m, T* P) {
-        const T* pm = p.fms + k * D;
-        const T* pP = p.fPs + k * (D * D);
+    // element of row r of the staged tile (time k); the row after the shard's last one comes from the halo
+    template <int LSW>
+    PSSGP_DEV static void element_row(const T (&in)[NIN][LSW], int r, long k, const Params& p, T* E, T* g, T* L) {
+        T m[D], P[NS];
 #pragma unroll
-        for (int i = 0; i < D; ++i) m[i] = __ldg(pm + i);
+        for (int i = 0; i < D; ++i) m[i] = in[2][r * D + i];
+        sym_pack(&in[3][r * D * D], P);
+        if (k + 1 < p.n) {
+            element(&in[0][r * D * D], &in[1][r * D * D], m, P, E, g, L);
+        } else {
+            T F[D * D], Qf[D * D];
 #pragma unroll
-        for (int i = 0; i < D; ++i)
-#pragma unroll
-            for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (__ldg(pP + i * D + j) + __ldg(pP + j * D + i));
+            for (int e = 0; e < D * D; ++e) {
+                F[e] = __ldg(p.Fnext + e);
+                Qf[e] = __ldg(p.Qnext + e);
+            }
+            element(F, Qf, m, P, E, g, L);
+        }
     }
 
-    PSSGP_DEV static void append(T* a, long j, const Params& p) {
-        const long k = p.n - 1 - j;
-        if (j == 0 && p.last_special) {
+    template <int LSW>
+    PSSGP_DEV static void append_row(T* a, const Ctx&, const T (&in)[NIN][LSW], int r, long k, const Params& p) {
+        if (k == p.n - 1 && p.last_special) {
+            // last_smoothing_element (parallel.py:155-156): nothing has been appended before it
 #pragma unroll
             for (int e = 0; e < D * D; ++e) a[oE + e] = T(0);
-            load_filtered(p, k, a + og, a + oL);
+#pragma unroll
+            for (int i = 0; i < D; ++i) a[og + i] = in[2][r * D + i];
+            sym_pack(&in[3][r * D * D], a + oL);
             return;
         }
         T E[D * D], g[D], L[NS];
-        element(p, k, E, g, L);
+        element_row(in, r, k, p, E, g, L);
         // new = elem_k o agg : E = E_k E_a ; g = E_k g_a + g_k ; L = E_k L_a E_k^T + L_k
         T En[D * D], gn[D], X[D * D], Ln[NS];
         mm_ff<T, D>(E, a + oE, En);
@@ -172,25 +180,26 @@ struct SmootherAlg {
         for (int e = 0; e < NSTATE; ++e) s[e] = p.init ? p.init[e] : T(0);
     }
 
-    PSSGP_DEV static void step(T* s, long j, const Params& p, T*) {
-        const long k = p.n - 1 - j;
-        if (j == 0 && p.last_special) {
-            load_filtered(p, k, s, s + D);
+    template <int LSW>
+    PSSGP_DEV static void step_row(T* s, const Ctx&, const T (&in)[NIN][LSW], T (&out)[NOUT][LSW], int r, long k,
+                                   const Params& p, T*) {
+        if (k == p.n - 1 && p.last_special) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = in[2][r * D + i];
+            sym_pack(&in[3][r * D * D], s + D);
         } else {
             T a[NAGG], s2[NSTATE];
-            element(p, k, a + oE, a + og, a + oL);
+            element_row(in, r, k, p, a + oE, a + og, a + oL);
             apply(s, a, s2);
 #pragma unroll
             for (int e = 0; e < NSTATE; ++e) s[e] = s2[e];
         }
-        T* om = p.sms + k * D;
-        T* oP = p.sPs + k * (D * D);
 #pragma unroll
-        for (int i = 0; i < D; ++i) om[i] = s[i];
+        for (int i = 0; i < D; ++i) out[0][r * D + i] = s[i];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int jj = 0; jj < D; ++jj) oP[i * D + jj] = s[D + sidx(i, jj)];
+            for (int jj = 0; jj < D; ++jj) out[1][r * D * D + i * D + jj] = s[D + sidx(i, jj)];
     }
 
     PSSGP_DEV static void expand_state(const T* s, T* out) {
