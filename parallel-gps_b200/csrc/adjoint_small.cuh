@@ -29,11 +29,14 @@ struct AdjointAlg {
     static constexpr int NAGG = oB + NS;
     static constexpr int NSTATE = D + NS;
     static constexpr int NACC = 1 + D;
-    // streaming tables: inputs F, Q, y at row k and fms, fPs at row k-1 (one-row shift); outputs dFs, dQs
+    // streaming tables: inputs F, Q, y, fms, fPs at row k; outputs dFs, dQs.  Step k needs the filtered
+    // moments of row k-1, so it is taken one row late: when row k-1 is visited, with (F, Q, y) of row k
+    // carried in registers (OUT_SHIFT = 1); the chunk's first row is finished by step_flush from a halo load.
     static constexpr bool REVERSE = true;
+    static constexpr int OUT_SHIFT = 1;
+    static constexpr bool FLUSH = true;
     static constexpr int NIN = 5, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? 1 : (a == 3 ? D : D * D); }
-    __host__ __device__ static constexpr int in_shift(int a) { return a >= 3 ? -1 : 0; }
     __host__ __device__ static constexpr int out_w(int) { return D * D; }
 
     struct Params {
@@ -91,54 +94,83 @@ struct AdjointAlg {
         c.g = p.g ? __ldg(p.g) : T(1);
     }
 
-    // Recomputes the forward quantities of time step k (row r of the staged tile).
-    template <int LSW>
-    PSSGP_DEV static void forward(const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p, Fwd& f) {
-#pragma unroll
-        for (int i = 0; i < D; ++i) f.h[i] = cx.h[i];
-        f.R = cx.R;
-        f.yk = in[2][r];
-        f.obs = !t_isnan(f.yk);
-        f.first = (k == 0 && p.first_special);
-#pragma unroll
-        for (int e = 0; e < D * D; ++e) f.F[e] = in[0][r * D * D + e];
+    // (F, Q, y) of the step that is taken when the next (earlier) row is visited
+    struct Carry {
+        T F[D * D];
         T Q[NS];
-        const T* qf = &in[1][r * D * D];
+        T y;
+        bool has;
+    };
+    PSSGP_DEV static void carry_init(Carry& c, const Ctx&, long, long, const Params&) { c.has = false; }
+    PSSGP_DEV static void carry_set(Carry& c, const T (&in)[NIN][WMAX]) {
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) c.F[e] = in[0][e];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (qf[i * D + j] + qf[j * D + i]);
+            for (int j = 0; j <= i; ++j) c.Q[sidx(i, j)] = T(0.5) * (in[1][i * D + j] + in[1][j * D + i]);
+        c.y = in[2][0];
+        c.has = true;
+    }
+    // filtered moments of row k-1 straight from global memory (chunk boundary), or the prior at k = 0
+    PSSGP_DEV static void halo_moments(long k, const Params& p, T* m, T* P) {
         if (k > 0) {
-            const T* pf = &in[4][r * D * D];
+            const T* pm = p.fms + (k - 1) * D;
+            const T* pP = p.fPs + (k - 1) * (D * D);
 #pragma unroll
-            for (int i = 0; i < D; ++i) f.m[i] = in[3][r * D + i];
+            for (int i = 0; i < D; ++i) m[i] = __ldg(pm + i);
 #pragma unroll
             for (int i = 0; i < D; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j) f.P[sidx(i, j)] = T(0.5) * (pf[i * D + j] + pf[j * D + i]);
+                for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (__ldg(pP + i * D + j) + __ldg(pP + j * D + i));
         } else {
 #pragma unroll
-            for (int i = 0; i < D; ++i) f.m[i] = p.m0 ? p.m0[i] : T(0);
+            for (int i = 0; i < D; ++i) m[i] = p.m0 ? p.m0[i] : T(0);
 #pragma unroll
             for (int i = 0; i < D; ++i)
 #pragma unroll
-                for (int j = 0; j <= i; ++j)
-                    f.P[sidx(i, j)] = T(0.5) * (p.P0[i * D + j] + p.P0[j * D + i]);
+                for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (p.P0[i * D + j] + p.P0[j * D + i]);
         }
+    }
+    PSSGP_DEV static void row_moments(const T (&in)[NIN][WMAX], T* m, T* P) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) m[i] = in[3][i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) P[sidx(i, j)] = T(0.5) * (in[4][i * D + j] + in[4][j * D + i]);
+    }
+
+    // Recomputes the forward quantities of time step k from (F, Q, y) of row k and the filtered moments
+    // (m, P) of row k-1.
+    PSSGP_DEV static void forward(const Ctx& cx, const Carry& c, const T* m, const T* P, long k, const Params& p,
+                                  Fwd& f) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) f.h[i] = cx.h[i];
+        f.R = cx.R;
+        f.yk = c.y;
+        f.obs = !t_isnan(f.yk);
+        f.first = (k == 0 && p.first_special);
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) f.F[e] = c.F[e];
+#pragma unroll
+        for (int i = 0; i < D; ++i) f.m[i] = m[i];
+#pragma unroll
+        for (int e = 0; e < NS; ++e) f.P[e] = P[e];
         T FP[D * D];
         mv_f<T, D>(f.F, f.m, f.mp);
         mm_fs<T, D>(f.F, f.P, FP);
-        sym_xat_plus<T, D>(FP, f.F, Q, f.Pp);
+        sym_xat_plus<T, D>(FP, f.F, c.Q, f.Pp);
         mv_s<T, D>(f.Pp, f.h, f.u);
         f.s = dot<T, D>(f.h, f.u) + f.R;
         f.r = f.yk - dot<T, D>(f.h, f.mp);
     }
 
     // Element (Abar, a, B) of time step k for an upstream gradient of 1.
-    template <int LSW>
-    PSSGP_DEV static void element(const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p, T* x) {
+    PSSGP_DEV static void element(const Ctx& cx, const Carry& c, const T* m, const T* P, long k, const Params& p,
+                                  T* x) {
         Fwd f;
-        forward(cx, in, r, k, p, f);
+        forward(cx, c, m, P, k, p, f);
         if (f.first) {
             // filter update acts on (m0, P0) directly, no likelihood term through this path
             identity(x);
@@ -199,13 +231,30 @@ struct AdjointAlg {
             }
     }
 
-    template <int LSW>
-    PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p) {
+    PSSGP_DEV static void append_step(T* a, const Ctx& cx, const Carry& c, const T* m, const T* P, long k,
+                                      const Params& p) {
         T x[NAGG], rr[NAGG];
-        element(cx, in, r, k, p, x);
+        element(cx, c, m, P, k, p, x);
         combine(a, x, rr);
 #pragma unroll
         for (int e = 0; e < NAGG; ++e) a[e] = rr[e];
+    }
+    // visiting row k: take step k+1 (if its inputs are carried), then carry (F, Q, y) of row k
+    PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][WMAX], long k, const Params& p, Carry& c) {
+        if (c.has) {
+            T m[D], P[NS];
+            row_moments(in, m, P);
+            append_step(a, cx, c, m, P, k + 1, p);
+        }
+        carry_set(c, in);
+    }
+    // step k_lo of the chunk, with the filtered moments of row k_lo - 1 from the halo
+    PSSGP_DEV static void append_flush(T* a, const Ctx& cx, long k_lo, const Params& p, Carry& c) {
+        if (c.has) {
+            T m[D], P[NS];
+            halo_moments(k_lo, p, m, P);
+            append_step(a, cx, c, m, P, k_lo, p);
+        }
     }
 
     PSSGP_DEV static void apply(const T* s, const T* x, T* s2) {
@@ -263,15 +312,14 @@ struct AdjointAlg {
     }
 
     // s = adjoint w.r.t. the filtered moments at time k; on exit w.r.t. those at time k-1.
-    template <int LSW>
-    PSSGP_DEV static void step_row(T* s, const Ctx& cx, const T (&in)[NIN][LSW], T (&out)[NOUT][LSW], int r, long k,
-                                   const Params& p, T* acc) {
+    PSSGP_DEV static void step_core(T* s, const Ctx& cx, const Carry& c, const T* mprev, const T* Pprev,
+                                    T (&out)[NOUT][WMAX], long k, const Params& p, T* acc) {
         const T g = cx.g;
         Fwd f;
-        forward(cx, in, r, k, p, f);
+        forward(cx, c, mprev, Pprev, k, p, f);
         T dmp[D], dPp[NS];
-        T* oF = &out[0][r * D * D];
-        T* oQ = &out[1][r * D * D];
+        T* oF = out[0];
+        T* oQ = out[1];
         if (f.first) {
             // (i) likelihood term of step 0 through the prediction from (m0, P0)
             T dPp0[NS], dmp0[D];
@@ -364,6 +412,28 @@ struct AdjointAlg {
             }
         // when the shard does not start at the global origin, the state after its first step is the
         // adjoint w.r.t. the previous shard's last filtered moments: the framework returns it.
+    }
+
+    // visiting row k: take step k+1 (outputs belong to row k+1), then carry (F, Q, y) of row k
+    PSSGP_DEV static bool step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                   const Params& p, T* acc, Carry& c) {
+        const bool has = c.has;
+        if (has) {
+            T m[D], P[NS];
+            row_moments(in, m, P);
+            step_core(s, cx, c, m, P, out, k + 1, p, acc);
+        }
+        carry_set(c, in);
+        return has;
+    }
+    PSSGP_DEV static bool step_flush(T* s, const Ctx& cx, T (&out)[NOUT][WMAX], long k_lo, const Params& p, T* acc,
+                                     Carry& c) {
+        if (c.has) {
+            T m[D], P[NS];
+            halo_moments(k_lo, p, m, P);
+            step_core(s, cx, c, m, P, out, k_lo, p, acc);
+        }
+        return c.has;
     }
 
     PSSGP_DEV static void expand_state(const T* s, T* out) {

@@ -82,7 +82,7 @@ int pick_chunk(const pssgp_handle* h, int64_t n, int threads_per_cta, int ls) {
         if (L < 8) L = 8;
     }
     L = ((L + ls - 1) / ls) * ls;
-    if (L > (1 << 30)) L = 1 << 30;
+    if (L > (1 << 22)) L = 1 << 22;  // 32-bit byte strides in the streaming kernels
     return (int)L;
 }
 

@@ -30,7 +30,8 @@ struct FilterAlg {
     static constexpr bool REVERSE = false;
     static constexpr int NIN = 3, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a < 2 ? D * D : 1; }
-    __host__ __device__ static constexpr int in_shift(int) { return 0; }
+    static constexpr int OUT_SHIFT = 0;
+    static constexpr bool FLUSH = false;
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {
@@ -76,12 +77,14 @@ struct FilterAlg {
 
     // Append time step k (row r of the staged tile) to the aggregate: conditional Kalman recursion given
     // the chunk-entry state.
-    template <int LSW>
-    PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][LSW], int r, long k, const Params& p) {
-        const T* F = &in[0][r * D * D];
+    struct Carry {};
+    PSSGP_DEV static void carry_init(Carry&, const Ctx&, long, long, const Params&) {}
+
+    PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][WMAX], long k, const Params& p, Carry&) {
+        const T* F = in[0];
         const T* h = cx.h;
         const T R = cx.R;
-        const T yk = in[2][r];
+        const T yk = in[2][0];
         T Ap[D * D], bp[D], Cp[NS];
         if (k == 0 && p.first_special) {
             // no prediction at the global first step (parallel.py:24-30)
@@ -93,7 +96,7 @@ struct FilterAlg {
             for (int e = 0; e < NS; ++e) Cp[e] = a[oC + e];
         } else {
             T Q[NS], FC[D * D];
-            sym_pack(&in[1][r * D * D], Q);
+            sym_pack(in[1], Q);
             mm_ff<T, D>(F, a + oA, Ap);
             mv_f<T, D>(F, a + ob, bp);
             mm_fs<T, D>(F, a + oC, FC);
@@ -244,15 +247,14 @@ struct FilterAlg {
     }
 
     // Seeded Kalman step k: s=(m,P) filtered at k-1 -> filtered at k; emits fms/fPs, accumulates ll.
-    template <int LSW>
-    PSSGP_DEV static void step_row(T* s, const Ctx& cx, const T (&in)[NIN][LSW], T (&out)[NOUT][LSW], int r, long k,
-                                   const Params& p, T* acc) {
-        const T* F = &in[0][r * D * D];
+    PSSGP_DEV static bool step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                   const Params& p, T* acc, Carry&) {
+        const T* F = in[0];
         const T* h = cx.h;
         const T R = cx.R;
-        const T yk = in[2][r];
+        const T yk = in[2][0];
         T Q[NS], FP[D * D], mp[D], Pp[NS];
-        sym_pack(&in[1][r * D * D], Q);
+        sym_pack(in[1], Q);
         mv_f<T, D>(F, s, mp);
         mm_fs<T, D>(F, s + D, FP);
         sym_xat_plus<T, D>(FP, F, Q, Pp);
@@ -287,11 +289,12 @@ struct FilterAlg {
             for (int e = 0; e < NS; ++e) s[D + e] = Pp[e];
         }
 #pragma unroll
-        for (int i = 0; i < D; ++i) out[0][r * D + i] = s[i];
+        for (int i = 0; i < D; ++i) out[0][i] = s[i];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int j = 0; j < D; ++j) out[1][r * D * D + i * D + j] = s[D + sidx(i, j)];
+            for (int j = 0; j < D; ++j) out[1][i * D + j] = s[D + sidx(i, j)];
+        return true;
     }
 
     // fold output: m[D] | P full [D,D]  (so that the caller can pass m0 = out, P0 = out + D to pssgp_pkf)

@@ -43,10 +43,10 @@ int stream_configure(int device) {
     const unsigned long long bit = 1ull << (device & 63);
     if (done & bit) return PSSGP_OK;
     cudaError_t e = cudaFuncSetAttribute(stream_reduce_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         Lay::NW * Lay::WARP_BYTES);
+                                         Lay::NW * Lay::WARP_BYTES_REDUCE);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(stream_apply_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 Lay::NW * Lay::WARP_BYTES);
+                                 Lay::NW * Lay::WARP_BYTES_APPLY);
     if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
     done |= bit;
     return PSSGP_OK;
@@ -71,9 +71,17 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
         for (int a = 0; a < Alg::NOUT; ++a)
             if (!aligned16(Alg::out_ptr(p, a)))
                 return set_err(PSSGP_ERR_INVALID, "output array %d is not 16-byte aligned", a);
-    const int L = pick_chunk(h, n, NW * 32, Lay::LS);
-    const int64_t nChunks = (n + L - 1) / L;
-    const int64_t nBlocks = (nChunks + NW * 32 - 1) / (NW * 32);
+    StreamPart sp;
+    sp.n = n;
+    sp.L = pick_chunk(h, n, NW * 32, Lay::LS);
+    const int64_t ctaRows = (int64_t)NW * 32 * sp.L;
+    sp.nMain = (int)(n / ctaRows);
+    const int64_t tail = n - (int64_t)sp.nMain * ctaRows;
+    sp.Ltail = (int)((((tail + NW * 32 - 1) / (NW * 32)) + Lay::LS - 1) / Lay::LS * Lay::LS);
+    if (sp.Ltail < Lay::LS) sp.Ltail = Lay::LS;
+    sp.nCta = sp.nMain + (tail > 0 ? 1 : 0);
+    const int L = sp.L;
+    const int64_t nBlocks = sp.nCta;
     const int64_t nW = nBlocks;  // one aggregate per CTA of K1
     const int64_t nChunksPad = nBlocks * NW * 32;
     constexpr int kind = Alg::KIND;
@@ -83,18 +91,20 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     if (!reuse) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * Alg::NAGG * (size_t)nChunksPad))) return rc;
         if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * Alg::NAGG * (size_t)nW))) return rc;
+        if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * Alg::NAGG * (size_t)nW * NW))) return rc;
     }
     if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * Alg::NSTATE * (size_t)nW))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (Alg::NACC > 0 ? Alg::NACC : 1) * (size_t)nBlocks))) return rc;
     T* lane = (T*)h->buf[WS_LANE + kind];
     T* wagg = (T*)h->buf[WS_WAGG + kind];
+    T* wexcl = (T*)h->buf[WS_WEXCL + kind];
     T* wstate = (T*)h->buf[WS_WSTATE];
     T* part = (T*)h->buf[WS_PART];
     int nl = 0;
     if (!reuse) {
         PSSGP_LAUNCH(h, Alg::name_reduce(), st,
-                     (stream_reduce_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES, st>>>(
-                         p, n, L, nChunks, nChunksPad, lane, wagg, nW)));
+                     (stream_reduce_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
+                         p, sp, nChunksPad, lane, wexcl, wagg)));
         ++nl;
     }
     int midThreads = kMidThreads;
@@ -109,8 +119,8 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     }
     PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_mid_kernel<Alg><<<1, midThreads, 0, st>>>(p, wagg, nW, wstate, final_state)));
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
-                 (stream_apply_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES, st>>>(
-                     p, n, L, nChunks, nChunksPad, lane, wstate, nW, part, h->ticket, acc_out)));
+                 (stream_apply_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
+                     p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out)));
     return check_launch(h, "scan", nl + 2);
 }
 

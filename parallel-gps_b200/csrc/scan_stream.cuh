@@ -5,33 +5,37 @@
 // single resident wave.  Three kernels per scan (filter / smoother / adjoint):
 //
 //   K1 stream_reduce : every thread folds its L steps into the chunk aggregate with the algebra's cheap
-//                      sequential `append_row`; warp Kogge-Stone scan + CTA fold with the generic
-//                      associative operator.  Stores the CTA-exclusive aggregate of every chunk and the
-//                      total of every CTA.
+//                      sequential `append_row`; warp Kogge-Stone scan with the generic associative
+//                      operator, then one warp scans the NW warp totals.  Stores the warp-exclusive
+//                      aggregate of every chunk, the CTA-exclusive aggregate of every warp and the total
+//                      of every CTA.
 //   K2 scan_mid      : one CTA scans the CTA totals and turns them into the *state* entering each CTA.
-//   K3 stream_apply  : every thread applies state o exclusive-aggregate and re-runs the seeded recursion
-//                      (`step_row`) over its L steps, producing the outputs.
+//   K3 stream_apply  : every thread applies state o warp-prefix o lane-prefix and re-runs the seeded
+//                      recursion (`step_row`) over its L steps, producing the outputs.
 //
-// Memory path (K1 and K3).  A thread walks its chunk sequentially (72-byte records at D = 3), which
-// read with plain loads is a dependent, latency-bound pattern at the 6-8 warps per SM that the
-// register-resident FP64 state allows.  Instead every thread owns a private shared-memory FIFO of NST
-// stages and prefetches its chunk through it with cp.async (LDGSTS, no register staging): per sub-step
-// the LS-row segment (16 * W bytes, 16-byte aligned because LS * sizeof(T) = 16) of every input array,
-// as 16-byte pieces with immediate offsets.  A slot's pitch is an odd number of 16-byte units, so the
-// 128-bit shared loads of a warp are bank-conflict free.  A stage is handed back to the copy engine as
-// soon as its last row has been fetched into registers, so the next sub-steps are in flight while the
-// FP64 pipe works.  Threads only ever read what they copied themselves: the streaming loop has no
-// barrier of any kind (cp.async.wait_group is the only synchronisation).  Outputs go straight from
-// registers to global memory with 16-byte streaming stores.
+// Memory path (K1 and K3).  A thread walks its chunk sequentially, so its rows are 72-byte (D = 3)
+// records strided by L rows between neighbouring lanes.  Every warp streams its 32 chunks through its
+// own shared-memory stages with cp.async (LDGSTS, no register staging): per sub-step, for each input
+// array, the LS-row segment (16 * W bytes, 16-byte aligned because LS * sizeof(T) = 16) of each of its
+// 32 chunks.  The copy is cooperative: a segment is NP 16-byte pieces, so 32 / NP whole segments fit one
+// warp instruction (lane -> (group g, piece off), fixed for the whole kernel; per instruction only a
+// pointer bump), and every global request is made of full contiguous segments.  The destination is a
+// per-lane slot whose pitch is an odd number of 16-byte units (bank-conflict-free 128-bit shared
+// loads).  A stage is handed back to the copy engine as soon as its last row has been fetched into
+// registers, so the copies of the next sub-steps are in flight while the FP64 pipe works; there is no
+// CTA-wide barrier in the streaming loop (warps are autonomous: cp.async.wait_group + __syncwarp).
+// Outputs take the mirror path: registers -> per-lane staging slot -> cooperative 16-byte streaming
+// stores.
 //
-// Reverse scans (smoother, adjoint) use the same time partition and walk chunks and rows in
-// descending time; nothing is physically reversed.  Arrays the algebra needs at row k+1 / k-1
-// (smoother: F, Q of the next step; adjoint: filtered moments of the previous step) are streamed with
-// a one-row shift (element-sized pieces, since a one-row shift breaks 16-byte alignment).
+// Reverse scans (smoother, adjoint) use the same time partition and walk chunks and rows in descending
+// time; nothing is physically reversed, and nothing is loaded with a row shift: what an algebra needs
+// from the neighbouring row (smoother: F, Q of step k+1; adjoint: the step itself is delayed by one row,
+// OUT_SHIFT = 1) is carried in registers from the previous iteration, the chunk-boundary row comes from a
+// direct (halo) load.
 //
-// An "Algebra" supplies: NAGG, NSTATE, NACC, REVERSE, Params, Ctx, the array tables (NIN, in_w,
-// in_shift, in_ptr, NOUT, out_w, out_ptr), identity, combine, apply, load_init, expand_state, finish,
-// append_row and step_row.
+// An "Algebra" supplies: NAGG, NSTATE, NACC, REVERSE, OUT_SHIFT, FLUSH, Params, Ctx, Carry, the array
+// tables (NIN, in_w, in_ptr, NOUT, out_w, out_ptr), identity, combine, apply, load_init, expand_state,
+// finish, carry_init, append_row / append_flush and step_row / step_flush.
 #pragma once
 #include "smalld.cuh"
 
@@ -45,7 +49,7 @@ PSSGP_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to
 template <int BYTES> PSSGP_DEV void cp_async(unsigned dst, const void* src) {
     static_assert(BYTES == 4 || BYTES == 8 || BYTES == 16, "cp.async size");
     if constexpr (BYTES == 16)
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src) : "memory");
     else if constexpr (BYTES == 8)
         asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(dst), "l"(src) : "memory");
     else
@@ -54,7 +58,6 @@ template <int BYTES> PSSGP_DEV void cp_async(unsigned dst, const void* src) {
 PSSGP_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> PSSGP_DEV void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
-// 16 bytes shared -> registers / registers -> shared / registers -> global (streaming store)
 PSSGP_DEV void ld_shared16(double* dst, const unsigned char* src) {
     const double2 v = *reinterpret_cast<const double2*>(src);
     dst[0] = v.x;
@@ -81,65 +84,197 @@ template <typename T> struct StreamGeom {
     static constexpr int LS = 16 / (int)sizeof(T);  // rows per sub-step: LS * W * sizeof(T) is a multiple of 16
     __host__ __device__ static constexpr int seg_bytes(int w) { return LS * w * (int)sizeof(T); }
     __host__ __device__ static constexpr int seg_units(int w) { return seg_bytes(w) / 16; }
-    __host__ __device__ static constexpr int pitch(int w) { return (seg_units(w) | 1) * 16; }  // odd number of 16-byte units
+    __host__ __device__ static constexpr int pitch(int w) { return (seg_units(w) | 1) * 16; }  // odd # of 16-byte units
+    // cooperative copy: GROUPS whole segments per warp instruction, ITERS instructions for 32 segments
+    __host__ __device__ static constexpr int groups(int w) { return 32 / seg_units(w); }
+    __host__ __device__ static constexpr int iters(int w) { return (32 + groups(w) - 1) / groups(w); }
 };
 
 template <typename Alg> struct StreamLayout {
     using T = typename Alg::scalar;
     using G = StreamGeom<T>;
     static constexpr int LS = G::LS;
-    __host__ __device__ static constexpr int in_off(int a) { return a == 0 ? 0 : in_off(a - 1) + 32 * G::pitch(Alg::in_w(a - 1)); }
+    __host__ __device__ static constexpr int in_off(int a) {
+        return a == 0 ? 0 : in_off(a - 1) + 32 * G::pitch(Alg::in_w(a - 1));
+    }
+    __host__ __device__ static constexpr int out_off(int a) {
+        return a == 0 ? 0 : out_off(a - 1) + 32 * G::pitch(Alg::out_w(a - 1));
+    }
     static constexpr int STAGE_BYTES = in_off(Alg::NIN);
+    static constexpr int OUT_BYTES = out_off(Alg::NOUT);
     static constexpr int NST = 2;
-    static constexpr int WARP_BYTES = NST * STAGE_BYTES;
+    static constexpr int WARP_BYTES_REDUCE = NST * STAGE_BYTES;
+    static constexpr int WARP_BYTES_APPLY = NST * STAGE_BYTES + OUT_BYTES;
     static constexpr int SMEM_BUDGET = 216 * 1024;
-    __host__ __device__ static constexpr int nw_fit() { return SMEM_BUDGET / WARP_BYTES; }
+    __host__ __device__ static constexpr int nw_fit() { return SMEM_BUDGET / WARP_BYTES_APPLY; }
     static constexpr int NW = nw_fit() > 8 ? 8 : (nw_fit() < 1 ? 1 : nw_fit());
 };
 
-// time row at which lane-chunk `c` starts sub-step `s`
-template <bool REVERSE> PSSGP_DEV long seg_row(long c, int s, int nsub, int L, int LS) {
-    return c * (long)L + (long)(REVERSE ? (nsub - 1 - s) : s) * LS;
+// Per-lane cursor of the cooperative copy of one array: this lane moves piece `off` of the segments of
+// lane-chunks g, g + GROUPS, g + 2 GROUPS, ...  `ptr` points at its piece of lane-chunk g for the next
+// sub-step to be issued and is bumped by one segment per sub-step.
+struct PieceCursor {
+    unsigned char* ptr;  // global
+    unsigned soff;       // byte offset of (slot g, piece off) inside the array's staging region
+    int g;               // first lane-chunk handled by this lane; >= 32 when the lane idles
+};
+
+template <typename T, int W, bool REVERSE>
+PSSGP_DEV PieceCursor make_cursor(const void* base, long k_lo0, int L, int nsub, int lane) {
+    // k_lo0 = first row of lane 0's chunk; lane-chunk j starts at k_lo0 + j L (forward) / k_lo0 - j L (reverse)
+    using G = StreamGeom<T>;
+    constexpr int NP = G::seg_units(W);
+    constexpr int SZ = (int)sizeof(T);
+    PieceCursor pc;
+    const int g = lane / NP;
+    const int off = lane - g * NP;
+    pc.g = (g < G::groups(W)) ? g : 32;
+    pc.soff = (unsigned)(g * G::pitch(W) + off * 16);
+    const long row0 = k_lo0 + (REVERSE ? -(long)g * L + (long)(nsub - 1) * G::LS : (long)g * L);  // first sub-step
+    pc.ptr = (unsigned char*)base + row0 * (long)(W * SZ) + off * 16;
+    return pc;
 }
 
-// Issues this lane's cp.async copies of input array A for one sub-step: the LS-row segment that starts
-// at time row `row0` of the lane's own chunk, into the lane's slot of the stage at `stage_addr`.
-template <typename Alg, int A>
-PSSGP_DEV void stream_issue_array(const typename Alg::Params& p, long n, long row0, int lane, unsigned stage_addr) {
-    using T = typename Alg::scalar;
+// Issues the copies of one array for one sub-step and advances the cursor to the next sub-step.
+// step = byte distance between the segments handled by consecutive instructions of this lane.
+// The fast variant (every piece of the warp lies inside the array: all but the warps at the two ends of
+// the series) is one address IMAD.WIDE + one LDGSTS per instruction; the checked variant is kept out of
+// line so that it costs neither registers nor instruction-cache footprint in the streaming loop.
+template <typename T, int W, bool REVERSE>
+PSSGP_DEV void issue_array_fast(PieceCursor& pc, int step, unsigned region_addr) {
     using G = StreamGeom<T>;
-    using Lay = StreamLayout<Alg>;
-    constexpr int W = Alg::in_w(A);
-    constexpr int SH = Alg::in_shift(A);
+    constexpr int GR = G::groups(W), IT = G::iters(W), PITCH = G::pitch(W);
+    if (pc.g < 32) {
+        const unsigned dst = region_addr + pc.soff;
+#pragma unroll
+        for (int i = 0; i < IT - 1; ++i) cp_async<16>(dst + i * GR * PITCH, pc.ptr + (long)i * step);
+        if (GR * IT <= 32 || pc.g + GR * (IT - 1) < 32)
+            cp_async<16>(dst + (IT - 1) * GR * PITCH, pc.ptr + (long)(IT - 1) * step);
+    }
+    pc.ptr += REVERSE ? -(long)G::seg_bytes(W) : (long)G::seg_bytes(W);
+}
+
+template <typename T, int W, bool REVERSE>
+__device__ __noinline__ void issue_array_checked(unsigned char* ptr, int g, const void* base, long total_bytes,
+                                                 int step, unsigned dst) {
+    using G = StreamGeom<T>;
+    constexpr int GR = G::groups(W), IT = G::iters(W), PITCH = G::pitch(W);
     constexpr int SZ = (int)sizeof(T);
-    constexpr int PB = (SH == 0) ? 16 : SZ;  // a one-row shift breaks 16-byte alignment: element-sized pieces
-    constexpr int SEG = G::seg_bytes(W);
-    constexpr int NP = SEG / PB;  // pieces per segment
-    const unsigned char* base = reinterpret_cast<const unsigned char*>(Alg::in_ptr(p, A));
-    const long total = n * (long)(W * SZ);
-    const long gb = (row0 + SH) * (long)(W * SZ);
-    const unsigned dst = stage_addr + Lay::in_off(A) + lane * G::pitch(W);
-    const unsigned char* src = base + gb;
-    if (gb >= 0 && gb + SEG <= total) {
+#pragma unroll 1
+    for (int i = 0; i < IT; ++i) {
+        if (g + GR * i < 32) {
+            const unsigned char* sp = ptr + (long)i * step;
+            const long gb = sp - (const unsigned char*)base;
+            if (gb >= 0 && gb + 16 <= total_bytes) {
+                cp_async<16>(dst + i * GR * PITCH, sp);
+            } else {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) cp_async<PB>(dst + i * PB, src + i * PB);
-    } else {
-        // segment crosses an end of the array: copy the elements that exist one by one
-#pragma unroll
-        for (int e = 0; e < SEG / SZ; ++e) {
-            const long ge = gb + (long)e * SZ;
-            if (ge >= 0 && ge + SZ <= total) cp_async<SZ>(dst + e * SZ, src + e * SZ);
+                for (int e = 0; e < 16 / SZ; ++e)
+                    if (gb + e * SZ >= 0 && gb + (e + 1) * SZ <= total_bytes)
+                        cp_async<SZ>(dst + i * GR * PITCH + e * SZ, sp + e * SZ);
+            }
         }
     }
 }
 
-template <typename Alg, int A = 0>
-PSSGP_DEV void stream_issue(const typename Alg::Params& p, long n, long row0, int lane, unsigned stage_addr) {
-    if constexpr (A < Alg::NIN) {
-        stream_issue_array<Alg, A>(p, n, row0, lane, stage_addr);
-        stream_issue<Alg, A + 1>(p, n, row0, lane, stage_addr);
+// Mirror of issue_array for an output array: staging slots -> global.
+template <typename T, int W, bool REVERSE>
+PSSGP_DEV void store_array_fast(PieceCursor& pc, int step, const unsigned char* region) {
+    using G = StreamGeom<T>;
+    constexpr int GR = G::groups(W), IT = G::iters(W), PITCH = G::pitch(W);
+    if (pc.g < 32) {
+        const unsigned char* src = region + pc.soff;
+#pragma unroll
+        for (int i = 0; i < IT - 1; ++i)
+            __stcs(reinterpret_cast<int4*>(pc.ptr + (long)i * step), *reinterpret_cast<const int4*>(src + i * GR * PITCH));
+        if (GR * IT <= 32 || pc.g + GR * (IT - 1) < 32)
+            __stcs(reinterpret_cast<int4*>(pc.ptr + (long)(IT - 1) * step),
+                   *reinterpret_cast<const int4*>(src + (IT - 1) * GR * PITCH));
+    }
+    pc.ptr += REVERSE ? -(long)G::seg_bytes(W) : (long)G::seg_bytes(W);
+}
+
+template <typename T, int W, bool REVERSE>
+__device__ __noinline__ void store_array_checked(unsigned char* ptr, int g, const void* base, long total_bytes,
+                                                 int step, const unsigned char* src) {
+    using G = StreamGeom<T>;
+    constexpr int GR = G::groups(W), IT = G::iters(W), PITCH = G::pitch(W);
+    constexpr int SZ = (int)sizeof(T);
+#pragma unroll 1
+    for (int i = 0; i < IT; ++i) {
+        if (g + GR * i < 32) {
+            unsigned char* sp = ptr + (long)i * step;
+            const long gb = sp - (const unsigned char*)base;
+            if (gb >= 0 && gb + 16 <= total_bytes) {
+                __stcs(reinterpret_cast<int4*>(sp), *reinterpret_cast<const int4*>(src + i * GR * PITCH));
+            } else {
+#pragma unroll
+                for (int e = 0; e < 16 / SZ; ++e)
+                    if (gb + e * SZ >= 0 && gb + (e + 1) * SZ <= total_bytes)
+                        *reinterpret_cast<T*>(sp + e * SZ) = *reinterpret_cast<const T*>(src + i * GR * PITCH + e * SZ);
+            }
+        }
     }
 }
+
+// All input arrays of an algebra.
+template <typename Alg> struct StreamIn {
+    using T = typename Alg::scalar;
+    using G = StreamGeom<T>;
+    using Lay = StreamLayout<Alg>;
+    PieceCursor pc[Alg::NIN];
+
+    template <int A = 0> PSSGP_DEV void init(const typename Alg::Params& p, long k_lo0, int L, int nsub, int lane) {
+        if constexpr (A < Alg::NIN) {
+            pc[A] = make_cursor<T, Alg::in_w(A), Alg::REVERSE>(Alg::in_ptr(p, A), k_lo0, L, nsub, lane);
+            init<A + 1>(p, k_lo0, L, nsub, lane);
+        }
+    }
+    template <int A = 0>
+    PSSGP_DEV void issue(const typename Alg::Params& p, long n, int L, bool fast, unsigned stage_addr) {
+        if constexpr (A < Alg::NIN) {
+            constexpr int W = Alg::in_w(A);
+            const int step = (Alg::REVERSE ? -L : L) * (int)(W * sizeof(T)) * G::groups(W);
+            if (fast) {
+                issue_array_fast<T, W, Alg::REVERSE>(pc[A], step, stage_addr + Lay::in_off(A));
+            } else {
+                issue_array_checked<T, W, Alg::REVERSE>(pc[A].ptr, pc[A].g, Alg::in_ptr(p, A), n * (long)(W * sizeof(T)),
+                                                        step, stage_addr + Lay::in_off(A) + pc[A].soff);
+                pc[A].ptr += Alg::REVERSE ? -(long)G::seg_bytes(W) : (long)G::seg_bytes(W);
+            }
+            issue<A + 1>(p, n, L, fast, stage_addr);
+        }
+    }
+};
+
+template <typename Alg> struct StreamOut {
+    using T = typename Alg::scalar;
+    using G = StreamGeom<T>;
+    using Lay = StreamLayout<Alg>;
+    PieceCursor pc[Alg::NOUT];
+
+    template <int A = 0> PSSGP_DEV void init(const typename Alg::Params& p, long k_lo0, int L, int nsub, int lane) {
+        if constexpr (A < Alg::NOUT) {
+            pc[A] = make_cursor<T, Alg::out_w(A), Alg::REVERSE>(Alg::out_ptr(p, A), k_lo0, L, nsub, lane);
+            init<A + 1>(p, k_lo0, L, nsub, lane);
+        }
+    }
+    template <int A = 0>
+    PSSGP_DEV void store(const typename Alg::Params& p, long n, int L, bool fast, const unsigned char* ostage) {
+        if constexpr (A < Alg::NOUT) {
+            constexpr int W = Alg::out_w(A);
+            const int step = (Alg::REVERSE ? -L : L) * (int)(W * sizeof(T)) * G::groups(W);
+            if (fast) {
+                store_array_fast<T, W, Alg::REVERSE>(pc[A], step, ostage + Lay::out_off(A));
+            } else {
+                store_array_checked<T, W, Alg::REVERSE>(pc[A].ptr, pc[A].g, Alg::out_ptr(p, A), n * (long)(W * sizeof(T)),
+                                                        step, ostage + Lay::out_off(A) + pc[A].soff);
+                pc[A].ptr += Alg::REVERSE ? -(long)G::seg_bytes(W) : (long)G::seg_bytes(W);
+            }
+            store<A + 1>(p, n, L, fast, ostage);
+        }
+    }
+};
 
 // Copies row r of this lane's slot of every input array from a stage into registers (128-bit shared
 // loads; a 16-byte unit shared by two rows is simply read by both).
@@ -170,24 +305,18 @@ PSSGP_DEV void stream_fetch_row(const unsigned char* stage, int lane, int r,
     }
 }
 
-// Registers -> global for row r of the LS-row segment that starts at time row `row0`: 16-byte streaming
-// stores for the units that lie inside the row, element stores for a unit shared with the next row.
-PSSGP_DEV void st_global16(unsigned char* dst, const double* v) {
-    __stcs(reinterpret_cast<double2*>(dst), make_double2(v[0], v[1]));
-}
-PSSGP_DEV void st_global16(unsigned char* dst, const float* v) {
-    __stcs(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
-}
+// Registers (row r) -> this lane's staging slot of every output array; units that straddle two rows are
+// written element by element.
 template <typename Alg, int A = 0>
-PSSGP_DEV void stream_store_row(const typename Alg::Params& p, long row0, int r,
-                                const typename Alg::scalar (&orow)[Alg::NOUT][Alg::WMAX]) {
+PSSGP_DEV void stream_stage_out_row(unsigned char* ostage, int lane, int r,
+                                    const typename Alg::scalar (&orow)[Alg::NOUT][Alg::WMAX]) {
     using T = typename Alg::scalar;
     using G = StreamGeom<T>;
+    using Lay = StreamLayout<Alg>;
     if constexpr (A < Alg::NOUT) {
         constexpr int W = Alg::out_w(A);
-        constexpr int SZ = (int)sizeof(T);
-        constexpr int EPU = 16 / SZ;
-        unsigned char* dst = reinterpret_cast<unsigned char*>(Alg::out_ptr(p, A)) + row0 * (long)(W * SZ);
+        constexpr int EPU = 16 / (int)sizeof(T);
+        unsigned char* dst = ostage + Lay::out_off(A) + lane * G::pitch(W);
         const int e_lo = r * W, e_hi = (r + 1) * W;
 #pragma unroll
         for (int u = 0; u < G::seg_units(W); ++u) {
@@ -195,54 +324,93 @@ PSSGP_DEV void stream_store_row(const typename Alg::Params& p, long row0, int r,
                 T tmp[EPU];
 #pragma unroll
                 for (int j = 0; j < EPU; ++j) tmp[j] = orow[A][u * EPU + j - e_lo];
-                st_global16(dst + u * 16, tmp);
+                st_shared16(dst + u * 16, tmp);
             } else if ((u + 1) * EPU > e_lo && u * EPU < e_hi) {
 #pragma unroll
                 for (int j = 0; j < EPU; ++j) {
                     const int e = u * EPU + j;
-                    if (e >= e_lo && e < e_hi) __stcs(reinterpret_cast<T*>(dst + e * SZ), orow[A][e - e_lo]);
+                    if (e >= e_lo && e < e_hi) *reinterpret_cast<T*>(dst + e * (int)sizeof(T)) = orow[A][e - e_lo];
                 }
             }
         }
-        stream_store_row<Alg, A + 1>(p, row0, r, orow);
+        stream_stage_out_row<Alg, A + 1>(ostage, lane, r, orow);
     }
 }
 
+// Partition of the time axis (host-computed): nMain "main" CTAs of NW*32 chunks of L rows each, all of
+// them complete, followed in time by at most one "tail" CTA that covers the remaining rows with its own
+// (shorter) chunk length Ltail.  Only the tail CTA ever sees a missing row, so only it pays for bounds
+// checks; being short it finishes early instead of holding up the single wave.
+struct StreamPart {
+    long n;
+    int L, Ltail;
+    int nMain, nCta;
+};
+
+// Geometry shared by K1 and K3.
+template <typename Alg> struct WarpGeom {
+    long lc;      // global logical chunk (scan order): index into the workspace arrays
+    long k_lo;    // first row of this lane's chunk
+    long k_lo0;   // first row of lane 0's chunk
+    int L, nsub;
+    bool fast;    // main CTA: every row of every chunk exists
+    PSSGP_DEV WarpGeom(const StreamPart& sp, int NW, int lane, int wid) {
+        constexpr int LS = StreamGeom<typename Alg::scalar>::LS;
+        const int tb = Alg::REVERSE ? (sp.nCta - 1 - (int)blockIdx.x) : (int)blockIdx.x;  // CTA in time order
+        fast = tb < sp.nMain;
+        L = fast ? sp.L : sp.Ltail;
+        nsub = L / LS;
+        const long row_begin = (long)(fast ? tb : sp.nMain) * ((long)NW * 32 * sp.L);
+        const int tl = wid * 32 + lane;                             // thread in scan order
+        const int ct = Alg::REVERSE ? (NW * 32 - 1 - tl) : tl;      // chunk of the CTA in time order
+        lc = (long)blockIdx.x * (NW * 32) + tl;
+        k_lo = row_begin + (long)ct * L;
+        k_lo0 = Alg::REVERSE ? (k_lo + (long)lane * L) : (k_lo - (long)lane * L);
+    }
+};
+
 // ---------------------------------------------------------------------------------------------
-// K1: chunk aggregates, CTA-exclusive prefixes, CTA totals
+// K1: chunk aggregates, warp-exclusive prefixes, CTA-exclusive warp prefixes, CTA totals
 // ---------------------------------------------------------------------------------------------
 template <typename Alg>
 __global__ void __launch_bounds__(StreamLayout<Alg>::NW * 32)
-stream_reduce_kernel(typename Alg::Params p, long n, int L, long nChunks, long nChunksPad,
-                     typename Alg::scalar* __restrict__ lane_excl, typename Alg::scalar* __restrict__ wagg,
-                     long nCta) {
+stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
+                     typename Alg::scalar* __restrict__ lane_excl, typename Alg::scalar* __restrict__ warp_excl,
+                     typename Alg::scalar* __restrict__ wagg) {
     using T = typename Alg::scalar;
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
+    const long nCta = sp.nCta;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char* wsm = smem_raw + wid * Lay::WARP_BYTES;
+    unsigned char* wsm = smem_raw + wid * Lay::WARP_BYTES_REDUCE;
     const unsigned wsm_addr = smem_addr(wsm);
-    const long lc = ((long)blockIdx.x * NW + wid) * 32 + lane;  // logical chunk (scan order)
-    const long c = Alg::REVERSE ? (nChunks - 1 - lc) : lc;      // time chunk
-    const int nsub = L / LS;
+    const WarpGeom<Alg> wg(sp, NW, lane, wid);
+    const int nsub = wg.nsub, L = wg.L;
+    const long n = sp.n;
 
     T a[Alg::NAGG];
     Alg::identity(a);
-    if (lc < nChunks) {
+    {
         typename Alg::Ctx ctx;
         Alg::load_ctx(p, ctx);
-#pragma unroll
+        StreamIn<Alg> in;
+        in.init(p, wg.k_lo0, L, nsub, lane);
+#pragma unroll 1
         for (int s = 0; s < NST; ++s) {
-            if (s < nsub)
-                stream_issue<Alg>(p, n, seg_row<Alg::REVERSE>(c, s, nsub, L, LS), lane, wsm_addr + s * Lay::STAGE_BYTES);
+            if (s < nsub) in.issue(p, n, L, wg.fast, wsm_addr + s * Lay::STAGE_BYTES);
             cp_async_commit();
         }
+        const bool mine = wg.k_lo < n;
+        typename Alg::Carry cr;
+        const long k_hi = wg.k_lo + L;
+        if (mine) Alg::carry_init(cr, ctx, wg.k_lo, k_hi < n ? k_hi : n, p);
 #pragma unroll 1
         for (int s = 0; s < nsub; ++s) {
             const int st = s % NST;
             cp_async_wait<NST - 1>();
-            const long k0 = seg_row<Alg::REVERSE>(c, s, nsub, L, LS);
+            __syncwarp();
+            const long k0 = wg.k_lo + (long)(Alg::REVERSE ? (nsub - 1 - s) : s) * LS;
 #pragma unroll
             for (int rr = 0; rr < LS; ++rr) {
                 const int r = Alg::REVERSE ? (LS - 1 - rr) : rr;
@@ -251,15 +419,17 @@ stream_reduce_kernel(typename Alg::Params p, long n, int L, long nChunks, long n
                 stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
                 if (rr == LS - 1) {
                     // the stage is drained: hand it back to the copy engine before the last row's arithmetic
-                    if (s + NST < nsub)
-                        stream_issue<Alg>(p, n, seg_row<Alg::REVERSE>(c, s + NST, nsub, L, LS), lane,
-                                          wsm_addr + st * Lay::STAGE_BYTES);
+                    __syncwarp();
+                    if (s + NST < nsub) in.issue(p, n, L, wg.fast, wsm_addr + st * Lay::STAGE_BYTES);
                     cp_async_commit();
                 }
-                if (k < n) Alg::append_row(a, ctx, row, 0, k, p);
+                if (mine && k < n) Alg::append_row(a, ctx, row, k, p, cr);
             }
         }
         cp_async_wait<0>();
+        if constexpr (Alg::FLUSH) {
+            if (mine) Alg::append_flush(a, ctx, wg.k_lo, p, cr);
+        }
     }
     // warp inclusive scan (earlier lane is the left operand)
 #pragma unroll 1
@@ -274,49 +444,53 @@ stream_reduce_kernel(typename Alg::Params p, long n, int L, long nChunks, long n
             for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
         }
     }
-    // CTA level: every warp folds the totals of the warps before it
+    // lane-exclusive prefix inside the warp
+    {
+        T ex[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
+        if (lane != 0) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + wg.lc] = ex[e];
+        }
+    }
+    // CTA level: warp 0 scans the NW warp totals
     __shared__ T shw[NW * Alg::NAGG];
     if (lane == 31) {
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) shw[wid * Alg::NAGG + e] = a[e];
     }
-    T ex[Alg::NAGG];
-#pragma unroll
-    for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
-    if (lane == 0) Alg::identity(ex);
     __syncthreads();
-    T wp[Alg::NAGG];  // aggregate of the warps before this one (wid > 0)
-    if (wid > 0) {
+    if (wid == 0) {
+        T w[Alg::NAGG];
+        if (lane < NW) {
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) wp[e] = shw[e];
-#pragma unroll 1
-        for (int w = 1; w < wid; ++w) {
-            T b[Alg::NAGG], r[Alg::NAGG];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) b[e] = shw[w * Alg::NAGG + e];
-            Alg::combine(wp, b, r);
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) wp[e] = r[e];
-        }
-        T r[Alg::NAGG];
-        Alg::combine(wp, ex, r);
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) ex[e] = r[e];
-    }
-    if (threadIdx.x != 0 && lc < nChunks) {
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + lc] = ex[e];
-    }
-    if (threadIdx.x == NW * 32 - 1) {
-        T tot[Alg::NAGG];
-        if (wid > 0) {
-            Alg::combine(wp, a, tot);
+            for (int e = 0; e < Alg::NAGG; ++e) w[e] = shw[lane * Alg::NAGG + e];
         } else {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) tot[e] = a[e];
+            Alg::identity(w);
         }
+#pragma unroll 1
+        for (int off = 1; off < NW; off <<= 1) {
+            T o[Alg::NAGG];
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blockIdx.x] = tot[e];
+            for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(w[e], off);
+            if (lane >= off && lane < NW) {
+                T r[Alg::NAGG];
+                Alg::combine(o, w, r);
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) w[e] = r[e];
+            }
+        }
+        // w = inclusive prefix over warps: warp l+1's exclusive prefix, and the CTA total at lane NW-1
+        const long gw = (long)blockIdx.x * NW + lane + 1;
+        if (lane < NW - 1) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) warp_excl[(long)e * (nCta * NW) + gw] = w[e];
+        }
+        if (lane == NW - 1) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blockIdx.x] = w[e];
+        }
     }
 }
 
@@ -325,51 +499,71 @@ stream_reduce_kernel(typename Alg::Params p, long n, int L, long nChunks, long n
 // ---------------------------------------------------------------------------------------------
 template <typename Alg>
 __global__ void __launch_bounds__(StreamLayout<Alg>::NW * 32)
-stream_apply_kernel(typename Alg::Params p, long n, int L, long nChunks, long nChunksPad,
+stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                     const typename Alg::scalar* __restrict__ lane_excl,
-                    const typename Alg::scalar* __restrict__ wstate, long nCta,
+                    const typename Alg::scalar* __restrict__ warp_excl,
+                    const typename Alg::scalar* __restrict__ wstate,
                     typename Alg::scalar* __restrict__ acc_part, unsigned int* __restrict__ ticket,
                     typename Alg::scalar* __restrict__ acc_out) {
     using T = typename Alg::scalar;
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
     constexpr int NACC1 = Alg::NACC > 0 ? Alg::NACC : 1;
+    const long nCta = sp.nCta;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    unsigned char* wsm = smem_raw + wid * Lay::WARP_BYTES;
+    unsigned char* wsm = smem_raw + wid * Lay::WARP_BYTES_APPLY;
+    unsigned char* osm = wsm + NST * Lay::STAGE_BYTES;
     const unsigned wsm_addr = smem_addr(wsm);
-    const long lc = ((long)blockIdx.x * NW + wid) * 32 + lane;
-    const long c = Alg::REVERSE ? (nChunks - 1 - lc) : lc;
-    const int nsub = L / LS;
+    const WarpGeom<Alg> wg(sp, NW, lane, wid);
+    const int nsub = wg.nsub, L = wg.L;
+    const long n = sp.n;
 
     T acc[NACC1];
 #pragma unroll
     for (int e = 0; e < NACC1; ++e) acc[e] = T(0);
-    if (lc < nChunks) {
+    {
         typename Alg::Ctx ctx;
         Alg::load_ctx(p, ctx);
-#pragma unroll
+        StreamIn<Alg> in;
+        in.init(p, wg.k_lo0, L, nsub, lane);
+        StreamOut<Alg> out;
+        out.init(p, wg.k_lo0, L, nsub, lane);
+#pragma unroll 1
         for (int s = 0; s < NST; ++s) {
-            if (s < nsub)
-                stream_issue<Alg>(p, n, seg_row<Alg::REVERSE>(c, s, nsub, L, LS), lane, wsm_addr + s * Lay::STAGE_BYTES);
+            if (s < nsub) in.issue(p, n, L, wg.fast, wsm_addr + s * Lay::STAGE_BYTES);
             cp_async_commit();
         }
+        const bool mine = wg.k_lo < n;
         T st8[Alg::NSTATE];
 #pragma unroll
         for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = wstate[(long)e * nCta + blockIdx.x];
-        if (threadIdx.x != 0) {
+        if (wid != 0) {
             T ex[Alg::NAGG], s2[Alg::NSTATE];
+            const long gw = (long)blockIdx.x * NW + wid;
 #pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = lane_excl[(long)e * nChunksPad + lc];
+            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = warp_excl[(long)e * (nCta * NW) + gw];
             Alg::apply(st8, ex, s2);
 #pragma unroll
             for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = s2[e];
         }
+        if (lane != 0 && mine) {
+            T ex[Alg::NAGG], s2[Alg::NSTATE];
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = lane_excl[(long)e * nChunksPad + wg.lc];
+            Alg::apply(st8, ex, s2);
+#pragma unroll
+            for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = s2[e];
+        }
+        typename Alg::Carry cr;
+        const long k_hi = wg.k_lo + L;
+        if (mine) Alg::carry_init(cr, ctx, wg.k_lo, k_hi < n ? k_hi : n, p);
 #pragma unroll 1
         for (int s = 0; s < nsub; ++s) {
             const int st = s % NST;
             cp_async_wait<NST - 1>();
-            const long k0 = seg_row<Alg::REVERSE>(c, s, nsub, L, LS);
+            __syncwarp();
+            const long k0 = wg.k_lo + (long)(Alg::REVERSE ? (nsub - 1 - s) : s) * LS;
 #pragma unroll
             for (int rr = 0; rr < LS; ++rr) {
                 const int r = Alg::REVERSE ? (LS - 1 - rr) : rr;
@@ -378,19 +572,41 @@ stream_apply_kernel(typename Alg::Params p, long n, int L, long nChunks, long nC
                 stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
                 if (rr == LS - 1) {
                     // the stage is drained: hand it back to the copy engine before the last row's arithmetic
-                    if (s + NST < nsub)
-                        stream_issue<Alg>(p, n, seg_row<Alg::REVERSE>(c, s + NST, nsub, L, LS), lane,
-                                          wsm_addr + st * Lay::STAGE_BYTES);
+                    __syncwarp();
+                    if (s + NST < nsub) in.issue(p, n, L, wg.fast, wsm_addr + st * Lay::STAGE_BYTES);
                     cp_async_commit();
                 }
-                if (k < n) {
-                    T orow[Alg::NOUT][Alg::WMAX];
-                    Alg::step_row(st8, ctx, row, orow, 0, k, p, acc);
-                    stream_store_row<Alg>(p, k0, r, orow);
+                T orow[Alg::NOUT][Alg::WMAX];
+                bool has = false;
+                if (mine && k < n) has = Alg::step_row(st8, ctx, row, orow, k, p, acc, cr);
+                if (Alg::OUT_SHIFT == 0) {
+                    if (has) stream_stage_out_row<Alg>(osm, lane, r, orow);
+                } else {
+                    // the step of row k+1 is taken when row k is visited (reverse scans only): its outputs
+                    // belong to the slot above; the top row completes the segment of the previous sub-step
+                    if (has) stream_stage_out_row<Alg>(osm, lane, (r + 1) % LS, orow);
+                    if (rr == 0 && s > 0) {
+                        __syncwarp();
+                        out.store(p, n, L, wg.fast, osm);
+                        __syncwarp();
+                    }
                 }
+            }
+            if (Alg::OUT_SHIFT == 0) {
+                __syncwarp();
+                out.store(p, n, L, wg.fast, osm);
+                __syncwarp();  // staging slots are rewritten by the next sub-step
             }
         }
         cp_async_wait<0>();
+        if constexpr (Alg::FLUSH) {
+            T orow[Alg::NOUT][Alg::WMAX];
+            bool has = false;
+            if (mine) has = Alg::step_flush(st8, ctx, orow, wg.k_lo, p, acc, cr);
+            if (has) stream_stage_out_row<Alg>(osm, lane, 0, orow);
+            __syncwarp();
+            out.store(p, n, L, wg.fast, osm);
+        }
     }
     if (Alg::NACC > 0) {
         // deterministic grid reduction: warp shuffle -> smem -> per-CTA partial -> last CTA sums in a fixed order

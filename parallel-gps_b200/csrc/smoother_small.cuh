@@ -26,11 +26,13 @@ struct SmootherAlg {
     static constexpr int NAGG = oL + NS;
     static constexpr int NSTATE = D + NS;
     static constexpr int NACC = 0;
-    // streaming tables: inputs F, Q at row k+1 (one-row shift), fms, fPs at row k; outputs sms, sPs at row k
+    // streaming tables: inputs F, Q, fms, fPs at row k; outputs sms, sPs at row k.  F, Q of step k+1 are
+    // carried in registers from the previous (later-in-time) row.
     static constexpr bool REVERSE = true;
+    static constexpr int OUT_SHIFT = 0;
+    static constexpr bool FLUSH = false;
     static constexpr int NIN = 4, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? D : D * D; }
-    __host__ __device__ static constexpr int in_shift(int a) { return a < 2 ? 1 : 0; }
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {
@@ -69,10 +71,11 @@ struct SmootherAlg {
             for (int j = 0; j <= i; ++j) Q[sidx(i, j)] = T(0.5) * (qf[i * D + j] + qf[j * D + i]);
     }
 
-    // element (E, g, L) of time k (parallel.py:159-166) from F_{k+1}, Q_{k+1} (full) and m_k, P_k (packed)
-    PSSGP_DEV static void element(const T* F, const T* Qf, const T* m, const T* P, T* E, T* g, T* L) {
+    // element (E, g, L) of time k (parallel.py:159-166) from F_{k+1}, Q_{k+1} and m_k, P_k (Q, P packed)
+    PSSGP_DEV static void element(const T* F, const T* Q, const T* m, const T* P, T* E, T* g, T* L) {
         T Pp[NS];
-        sym_pack(Qf, Pp);
+#pragma unroll
+        for (int e = 0; e < NS; ++e) Pp[e] = Q[e];
         T FP[D * D];
         mm_fs<T, D>(F, P, FP);
         sym_xat_plus<T, D>(FP, F, Pp, Pp);  // Pp = FP F^T + Q
@@ -106,39 +109,48 @@ struct SmootherAlg {
             }
     }
 
-    // element of row r of the staged tile (time k); the row after the shard's last one comes from the halo
-    template <int LSW>
-    PSSGP_DEV static void element_row(const T (&in)[NIN][LSW], int r, long k, const Params& p, T* E, T* g, T* L) {
-        T m[D], P[NS];
+    // F, Q of the step after the row being visited
+    struct Carry {
+        T F[D * D];
+        T Q[NS];
+    };
+    PSSGP_DEV static void carry_load(Carry& c, const T* f, const T* q) {
+        T qf[D * D];
 #pragma unroll
-        for (int i = 0; i < D; ++i) m[i] = in[2][r * D + i];
-        sym_pack(&in[3][r * D * D], P);
-        if (k + 1 < p.n) {
-            element(&in[0][r * D * D], &in[1][r * D * D], m, P, E, g, L);
-        } else {
-            T F[D * D], Qf[D * D];
-#pragma unroll
-            for (int e = 0; e < D * D; ++e) {
-                F[e] = __ldg(p.Fnext + e);
-                Qf[e] = __ldg(p.Qnext + e);
-            }
-            element(F, Qf, m, P, E, g, L);
+        for (int e = 0; e < D * D; ++e) {
+            c.F[e] = __ldg(f + e);
+            qf[e] = __ldg(q + e);
         }
+        sym_pack(qf, c.Q);
+    }
+    // k_hi = one past the chunk's last (first visited) row: its F, Q come from the next chunk or the halo
+    PSSGP_DEV static void carry_init(Carry& c, const Ctx&, long, long k_hi, const Params& p) {
+        if (k_hi < p.n)
+            carry_load(c, p.Fs + k_hi * (D * D), p.Qs + k_hi * (D * D));
+        else if (!p.last_special)
+            carry_load(c, p.Fnext, p.Qnext);
+    }
+    PSSGP_DEV static void carry_set(Carry& c, const T (&in)[NIN][WMAX]) {
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) c.F[e] = in[0][e];
+        sym_pack(in[1], c.Q);
     }
 
-    template <int LSW>
-    PSSGP_DEV static void append_row(T* a, const Ctx&, const T (&in)[NIN][LSW], int r, long k, const Params& p) {
+    PSSGP_DEV static void append_row(T* a, const Ctx&, const T (&in)[NIN][WMAX], long k, const Params& p, Carry& c) {
         if (k == p.n - 1 && p.last_special) {
             // last_smoothing_element (parallel.py:155-156): nothing has been appended before it
 #pragma unroll
             for (int e = 0; e < D * D; ++e) a[oE + e] = T(0);
 #pragma unroll
-            for (int i = 0; i < D; ++i) a[og + i] = in[2][r * D + i];
-            sym_pack(&in[3][r * D * D], a + oL);
+            for (int i = 0; i < D; ++i) a[og + i] = in[2][i];
+            sym_pack(in[3], a + oL);
+            carry_set(c, in);
             return;
         }
-        T E[D * D], g[D], L[NS];
-        element_row(in, r, k, p, E, g, L);
+        T E[D * D], g[D], L[NS], P[NS];
+        sym_pack(in[3], P);
+        element(c.F, c.Q, in[2], P, E, g, L);
+        carry_set(c, in);
         // new = elem_k o agg : E = E_k E_a ; g = E_k g_a + g_k ; L = E_k L_a E_k^T + L_k
         T En[D * D], gn[D], X[D * D], Ln[NS];
         mm_ff<T, D>(E, a + oE, En);
@@ -180,26 +192,28 @@ struct SmootherAlg {
         for (int e = 0; e < NSTATE; ++e) s[e] = p.init ? p.init[e] : T(0);
     }
 
-    template <int LSW>
-    PSSGP_DEV static void step_row(T* s, const Ctx&, const T (&in)[NIN][LSW], T (&out)[NOUT][LSW], int r, long k,
-                                   const Params& p, T*) {
+    PSSGP_DEV static bool step_row(T* s, const Ctx&, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                   const Params& p, T*, Carry& c) {
         if (k == p.n - 1 && p.last_special) {
 #pragma unroll
-            for (int i = 0; i < D; ++i) s[i] = in[2][r * D + i];
-            sym_pack(&in[3][r * D * D], s + D);
+            for (int i = 0; i < D; ++i) s[i] = in[2][i];
+            sym_pack(in[3], s + D);
         } else {
-            T a[NAGG], s2[NSTATE];
-            element_row(in, r, k, p, a + oE, a + og, a + oL);
+            T a[NAGG], s2[NSTATE], P[NS];
+            sym_pack(in[3], P);
+            element(c.F, c.Q, in[2], P, a + oE, a + og, a + oL);
             apply(s, a, s2);
 #pragma unroll
             for (int e = 0; e < NSTATE; ++e) s[e] = s2[e];
         }
+        carry_set(c, in);
 #pragma unroll
-        for (int i = 0; i < D; ++i) out[0][r * D + i] = s[i];
+        for (int i = 0; i < D; ++i) out[0][i] = s[i];
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
-            for (int jj = 0; jj < D; ++jj) out[1][r * D * D + i * D + jj] = s[D + sidx(i, jj)];
+            for (int jj = 0; jj < D; ++jj) out[1][i * D + jj] = s[D + sidx(i, jj)];
+        return true;
     }
 
     PSSGP_DEV static void expand_state(const T* s, T* out) {

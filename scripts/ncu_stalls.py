@@ -10,6 +10,6 @@ cols = [i for i, h in enumerate(hdr) if h.startswith("smsp__average_warps_issue_
 for r in rows[2:]:
     if pat and not pat.search(r[ki]):
         continue
-    vals = sorted([(float(r[i].replace(",", "")), hdr[i][len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for i in cols if r[i]], reverse=True)[:6]
+    vals = sorted([(float(r[i].replace(",", "")), hdr[i][len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]) for i in cols if r[i]], reverse=True)[:18]
     print(r[ki][:70])
     print("    " + ", ".join(f"{n}={v:.2f}" for v, n in vals))
