@@ -8,7 +8,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpssgp_b200.so")
+# PSSGP_B200_LIB points at another build of the same library (kernel-tuning experiments)
+LIB_PATH = os.environ.get("PSSGP_B200_LIB") or os.path.join(_HERE, "lib", "libpssgp_b200.so")
 
 PSSGP_F64 = 0
 PSSGP_F32 = 1

@@ -35,6 +35,7 @@ struct AdjointAlg {
     static constexpr bool REVERSE = true;
     static constexpr int OUT_SHIFT = 1;
     static constexpr bool FLUSH = true;
+    static constexpr bool HAS_DONE = false;
     static constexpr int NIN = 5, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? 1 : (a == 3 ? D : D * D); }
     __host__ __device__ static constexpr int out_w(int) { return D * D; }
@@ -102,7 +103,7 @@ struct AdjointAlg {
         bool has;
     };
     PSSGP_DEV static void carry_init(Carry& c, const Ctx&, long, long, const Params&) { c.has = false; }
-    PSSGP_DEV static void carry_set(Carry& c, const T (&in)[NIN][WMAX]) {
+    PSSGP_DEV static void carry_set(Carry& c, const T (&in)[NIN][WMAX], long k, const Params& p) {
 #pragma unroll
         for (int e = 0; e < D * D; ++e) c.F[e] = in[0][e];
 #pragma unroll
@@ -178,7 +179,7 @@ struct AdjointAlg {
                 T u0[D];
                 mv_s<T, D>(f.P, f.h, u0);
                 const T s0 = dot<T, D>(f.h, u0) + f.R;
-                const T is = T(1) / s0;
+                const T is = t_rcp(s0);
 #pragma unroll
                 for (int i = 0; i < D; ++i)
 #pragma unroll
@@ -195,7 +196,7 @@ struct AdjointAlg {
             for (int e = 0; e < NS; ++e) x[oB + e] = T(0);
             return;
         }
-        const T is = T(1) / f.s;
+        const T is = t_rcp(f.s);
         T w[D];  // F^T h
         mv_t<T, D>(f.F, f.h, w);
 #pragma unroll
@@ -246,7 +247,7 @@ struct AdjointAlg {
             row_moments(in, m, P);
             append_step(a, cx, c, m, P, k + 1, p);
         }
-        carry_set(c, in);
+        carry_set(c, in, k, p);
     }
     // step k_lo of the chunk, with the filtered moments of row k_lo - 1 from the halo
     PSSGP_DEV static void append_flush(T* a, const Ctx& cx, long k_lo, const Params& p, Carry& c) {
@@ -284,7 +285,7 @@ struct AdjointAlg {
     // accumulating dR and dH.  with_ll: include the log-density term of this step.
     PSSGP_DEV static void update_adjoint(const T* h, const T* mp, const T* Pp, const T* u, T s, T r, bool with_ll,
                                          const T* dm, const T* dP, T* dmp, T* dPp, T* acc) {
-        const T is = T(1) / s;
+        const T is = t_rcp(s);
         const T udm = dot<T, D>(u, dm);
         T Pu[D];
         mv_s<T, D>(dP, u, Pu);
@@ -328,7 +329,7 @@ struct AdjointAlg {
 #pragma unroll
             for (int e = 0; e < D; ++e) dmp0[e] = T(0);
             if (f.obs) {
-                const T is = T(1) / f.s;
+                const T is = t_rcp(f.s);
                 const T sbar = T(0.5) * (f.r * f.r * is * is - is);
                 const T rbar = -f.r * is;
                 acc[0] += sbar;
@@ -423,7 +424,7 @@ struct AdjointAlg {
             row_moments(in, m, P);
             step_core(s, cx, c, m, P, out, k + 1, p, acc);
         }
-        carry_set(c, in);
+        carry_set(c, in, k, p);
         return has;
     }
     PSSGP_DEV static bool step_flush(T* s, const Ctx& cx, T (&out)[NOUT][WMAX], long k_lo, const Params& p, T* acc,

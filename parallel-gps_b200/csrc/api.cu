@@ -123,6 +123,7 @@ int pssgp_create(pssgp_handle** out, int device) {
         return set_err(PSSGP_ERR_CUDA, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
     }
     h->num_sms = sms;
+    if (const char* env = getenv("PSSGP_CHUNK")) h->chunk_opt = atoll(env);  // tuning aid: same as option "chunk"
     e = cudaMalloc((void**)&h->ticket, 64);
     if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 64);
     if (e != cudaSuccess) {

@@ -32,6 +32,7 @@ struct FilterAlg {
     __host__ __device__ static constexpr int in_w(int a) { return a < 2 ? D * D : 1; }
     static constexpr int OUT_SHIFT = 0;
     static constexpr bool FLUSH = false;
+    static constexpr bool HAS_DONE = true;  // step_done folds the chunk's log-likelihood pieces into acc
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {
@@ -77,8 +78,20 @@ struct FilterAlg {
 
     // Append time step k (row r of the staged tile) to the aggregate: conditional Kalman recursion given
     // the chunk-entry state.
-    struct Carry {};
-    PSSGP_DEV static void carry_init(Carry&, const Ctx&, long, long, const Params&) {}
+    // per-chunk pieces of the log-likelihood (K3): sum of log innovation variances, quadratic term, count
+    struct Carry {
+        LogSum<T> ls;
+        T quad;
+        int nobs;
+    };
+    PSSGP_DEV static void carry_init(Carry& c, const Ctx&, long, long, const Params&) {
+        c.ls.init();
+        c.quad = T(0);
+        c.nobs = 0;
+    }
+    PSSGP_DEV static void step_done(T* acc, const Carry& c) {
+        acc[0] = T(-0.5) * (c.ls.value() + T(c.nobs) * T(1.8378770664093454835606594728112) + c.quad);
+    }
 
     PSSGP_DEV static void append_row(T* a, const Ctx& cx, const T (&in)[NIN][WMAX], long k, const Params& p, Carry&) {
         const T* F = in[0];
@@ -116,7 +129,7 @@ struct FilterAlg {
         const T s = dot<T, D>(h, u) + R;
         mv_t<T, D>(Ap, h, w);  // (H A')^T
         const T e0 = yk - dot<T, D>(h, bp);
-        const T is = T(1) / s;
+        const T is = t_rcp(s);
 #pragma unroll
         for (int i = 0; i < D; ++i) {
             a[oE + i] = fma(w[i], e0 * is, a[oE + i]);
@@ -248,7 +261,7 @@ struct FilterAlg {
 
     // Seeded Kalman step k: s=(m,P) filtered at k-1 -> filtered at k; emits fms/fPs, accumulates ll.
     PSSGP_DEV static bool step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
-                                   const Params& p, T* acc, Carry&) {
+                                   const Params& p, T* acc, Carry& cr) {
         const T* F = in[0];
         const T* h = cx.h;
         const T R = cx.R;
@@ -263,7 +276,13 @@ struct FilterAlg {
         mv_s<T, D>(Pp, h, u);
         T sv = dot<T, D>(h, u) + R;
         T e0 = yk - dot<T, D>(h, mp);
-        if (obs) acc[0] += T(-0.5) * (t_log(T(6.283185307179586476925286766559) * sv) + e0 * e0 / sv);
+        T is = t_rcp(sv);
+        if (obs) {
+            // log N(y; H mp, sv): the log-determinant part goes through the running LogSum of the chunk
+            cr.ls.add(sv);
+            cr.quad = fma(e0 * e0, is, cr.quad);
+            cr.nobs += 1;
+        }
         if (k == 0 && p.first_special) {
             // the filter update at the global first step acts on (m0, P0) directly (parallel.py:24-30)
 #pragma unroll
@@ -273,9 +292,9 @@ struct FilterAlg {
             mv_s<T, D>(Pp, h, u);
             sv = dot<T, D>(h, u) + R;
             e0 = yk - dot<T, D>(h, mp);
+            is = t_rcp(sv);
         }
         if (obs) {
-            const T is = T(1) / sv;
 #pragma unroll
             for (int i = 0; i < D; ++i) s[i] = fma(u[i], e0 * is, mp[i]);
 #pragma unroll

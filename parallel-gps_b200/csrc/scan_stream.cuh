@@ -39,6 +39,10 @@
 #pragma once
 #include "smalld.cuh"
 
+#ifndef PSSGP_NWCAP
+#define PSSGP_NWCAP 8
+#endif
+
 namespace pssgp {
 
 // ---------------------------------------------------------------------------------------------
@@ -107,7 +111,8 @@ template <typename Alg> struct StreamLayout {
     static constexpr int WARP_BYTES_APPLY = NST * STAGE_BYTES + OUT_BYTES;
     static constexpr int SMEM_BUDGET = 216 * 1024;
     __host__ __device__ static constexpr int nw_fit() { return SMEM_BUDGET / WARP_BYTES_APPLY; }
-    static constexpr int NW = nw_fit() > 8 ? 8 : (nw_fit() < 1 ? 1 : nw_fit());
+    static constexpr int NWCAP = PSSGP_NWCAP;
+    static constexpr int NW = nw_fit() > NWCAP ? NWCAP : (nw_fit() < 1 ? 1 : nw_fit());
 };
 
 // Per-lane cursor of the cooperative copy of one array: this lane moves piece `off` of the segments of
@@ -423,7 +428,11 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                     if (s + NST < nsub) in.issue(p, n, L, wg.fast, wsm_addr + st * Lay::STAGE_BYTES);
                     cp_async_commit();
                 }
+#ifdef PSSGP_DRYRUN  // memory-pipeline probe: no arithmetic (results are wrong)
+                if (mine && k < n) a[0] += row[0][0] + row[1][Alg::in_w(1) - 1] + row[Alg::NIN - 1][0];
+#else
                 if (mine && k < n) Alg::append_row(a, ctx, row, k, p, cr);
+#endif
             }
         }
         cp_async_wait<0>();
@@ -606,6 +615,9 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             if (has) stream_stage_out_row<Alg>(osm, lane, 0, orow);
             __syncwarp();
             out.store(p, n, L, wg.fast, osm);
+        }
+        if constexpr (Alg::HAS_DONE) {
+            if (mine) Alg::step_done(acc, cr);
         }
     }
     if (Alg::NACC > 0) {

@@ -19,6 +19,67 @@ PSSGP_DEV float t_log(float x) { return logf(x); }
 PSSGP_DEV double t_sqrt(double x) { return sqrt(x); }
 PSSGP_DEV float t_sqrt(float x) { return sqrtf(x); }
 
+// Reciprocal of a normal, finite number: hardware seed (MUFU.RCP64H, ~20 bits) + two Newton steps, 5
+// instructions instead of the ~20 of an IEEE division with its slow path.  Accurate to about 1 ulp, which
+// is all the callers (pivots, innovation variances) need.
+PSSGP_DEV double t_rcp(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = fma(fma(-x, r, 1.0), r, r);
+    r = fma(fma(-x, r, 1.0), r, r);
+    return r;
+}
+PSSGP_DEV float t_rcp(float x) { return __frcp_rn(x); }
+
+// Running sum of log(x_i) kept as (mantissa product, exponent sum): one logarithm per chunk instead of
+// one per time step (an FP64 log is ~80 instructions).  x must be positive and finite; anything else is
+// routed through log() so that NaN / -inf still propagate.
+template <typename T> struct LogSum;
+template <> struct LogSum<double> {
+    double m, extra;
+    int e, cnt;
+    PSSGP_DEV void init() { m = 1.0; extra = 0.0; e = 0; cnt = 0; }
+    PSSGP_DEV void renorm() {
+        const long long b = __double_as_longlong(m);
+        e += (int)((b >> 52) & 0x7ff) - 1022;
+        m = __longlong_as_double((b & 0x800fffffffffffffLL) | 0x3fe0000000000000LL);
+    }
+    PSSGP_DEV void add(double x) {
+        const long long b = __double_as_longlong(x);
+        const int be = (int)((b >> 52) & 0x7ff);
+        if (b > 0 && be != 0 && be != 0x7ff) {
+            e += be - 1022;
+            m *= __longlong_as_double((b & 0x000fffffffffffffLL) | 0x3fe0000000000000LL);  // in [0.5, 1)
+            if ((++cnt & 511) == 0) renorm();
+        } else {
+            extra += log(x);
+        }
+    }
+    PSSGP_DEV double value() const { return log(m) + (double)e * 0.69314718055994530942 + extra; }
+};
+template <> struct LogSum<float> {
+    float m, extra;
+    int e, cnt;
+    PSSGP_DEV void init() { m = 1.0f; extra = 0.0f; e = 0; cnt = 0; }
+    PSSGP_DEV void renorm() {
+        const int b = __float_as_int(m);
+        e += ((b >> 23) & 0xff) - 126;
+        m = __int_as_float((b & 0x807fffff) | 0x3f000000);
+    }
+    PSSGP_DEV void add(float x) {
+        const int b = __float_as_int(x);
+        const int be = (b >> 23) & 0xff;
+        if (b > 0 && be != 0 && be != 0xff) {
+            e += be - 126;
+            m *= __int_as_float((b & 0x007fffff) | 0x3f000000);
+            if ((++cnt & 63) == 0) renorm();
+        } else {
+            extra += logf(x);
+        }
+    }
+    PSSGP_DEV float value() const { return logf(m) + (float)e * 0.69314718f + extra; }
+};
+
 // C(full) = A(full) * B(full)
 template <typename T, int D> PSSGP_DEV void mm_ff(const T* A, const T* B, T* C) {
 #pragma unroll
@@ -179,7 +240,7 @@ template <typename T, int D, int NR> PSSGP_DEV void lu_solve(T* M, T* B) {
                 B[r * NR + j] = sw ? a : b;
             }
         }
-        T inv = T(1) / M[c * D + c];
+        T inv = t_rcp(M[c * D + c]);
 #pragma unroll
         for (int j = c + 1; j < D; ++j) M[c * D + j] *= inv;
 #pragma unroll
@@ -204,49 +265,52 @@ template <typename T, int D, int NR> PSSGP_DEV void lu_solve(T* M, T* B) {
         }
 }
 
-// Cholesky of a packed symmetric matrix in place (lower factor, packed); returns false if not SPD.
-template <typename T, int D> PSSGP_DEV void chol_packed(T* S) {
+// LDL^T of a packed symmetric positive definite matrix in place: unit lower factor in the strict lower
+// triangle, the RECIPROCALS of the pivots d_j on the diagonal (no square roots; three reciprocals serve
+// the factorisation and both triangular solves).
+template <typename T, int D> PSSGP_DEV void ldl_packed(T* S) {
 #pragma unroll
     for (int j = 0; j < D; ++j) {
         T d = S[sidx(j, j)];
+        T w[D > 1 ? D - 1 : 1];  // w[k] = L[j][k] d_k
 #pragma unroll
-        for (int k = 0; k < j; ++k) d = fma(-S[sidx(j, k)], S[sidx(j, k)], d);
-        d = t_sqrt(d);
-        S[sidx(j, j)] = d;
-        T inv = T(1) / d;
+        for (int k = 0; k < j; ++k) {
+            w[k] = S[sidx(j, k)];  // still holds L[j][k] d_k at this point (scaled below)
+            d = fma(-w[k], w[k] * S[sidx(k, k)], d);
+        }
+#pragma unroll
+        for (int k = 0; k < j; ++k) S[sidx(j, k)] = w[k] * S[sidx(k, k)];  // L[j][k]
+        const T inv = t_rcp(d);
+        S[sidx(j, j)] = inv;
 #pragma unroll
         for (int i = j + 1; i < D; ++i) {
             T v = S[sidx(i, j)];
 #pragma unroll
-            for (int k = 0; k < j; ++k) v = fma(-S[sidx(i, k)], S[sidx(j, k)], v);
-            S[sidx(i, j)] = v * inv;
+            for (int k = 0; k < j; ++k) v = fma(-S[sidx(i, k)], S[sidx(j, k)], v);  // S[i][k] still holds L[i][k] d_k
+            S[sidx(i, j)] = v;  // L[i][j] d_j (scaled when row i is factored)
         }
     }
 }
-// Solve (L L^T) X = B in place, B is D x NR row-major, L packed lower.
-template <typename T, int D, int NR> PSSGP_DEV void chol_solve(const T* L, T* B) {
+// Solve (L D L^T) X = B in place, B is D x NR row-major, factor from ldl_packed.
+template <typename T, int D, int NR> PSSGP_DEV void ldl_solve(const T* L, T* B) {
 #pragma unroll
-    for (int i = 0; i < D; ++i) {
-        T inv = T(1) / L[sidx(i, i)];
+    for (int i = 0; i < D; ++i)
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
             T v = B[i * NR + j];
 #pragma unroll
             for (int k = 0; k < i; ++k) v = fma(-L[sidx(i, k)], B[k * NR + j], v);
-            B[i * NR + j] = v * inv;
+            B[i * NR + j] = v;
         }
-    }
 #pragma unroll
-    for (int i = D - 1; i >= 0; --i) {
-        T inv = T(1) / L[sidx(i, i)];
+    for (int i = D - 1; i >= 0; --i)
 #pragma unroll
         for (int j = 0; j < NR; ++j) {
-            T v = B[i * NR + j];
+            T v = B[i * NR + j] * L[sidx(i, i)];
 #pragma unroll
             for (int k = i + 1; k < D; ++k) v = fma(-L[sidx(k, i)], B[k * NR + j], v);
-            B[i * NR + j] = v * inv;
+            B[i * NR + j] = v;
         }
-    }
 }
 
 template <typename T> PSSGP_DEV T shfl_up_t(T v, int delta) { return __shfl_up_sync(0xffffffffu, v, delta); }

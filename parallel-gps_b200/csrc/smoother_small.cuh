@@ -31,6 +31,7 @@ struct SmootherAlg {
     static constexpr bool REVERSE = true;
     static constexpr int OUT_SHIFT = 0;
     static constexpr bool FLUSH = false;
+    static constexpr bool HAS_DONE = false;
     static constexpr int NIN = 4, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? D : D * D; }
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
@@ -79,11 +80,11 @@ struct SmootherAlg {
         T FP[D * D];
         mm_fs<T, D>(F, P, FP);
         sym_xat_plus<T, D>(FP, F, Pp, Pp);  // Pp = FP F^T + Q
-        chol_packed<T, D>(Pp);
+        ldl_packed<T, D>(Pp);
         T X[D * D];
 #pragma unroll
         for (int e = 0; e < D * D; ++e) X[e] = FP[e];
-        chol_solve<T, D, D>(Pp, X);  // X = Pp^{-1} F P ; E = X^T
+        ldl_solve<T, D, D>(Pp, X);  // X = Pp^{-1} F P ; E = X^T
 #pragma unroll
         for (int i = 0; i < D; ++i)
 #pragma unroll
