@@ -73,13 +73,31 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
                 return set_err(PSSGP_ERR_INVALID, "output array %d is not 16-byte aligned", a);
     StreamPart sp;
     sp.n = n;
-    sp.L = pick_chunk(h, n, NW * 32, Lay::LS);
-    const int64_t ctaRows = (int64_t)NW * 32 * sp.L;
-    sp.nMain = (int)(n / ctaRows);
-    const int64_t tail = n - (int64_t)sp.nMain * ctaRows;
-    sp.Ltail = (int)((((tail + NW * 32 - 1) / (NW * 32)) + Lay::LS - 1) / Lay::LS * Lay::LS);
-    if (sp.Ltail < Lay::LS) sp.Ltail = Lay::LS;
-    sp.nCta = sp.nMain + (tail > 0 ? 1 : 0);
+    {
+        constexpr int LS = Lay::LS;
+        const int64_t cta_chunks = (int64_t)NW * 32;
+        const int64_t C = h->num_sms > 1 ? h->num_sms - 1 : 1;  // main CTAs of the single wave (+ 1 tail CTA)
+        int64_t tail;
+        if (h->chunk_opt <= 0 && n >= C * cta_chunks * 8) {
+            // two chunk lengths L and L - LS: exactly C complete main CTAs, fewer than cta_chunks * LS rows left over
+            const int64_t L = (n / (C * cta_chunks * LS) + 1) * LS;       // C CTAs of L rows per chunk overshoot n
+            const int64_t shortfall = C * cta_chunks * L - n;              // > 0 rows to give back, LS rows per chunk
+            int64_t nShort = (shortfall + cta_chunks * LS - 1) / (cta_chunks * LS);
+            if (nShort > C) nShort = C;
+            sp.L = (int)L;
+            sp.nMain = (int)C;
+            sp.nLong = (int)(C - nShort);
+            tail = n - ((int64_t)sp.nLong * L + nShort * (L - LS)) * cta_chunks;
+        } else {
+            sp.L = pick_chunk(h, n, NW * 32, LS);
+            sp.nMain = (int)(n / (cta_chunks * sp.L));
+            sp.nLong = sp.nMain;
+            tail = n - (int64_t)sp.nMain * cta_chunks * sp.L;
+        }
+        sp.Ltail = (int)((((tail + cta_chunks - 1) / cta_chunks) + LS - 1) / LS * LS);
+        if (sp.Ltail < LS) sp.Ltail = LS;
+        sp.nCta = sp.nMain + (tail > 0 ? 1 : 0);
+    }
     const int L = sp.L;
     const int64_t nBlocks = sp.nCta;
     const int64_t nW = nBlocks;  // one aggregate per CTA of K1
@@ -101,11 +119,14 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     T* wstate = (T*)h->buf[WS_WSTATE];
     T* part = (T*)h->buf[WS_PART];
     int nl = 0;
+    bool fused_mid = false;
     if (!reuse) {
         PSSGP_LAUNCH(h, Alg::name_reduce(), st,
                      (stream_reduce_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
-                         p, sp, nChunksPad, lane, wexcl, wagg)));
+                         p, sp, nChunksPad, lane, wexcl, wagg, mode == SCAN_FULL ? wstate : nullptr, final_state,
+                         h->ticket + 1)));
         ++nl;
+        fused_mid = (mode == SCAN_FULL);
     }
     int midThreads = kMidThreads;
     if (nW < kMidThreads) midThreads = (int)(((nW + 31) / 32) * 32);
@@ -117,11 +138,14 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
         h->pending_L[kind] = L;
         return check_launch(h, "scan summary", nl + 1);
     }
-    PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_mid_kernel<Alg><<<1, midThreads, 0, st>>>(p, wagg, nW, wstate, final_state)));
+    if (!fused_mid) {
+        PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_mid_kernel<Alg><<<1, midThreads, 0, st>>>(p, wagg, nW, wstate, final_state)));
+        ++nl;
+    }
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
                  (stream_apply_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
                      p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out)));
-    return check_launch(h, "scan", nl + 2);
+    return check_launch(h, "scan", nl + 1);
 }
 
 template <typename Alg>

@@ -8,14 +8,14 @@ namespace pssgp {
 
 constexpr int kMidThreads = 256;
 
-// Single CTA.  wstate[s*nW + w] = state entering CTA w of K1/K3.  final_state = state after everything.
+// One CTA (all of its threads).  wstate[s*nW + w] = state entering CTA w of K1/K3.  final_state = state after
+// everything.  sh: 32 * NAGG scalars of shared memory.  Runs either as its own kernel (scan_mid_kernel) or at
+// the end of K1 in the CTA that finishes last (scan_stream.cuh).
 template <typename Alg>
-__global__ void __launch_bounds__(kMidThreads)
-scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__ wagg, long nW,
-                typename Alg::scalar* __restrict__ wstate,
-                typename Alg::scalar* __restrict__ final_state) {
+__device__ __forceinline__ void scan_mid_body(const typename Alg::Params& p, const typename Alg::scalar* wagg, long nW,
+                                              typename Alg::scalar* wstate, typename Alg::scalar* final_state,
+                                              typename Alg::scalar* sh) {
     using T = typename Alg::scalar;
-    __shared__ T sh[32 * Alg::NAGG];
     const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
     const int nthreads = blockDim.x;
@@ -28,7 +28,7 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
     for (long i = i0; i < i1; ++i) {
         T b[Alg::NAGG], r[Alg::NAGG];
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) b[e] = wagg[(long)e * nW + i];
+        for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
         if (i == i0) {
 #pragma unroll
             for (int e = 0; e < Alg::NAGG; ++e) a[e] = b[e];
@@ -70,11 +70,11 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
             Alg::identity(w);
         }
 #pragma unroll 1
-        for (int off = 1; off < 32; off <<= 1) {
+        for (int off = 1; off < nwarps; off <<= 1) {
             T o[Alg::NAGG];
 #pragma unroll
             for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(w[e], off);
-            if (lane >= off) {
+            if (lane >= off && lane < nwarps) {
                 T r[Alg::NAGG];
                 Alg::combine(o, w, r);
 #pragma unroll
@@ -112,7 +112,7 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
         for (int e = 0; e < Alg::NSTATE; ++e) wstate[(long)e * nW + i] = s[e];
         T b[Alg::NAGG], s2[Alg::NSTATE];
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) b[e] = wagg[(long)e * nW + i];
+        for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
         Alg::apply(s, b, s2);
 #pragma unroll
         for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
@@ -120,6 +120,14 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
     // the thread that owns the last warp total holds the final state
     if (final_state != nullptr && i1 == nW && i0 < nW) Alg::expand_state(s, final_state);
     if (final_state != nullptr && nW == 0 && tid == 0) Alg::expand_state(s, final_state);
+}
+
+template <typename Alg>
+__global__ void __launch_bounds__(kMidThreads)
+scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__ wagg, long nW,
+                typename Alg::scalar* __restrict__ wstate, typename Alg::scalar* __restrict__ final_state) {
+    __shared__ typename Alg::scalar sh[32 * Alg::NAGG];
+    scan_mid_body<Alg>(p, wagg, nW, wstate, final_state, sh);
 }
 
 // Single CTA: out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding).

@@ -37,6 +37,7 @@
 // tables (NIN, in_w, in_ptr, NOUT, out_w, out_ptr), identity, combine, apply, load_init, expand_state,
 // finish, carry_init, append_row / append_flush and step_row / step_flush.
 #pragma once
+#include "scan_small.cuh"
 #include "smalld.cuh"
 
 #ifndef PSSGP_NWCAP
@@ -342,14 +343,15 @@ PSSGP_DEV void stream_stage_out_row(unsigned char* ostage, int lane, int r,
     }
 }
 
-// Partition of the time axis (host-computed): nMain "main" CTAs of NW*32 chunks of L rows each, all of
-// them complete, followed in time by at most one "tail" CTA that covers the remaining rows with its own
-// (shorter) chunk length Ltail.  Only the tail CTA ever sees a missing row, so only it pays for bounds
-// checks; being short it finishes early instead of holding up the single wave.
+// Partition of the time axis (host-computed): nMain "main" CTAs of NW*32 complete chunks each - the first
+// nLong of them with chunks of L rows, the others with chunks of L - LS rows, so that nMain can be made
+// (number of SMs - 1) whatever n is - followed in time by at most one "tail" CTA that covers the remaining
+// rows with its own (short) chunk length Ltail.  Only the tail CTA ever sees a missing row, so only it pays
+// for bounds checks; being short it finishes early instead of holding up the single wave.
 struct StreamPart {
     long n;
     int L, Ltail;
-    int nMain, nCta;
+    int nLong, nMain, nCta;
 };
 
 // Geometry shared by K1 and K3.
@@ -363,9 +365,10 @@ template <typename Alg> struct WarpGeom {
         constexpr int LS = StreamGeom<typename Alg::scalar>::LS;
         const int tb = Alg::REVERSE ? (sp.nCta - 1 - (int)blockIdx.x) : (int)blockIdx.x;  // CTA in time order
         fast = tb < sp.nMain;
-        L = fast ? sp.L : sp.Ltail;
+        L = tb < sp.nLong ? sp.L : (fast ? sp.L - LS : sp.Ltail);
         nsub = L / LS;
-        const long row_begin = (long)(fast ? tb : sp.nMain) * ((long)NW * 32 * sp.L);
+        const int tbm = fast ? tb : sp.nMain;  // main CTAs before this one
+        const long row_begin = ((long)tbm * sp.L - (long)(tbm > sp.nLong ? tbm - sp.nLong : 0) * LS) * (NW * 32);
         const int tl = wid * 32 + lane;                             // thread in scan order
         const int ct = Alg::REVERSE ? (NW * 32 - 1 - tl) : tl;      // chunk of the CTA in time order
         lc = (long)blockIdx.x * (NW * 32) + tl;
@@ -381,7 +384,8 @@ template <typename Alg>
 __global__ void __launch_bounds__(StreamLayout<Alg>::NW * 32)
 stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                      typename Alg::scalar* __restrict__ lane_excl, typename Alg::scalar* __restrict__ warp_excl,
-                     typename Alg::scalar* __restrict__ wagg) {
+                     typename Alg::scalar* __restrict__ wagg, typename Alg::scalar* wstate,
+                     typename Alg::scalar* final_state, unsigned int* ticket) {
     using T = typename Alg::scalar;
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
@@ -499,6 +503,24 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         if (lane == NW - 1) {
 #pragma unroll
             for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blockIdx.x] = w[e];
+        }
+    }
+    // K2 folded into K1: the CTA that finishes last scans the CTA totals (wstate == nullptr: the caller runs
+    // scan_mid_kernel / scan_total_kernel itself)
+    if (wstate != nullptr) {
+        __shared__ bool is_last;
+        __shared__ T sh_mid[32 * Alg::NAGG];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            scan_mid_body<Alg>(p, wagg, nCta, wstate, final_state, sh_mid);
+            if (threadIdx.x == 0) *ticket = 0u;
         }
     }
 }

@@ -110,8 +110,15 @@ class TimeShard:
             out["dFs"], out["dQs"] = dFs, dQs
         return out
 
+    @staticmethod
+    def _aligned(t):
+        # the streaming kernels move 16-byte pieces: a shard sliced out of a longer array may start off a 16-byte
+        # boundary.  Done once here so that the summary and the full call see the same pointer (workspace reuse).
+        return t if t is None or not t.is_cuda or t.data_ptr() % 16 == 0 else t.clone()
+
     def filter_smoother_grad(self, P0, Fs, Qs, H, R, y, g_ll):
         """One full step: returns (ll, sms, sPs, (dP0, dFs, dQs, dH, dR)); ll and the small gradients are global."""
+        Fs, Qs, y = self._aligned(Fs), self._aligned(Qs), self._aligned(y)
         fms, fPs, ll = self.filter(P0, Fs, Qs, H, R, y, reduce_ll=False)
         o = self.smoother_and_grad(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=ll)
         return o["ll"], o["sms"], o["sPs"], (o["dP0"], o["dFs"], o["dQs"], o["dH"], o["dR"])

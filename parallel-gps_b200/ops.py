@@ -17,6 +17,11 @@ def nstate(d):
     return d + d * (d + 1) // 2
 
 
+def _al(t):
+    """The streaming kernels move 16-byte pieces: a sliced view may start off a 16-byte boundary."""
+    return t if t is None or t.data_ptr() % 16 == 0 else t.clone()
+
+
 def discretise(F, Pinf, dts):
     """(F[d,d], Pinf[d,d], dts[n]) -> (Fs[n,d,d], Qs[n,d,d]);  C ABI: pssgp_discretise."""
     n, d = dts.numel(), F.shape[0]
@@ -41,6 +46,7 @@ def discretise_backward(F, Pinf, dts, Fs, dFs, dQs):
 def pkf(P0, Fs, Qs, H, R, y, m0=None, first_special=True, want_ll=True, want_final=False):
     """C ABI: pssgp_pkf.  H[d], R[1], y[n] flat.  -> fms, fPs, ll(1-elem tensor or None), final_state or None
     (final_state = m[d] | P[d,d])."""
+    Fs, Qs, y = _al(Fs), _al(Qs), _al(y)
     n, d = Fs.shape[0], Fs.shape[1]
     fms = torch.empty((n, d), dtype=Fs.dtype, device=Fs.device)
     fPs = torch.empty((n, d, d), dtype=Fs.dtype, device=Fs.device)
@@ -54,6 +60,7 @@ def pkf(P0, Fs, Qs, H, R, y, m0=None, first_special=True, want_ll=True, want_fin
 
 def pks(Fs, Qs, fms, fPs, last_special=True, Fnext=None, Qnext=None, init=None, want_first=False):
     """C ABI: pssgp_pks. -> sms, sPs, first_state or None."""
+    Fs, Qs, fms, fPs = _al(Fs), _al(Qs), _al(fms), _al(fPs)
     n, d = Fs.shape[0], Fs.shape[1]
     sms = torch.empty((n, d), dtype=Fs.dtype, device=Fs.device)
     sPs = torch.empty((n, d, d), dtype=Fs.dtype, device=Fs.device)
@@ -66,6 +73,7 @@ def pks(Fs, Qs, fms, fPs, last_special=True, Fnext=None, Qnext=None, init=None, 
 
 def pkf_backward(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=None, first_special=True, adj_init=None, want_first=False):
     """C ABI: pssgp_pkf_backward. g_ll: 1-elem device tensor. -> dP0, dFs, dQs, dH, dR[, adj_first]."""
+    Fs, Qs, y, fms, fPs = _al(Fs), _al(Qs), _al(y), _al(fms), _al(fPs)
     n, d = Fs.shape[0], Fs.shape[1]
     kw = dict(dtype=Fs.dtype, device=Fs.device)
     dP0 = torch.zeros((d, d), **kw)

@@ -227,33 +227,36 @@ int main() {
     {                                                                                                        \
         constexpr int SEG = LSR * W * 8, NP = SEG / 16, PITCH = (NP | 1) * 16, STAGE = NARR * 32 * PITCH;    \
         int smem = NWARPS * NSTG * STAGE;                                                                    \
-        int L = (int)(rows / ((long)SMS * NWARPS * 32));                                                     \
-        L = L / LSR * LSR;                                                                                   \
+        int L = (int)((rows + (long)SMS * NWARPS * 32 - 1) / ((long)SMS * NWARPS * 32));                     \
+        L = (L + LSR - 1) / LSR * LSR;                                                                       \
         int ctas = (int)(rows / ((long)NWARPS * 32 * L));                                                    \
         if (smem <= 227 * 1024) {                                                                            \
             CK(cudaFuncSetAttribute(k_coop<LSR, NSTG, NARR, CA>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
             char nm[128];                                                                                    \
             snprintf(nm, 128, "coop LS=%d NST=%d %s warps=%d L=%d ctas=%d", LSR, NSTG, CA ? "ca" : "cg", NWARPS, L, ctas); \
-            report(nm, timeit([&] { k_coop<LSR, NSTG, NARR, CA><<<ctas, NWARPS * 32, smem>>>(buf, rows, L, out); })); \
+            float us = timeit([&] { k_coop<LSR, NSTG, NARR, CA><<<ctas, NWARPS * 32, smem>>>(buf, rows, L, out); }); \
+            printf("%-44s %8.1f us  %7.1f GB/s\n", nm, us, (double)ctas * NWARPS * 32 * L * W * 8 * NARR / us * 1e-3);   \
         }                                                                                                    \
     }
     RUN_COOP(2, 2, false, 8)
     RUN_COOP(2, 2, true, 8)
     RUN_COOP(2, 3, false, 8)
-    RUN_COOP(2, 4, false, 8)
     RUN_COOP(2, 2, false, 11)
-    RUN_COOP(2, 3, false, 11)
+    RUN_COOP(2, 2, false, 6)
     RUN_COOP(2, 2, false, 4)
+    RUN_COOP(2, 4, false, 4)
     RUN_COOP(4, 2, false, 5)
-    RUN_COOP(4, 3, false, 4)
+    RUN_COOP(4, 2, false, 4)
+    RUN_COOP(4, 3, false, 3)
     RUN_COOP(8, 2, false, 3)
+    RUN_COOP(8, 2, false, 2)
 
 #define RUN_BULK(LSR, NSTG, NWARPS)                                                                          \
     {                                                                                                        \
         constexpr int SEG = LSR * W * 8, NP = SEG / 16, PITCH = (NP | 1) * 16, STAGE = NARR * 32 * PITCH;    \
         int smem = NWARPS * NSTG * STAGE;                                                                    \
-        int L = (int)(rows / ((long)SMS * NWARPS * 32));                                                     \
-        L = L / LSR * LSR;                                                                                   \
+        int L = (int)((rows + (long)SMS * NWARPS * 32 - 1) / ((long)SMS * NWARPS * 32));                     \
+        L = (L + LSR - 1) / LSR * LSR;                                                                       \
         int ctas = (int)(rows / ((long)NWARPS * 32 * L));                                                    \
         if (smem <= 220 * 1024) {                                                                            \
             CK(cudaFuncSetAttribute(k_bulk<LSR, NSTG, NARR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); \
