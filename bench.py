@@ -216,9 +216,8 @@ def main():
 
     def device_step():
         if shard is None:
-            fms, fPs, ll, _ = ops.pkf(Pinf, Fs, Qs, H, R, y_dev)
-            sms, sPs, _ = ops.pks(Fs, Qs, fms, fPs)
-            grads = ops.pkf_backward(Pinf, Fs, Qs, H, R, y_dev, fms, fPs, g_ll)
+            # one C-ABI call: pkf (+ll), pks and pkf_backward sharing their passes over the LGSSM
+            (fms, fPs, ll), (sms, sPs), grads = ops.pkfs_grad(Pinf, Fs, Qs, H, R, y_dev, g_ll)
             return ll, sms, sPs, grads
         return shard.filter_smoother_grad(Pinf, Fs, Qs, H, R, y_dev, g_ll)
 
@@ -314,6 +313,7 @@ def main():
     s = 8
     alg_bytes = {  # algorithmic bytes per time step of each kernel
         "pkf_reduce": s * (2 * d * d + 1), "pkf_apply": s * (3 * d * d + d + 1), "pkf_mid": 0,
+        "pkf_apply_fused": s * (3 * d * d + d + 1), "pks_bwd_apply_fused": s * (8 * d * d + 2 * d + 1),
         "pks_reduce": s * (3 * d * d + d), "pks_apply": s * (4 * d * d + 2 * d), "pks_mid": 0,
         "pkf_bwd_reduce": s * (3 * d * d + d + 1), "pkf_bwd_apply": s * (5 * d * d + d + 1), "pkf_bwd_mid": 0,
     }

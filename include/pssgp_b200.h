@@ -107,6 +107,21 @@ int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d,
                        void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* adj_first, void* stream);
 
 /*
+ * Fused filter + log-likelihood + smoother + gradient over ONE shard that holds the whole series
+ * (first step and last step are the global ones): the outputs of pssgp_pkf (fms, fPs, ll), pssgp_pks
+ * (sms, sPs) and pssgp_pkf_backward (dP0, dFs, dQs, dH, dR) for the same LGSSM in one call.  This is the
+ * pkfs (pssgp/kalman/parallel.py:199-201) + TF-autodiff training step of the reference with the three
+ * scans sharing their passes over (Fs, Qs, y): for d <= 4 the forward filter pass also builds the chunk
+ * aggregates of both reverse scans, so the LGSSM is read three times instead of six
+ * (csrc/fused_small.cuh).  Other state dimensions run the three scans one after the other.  m0 = 0.
+ */
+int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d,
+                    const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,
+                    const void* y, const void* g_ll,
+                    void* fms, void* fPs, void* ll, void* sms, void* sPs,
+                    void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream);
+
+/*
  * Time-sharded scans (one contiguous shard of the time axis per GPU).  *_summary runs the local
  * reduce and writes the shard's aggregate element so that ranks can all-gather them:
  *   filter   (A,b,C,J,eta): d*d + 2d + d(d+1) values      smoother (E,g,L): d*d + d + d(d+1)/2

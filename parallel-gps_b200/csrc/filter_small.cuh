@@ -32,7 +32,8 @@ struct FilterAlg {
     __host__ __device__ static constexpr int in_w(int a) { return a < 2 ? D * D : 1; }
     static constexpr int OUT_SHIFT = 0;
     static constexpr bool FLUSH = false;
-    static constexpr bool HAS_DONE = true;  // step_done folds the chunk's log-likelihood pieces into acc
+    static constexpr bool HAS_DONE = true;
+    static constexpr bool HAS_SIDE = false;  // fused_small.cuh: extra per-chunk aggregates built by K3  // step_done folds the chunk's log-likelihood pieces into acc
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {

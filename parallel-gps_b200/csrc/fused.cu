@@ -1,0 +1,158 @@
+// C ABI: pssgp_pkfs_grad — filter + log-likelihood + smoother + gradient in one call (see include/pssgp_b200.h).
+#include "fused_small.cuh"
+#include "scan_run.cuh"
+
+namespace pssgp {
+
+constexpr int kNotFused = -12345;  // this (dtype, d) has no common partition: run the three scans one after the other
+
+template <typename Alg>
+int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPart& sp, const typename Alg::scalar* lane,
+                 const typename Alg::scalar* wexcl, const typename Alg::scalar* wstate, typename Alg::scalar* part,
+                 typename Alg::scalar* acc_out, cudaStream_t st) {
+    using Lay = StreamLayout<Alg>;
+    constexpr int NW = Lay::NW;
+    const long nChunksPad = (long)sp.nCta * NW * 32;
+    PSSGP_LAUNCH(h, Alg::name_apply(), st,
+                 (stream_apply_kernel<Alg><<<(unsigned)sp.nCta, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
+                     p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out)));
+    return PSSGP_OK;
+}
+
+template <typename T, int D>
+int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
+                   const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll, void* sms, void* sPs,
+                   void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
+    using FA = FilterAlg<T, D>;
+    using FF = FusedFwdAlg<T, D>;
+    using SA = SmootherAlg<T, D>;
+    using AA = AdjointAlg<T, D>;
+    constexpr int NW = StreamLayout<FA>::NW;
+    constexpr int LS = StreamLayout<FA>::LS;
+    // the fused step needs one partition of the time axis for all of its kernels
+    if constexpr (StreamLayout<FF>::NW != NW || StreamLayout<SA>::NW != NW || StreamLayout<AA>::NW != NW) {
+        return kNotFused;
+    } else {
+    int rc;
+    if ((rc = stream_configure<FA>(h->device))) return rc;
+    if ((rc = stream_configure_apply<FF>(h->device))) return rc;
+    if ((rc = stream_configure<SA>(h->device))) return rc;
+    if ((rc = stream_configure<AA>(h->device))) return rc;
+    const void* arrs[] = {Fs, Qs, y, fms, fPs, sms, sPs, dFs, dQs};
+    for (const void* a : arrs)
+        if (!aligned16(a)) return set_err(PSSGP_ERR_INVALID, "pkfs_grad: arrays must be 16-byte aligned");
+    const StreamPart sp = make_partition<NW, LS>(h, n);
+    const int64_t nCta = sp.nCta;
+    const int64_t nChunksPad = nCta * NW * 32;
+    h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = h->pending_key[KIND_ADJOINT] = nullptr;
+    const int NAGG[3] = {FA::NAGG, SA::NAGG, AA::NAGG};
+    for (int kind = 0; kind < 3; ++kind) {
+        if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
+        if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * NAGG[kind] * (size_t)nCta))) return rc;
+        if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * NAGG[kind] * (size_t)nCta * NW))) return rc;
+    }
+    if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * FA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_WSTATE_S, sizeof(T) * SA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_WSTATE_A, sizeof(T) * AA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (AA::NACC + 1) * (size_t)nCta))) return rc;
+    T* part = (T*)h->buf[WS_PART];
+
+    typename FF::Params fp;
+    fp.Fs = (const T*)Fs;
+    fp.Qs = (const T*)Qs;
+    fp.y = (const T*)y;
+    fp.H = (const T*)H;
+    fp.R = (const T*)R;
+    fp.P0 = (const T*)P0;
+    fp.m0 = nullptr;
+    fp.fms = (T*)fms;
+    fp.fPs = (T*)fPs;
+    fp.first_special = 1;
+    fp.n = n;
+    fp.sm = {(T*)h->buf[WS_LANE + KIND_SMOOTHER], (T*)h->buf[WS_WEXCL + KIND_SMOOTHER],
+             (T*)h->buf[WS_WAGG + KIND_SMOOTHER], (T*)h->buf[WS_WSTATE_S]};
+    fp.ad = {(T*)h->buf[WS_LANE + KIND_ADJOINT], (T*)h->buf[WS_WEXCL + KIND_ADJOINT],
+             (T*)h->buf[WS_WAGG + KIND_ADJOINT], (T*)h->buf[WS_WSTATE_A]};
+    fp.side_ticket = h->ticket + 1;
+
+    // K1: chunk aggregates of the filter + scan over the CTA totals
+    {
+        const typename FA::Params& bp = fp;
+        using Lay = StreamLayout<FA>;
+        PSSGP_LAUNCH(h, FA::name_reduce(), st,
+                     (stream_reduce_kernel<FA><<<(unsigned)nCta, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
+                         bp, sp, nChunksPad, (T*)h->buf[WS_LANE + KIND_FILTER], (T*)h->buf[WS_WEXCL + KIND_FILTER],
+                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1)));
+    }
+    // K2': seeded filter recursion + chunk aggregates and CTA-level scans of both reverse scans
+    launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
+                     (const T*)h->buf[WS_WSTATE], part, (T*)ll, st);
+    // K3: smoother and adjoint recursions seeded by the states K2' produced
+    typename SA::Params sp_;
+    sp_.Fs = (const T*)Fs;
+    sp_.Qs = (const T*)Qs;
+    sp_.fms = (const T*)fms;
+    sp_.fPs = (const T*)fPs;
+    sp_.sms = (T*)sms;
+    sp_.sPs = (T*)sPs;
+    sp_.n = n;
+    sp_.last_special = 1;
+    sp_.Fnext = sp_.Qnext = sp_.init = nullptr;
+    launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st);
+    typename AA::Params ap;
+    ap.Fs = (const T*)Fs;
+    ap.Qs = (const T*)Qs;
+    ap.y = (const T*)y;
+    ap.H = (const T*)H;
+    ap.R = (const T*)R;
+    ap.P0 = (const T*)P0;
+    ap.m0 = nullptr;
+    ap.fms = (const T*)fms;
+    ap.fPs = (const T*)fPs;
+    ap.g = (const T*)g_ll;
+    ap.init = nullptr;
+    ap.dFs = (T*)dFs;
+    ap.dQs = (T*)dQs;
+    ap.dP0 = (T*)dP0;
+    ap.dH = (T*)dH;
+    ap.dR = (T*)dR;
+    ap.first_state = nullptr;
+    ap.n = n;
+    ap.first_special = 1;
+    launch_apply<AA>(h, ap, sp, fp.ad.lane_excl, fp.ad.warp_excl, fp.ad.wstate, part, (T*)dR, st);
+    return check_launch(h, "pkfs_grad", 4);
+    }
+}
+
+static int fused_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+                          const void* H, const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll,
+                          void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
+    DISPATCH_SMALL(pkfs_grad_impl, h, n, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
+    return kNotFused;
+}
+
+}  // namespace pssgp
+
+using namespace pssgp;
+
+extern "C" {
+
+int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+                    const void* H, const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll,
+                    void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !g_ll || !fms || !fPs || !sms || !sPs || !dP0 || !dFs || !dQs || !dH || !dR)
+        return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = fused_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
+    if (rc != kNotFused) return rc;
+    // generic state dimension (or no common partition): the three scans one after the other
+    if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;
+    if ((rc = pssgp_pks(h, dtype, n, d, Fs, Qs, fms, fPs, 1, nullptr, nullptr, nullptr, sms, sPs, nullptr, stream)))
+        return rc;
+    return pssgp_pkf_backward(h, dtype, n, d, P0, nullptr, Fs, Qs, H, R, y, fms, fPs, g_ll, 1, nullptr, dP0, dFs, dQs,
+                              dH, dR, nullptr, stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,278 @@
+// Fused filter + smoother + log-likelihood-gradient step for D <= 4: algebras that let the three scans
+// of pkf / pks / pkf_backward share their passes over the LGSSM.
+//
+//   K1  stream_reduce<FilterAlg>          read F, Q, y                  (chunk aggregates of the filter)
+//   K2' stream_apply<FusedFwdAlg>         read F, Q, y; write fms, fPs  + while the filtered moments of a
+//                                         chunk are in registers, the chunk aggregates of BOTH reverse scans
+//                                         (smoother (E, g, L), adjoint (Abar, a, B)), built in ascending time
+//                                         by composing every new element on the "later" side; the CTA-level
+//                                         reverse scans and the scan over CTA totals follow in the same kernel
+//   K3' stream_apply<FusedRevAlg>         read F, Q, y, fms, fPs; write sms, sPs, dFs, dQs
+//
+// so the reduce passes of the smoother and of the adjoint (and their re-reads of F, Q, y, fms, fPs) disappear
+// and the two reverse apply passes share one read of their inputs.  Same arithmetic per element as
+// smoother_small.cuh / adjoint_small.cuh (reference: pssgp/kalman/parallel.py:155-184 for the smoother,
+// TF autodiff of :121-152 for the gradient); only the association order of the chunk aggregates differs.
+// Single shard only (first step and last step are the global ones).
+#pragma once
+#include "adjoint_small.cuh"
+#include "filter_small.cuh"
+#include "scan_stream.cuh"
+#include "smoother_small.cuh"
+
+namespace pssgp {
+
+// Workspace of one reverse scan as the forward kernel fills it (same layout as run_scan's).
+template <typename T>
+struct SideWs {
+    T* lane_excl;
+    T* warp_excl;
+    T* wagg;
+    T* wstate;
+};
+
+template <typename T, int D>
+struct FusedFwdAlg : FilterAlg<T, D> {
+    using Base = FilterAlg<T, D>;
+    using SA = SmootherAlg<T, D>;
+    using AA = AdjointAlg<T, D>;
+    static const char* name_apply() { return "pkf_apply_fused"; }
+    static constexpr bool HAS_SIDE = true;
+    static constexpr int NS = Base::NS, NIN = Base::NIN, NOUT = Base::NOUT, WMAX = Base::WMAX;
+    using Ctx = typename Base::Ctx;
+
+    struct Params : Base::Params {
+        long n;
+        SideWs<T> sm, ad;
+        unsigned int* side_ticket;
+    };
+
+    struct Carry : Base::Carry {
+        T sa[SA::NAGG];   // e_{k_lo} o ... (smoother elements of this chunk appended so far)
+        T aa[AA::NAGG];   // adjoint elements of this chunk appended so far
+        long k_lo;
+    };
+    PSSGP_DEV static void carry_init(Carry& c, const Ctx& cx, long k_lo, long k_hi, const Params& p) {
+        Base::carry_init(c, cx, k_lo, k_hi, p);
+        SA::identity(c.sa);
+        AA::identity(c.aa);
+        c.k_lo = k_lo;
+    }
+    PSSGP_DEV static void step_done(T* acc, const Carry& c) { Base::step_done(acc, c); }
+
+    // sa <- sa o e  with e = (E, g, L) later in time than everything in sa
+    PSSGP_DEV static void push_smoother(Carry& c, const T* el) {
+        T r[SA::NAGG];
+        SA::combine(el, c.sa, r);
+#pragma unroll
+        for (int e = 0; e < SA::NAGG; ++e) c.sa[e] = r[e];
+    }
+    // smoothing element of time k-1 from FP = F_k P_{k-1}, Pp = F_k P_{k-1} F_k^T + Q_k, mp = F_k m_{k-1}
+    PSSGP_DEV static void smoother_element(const T* FP, const T* Pp, const T* m, const T* P, const T* mp, T* el) {
+        T S[NS], X[D * D];
+#pragma unroll
+        for (int e = 0; e < NS; ++e) S[e] = Pp[e];
+        ldl_packed<T, D>(S);
+#pragma unroll
+        for (int e = 0; e < D * D; ++e) X[e] = FP[e];
+        ldl_solve<T, D, D>(S, X);  // X = Pp^{-1} F P ; E = X^T
+        T* E = el + SA::oE;
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) E[i * D + j] = X[j * D + i];
+        T Emp[D];
+        mv_f<T, D>(E, mp, Emp);
+#pragma unroll
+        for (int i = 0; i < D; ++i) el[SA::og + i] = m[i] - Emp[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j <= i; ++j) {
+                T a1 = T(0), a2 = T(0);
+#pragma unroll
+                for (int kk = 0; kk < D; ++kk) {
+                    a1 = fma(E[i * D + kk], FP[kk * D + j], a1);
+                    a2 = fma(E[j * D + kk], FP[kk * D + i], a2);
+                }
+                el[SA::oL + sidx(i, j)] = P[sidx(i, j)] - T(0.5) * (a1 + a2);
+            }
+    }
+
+    // Seeded Kalman step k (FilterAlg::step_row) + smoothing element of time k-1 + adjoint element of step k.
+    PSSGP_DEV static bool step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                   const Params& p, T* acc, Carry& cr) {
+        const T* F = in[0];
+        const T* h = cx.h;
+        const T R = cx.R;
+        const T yk = in[2][0];
+        T Q[NS], FP[D * D], mp[D], Pp[NS];
+        Base::sym_pack(in[1], Q);
+        mv_f<T, D>(F, s, mp);
+        mm_fs<T, D>(F, s + D, FP);
+        sym_xat_plus<T, D>(FP, F, Q, Pp);
+        const bool obs = !t_isnan(yk);
+        const bool first = (k == 0 && p.first_special);
+        T u[D];
+        mv_s<T, D>(Pp, h, u);
+        T sv = dot<T, D>(h, u) + R;
+        T e0 = yk - dot<T, D>(h, mp);
+        T is = t_rcp(sv);
+        if (obs) {
+            cr.ls.add(sv);
+            cr.quad = fma(e0 * e0, is, cr.quad);
+            cr.nobs += 1;
+        }
+        // smoothing element of time k-1 (parallel.py:159-166); the one before the chunk's first row belongs
+        // to the previous chunk (its owner builds it from a halo row in side_flush)
+        if (k > cr.k_lo) {
+            T el[SA::NAGG];
+            smoother_element(FP, Pp, s, s + D, mp, el);
+            push_smoother(cr, el);
+        }
+        if (first) {
+            // the filter update at the global first step acts on (m0, P0) directly (parallel.py:24-30)
+#pragma unroll
+            for (int i = 0; i < D; ++i) mp[i] = s[i];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) Pp[e] = s[D + e];
+            mv_s<T, D>(Pp, h, u);
+            sv = dot<T, D>(h, u) + R;
+            e0 = yk - dot<T, D>(h, mp);
+            is = t_rcp(sv);
+        }
+        // adjoint element of step k (adjoint_small.cuh element()): x = (Abar, a, B), appended on the later side
+        {
+            T x[AA::NAGG];
+            if (first) {
+                AA::identity(x);
+                if (obs) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i)
+#pragma unroll
+                        for (int j = 0; j < D; ++j) x[AA::oA + i * D + j] -= u[i] * is * h[j];
+                }
+            } else if (!obs) {
+#pragma unroll
+                for (int e = 0; e < D * D; ++e) x[AA::oA + e] = F[e];
+#pragma unroll
+                for (int e = 0; e < D; ++e) x[AA::oa + e] = T(0);
+#pragma unroll
+                for (int e = 0; e < NS; ++e) x[AA::oB + e] = T(0);
+            } else {
+                T w[D];  // F^T h
+                mv_t<T, D>(F, h, w);
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j < D; ++j) x[AA::oA + i * D + j] = fma(-u[i] * is, w[j], F[i * D + j]);
+                const T ris = e0 * is;
+#pragma unroll
+                for (int i = 0; i < D; ++i) x[AA::oa + i] = w[i] * ris;
+#pragma unroll
+                for (int i = 0; i < D; ++i)
+#pragma unroll
+                    for (int j = 0; j <= i; ++j) x[AA::oB + sidx(i, j)] = T(0.5) * (ris * ris - is) * w[i] * w[j];
+            }
+            T r[AA::NAGG];
+            AA::combine(x, cr.aa, r);
+#pragma unroll
+            for (int e = 0; e < AA::NAGG; ++e) cr.aa[e] = r[e];
+        }
+        if (obs) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = fma(u[i], e0 * is, mp[i]);
+#pragma unroll
+            for (int i = 0; i < D; ++i)
+#pragma unroll
+                for (int j = 0; j <= i; ++j) s[D + sidx(i, j)] = fma(-u[i] * is, u[j], Pp[sidx(i, j)]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = mp[i];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) s[D + e] = Pp[e];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) out[0][i] = s[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) out[1][i * D + j] = s[D + sidx(i, j)];
+        return true;
+    }
+
+    // After the chunk's last row (s = filtered moments at k_hi - 1): the smoothing element of time k_hi - 1,
+    // from the halo row k_hi, or last_smoothing_element (parallel.py:155-156) at the end of the series.
+    PSSGP_DEV static void side_flush(const T* s, long k_hi, const Params& p, Carry& cr) {
+        T el[SA::NAGG];
+        if (k_hi >= p.n) {
+#pragma unroll
+            for (int e = 0; e < D * D; ++e) el[SA::oE + e] = T(0);
+#pragma unroll
+            for (int i = 0; i < D; ++i) el[SA::og + i] = s[i];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) el[SA::oL + e] = s[D + e];
+        } else {
+            T F[D * D], qf[D * D], Q[NS], FP[D * D], mp[D], Pp[NS];
+            const T* pf = p.Fs + k_hi * (D * D);
+            const T* pq = p.Qs + k_hi * (D * D);
+#pragma unroll
+            for (int e = 0; e < D * D; ++e) {
+                F[e] = __ldg(pf + e);
+                qf[e] = __ldg(pq + e);
+            }
+            Base::sym_pack(qf, Q);
+            mv_f<T, D>(F, s, mp);
+            mm_fs<T, D>(F, s + D, FP);
+            sym_xat_plus<T, D>(FP, F, Q, Pp);
+            smoother_element(FP, Pp, s, s + D, mp, el);
+        }
+        push_smoother(cr, el);
+    }
+
+    // CTA-level reverse scans of both side aggregates, then (last CTA to arrive) the scans over the CTA totals:
+    // the two halves of the CTA run them side by side.  All threads of the CTA call this.
+    template <int NW>
+    PSSGP_DEV static void side_finish(const Params& p, Carry& cr, int lane, int wid, long nCta, long nChunksPad) {
+        __shared__ T shw_s[NW * SA::NAGG];
+        __shared__ T shw_a[NW * AA::NAGG];
+        const long blk_s = nCta - 1 - (long)blockIdx.x;
+        cta_scan_publish<SA, NW, true>(cr.sa, lane, wid, blk_s, nCta, nChunksPad, p.sm.lane_excl, p.sm.warp_excl,
+                                       p.sm.wagg, shw_s);
+        cta_scan_publish<AA, NW, true>(cr.aa, lane, wid, blk_s, nCta, nChunksPad, p.ad.lane_excl, p.ad.warp_excl,
+                                       p.ad.wagg, shw_a);
+        __shared__ bool is_last;
+        __shared__ T sh_mid_s[32 * SA::NAGG];
+        __shared__ T sh_mid_a[32 * AA::NAGG];
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int t = atomicAdd(p.side_ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (is_last) {
+            __threadfence();
+            constexpr int HALF = (NW / 2) * 32;
+            if (NW >= 2) {
+                if ((int)threadIdx.x < HALF) {
+                    typename SA::Params sp{};
+                    scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, HALF, 1);
+                } else if ((int)threadIdx.x < 2 * HALF) {
+                    typename AA::Params ap{};
+                    scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, (int)threadIdx.x - HALF,
+                                      HALF, 2);
+                }
+            } else {
+                typename SA::Params sp{};
+                scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, 32, 1);
+                typename AA::Params ap{};
+                scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, (int)threadIdx.x, 32, 2);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) *p.side_ticket = 0u;
+        }
+    }
+};
+
+}  // namespace pssgp

@@ -52,7 +52,52 @@ int stream_configure(int device) {
     return PSSGP_OK;
 }
 
+// Same for an algebra that only ever runs K3 (the fused algebras of fused_small.cuh).
+template <typename Alg>
+int stream_configure_apply(int device) {
+    using Lay = StreamLayout<Alg>;
+    static unsigned long long done = 0ull;
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done & bit) return PSSGP_OK;
+    cudaError_t e = cudaFuncSetAttribute(stream_apply_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         Lay::NW * Lay::WARP_BYTES_APPLY);
+    if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e));
+    done |= bit;
+    return PSSGP_OK;
+}
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// Partition of the time axis for CTAs of NW warps (see StreamPart): one resident wave, all SMs but one busy
+// with complete chunks, at most one short tail CTA.
+template <int NW, int LS>
+StreamPart make_partition(const pssgp_handle* h, int64_t n) {
+    StreamPart sp;
+    sp.n = n;
+    const int64_t cta_chunks = (int64_t)NW * 32;
+    const int64_t C = h->num_sms > 1 ? h->num_sms - 1 : 1;  // main CTAs of the single wave (+ 1 tail CTA)
+    int64_t tail;
+    if (h->chunk_opt <= 0 && n >= C * cta_chunks * 8) {
+        // two chunk lengths L and L - LS: exactly C complete main CTAs, fewer than cta_chunks * LS rows left over
+        const int64_t L = (n / (C * cta_chunks * LS) + 1) * LS;       // C CTAs of L rows per chunk overshoot n
+        const int64_t shortfall = C * cta_chunks * L - n;              // > 0 rows to give back, LS rows per chunk
+        int64_t nShort = (shortfall + cta_chunks * LS - 1) / (cta_chunks * LS);
+        if (nShort > C) nShort = C;
+        sp.L = (int)L;
+        sp.nMain = (int)C;
+        sp.nLong = (int)(C - nShort);
+        tail = n - ((int64_t)sp.nLong * L + nShort * (L - LS)) * cta_chunks;
+    } else {
+        sp.L = pick_chunk(h, n, NW * 32, LS);
+        sp.nMain = (int)(n / (cta_chunks * sp.L));
+        sp.nLong = sp.nMain;
+        tail = n - (int64_t)sp.nMain * cta_chunks * sp.L;
+    }
+    sp.Ltail = (int)((((tail + cta_chunks - 1) / cta_chunks) + LS - 1) / LS * LS);
+    if (sp.Ltail < LS) sp.Ltail = LS;
+    sp.nCta = sp.nMain + (tail > 0 ? 1 : 0);
+    return sp;
+}
 
 // Runs K1/K2/K3 for an algebra.  SCAN_SUMMARY: K1 + total only (shard summary for time sharding); the
 // chunk aggregates stay in the workspace and the next SCAN_FULL call with the same key skips K1.
@@ -71,33 +116,7 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
         for (int a = 0; a < Alg::NOUT; ++a)
             if (!aligned16(Alg::out_ptr(p, a)))
                 return set_err(PSSGP_ERR_INVALID, "output array %d is not 16-byte aligned", a);
-    StreamPart sp;
-    sp.n = n;
-    {
-        constexpr int LS = Lay::LS;
-        const int64_t cta_chunks = (int64_t)NW * 32;
-        const int64_t C = h->num_sms > 1 ? h->num_sms - 1 : 1;  // main CTAs of the single wave (+ 1 tail CTA)
-        int64_t tail;
-        if (h->chunk_opt <= 0 && n >= C * cta_chunks * 8) {
-            // two chunk lengths L and L - LS: exactly C complete main CTAs, fewer than cta_chunks * LS rows left over
-            const int64_t L = (n / (C * cta_chunks * LS) + 1) * LS;       // C CTAs of L rows per chunk overshoot n
-            const int64_t shortfall = C * cta_chunks * L - n;              // > 0 rows to give back, LS rows per chunk
-            int64_t nShort = (shortfall + cta_chunks * LS - 1) / (cta_chunks * LS);
-            if (nShort > C) nShort = C;
-            sp.L = (int)L;
-            sp.nMain = (int)C;
-            sp.nLong = (int)(C - nShort);
-            tail = n - ((int64_t)sp.nLong * L + nShort * (L - LS)) * cta_chunks;
-        } else {
-            sp.L = pick_chunk(h, n, NW * 32, LS);
-            sp.nMain = (int)(n / (cta_chunks * sp.L));
-            sp.nLong = sp.nMain;
-            tail = n - (int64_t)sp.nMain * cta_chunks * sp.L;
-        }
-        sp.Ltail = (int)((((tail + cta_chunks - 1) / cta_chunks) + LS - 1) / LS * LS);
-        if (sp.Ltail < LS) sp.Ltail = LS;
-        sp.nCta = sp.nMain + (tail > 0 ? 1 : 0);
-    }
+    const StreamPart sp = make_partition<NW, Lay::LS>(h, n);
     const int L = sp.L;
     const int64_t nBlocks = sp.nCta;
     const int64_t nW = nBlocks;  // one aggregate per CTA of K1

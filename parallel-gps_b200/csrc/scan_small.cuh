@@ -11,14 +11,19 @@ constexpr int kMidThreads = 256;
 // One CTA (all of its threads).  wstate[s*nW + w] = state entering CTA w of K1/K3.  final_state = state after
 // everything.  sh: 32 * NAGG scalars of shared memory.  Runs either as its own kernel (scan_mid_kernel) or at
 // the end of K1 in the CTA that finishes last (scan_stream.cuh).
+// Barrier over a group of `nthreads` threads (multiple of 32) of the CTA: id 0 with the whole CTA is
+// __syncthreads(); other ids let two halves of a CTA run independent scans side by side.
+__device__ __forceinline__ void group_sync(int bar_id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthreads) : "memory");
+}
+
+// tid / nthreads: this thread's index in, and the size of, the thread group that runs the scan (whole warps).
 template <typename Alg>
 __device__ __forceinline__ void scan_mid_body(const typename Alg::Params& p, const typename Alg::scalar* wagg, long nW,
                                               typename Alg::scalar* wstate, typename Alg::scalar* final_state,
-                                              typename Alg::scalar* sh) {
+                                              typename Alg::scalar* sh, int tid, int nthreads, int bar_id) {
     using T = typename Alg::scalar;
-    const int tid = threadIdx.x;
     const int lane = tid & 31, wid = tid >> 5;
-    const int nthreads = blockDim.x;
     const long per = (nW + nthreads - 1) / nthreads;
     long i0 = (long)tid * per, i1 = i0 + per;
     if (i0 > nW) i0 = nW;
@@ -59,7 +64,7 @@ __device__ __forceinline__ void scan_mid_body(const typename Alg::Params& p, con
 #pragma unroll
     for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
     if (lane == 0) Alg::identity(ex);
-    __syncthreads();
+    group_sync(bar_id, nthreads);
     const int nwarps = nthreads >> 5;
     if (wid == 0) {
         T w[Alg::NAGG];
@@ -89,7 +94,7 @@ __device__ __forceinline__ void scan_mid_body(const typename Alg::Params& p, con
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) sh[e * 32 + lane] = wx[e];
     }
-    __syncthreads();
+    group_sync(bar_id, nthreads);
     T s[Alg::NSTATE];
     Alg::load_init(p, s);
     if (wid > 0) {
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kMidThreads)
 scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__ wagg, long nW,
                 typename Alg::scalar* __restrict__ wstate, typename Alg::scalar* __restrict__ final_state) {
     __shared__ typename Alg::scalar sh[32 * Alg::NAGG];
-    scan_mid_body<Alg>(p, wagg, nW, wstate, final_state, sh);
+    scan_mid_body<Alg>(p, wagg, nW, wstate, final_state, sh, (int)threadIdx.x, (int)blockDim.x, 0);
 }
 
 // Single CTA: out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding).

@@ -43,6 +43,12 @@
 #ifndef PSSGP_NWCAP
 #define PSSGP_NWCAP 8
 #endif
+#ifndef PSSGP_NST
+#define PSSGP_NST 1  // cp.async stages per warp (1: a stage is refilled while its last row is being processed)
+#endif
+#ifndef PSSGP_DIRECT_OUT
+#define PSSGP_DIRECT_OUT 0  // 1: outputs go straight from registers to global memory (no staging slots)
+#endif
 
 namespace pssgp {
 
@@ -106,8 +112,9 @@ template <typename Alg> struct StreamLayout {
         return a == 0 ? 0 : out_off(a - 1) + 32 * G::pitch(Alg::out_w(a - 1));
     }
     static constexpr int STAGE_BYTES = in_off(Alg::NIN);
-    static constexpr int OUT_BYTES = out_off(Alg::NOUT);
-    static constexpr int NST = 2;
+    static constexpr bool DIRECT_OUT = PSSGP_DIRECT_OUT != 0;
+    static constexpr int OUT_BYTES = DIRECT_OUT ? 0 : out_off(Alg::NOUT);
+    static constexpr int NST = PSSGP_NST;
     static constexpr int WARP_BYTES_REDUCE = NST * STAGE_BYTES;
     static constexpr int WARP_BYTES_APPLY = NST * STAGE_BYTES + OUT_BYTES;
     static constexpr int SMEM_BUDGET = 216 * 1024;
@@ -343,6 +350,46 @@ PSSGP_DEV void stream_stage_out_row(unsigned char* ostage, int lane, int r,
     }
 }
 
+// Registers -> global memory directly (no staging): row `krow` of every output array, 16-byte stores where
+// the row's elements are 16-byte aligned, scalar stores for the odd ends.  Neighbouring lanes write rows that
+// are a whole chunk apart, so every store instruction touches 32 different lines; L2 merges the partial
+// sectors of consecutive rows before they are written back.
+template <typename Alg, int A = 0>
+PSSGP_DEV void stream_direct_out_row(const typename Alg::Params& p, long krow,
+                                     const typename Alg::scalar (&orow)[Alg::NOUT][Alg::WMAX]) {
+    using T = typename Alg::scalar;
+    if constexpr (A < Alg::NOUT) {
+        constexpr int W = Alg::out_w(A);
+        constexpr int EPU = 16 / (int)sizeof(T);
+        T* dst = Alg::out_ptr(p, A) + krow * W;
+        const int mis = (int)((krow * W) & (EPU - 1));  // elements past the previous 16-byte boundary
+#pragma unroll
+        for (int m = 0; m < EPU; ++m) {
+            if (mis == m) {
+                constexpr int dummy = 0;
+                (void)dummy;
+                const int head = (EPU - m) % EPU < W ? (EPU - m) % EPU : W;
+#pragma unroll
+                for (int e = 0; e < W; ++e) {
+                    if (e < head) {
+                        __stcs(dst + e, orow[A][e]);
+                    } else if ((e - head) % EPU == 0 && e + EPU <= W) {
+                        if constexpr (sizeof(T) == 8) {
+                            __stcs(reinterpret_cast<double2*>(dst + e), make_double2((double)orow[A][e], (double)orow[A][e + 1]));
+                        } else {
+                            __stcs(reinterpret_cast<float4*>(dst + e), make_float4((float)orow[A][e], (float)orow[A][e + 1],
+                                                                                    (float)orow[A][(e + 2) % W], (float)orow[A][(e + 3) % W]));
+                        }
+                    } else if (e >= head + ((W - head) / EPU) * EPU) {
+                        __stcs(dst + e, orow[A][e]);
+                    }
+                }
+            }
+        }
+        stream_direct_out_row<Alg, A + 1>(p, krow, orow);
+    }
+}
+
 // Partition of the time axis (host-computed): nMain "main" CTAs of NW*32 complete chunks each - the first
 // nLong of them with chunks of L rows, the others with chunks of L - LS rows, so that nMain can be made
 // (number of SMs - 1) whatever n is - followed in time by at most one "tail" CTA that covers the remaining
@@ -376,6 +423,87 @@ template <typename Alg> struct WarpGeom {
         k_lo0 = Alg::REVERSE ? (k_lo + (long)lane * L) : (k_lo - (long)lane * L);
     }
 };
+
+// ---------------------------------------------------------------------------------------------
+// CTA-level scan of the per-thread chunk aggregates (tail of K1; also used by the fused forward kernel for
+// the aggregates of the reverse scans, FLIP = true: the thread that holds time-chunk c of a CTA plays the
+// role of scan-order thread NW*32-1-c, exactly as WarpGeom maps the threads of a REVERSE algebra).
+// Stores the lane-exclusive prefix of every chunk, the CTA-exclusive prefix of every warp and the CTA total.
+// blk_s = this CTA's index in scan order.  shw: NW * NAGG scalars of shared memory.  All threads must call.
+// ---------------------------------------------------------------------------------------------
+template <typename Alg, int NW, bool FLIP>
+PSSGP_DEV void cta_scan_publish(typename Alg::scalar (&a)[Alg::NAGG], int lane, int wid, long blk_s, long nCta,
+                                long nChunksPad, typename Alg::scalar* __restrict__ lane_excl,
+                                typename Alg::scalar* __restrict__ warp_excl, typename Alg::scalar* __restrict__ wagg,
+                                typename Alg::scalar* shw) {
+    using T = typename Alg::scalar;
+    if (FLIP) {
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) a[e] = shfl_idx_t(a[e], 31 - lane);
+        wid = NW - 1 - wid;
+    }
+    const long lc = blk_s * (NW * 32) + wid * 32 + lane;
+    // warp inclusive scan (earlier lane is the left operand)
+#pragma unroll 1
+    for (int off = 1; off < 32; off <<= 1) {
+        T o[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(a[e], off);
+        if (lane >= off) {
+            T r[Alg::NAGG];
+            Alg::combine(o, a, r);
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
+        }
+    }
+    // lane-exclusive prefix inside the warp
+    {
+        T ex[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
+        if (lane != 0) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + lc] = ex[e];
+        }
+    }
+    // CTA level: one warp scans the NW warp totals
+    if (lane == 31) {
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) shw[wid * Alg::NAGG + e] = a[e];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        T w[Alg::NAGG];
+        if (lane < NW) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) w[e] = shw[lane * Alg::NAGG + e];
+        } else {
+            Alg::identity(w);
+        }
+#pragma unroll 1
+        for (int off = 1; off < NW; off <<= 1) {
+            T o[Alg::NAGG];
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(w[e], off);
+            if (lane >= off && lane < NW) {
+                T r[Alg::NAGG];
+                Alg::combine(o, w, r);
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) w[e] = r[e];
+            }
+        }
+        // w = inclusive prefix over warps: warp l+1's exclusive prefix, and the CTA total at lane NW-1
+        const long gw = blk_s * NW + lane + 1;
+        if (lane < NW - 1) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) warp_excl[(long)e * (nCta * NW) + gw] = w[e];
+        }
+        if (lane == NW - 1) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blk_s] = w[e];
+        }
+    }
+}
 
 // ---------------------------------------------------------------------------------------------
 // K1: chunk aggregates, warp-exclusive prefixes, CTA-exclusive warp prefixes, CTA totals
@@ -444,67 +572,8 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             if (mine) Alg::append_flush(a, ctx, wg.k_lo, p, cr);
         }
     }
-    // warp inclusive scan (earlier lane is the left operand)
-#pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
-        T o[Alg::NAGG];
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(a[e], off);
-        if (lane >= off) {
-            T r[Alg::NAGG];
-            Alg::combine(o, a, r);
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
-        }
-    }
-    // lane-exclusive prefix inside the warp
-    {
-        T ex[Alg::NAGG];
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
-        if (lane != 0) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + wg.lc] = ex[e];
-        }
-    }
-    // CTA level: warp 0 scans the NW warp totals
     __shared__ T shw[NW * Alg::NAGG];
-    if (lane == 31) {
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) shw[wid * Alg::NAGG + e] = a[e];
-    }
-    __syncthreads();
-    if (wid == 0) {
-        T w[Alg::NAGG];
-        if (lane < NW) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) w[e] = shw[lane * Alg::NAGG + e];
-        } else {
-            Alg::identity(w);
-        }
-#pragma unroll 1
-        for (int off = 1; off < NW; off <<= 1) {
-            T o[Alg::NAGG];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(w[e], off);
-            if (lane >= off && lane < NW) {
-                T r[Alg::NAGG];
-                Alg::combine(o, w, r);
-#pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) w[e] = r[e];
-            }
-        }
-        // w = inclusive prefix over warps: warp l+1's exclusive prefix, and the CTA total at lane NW-1
-        const long gw = (long)blockIdx.x * NW + lane + 1;
-        if (lane < NW - 1) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) warp_excl[(long)e * (nCta * NW) + gw] = w[e];
-        }
-        if (lane == NW - 1) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blockIdx.x] = w[e];
-        }
-    }
+    cta_scan_publish<Alg, NW, false>(a, lane, wid, (long)blockIdx.x, nCta, nChunksPad, lane_excl, warp_excl, wagg, shw);
     // K2 folded into K1: the CTA that finishes last scans the CTA totals (wstate == nullptr: the caller runs
     // scan_mid_kernel / scan_total_kernel itself)
     if (wstate != nullptr) {
@@ -519,7 +588,7 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         __syncthreads();
         if (is_last) {
             __threadfence();
-            scan_mid_body<Alg>(p, wagg, nCta, wstate, final_state, sh_mid);
+            scan_mid_body<Alg>(p, wagg, nCta, wstate, final_state, sh_mid, (int)threadIdx.x, (int)blockDim.x, 0);
             if (threadIdx.x == 0) *ticket = 0u;
         }
     }
@@ -588,7 +657,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         }
         typename Alg::Carry cr;
         const long k_hi = wg.k_lo + L;
-        if (mine) Alg::carry_init(cr, ctx, wg.k_lo, k_hi < n ? k_hi : n, p);
+        if (mine || Alg::HAS_SIDE) Alg::carry_init(cr, ctx, wg.k_lo, k_hi < n ? k_hi : n, p);
 #pragma unroll 1
         for (int s = 0; s < nsub; ++s) {
             const int st = s % NST;
@@ -610,7 +679,9 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                 T orow[Alg::NOUT][Alg::WMAX];
                 bool has = false;
                 if (mine && k < n) has = Alg::step_row(st8, ctx, row, orow, k, p, acc, cr);
-                if (Alg::OUT_SHIFT == 0) {
+                if constexpr (Lay::DIRECT_OUT) {
+                    if (has) stream_direct_out_row<Alg>(p, k + Alg::OUT_SHIFT, orow);
+                } else if (Alg::OUT_SHIFT == 0) {
                     if (has) stream_stage_out_row<Alg>(osm, lane, r, orow);
                 } else {
                     // the step of row k+1 is taken when row k is visited (reverse scans only): its outputs
@@ -623,7 +694,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                     }
                 }
             }
-            if (Alg::OUT_SHIFT == 0) {
+            if (!Lay::DIRECT_OUT && Alg::OUT_SHIFT == 0) {
                 __syncwarp();
                 out.store(p, n, L, wg.fast, osm);
                 __syncwarp();  // staging slots are rewritten by the next sub-step
@@ -634,12 +705,21 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             T orow[Alg::NOUT][Alg::WMAX];
             bool has = false;
             if (mine) has = Alg::step_flush(st8, ctx, orow, wg.k_lo, p, acc, cr);
-            if (has) stream_stage_out_row<Alg>(osm, lane, 0, orow);
-            __syncwarp();
-            out.store(p, n, L, wg.fast, osm);
+            if constexpr (Lay::DIRECT_OUT) {
+                if (has) stream_direct_out_row<Alg>(p, wg.k_lo, orow);
+            } else {
+                if (has) stream_stage_out_row<Alg>(osm, lane, 0, orow);
+                __syncwarp();
+                out.store(p, n, L, wg.fast, osm);
+            }
         }
         if constexpr (Alg::HAS_DONE) {
             if (mine) Alg::step_done(acc, cr);
+        }
+        if constexpr (Alg::HAS_SIDE) {
+            // chunk aggregates of the scans that run in the opposite direction (fused_small.cuh)
+            if (mine) Alg::side_flush(st8, k_hi < n ? k_hi : n, p, cr);
+            Alg::template side_finish<NW>(p, cr, lane, wid, nCta, nChunksPad);
         }
     }
     if (Alg::NACC > 0) {

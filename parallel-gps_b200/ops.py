@@ -92,6 +92,24 @@ def pkf_backward(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=None, first_special=Tru
     return dP0, dFs, dQs, dH, dR
 
 
+def pkfs_grad(P0, Fs, Qs, H, R, y, g_ll):
+    """C ABI: pssgp_pkfs_grad (filter + log-likelihood + smoother + gradient of one whole series, fused).
+    -> (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR)."""
+    Fs, Qs, y = _al(Fs), _al(Qs), _al(y)
+    n, d = Fs.shape[0], Fs.shape[1]
+    kw = dict(dtype=Fs.dtype, device=Fs.device)
+    fms, sms = torch.empty((n, d), **kw), torch.empty((n, d), **kw)
+    fPs, sPs, dFs, dQs = (torch.empty((n, d, d), **kw) for _ in range(4))
+    ll, dR = torch.empty((1,), **kw), torch.empty((1,), **kw)
+    dP0 = torch.zeros((d, d), **kw)
+    dH = torch.empty((d,), **kw)
+    _lib.check(_lib.lib().pssgp_pkfs_grad(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs),
+                                         A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(g_ll), A.ptr(fms), A.ptr(fPs), A.ptr(ll),
+                                         A.ptr(sms), A.ptr(sPs), A.ptr(dP0), A.ptr(dFs), A.ptr(dQs), A.ptr(dH),
+                                         A.ptr(dR), A.stream_ptr(Fs.device)))
+    return (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR)
+
+
 # ---- time sharding (one contiguous shard per GPU) --------------------------------------------------------
 SMALL_D = 4  # d <= SMALL_D: register-resident kernels with packed symmetric aggregates; above: full matrices
 

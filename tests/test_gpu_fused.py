@@ -1,0 +1,124 @@
+"""GPU parity of the fused filter + smoother + gradient step (C ABI pssgp_pkfs_grad) against the CPU oracle
+(pkf, pks and torch autograd through pkf) — FP64 <= 1e-9 relative to ||reference||_inf, and against the
+three separate entry points at the benchmark's size."""
+import numpy as np
+import pytest
+import torch
+
+from util import O, make_problem, pkg, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda", 0)
+TOL = 1e-9
+
+
+def _ops():
+    pkg()
+    from pssgp_b200 import ops
+    return ops
+
+
+def sym(X):
+    return 0.5 * (X + X.transpose(-1, -2))
+
+
+def _check_against_oracle(name, T, seed, nan_frac=0.05, chunk=0):
+    ops = _ops()
+    from pssgp_b200 import _lib
+    t, y, cov, ssm = make_problem(name, T, seed=seed, nan_frac=nan_frac)
+    P0, Fs, Qs, H, R = [x.clone().requires_grad_(True) for x in ssm]
+    fm, fP, ll = O.pkf((P0, Fs, Qs, H, R), y[:, None], True)
+    g = 0.7
+    gP0, gFs, gQs, gH, gR = torch.autograd.grad(g * ll, (P0, Fs, Qs, H, R))
+    with torch.no_grad():
+        rsm, rsP = O.pks(ssm, fm.detach(), fP.detach())
+    d = lambda x: x.detach().to(DEV).contiguous()
+    yd = torch.as_tensor(y).to(DEV)
+    h = _lib.handle(torch.cuda.current_device())
+    h.set_option("chunk", chunk)
+    try:
+        (fms, fPs, lld), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(
+            d(P0), d(Fs), d(Qs), d(H).reshape(-1), d(R).reshape(-1), yd, torch.tensor([g], dtype=torch.float64, device=DEV))
+    finally:
+        h.set_option("chunk", 0)
+    assert rel_err(fms.cpu(), fm) < TOL and rel_err(fPs.cpu(), fP) < TOL
+    assert abs(float(lld) - float(ll)) <= TOL * max(1.0, abs(float(ll)))
+    assert rel_err(sms.cpu(), rsm) < TOL and rel_err(sPs.cpu(), rsP) < TOL
+    assert rel_err(dFs.cpu(), gFs) < TOL
+    assert rel_err(dQs.cpu(), sym(gQs)) < TOL
+    assert rel_err(dP0.cpu(), sym(gP0)) < TOL
+    scale = max(float(gH.abs().max()), 1e-300)
+    assert float((dH.cpu() - gH.reshape(-1)).abs().max()) / scale < TOL
+    assert abs(float(dR) - float(gR)) <= TOL * abs(float(gR))
+
+
+@pytest.mark.parametrize("name", ["matern12", "matern32", "matern52", "m32xm32", "rbf6"])
+@pytest.mark.parametrize("T", [1, 2, 3, 33, 129, 1000, 4097, 20011])
+def test_fused_step_vs_oracle(name, T):
+    if name == "rbf6" and T > 1000:
+        pytest.skip("generic-d path is covered by test_gpu_generic_d.py; here only the fall-through of the fused entry")
+    _check_against_oracle(name, T, seed=T + 2)
+
+
+@pytest.mark.parametrize("chunk", [2, 4, 8, 64, 258])
+def test_fused_step_chunk_invariance(chunk):
+    _check_against_oracle("matern52", 5003, seed=11, chunk=chunk)
+
+
+@pytest.mark.parametrize("variant", ["first", "last", "all", "none"])
+def test_fused_step_missing_observations(variant):
+    ops = _ops()
+    t, y, cov, ssm = make_problem("matern32", 700, seed=1, nan_frac=0.0)
+    yy = y.copy()
+    if variant == "first":
+        yy[0] = np.nan
+    elif variant == "last":
+        yy[-1] = np.nan
+    elif variant == "all":
+        yy[:] = np.nan
+    P0, Fs, Qs, H, R = [x.clone().requires_grad_(True) for x in ssm]
+    fm, fP, ll = O.pkf((P0, Fs, Qs, H, R), yy[:, None], True)
+    with torch.no_grad():
+        rsm, rsP = O.pks(ssm, fm.detach(), fP.detach())
+    d = lambda x: x.detach().to(DEV).contiguous()
+    (fms, fPs, lld), (sms, sPs), grads = ops.pkfs_grad(d(P0), d(Fs), d(Qs), d(H).reshape(-1), d(R).reshape(-1),
+                                                       torch.as_tensor(yy).to(DEV),
+                                                       torch.ones(1, dtype=torch.float64, device=DEV))
+    assert rel_err(fPs.cpu(), fP) < TOL and rel_err(sPs.cpu(), rsP) < TOL
+    assert float((sms.cpu() - rsm).abs().max()) < 1e-9
+    assert abs(float(lld) - float(ll)) <= TOL * max(1.0, abs(float(ll)))
+    if variant != "all":
+        gFs, gQs = torch.autograd.grad(ll, (Fs, Qs))
+        assert rel_err(grads[1].cpu(), gFs) < TOL and rel_err(grads[2].cpu(), sym(gQs)) < TOL
+    else:
+        assert float(grads[1].abs().max()) == 0.0 and float(grads[2].abs().max()) == 0.0
+
+
+def test_fused_step_matches_separate_calls_at_bench_size():
+    """N = 1e6 (BASELINE configs[1]): the oracle is too slow, so the fused step is checked against the
+    three separate scans (themselves oracle-checked at small sizes) and through the identity
+    'smoothed == filtered at the last step'."""
+    ops = _ops()
+    import bench
+    from pssgp_b200 import kernels
+    n = 1_000_000
+    t, y = bench.make_series(n)
+    with torch.no_grad():
+        sde = kernels.Matern52(1.0, 1.0).get_sde()
+    F, Pinf, H = sde.F.to(DEV).contiguous(), sde.P0.to(DEV).contiguous(), sde.H.to(DEV).reshape(-1).contiguous()
+    R = torch.tensor([0.1], dtype=torch.float64, device=DEV)
+    td = torch.as_tensor(t).to(DEV)
+    dts = td - torch.cat([torch.zeros(1, dtype=torch.float64, device=DEV), td[:-1]])
+    yd = torch.as_tensor(y).to(DEV)
+    g1 = torch.ones(1, dtype=torch.float64, device=DEV)
+    Fs, Qs = ops.discretise(F, Pinf, dts)
+    fms, fPs, ll, _ = ops.pkf(Pinf, Fs, Qs, H, R, yd)
+    sms, sPs, _ = ops.pks(Fs, Qs, fms, fPs)
+    ref_g = ops.pkf_backward(Pinf, Fs, Qs, H, R, yd, fms, fPs, g1)
+    (fms2, fPs2, ll2), (sms2, sPs2), g2 = ops.pkfs_grad(Pinf, Fs, Qs, H, R, yd, g1)
+    assert rel_err(fms2.cpu(), fms.cpu()) < 1e-12 and rel_err(fPs2.cpu(), fPs.cpu()) < 1e-12
+    assert abs(float(ll2) - float(ll)) <= 1e-12 * abs(float(ll))
+    assert rel_err(sms2.cpu(), sms.cpu()) < TOL and rel_err(sPs2.cpu(), sPs.cpu()) < TOL
+    for a, b in zip(g2, ref_g):
+        assert rel_err(a.cpu(), b.cpu()) < TOL
+    assert torch.equal(sms2[-1], fms2[-1])
