@@ -40,7 +40,8 @@ const char* pssgp_last_error(void);
 int pssgp_create(pssgp_handle** out, int device);
 int pssgp_destroy(pssgp_handle* h);
 /* Options: "chunk" = time steps per thread-chunk (0 = heuristic); "timing" = 1 brackets every
- * kernel launch with CUDA events on its stream (read back with pssgp_timing_report). */
+ * kernel launch with CUDA events on its stream (read back with pssgp_timing_report);
+ * "fused_reverse" = 1 makes pssgp_pkfs_grad run the smoother and adjoint recursions in one kernel. */
 int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t pssgp_launch_count(const pssgp_handle* h);

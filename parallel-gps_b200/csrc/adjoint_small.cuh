@@ -37,6 +37,8 @@ struct AdjointAlg {
     static constexpr bool FLUSH = true;
     static constexpr bool HAS_DONE = false;
     static constexpr bool HAS_SIDE = false;  // fused_small.cuh: extra per-chunk aggregates built by K3
+    static constexpr bool OUT8 = false;      // scan_stream.cuh: per-row output staging
+    __host__ __device__ static constexpr int out_shift(int) { return OUT_SHIFT; }
     static constexpr int NIN = 5, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? 1 : (a == 3 ? D : D * D); }
     __host__ __device__ static constexpr int out_w(int) { return D * D; }

@@ -160,6 +160,10 @@ int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value) {
         h->chunk_opt = value;
         return PSSGP_OK;
     }
+    if (strcmp(name, "fused_reverse") == 0) {
+        h->fused_reverse = value != 0;
+        return PSSGP_OK;
+    }
     return set_err(PSSGP_ERR_INVALID, "unknown option '%s'", name);
 }
 

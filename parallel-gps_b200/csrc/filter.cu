@@ -84,3 +84,9 @@ int pssgp_filter_fold(pssgp_handle* h, int dtype, int d, int nshards_before, con
 }
 
 }  // extern "C"
+
+#ifdef PSSGP_PHASES
+extern "C" int pssgp_debug_phases(unsigned long long* out, int count) {
+    return (int)cudaMemcpyFromSymbol(out, pssgp::g_phase, sizeof(unsigned long long) * count);
+}
+#endif

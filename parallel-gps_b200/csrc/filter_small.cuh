@@ -34,6 +34,8 @@ struct FilterAlg {
     static constexpr bool FLUSH = false;
     static constexpr bool HAS_DONE = true;
     static constexpr bool HAS_SIDE = false;  // fused_small.cuh: extra per-chunk aggregates built by K3  // step_done folds the chunk's log-likelihood pieces into acc
+    static constexpr bool OUT8 = false;      // scan_stream.cuh: per-row output staging
+    __host__ __device__ static constexpr int out_shift(int) { return OUT_SHIFT; }
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
 
     struct Params {

@@ -27,6 +27,7 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     using FF = FusedFwdAlg<T, D>;
     using SA = SmootherAlg<T, D>;
     using AA = AdjointAlg<T, D>;
+    using FR = FusedRevAlg<T, D>;
     constexpr int NW = StreamLayout<FA>::NW;
     constexpr int LS = StreamLayout<FA>::LS;
     // the fused step needs one partition of the time axis for all of its kernels
@@ -45,15 +46,15 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
     h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = h->pending_key[KIND_ADJOINT] = nullptr;
-    const int NAGG[3] = {FA::NAGG, SA::NAGG, AA::NAGG};
+    // the two reverse scans share one workspace (smoother rows first) so that K3' sees one aggregate / state
+    const int NAGG[3] = {FA::NAGG, SA::NAGG + AA::NAGG, AA::NAGG};
     for (int kind = 0; kind < 3; ++kind) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
         if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * NAGG[kind] * (size_t)nCta))) return rc;
         if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * NAGG[kind] * (size_t)nCta * NW))) return rc;
     }
     if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * FA::NSTATE * (size_t)nCta))) return rc;
-    if ((rc = ws_reserve(h, WS_WSTATE_S, sizeof(T) * SA::NSTATE * (size_t)nCta))) return rc;
-    if ((rc = ws_reserve(h, WS_WSTATE_A, sizeof(T) * AA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_WSTATE_S, sizeof(T) * (SA::NSTATE + AA::NSTATE) * (size_t)nCta))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (AA::NACC + 1) * (size_t)nCta))) return rc;
     T* part = (T*)h->buf[WS_PART];
 
@@ -71,8 +72,8 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     fp.n = n;
     fp.sm = {(T*)h->buf[WS_LANE + KIND_SMOOTHER], (T*)h->buf[WS_WEXCL + KIND_SMOOTHER],
              (T*)h->buf[WS_WAGG + KIND_SMOOTHER], (T*)h->buf[WS_WSTATE_S]};
-    fp.ad = {(T*)h->buf[WS_LANE + KIND_ADJOINT], (T*)h->buf[WS_WEXCL + KIND_ADJOINT],
-             (T*)h->buf[WS_WAGG + KIND_ADJOINT], (T*)h->buf[WS_WSTATE_A]};
+    fp.ad = {fp.sm.lane_excl + (size_t)SA::NAGG * nChunksPad, fp.sm.warp_excl + (size_t)SA::NAGG * nCta * NW,
+             (T*)h->buf[WS_WAGG + KIND_ADJOINT], fp.sm.wstate + (size_t)SA::NSTATE * nCta};
     fp.side_ticket = h->ticket + 1;
 
     // K1: chunk aggregates of the filter + scan over the CTA totals
@@ -98,7 +99,6 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     sp_.n = n;
     sp_.last_special = 1;
     sp_.Fnext = sp_.Qnext = sp_.init = nullptr;
-    launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st);
     typename AA::Params ap;
     ap.Fs = (const T*)Fs;
     ap.Qs = (const T*)Qs;
@@ -119,6 +119,20 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     ap.first_state = nullptr;
     ap.n = n;
     ap.first_special = 1;
+    if constexpr (StreamLayout<FR>::NW == NW) {
+        // option "fused_reverse": one kernel for both reverse recursions (one read of F, Q, y, fms, fPs instead of
+        // two).  Off by default: at d = 3 / FP64 the fused kernel is issue-bound at 254 registers per thread and
+        // takes longer (198 us) than the two separate ones (80 + 98 us); see DESIGN.md.
+        if (h->fused_reverse) {
+            if ((rc = stream_configure_apply<FR>(h->device))) return rc;
+            typename FR::Params rp;
+            rp.s = sp_;
+            rp.a = ap;
+            launch_apply<FR>(h, rp, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)dR, st);
+            return check_launch(h, "pkfs_grad", 3);
+        }
+    }
+    launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st);
     launch_apply<AA>(h, ap, sp, fp.ad.lane_excl, fp.ad.warp_excl, fp.ad.wstate, part, (T*)dR, st);
     return check_launch(h, "pkfs_grad", 4);
     }

@@ -275,4 +275,105 @@ struct FusedFwdAlg : FilterAlg<T, D> {
     }
 };
 
+// K3': RTS smoother recursion + adjoint recursion of the log-likelihood in one descending pass: both need
+// (F, Q) of row k+1 carried in registers and the filtered moments of row k from the same staged row.
+// State / aggregates are the smoother's followed by the adjoint's.  Outputs sms, sPs belong to the visited
+// row (out_shift 0), dFs, dQs to the row above it (out_shift 1, see adjoint_small.cuh).
+template <typename T, int D>
+struct FusedRevAlg {
+    using scalar = T;
+    using SA = SmootherAlg<T, D>;
+    using AA = AdjointAlg<T, D>;
+    static const char* name_apply() { return "pks_bwd_apply_fused"; }
+    static constexpr int NS = nsym(D);
+    static constexpr int NAGG = SA::NAGG + AA::NAGG;
+    static constexpr int NSTATE = SA::NSTATE + AA::NSTATE;
+    static constexpr int NACC = AA::NACC;
+    static constexpr bool REVERSE = true;
+    static constexpr int OUT_SHIFT = 1;
+    static constexpr bool FLUSH = true;
+    static constexpr bool HAS_DONE = false;
+    static constexpr bool HAS_SIDE = false;
+    static constexpr bool OUT8 = true;
+    static constexpr int NIN = 5, NOUT = 4, WMAX = D * D;
+    __host__ __device__ static constexpr int in_w(int a) { return AA::in_w(a); }
+    __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }
+    __host__ __device__ static constexpr int out_shift(int a) { return a < 2 ? 0 : 1; }
+
+    struct Params {
+        typename SA::Params s;
+        typename AA::Params a;
+    };
+    __host__ __device__ __forceinline__ static const T* in_ptr(const Params& p, int a) { return AA::in_ptr(p.a, a); }
+    __host__ __device__ __forceinline__ static T* out_ptr(const Params& p, int a) {
+        return a == 0 ? p.s.sms : (a == 1 ? p.s.sPs : (a == 2 ? p.a.dFs : p.a.dQs));
+    }
+    using Ctx = typename AA::Ctx;
+    PSSGP_DEV static void load_ctx(const Params& p, Ctx& c) { AA::load_ctx(p.a, c); }
+
+    // (F, Q, y) of the row above the one being visited; `has`: the adjoint step of that row is this chunk's
+    using Carry = typename AA::Carry;
+    PSSGP_DEV static void carry_init(Carry& c, const Ctx&, long, long k_hi, const Params& p) {
+        c.has = false;
+        if (k_hi < p.s.n) {
+            const T* pf = p.s.Fs + k_hi * (D * D);
+            const T* pq = p.s.Qs + k_hi * (D * D);
+            T qf[D * D];
+#pragma unroll
+            for (int e = 0; e < D * D; ++e) {
+                c.F[e] = __ldg(pf + e);
+                qf[e] = __ldg(pq + e);
+            }
+            SA::sym_pack(qf, c.Q);
+        }
+    }
+
+    PSSGP_DEV static void apply(const T* s, const T* a, T* s2) {
+        SA::apply(s, a, s2);
+        AA::apply(s + SA::NSTATE, a + SA::NAGG, s2 + SA::NSTATE);
+    }
+
+    PSSGP_DEV static int step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                  const Params& p, T* acc, Carry& c) {
+        T m[D], P[NS];
+        AA::row_moments(in, m, P);
+        // smoother (smoother_small.cuh step_row)
+        if (k == p.s.n - 1 && p.s.last_special) {
+#pragma unroll
+            for (int i = 0; i < D; ++i) s[i] = m[i];
+#pragma unroll
+            for (int e = 0; e < NS; ++e) s[D + e] = P[e];
+        } else {
+            T a[SA::NAGG], s2[SA::NSTATE];
+            SA::element(c.F, c.Q, m, P, a + SA::oE, a + SA::og, a + SA::oL);
+            SA::apply(s, a, s2);
+#pragma unroll
+            for (int e = 0; e < SA::NSTATE; ++e) s[e] = s2[e];
+        }
+#pragma unroll
+        for (int i = 0; i < D; ++i) out[0][i] = s[i];
+#pragma unroll
+        for (int i = 0; i < D; ++i)
+#pragma unroll
+            for (int j = 0; j < D; ++j) out[1][i * D + j] = s[D + sidx(i, j)];
+        // adjoint step of row k+1 (adjoint_small.cuh step_row)
+        int mask = 1;
+        if (c.has) {
+            AA::step_core(s + SA::NSTATE, cx, c, m, P, *reinterpret_cast<T(*)[2][WMAX]>(&out[2]), k + 1, p.a, acc);
+            mask |= 2;
+        }
+        AA::carry_set(c, in, k, p.a);
+        return mask;
+    }
+    PSSGP_DEV static int step_flush(T* s, const Ctx& cx, T (&out)[NOUT][WMAX], long k_lo, const Params& p, T* acc,
+                                    Carry& c) {
+        if (!c.has) return 0;
+        T m[D], P[NS];
+        AA::halo_moments(k_lo, p.a, m, P);
+        AA::step_core(s + SA::NSTATE, cx, c, m, P, *reinterpret_cast<T(*)[2][WMAX]>(&out[2]), k_lo, p.a, acc);
+        return 2;
+    }
+    PSSGP_DEV static void finish(const Params& p, int e, T tot, T* acc_out) { AA::finish(p.a, e, tot, acc_out); }
+};
+
 }  // namespace pssgp

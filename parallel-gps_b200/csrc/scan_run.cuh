@@ -69,7 +69,7 @@ int stream_configure_apply(int device) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // Partition of the time axis for CTAs of NW warps (see StreamPart): one resident wave, all SMs but one busy
-// with complete chunks, at most one short tail CTA.
+// with complete chunks of two lengths mixed inside every CTA, at most one short tail CTA.
 template <int NW, int LS>
 StreamPart make_partition(const pssgp_handle* h, int64_t n) {
     StreamPart sp;
@@ -78,19 +78,19 @@ StreamPart make_partition(const pssgp_handle* h, int64_t n) {
     const int64_t C = h->num_sms > 1 ? h->num_sms - 1 : 1;  // main CTAs of the single wave (+ 1 tail CTA)
     int64_t tail;
     if (h->chunk_opt <= 0 && n >= C * cta_chunks * 8) {
-        // two chunk lengths L and L - LS: exactly C complete main CTAs, fewer than cta_chunks * LS rows left over
-        const int64_t L = (n / (C * cta_chunks * LS) + 1) * LS;       // C CTAs of L rows per chunk overshoot n
-        const int64_t shortfall = C * cta_chunks * L - n;              // > 0 rows to give back, LS rows per chunk
-        int64_t nShort = (shortfall + cta_chunks * LS - 1) / (cta_chunks * LS);
-        if (nShort > C) nShort = C;
-        sp.L = (int)L;
+        const int64_t units = n / (32 * LS);               // warp-rows of LS rows each
+        const int64_t base_units = units / (C * NW);       // every warp gets at least this many
+        const int64_t n_long = units - base_units * C * NW;  // warps with one more: < C * NW
+        sp.L = (int)((base_units + 1) * LS);
+        sp.wl = (int)(n_long / C);
+        sp.cl = (int)(n_long % C);
         sp.nMain = (int)C;
-        sp.nLong = (int)(C - nShort);
-        tail = n - ((int64_t)sp.nLong * L + nShort * (L - LS)) * cta_chunks;
+        tail = n - units * 32 * LS;
     } else {
         sp.L = pick_chunk(h, n, NW * 32, LS);
+        sp.wl = NW;  // every warp "long"
+        sp.cl = 0;
         sp.nMain = (int)(n / (cta_chunks * sp.L));
-        sp.nLong = sp.nMain;
         tail = n - (int64_t)sp.nMain * cta_chunks * sp.L;
     }
     sp.Ltail = (int)((((tail + cta_chunks - 1) / cta_chunks) + LS - 1) / LS * LS);

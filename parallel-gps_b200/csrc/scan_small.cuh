@@ -8,6 +8,21 @@ namespace pssgp {
 
 constexpr int kMidThreads = 256;
 
+#ifdef PSSGP_PHASES  // tuning aid: %globaltimer stamps of the phases of K1 and of the scan over CTA totals (thread 0 of every CTA)
+static __device__ unsigned long long g_phase[1024 * 8];
+PSSGP_DEV void phase_stamp(int slot) {
+    if (threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_phase[blockIdx.x * 8 + slot] = t;
+    }
+}
+#define PSSGP_PHASE(slot) phase_stamp(slot)
+#else
+#define PSSGP_PHASE(slot)
+#endif
+
+
 // One CTA (all of its threads).  wstate[s*nW + w] = state entering CTA w of K1/K3.  final_state = state after
 // everything.  sh: 32 * NAGG scalars of shared memory.  Runs either as its own kernel (scan_mid_kernel) or at
 // the end of K1 in the CTA that finishes last (scan_stream.cuh).
@@ -43,84 +58,91 @@ __device__ __forceinline__ void scan_mid_body(const typename Alg::Params& p, con
             for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
         }
     }
-    // block-level exclusive scan of the per-thread aggregates
+    PSSGP_PHASE(4);
+    // Block-level exclusive scan of the per-thread aggregates.  The warp level (5 shuffle steps) and the level over
+    // warp totals (done by warp 0) run through ONE loop body, and all the applies below through another one: every
+    // inlined copy of combine / apply is several KB of straight-line code that would be fetched cold from the
+    // instruction cache for a handful of executions (measured ~3.5 us per cold copy of FilterAlg::combine, ~0.5 us warm).
+    const int nwarps = nthreads >> 5;
+    int logw = 0;
+    while ((1 << logw) < nwarps) ++logw;
+    T ex[Alg::NAGG];  // lane-exclusive within the warp
 #pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int lvl = 0;; ++lvl) {
+        if (lvl == 5) {
+            PSSGP_PHASE(5);
+            if (lane == 31) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) sh[e * 32 + wid] = a[e];
+            }
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
+            if (lane == 0) Alg::identity(ex);
+            group_sync(bar_id, nthreads);
+            if (wid != 0) break;
+            if (lane < nwarps) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) a[e] = sh[e * 32 + lane];
+            } else {
+                Alg::identity(a);
+            }
+        }
+        if (lvl == 5 + logw) break;
+        const int off = 1 << (lvl < 5 ? lvl : lvl - 5);
         T o[Alg::NAGG];
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(a[e], off);
-        if (lane >= off) {
+        if (lane >= off && (lvl < 5 || lane < nwarps)) {
             T r[Alg::NAGG];
             Alg::combine(o, a, r);
 #pragma unroll
             for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
         }
     }
-    if (lane == 31) {
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) sh[e * 32 + wid] = a[e];
-    }
-    T ex[Alg::NAGG];  // lane-exclusive within the warp
-#pragma unroll
-    for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
-    if (lane == 0) Alg::identity(ex);
-    group_sync(bar_id, nthreads);
-    const int nwarps = nthreads >> 5;
     if (wid == 0) {
-        T w[Alg::NAGG];
-        if (lane < nwarps) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) w[e] = sh[e * 32 + lane];
-        } else {
-            Alg::identity(w);
-        }
-#pragma unroll 1
-        for (int off = 1; off < nwarps; off <<= 1) {
-            T o[Alg::NAGG];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(w[e], off);
-            if (lane >= off && lane < nwarps) {
-                T r[Alg::NAGG];
-                Alg::combine(o, w, r);
-#pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) w[e] = r[e];
-            }
-        }
         // exclusive over warps
         T wx[Alg::NAGG];
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) wx[e] = shfl_up_t(w[e], 1);
+        for (int e = 0; e < Alg::NAGG; ++e) wx[e] = shfl_up_t(a[e], 1);
         if (lane == 0) Alg::identity(wx);
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) sh[e * 32 + lane] = wx[e];
     }
     group_sync(bar_id, nthreads);
+    PSSGP_PHASE(6);
     T s[Alg::NSTATE];
     Alg::load_init(p, s);
-    if (wid > 0) {
-        T w[Alg::NAGG];
+    // s = init o (prefix of the earlier warps) o (prefix of the earlier lanes), then item by item
+    const bool want_final = final_state != nullptr && i1 == nW;
+    const long nsteps = 2 + (i1 - i0);
+#pragma unroll 1
+    for (long j = 0; j < nsteps; ++j) {
+        T b[Alg::NAGG];
+        bool act;
+        if (j == 0) {
+            act = wid > 0;
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) w[e] = sh[e * 32 + wid];
-        T s2[Alg::NSTATE];
-        Alg::apply(s, w, s2);
+            for (int e = 0; e < Alg::NAGG; ++e) b[e] = sh[e * 32 + wid];
+        } else if (j == 1) {
+            act = lane > 0;
 #pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
-    }
-    if (lane > 0) {
-        T s2[Alg::NSTATE];
-        Alg::apply(s, ex, s2);
+            for (int e = 0; e < Alg::NAGG; ++e) b[e] = ex[e];
+        } else {
+            const long i = i0 + (j - 2);
 #pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
-    }
-    for (long i = i0; i < i1; ++i) {
+            for (int e = 0; e < Alg::NSTATE; ++e) wstate[(long)e * nW + i] = s[e];
+            act = (i + 1 < i1) || want_final;  // the state after the last item is only needed as the final state
+            if (act) {
 #pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) wstate[(long)e * nW + i] = s[e];
-        T b[Alg::NAGG], s2[Alg::NSTATE];
+                for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
+            }
+        }
+        if (act) {
+            T s2[Alg::NSTATE];
+            Alg::apply(s, b, s2);
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
-        Alg::apply(s, b, s2);
-#pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
+            for (int e = 0; e < Alg::NSTATE; ++e) s[e] = s2[e];
+        }
     }
     // the thread that owns the last warp total holds the final state
     if (final_state != nullptr && i1 == nW && i0 < nW) Alg::expand_state(s, final_state);

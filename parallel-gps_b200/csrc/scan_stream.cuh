@@ -46,9 +46,6 @@
 #ifndef PSSGP_NST
 #define PSSGP_NST 1  // cp.async stages per warp (1: a stage is refilled while its last row is being processed)
 #endif
-#ifndef PSSGP_DIRECT_OUT
-#define PSSGP_DIRECT_OUT 0  // 1: outputs go straight from registers to global memory (no staging slots)
-#endif
 
 namespace pssgp {
 
@@ -101,6 +98,13 @@ template <typename T> struct StreamGeom {
     __host__ __device__ static constexpr int iters(int w) { return (32 + groups(w) - 1) / groups(w); }
 };
 
+// Per-row output staging (OUT8): a segment is ONE row of W elements, a piece is one element.
+template <typename T> struct RowGeom {
+    __host__ __device__ static constexpr int pitch(int w) { return (w | 1) * (int)sizeof(T); }  // odd # of elements
+    __host__ __device__ static constexpr int groups(int w) { return 32 / w; }                   // whole rows per instruction
+    __host__ __device__ static constexpr int iters(int w) { return (32 + groups(w) - 1) / groups(w); }
+};
+
 template <typename Alg> struct StreamLayout {
     using T = typename Alg::scalar;
     using G = StreamGeom<T>;
@@ -112,8 +116,13 @@ template <typename Alg> struct StreamLayout {
         return a == 0 ? 0 : out_off(a - 1) + 32 * G::pitch(Alg::out_w(a - 1));
     }
     static constexpr int STAGE_BYTES = in_off(Alg::NIN);
-    static constexpr bool DIRECT_OUT = PSSGP_DIRECT_OUT != 0;
-    static constexpr int OUT_BYTES = DIRECT_OUT ? 0 : out_off(Alg::NOUT);
+    // OUT8 algebras stage and store their outputs one row at a time in element-sized pieces (half the staging
+    // memory of the 16-byte path, which needs LS rows per segment; twice the store instructions)
+    static constexpr bool OUT8 = Alg::OUT8;
+    __host__ __device__ static constexpr int out_off8(int a) {
+        return a == 0 ? 0 : out_off8(a - 1) + 32 * RowGeom<T>::pitch(Alg::out_w(a - 1));
+    }
+    static constexpr int OUT_BYTES = OUT8 ? out_off8(Alg::NOUT) : out_off(Alg::NOUT);
     static constexpr int NST = PSSGP_NST;
     static constexpr int WARP_BYTES_REDUCE = NST * STAGE_BYTES;
     static constexpr int WARP_BYTES_APPLY = NST * STAGE_BYTES + OUT_BYTES;
@@ -289,6 +298,86 @@ template <typename Alg> struct StreamOut {
     }
 };
 
+// Bounds-checked variant of the per-row store (tail CTA only; out of line like issue_array_checked).
+template <typename T, int W>
+__device__ __noinline__ void store_row_checked(unsigned char* ptr, int g, const void* base, long total_bytes, long step,
+                                               const unsigned char* src) {
+    using G = RowGeom<T>;
+    constexpr int GR = G::groups(W), IT = G::iters(W), PITCH = G::pitch(W);
+#pragma unroll 1
+    for (int i = 0; i < IT; ++i) {
+        if (g + GR * i < 32) {
+            unsigned char* dp = ptr + (long)i * step;
+            const long gb = dp - (const unsigned char*)base;
+            if (gb >= 0 && gb + (long)sizeof(T) <= total_bytes)
+                *reinterpret_cast<T*>(dp) = *reinterpret_cast<const T*>(src + i * GR * PITCH);
+        }
+    }
+}
+
+// Output arrays of an OUT8 algebra: one cursor per array pointing at this lane's piece of the NEXT row to be
+// written (rows are written in visiting order, one per call, for every array of a shift class at once).
+template <typename Alg> struct StreamOut8 {
+    using T = typename Alg::scalar;
+    using G = RowGeom<T>;
+    using Lay = StreamLayout<Alg>;
+    PieceCursor pc[Alg::NOUT];
+
+    template <int A = 0> PSSGP_DEV void init(const typename Alg::Params& p, long k_lo0, int L, int lane) {
+        if constexpr (A < Alg::NOUT) {
+            constexpr int W = Alg::out_w(A);
+            const int g = lane / W, off = lane - g * W;
+            pc[A].g = (g < G::groups(W)) ? g : 32;
+            pc[A].soff = (unsigned)(g * G::pitch(W) + off * (int)sizeof(T));
+            const long row0 = k_lo0 + (Alg::REVERSE ? -(long)g * L + (L - 1) : (long)g * L);
+            pc[A].ptr = (unsigned char*)Alg::out_ptr(p, A) + (row0 * W + off) * (long)sizeof(T);
+            init<A + 1>(p, k_lo0, L, lane);
+        }
+    }
+    // stores the staged row of every array whose out_shift is SHIFT and moves their cursors to the next row
+    template <int SHIFT, int A = 0>
+    PSSGP_DEV void store(const typename Alg::Params& p, long n, int L, bool fast, const unsigned char* ostage) {
+        if constexpr (A < Alg::NOUT) {
+            if constexpr (Alg::out_shift(A) == SHIFT) {
+                constexpr int W = Alg::out_w(A);
+                constexpr int GR = G::groups(W), IT = G::iters(W), PITCH = G::pitch(W);
+                const long step = (long)(Alg::REVERSE ? -L : L) * (long)(W * sizeof(T)) * GR;
+                const unsigned char* src = ostage + Lay::out_off8(A) + pc[A].soff;
+                if (fast) {
+                    if (pc[A].g < 32) {
+#pragma unroll
+                        for (int i = 0; i < IT; ++i)
+                            if (GR * IT <= 32 || i < IT - 1 || pc[A].g + GR * i < 32)
+                                __stcs(reinterpret_cast<T*>(pc[A].ptr + (long)i * step),
+                                       *reinterpret_cast<const T*>(src + i * GR * PITCH));
+                    }
+                } else {
+                    store_row_checked<T, W>(pc[A].ptr, pc[A].g, Alg::out_ptr(p, A), n * (long)(W * sizeof(T)), step, src);
+                }
+                pc[A].ptr += Alg::REVERSE ? -(long)(W * sizeof(T)) : (long)(W * sizeof(T));
+            }
+            store<SHIFT, A + 1>(p, n, L, fast, ostage);
+        }
+    }
+};
+
+// Registers -> this lane's one-row staging slot of every output array whose bit (1 << out_shift) is set in mask.
+template <typename Alg, int A = 0>
+PSSGP_DEV void stream_stage_out_row8(unsigned char* ostage, int lane, int mask,
+                                     const typename Alg::scalar (&orow)[Alg::NOUT][Alg::WMAX]) {
+    using T = typename Alg::scalar;
+    using Lay = StreamLayout<Alg>;
+    if constexpr (A < Alg::NOUT) {
+        constexpr int W = Alg::out_w(A);
+        if ((mask >> Alg::out_shift(A)) & 1) {
+            T* dst = reinterpret_cast<T*>(ostage + Lay::out_off8(A) + lane * RowGeom<T>::pitch(W));
+#pragma unroll
+            for (int e = 0; e < W; ++e) dst[e] = orow[A][e];
+        }
+        stream_stage_out_row8<Alg, A + 1>(ostage, lane, mask, orow);
+    }
+}
+
 // Copies row r of this lane's slot of every input array from a stage into registers (128-bit shared
 // loads; a 16-byte unit shared by two rows is simply read by both).
 template <typename Alg, int A = 0>
@@ -315,6 +404,23 @@ PSSGP_DEV void stream_fetch_row(const unsigned char* stage, int lane, int r,
             }
         }
         stream_fetch_row<Alg, A + 1>(stage, lane, r, row);
+    }
+}
+
+// Same with a run-time row index (element-sized shared loads): lets the row loop stay rolled, which halves the
+// code of the loop body (OUT8 algebras: the fused reverse step is otherwise too large for the instruction cache).
+template <typename Alg, int A = 0>
+PSSGP_DEV void stream_fetch_row_rt(const unsigned char* stage, int lane, int r,
+                                   typename Alg::scalar (&row)[Alg::NIN][Alg::WMAX]) {
+    using T = typename Alg::scalar;
+    using G = StreamGeom<T>;
+    using Lay = StreamLayout<Alg>;
+    if constexpr (A < Alg::NIN) {
+        constexpr int W = Alg::in_w(A);
+        const T* src = reinterpret_cast<const T*>(stage + Lay::in_off(A) + lane * G::pitch(W)) + r * W;
+#pragma unroll
+        for (int e = 0; e < W; ++e) row[A][e] = src[e];
+        stream_fetch_row_rt<Alg, A + 1>(stage, lane, r, row);
     }
 }
 
@@ -350,55 +456,17 @@ PSSGP_DEV void stream_stage_out_row(unsigned char* ostage, int lane, int r,
     }
 }
 
-// Registers -> global memory directly (no staging): row `krow` of every output array, 16-byte stores where
-// the row's elements are 16-byte aligned, scalar stores for the odd ends.  Neighbouring lanes write rows that
-// are a whole chunk apart, so every store instruction touches 32 different lines; L2 merges the partial
-// sectors of consecutive rows before they are written back.
-template <typename Alg, int A = 0>
-PSSGP_DEV void stream_direct_out_row(const typename Alg::Params& p, long krow,
-                                     const typename Alg::scalar (&orow)[Alg::NOUT][Alg::WMAX]) {
-    using T = typename Alg::scalar;
-    if constexpr (A < Alg::NOUT) {
-        constexpr int W = Alg::out_w(A);
-        constexpr int EPU = 16 / (int)sizeof(T);
-        T* dst = Alg::out_ptr(p, A) + krow * W;
-        const int mis = (int)((krow * W) & (EPU - 1));  // elements past the previous 16-byte boundary
-#pragma unroll
-        for (int m = 0; m < EPU; ++m) {
-            if (mis == m) {
-                constexpr int dummy = 0;
-                (void)dummy;
-                const int head = (EPU - m) % EPU < W ? (EPU - m) % EPU : W;
-#pragma unroll
-                for (int e = 0; e < W; ++e) {
-                    if (e < head) {
-                        __stcs(dst + e, orow[A][e]);
-                    } else if ((e - head) % EPU == 0 && e + EPU <= W) {
-                        if constexpr (sizeof(T) == 8) {
-                            __stcs(reinterpret_cast<double2*>(dst + e), make_double2((double)orow[A][e], (double)orow[A][e + 1]));
-                        } else {
-                            __stcs(reinterpret_cast<float4*>(dst + e), make_float4((float)orow[A][e], (float)orow[A][e + 1],
-                                                                                    (float)orow[A][(e + 2) % W], (float)orow[A][(e + 3) % W]));
-                        }
-                    } else if (e >= head + ((W - head) / EPU) * EPU) {
-                        __stcs(dst + e, orow[A][e]);
-                    }
-                }
-            }
-        }
-        stream_direct_out_row<Alg, A + 1>(p, krow, orow);
-    }
-}
-
-// Partition of the time axis (host-computed): nMain "main" CTAs of NW*32 complete chunks each - the first
-// nLong of them with chunks of L rows, the others with chunks of L - LS rows, so that nMain can be made
-// (number of SMs - 1) whatever n is - followed in time by at most one "tail" CTA that covers the remaining
-// rows with its own (short) chunk length Ltail.  Only the tail CTA ever sees a missing row, so only it pays
-// for bounds checks; being short it finishes early instead of holding up the single wave.
+// Partition of the time axis (host-computed): nMain "main" CTAs of NW warps x 32 complete chunks, followed in
+// time by at most one "tail" CTA that covers the remaining rows with its own (short) chunk length Ltail.  Inside a
+// main CTA the first warps (in time order) have chunks of L rows and the others of L - LS rows: wl + 1 long warps
+// in the first cl CTAs, wl in the others, so that nMain can be (number of SMs - 1) whatever n is, every main
+// CTA carries the same number of rows to within 32 * LS, and fewer than 32 * LS rows are left for the tail CTA.
+// Only the tail CTA ever sees a missing row, so only it pays for bounds checks.
 struct StreamPart {
     long n;
     int L, Ltail;
-    int nLong, nMain, nCta;
+    int wl, cl;
+    int nMain, nCta;
 };
 
 // Geometry shared by K1 and K3.
@@ -406,20 +474,28 @@ template <typename Alg> struct WarpGeom {
     long lc;      // global logical chunk (scan order): index into the workspace arrays
     long k_lo;    // first row of this lane's chunk
     long k_lo0;   // first row of lane 0's chunk
-    int L, nsub;
+    int L, nsub;  // rows per chunk and sub-steps of this warp
     bool fast;    // main CTA: every row of every chunk exists
     PSSGP_DEV WarpGeom(const StreamPart& sp, int NW, int lane, int wid) {
         constexpr int LS = StreamGeom<typename Alg::scalar>::LS;
         const int tb = Alg::REVERSE ? (sp.nCta - 1 - (int)blockIdx.x) : (int)blockIdx.x;  // CTA in time order
         fast = tb < sp.nMain;
-        L = tb < sp.nLong ? sp.L : (fast ? sp.L - LS : sp.Ltail);
-        nsub = L / LS;
         const int tbm = fast ? tb : sp.nMain;  // main CTAs before this one
-        const long row_begin = ((long)tbm * sp.L - (long)(tbm > sp.nLong ? tbm - sp.nLong : 0) * LS) * (NW * 32);
+        const long long_before = (long)tbm * sp.wl + (tbm < sp.cl ? tbm : sp.cl);  // long warps before this CTA
+        const long row_begin = ((long)tbm * NW * (sp.L - LS) + long_before * LS) * 32;
         const int tl = wid * 32 + lane;                             // thread in scan order
         const int ct = Alg::REVERSE ? (NW * 32 - 1 - tl) : tl;      // chunk of the CTA in time order
         lc = (long)blockIdx.x * (NW * 32) + tl;
-        k_lo = row_begin + (long)ct * L;
+        if (fast) {
+            const int nl = sp.wl + (tb < sp.cl ? 1 : 0);  // long warps of this CTA
+            const int wt = ct >> 5, lw = ct & 31;         // warp (time order) and chunk inside it
+            L = wt < nl ? sp.L : sp.L - LS;
+            k_lo = row_begin + ((long)wt * (sp.L - LS) + (long)(wt < nl ? wt : nl) * LS) * 32 + (long)lw * L;
+        } else {
+            L = sp.Ltail;
+            k_lo = row_begin + (long)ct * L;
+        }
+        nsub = L / LS;
         k_lo0 = Alg::REVERSE ? (k_lo + (long)lane * L) : (k_lo - (long)lane * L);
     }
 };
@@ -432,75 +508,68 @@ template <typename Alg> struct WarpGeom {
 // blk_s = this CTA's index in scan order.  shw: NW * NAGG scalars of shared memory.  All threads must call.
 // ---------------------------------------------------------------------------------------------
 template <typename Alg, int NW, bool FLIP>
-PSSGP_DEV void cta_scan_publish(typename Alg::scalar (&a)[Alg::NAGG], int lane, int wid, long blk_s, long nCta,
+PSSGP_DEV void cta_scan_publish(const typename Alg::scalar (&a_in)[Alg::NAGG], int lane, int wid, long blk_s, long nCta,
                                 long nChunksPad, typename Alg::scalar* __restrict__ lane_excl,
                                 typename Alg::scalar* __restrict__ warp_excl, typename Alg::scalar* __restrict__ wagg,
                                 typename Alg::scalar* shw) {
     using T = typename Alg::scalar;
-    if (FLIP) {
+    // private copy: it is handed to the out-of-line operators by address, which would otherwise pull the caller's
+    // register-resident aggregate into local memory for the whole kernel
+    T a[Alg::NAGG];
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) a[e] = shfl_idx_t(a[e], 31 - lane);
-        wid = NW - 1 - wid;
-    }
+    for (int e = 0; e < Alg::NAGG; ++e) a[e] = FLIP ? shfl_idx_t(a_in[e], 31 - lane) : a_in[e];
+    if (FLIP) wid = NW - 1 - wid;
     const long lc = blk_s * (NW * 32) + wid * 32 + lane;
-    // warp inclusive scan (earlier lane is the left operand)
+    // Warp-inclusive scan (5 shuffle steps; the earlier lane is the left operand), then the scan over the NW warp
+    // totals by warp 0, through ONE loop body so that the CTA executes a single inlined copy of combine
+    // (see scan_mid_body about cold instruction fetches).
+    constexpr int LOGNW = NW > 16 ? 5 : (NW > 8 ? 4 : (NW > 4 ? 3 : (NW > 2 ? 2 : (NW > 1 ? 1 : 0))));
 #pragma unroll 1
-    for (int off = 1; off < 32; off <<= 1) {
+    for (int lvl = 0;; ++lvl) {
+        if (lvl == 5) {
+            // lane-exclusive prefix inside the warp
+            T ex[Alg::NAGG];
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
+            if (lane != 0) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + lc] = ex[e];
+            }
+            if (lane == 31) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) shw[wid * Alg::NAGG + e] = a[e];
+            }
+            __syncthreads();
+            if (wid != 0) break;
+            if (lane < NW) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) a[e] = shw[lane * Alg::NAGG + e];
+            } else {
+                Alg::identity(a);
+            }
+        }
+        if (lvl == 5 + LOGNW) break;
+        const int off = 1 << (lvl < 5 ? lvl : lvl - 5);
         T o[Alg::NAGG];
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(a[e], off);
-        if (lane >= off) {
+        if (lane >= off && (lvl < 5 || lane < NW)) {
             T r[Alg::NAGG];
             Alg::combine(o, a, r);
 #pragma unroll
             for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
         }
     }
-    // lane-exclusive prefix inside the warp
-    {
-        T ex[Alg::NAGG];
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
-        if (lane != 0) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) lane_excl[(long)e * nChunksPad + lc] = ex[e];
-        }
-    }
-    // CTA level: one warp scans the NW warp totals
-    if (lane == 31) {
-#pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) shw[wid * Alg::NAGG + e] = a[e];
-    }
-    __syncthreads();
     if (wid == 0) {
-        T w[Alg::NAGG];
-        if (lane < NW) {
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) w[e] = shw[lane * Alg::NAGG + e];
-        } else {
-            Alg::identity(w);
-        }
-#pragma unroll 1
-        for (int off = 1; off < NW; off <<= 1) {
-            T o[Alg::NAGG];
-#pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(w[e], off);
-            if (lane >= off && lane < NW) {
-                T r[Alg::NAGG];
-                Alg::combine(o, w, r);
-#pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) w[e] = r[e];
-            }
-        }
-        // w = inclusive prefix over warps: warp l+1's exclusive prefix, and the CTA total at lane NW-1
+        // a = inclusive prefix over warps: warp l+1's exclusive prefix, and the CTA total at lane NW-1
         const long gw = blk_s * NW + lane + 1;
         if (lane < NW - 1) {
 #pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) warp_excl[(long)e * (nCta * NW) + gw] = w[e];
+            for (int e = 0; e < Alg::NAGG; ++e) warp_excl[(long)e * (nCta * NW) + gw] = a[e];
         }
         if (lane == NW - 1) {
 #pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blk_s] = w[e];
+            for (int e = 0; e < Alg::NAGG; ++e) wagg[(long)e * nCta + blk_s] = a[e];
         }
     }
 }
@@ -525,6 +594,7 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
     const WarpGeom<Alg> wg(sp, NW, lane, wid);
     const int nsub = wg.nsub, L = wg.L;
     const long n = sp.n;
+    PSSGP_PHASE(0);
 
     T a[Alg::NAGG];
     Alg::identity(a);
@@ -573,7 +643,9 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         }
     }
     __shared__ T shw[NW * Alg::NAGG];
+    PSSGP_PHASE(1);
     cta_scan_publish<Alg, NW, false>(a, lane, wid, (long)blockIdx.x, nCta, nChunksPad, lane_excl, warp_excl, wagg, shw);
+    PSSGP_PHASE(2);
     // K2 folded into K1: the CTA that finishes last scans the CTA totals (wstate == nullptr: the caller runs
     // scan_mid_kernel / scan_total_kernel itself)
     if (wstate != nullptr) {
@@ -586,10 +658,13 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             is_last = (t == gridDim.x - 1);
         }
         __syncthreads();
+        PSSGP_PHASE(3);
         if (is_last) {
             __threadfence();
             scan_mid_body<Alg>(p, wagg, nCta, wstate, final_state, sh_mid, (int)threadIdx.x, (int)blockDim.x, 0);
             if (threadIdx.x == 0) *ticket = 0u;
+            __syncthreads();
+            PSSGP_PHASE(7);
         }
     }
 }
@@ -609,6 +684,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
     constexpr int NACC1 = Alg::NACC > 0 ? Alg::NACC : 1;
+    constexpr int ROW_UNROLL = Lay::OUT8 ? 1 : LS;  // OUT8: one rolled copy of the row body (run-time row index)
     const long nCta = sp.nCta;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -628,7 +704,9 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         StreamIn<Alg> in;
         in.init(p, wg.k_lo0, L, nsub, lane);
         StreamOut<Alg> out;
-        out.init(p, wg.k_lo0, L, nsub, lane);
+        StreamOut8<Alg> out8;
+        if constexpr (Lay::OUT8) out8.init(p, wg.k_lo0, L, lane);
+        else out.init(p, wg.k_lo0, L, nsub, lane);
 #pragma unroll 1
         for (int s = 0; s < NST; ++s) {
             if (s < nsub) in.issue(p, n, L, wg.fast, wsm_addr + s * Lay::STAGE_BYTES);
@@ -636,24 +714,30 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         }
         const bool mine = wg.k_lo < n;
         T st8[Alg::NSTATE];
+        {
+            // state entering this chunk = CTA state o warp prefix o lane prefix, on temporaries (see cta_scan_publish)
+            T sl[Alg::NSTATE];
 #pragma unroll
-        for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = wstate[(long)e * nCta + blockIdx.x];
-        if (wid != 0) {
-            T ex[Alg::NAGG], s2[Alg::NSTATE];
-            const long gw = (long)blockIdx.x * NW + wid;
+            for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = wstate[(long)e * nCta + blockIdx.x];
+            if (wid != 0) {
+                T ex[Alg::NAGG], s2[Alg::NSTATE];
+                const long gw = (long)blockIdx.x * NW + wid;
 #pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = warp_excl[(long)e * (nCta * NW) + gw];
-            Alg::apply(st8, ex, s2);
+                for (int e = 0; e < Alg::NAGG; ++e) ex[e] = warp_excl[(long)e * (nCta * NW) + gw];
+                Alg::apply(sl, ex, s2);
 #pragma unroll
-            for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = s2[e];
-        }
-        if (lane != 0 && mine) {
-            T ex[Alg::NAGG], s2[Alg::NSTATE];
+                for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = s2[e];
+            }
+            if (lane != 0 && mine) {
+                T ex[Alg::NAGG], s2[Alg::NSTATE];
 #pragma unroll
-            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = lane_excl[(long)e * nChunksPad + wg.lc];
-            Alg::apply(st8, ex, s2);
+                for (int e = 0; e < Alg::NAGG; ++e) ex[e] = lane_excl[(long)e * nChunksPad + wg.lc];
+                Alg::apply(sl, ex, s2);
 #pragma unroll
-            for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = s2[e];
+                for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = s2[e];
+            }
+#pragma unroll
+            for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = sl[e];
         }
         typename Alg::Carry cr;
         const long k_hi = wg.k_lo + L;
@@ -664,12 +748,13 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             cp_async_wait<NST - 1>();
             __syncwarp();
             const long k0 = wg.k_lo + (long)(Alg::REVERSE ? (nsub - 1 - s) : s) * LS;
-#pragma unroll
+#pragma unroll ROW_UNROLL
             for (int rr = 0; rr < LS; ++rr) {
                 const int r = Alg::REVERSE ? (LS - 1 - rr) : rr;
                 const long k = k0 + r;
                 T row[Alg::NIN][Alg::WMAX];
-                stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
+                if constexpr (Lay::OUT8) stream_fetch_row_rt<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
+                else stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
                 if (rr == LS - 1) {
                     // the stage is drained: hand it back to the copy engine before the last row's arithmetic
                     __syncwarp();
@@ -677,24 +762,34 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                     cp_async_commit();
                 }
                 T orow[Alg::NOUT][Alg::WMAX];
-                bool has = false;
-                if (mine && k < n) has = Alg::step_row(st8, ctx, row, orow, k, p, acc, cr);
-                if constexpr (Lay::DIRECT_OUT) {
-                    if (has) stream_direct_out_row<Alg>(p, k + Alg::OUT_SHIFT, orow);
-                } else if (Alg::OUT_SHIFT == 0) {
-                    if (has) stream_stage_out_row<Alg>(osm, lane, r, orow);
+                if constexpr (Lay::OUT8) {
+                    // one row at a time: step_row returns a mask of out_shift classes it produced (bit 0: outputs
+                    // of row k, bit 1: outputs of row k+1, delayed by one visit)
+                    int hm = 0;
+                    if (mine && k < n) hm = Alg::step_row(st8, ctx, row, orow, k, p, acc, cr);
+                    stream_stage_out_row8<Alg>(osm, lane, hm, orow);
+                    __syncwarp();
+                    out8.template store<0>(p, n, L, wg.fast, osm);
+                    if (!(s == 0 && rr == 0)) out8.template store<1>(p, n, L, wg.fast, osm);
+                    __syncwarp();
                 } else {
-                    // the step of row k+1 is taken when row k is visited (reverse scans only): its outputs
-                    // belong to the slot above; the top row completes the segment of the previous sub-step
-                    if (has) stream_stage_out_row<Alg>(osm, lane, (r + 1) % LS, orow);
-                    if (rr == 0 && s > 0) {
-                        __syncwarp();
-                        out.store(p, n, L, wg.fast, osm);
-                        __syncwarp();
+                    bool has = false;
+                    if (mine && k < n) has = Alg::step_row(st8, ctx, row, orow, k, p, acc, cr);
+                    if (Alg::OUT_SHIFT == 0) {
+                        if (has) stream_stage_out_row<Alg>(osm, lane, r, orow);
+                    } else {
+                        // the step of row k+1 is taken when row k is visited (reverse scans only): its outputs
+                        // belong to the slot above; the top row completes the segment of the previous sub-step
+                        if (has) stream_stage_out_row<Alg>(osm, lane, (r + 1) % LS, orow);
+                        if (rr == 0 && s > 0) {
+                            __syncwarp();
+                            out.store(p, n, L, wg.fast, osm);
+                            __syncwarp();
+                        }
                     }
                 }
             }
-            if (!Lay::DIRECT_OUT && Alg::OUT_SHIFT == 0) {
+            if (!Lay::OUT8 && Alg::OUT_SHIFT == 0) {
                 __syncwarp();
                 out.store(p, n, L, wg.fast, osm);
                 __syncwarp();  // staging slots are rewritten by the next sub-step
@@ -703,11 +798,15 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         cp_async_wait<0>();
         if constexpr (Alg::FLUSH) {
             T orow[Alg::NOUT][Alg::WMAX];
-            bool has = false;
-            if (mine) has = Alg::step_flush(st8, ctx, orow, wg.k_lo, p, acc, cr);
-            if constexpr (Lay::DIRECT_OUT) {
-                if (has) stream_direct_out_row<Alg>(p, wg.k_lo, orow);
+            if constexpr (Lay::OUT8) {
+                int hm = 0;
+                if (mine) hm = Alg::step_flush(st8, ctx, orow, wg.k_lo, p, acc, cr);
+                stream_stage_out_row8<Alg>(osm, lane, hm & 2, orow);
+                __syncwarp();
+                out8.template store<1>(p, n, L, wg.fast, osm);
             } else {
+                bool has = false;
+                if (mine) has = Alg::step_flush(st8, ctx, orow, wg.k_lo, p, acc, cr);
                 if (has) stream_stage_out_row<Alg>(osm, lane, 0, orow);
                 __syncwarp();
                 out.store(p, n, L, wg.fast, osm);

@@ -33,6 +33,8 @@ struct SmootherAlg {
     static constexpr bool FLUSH = false;
     static constexpr bool HAS_DONE = false;
     static constexpr bool HAS_SIDE = false;  // fused_small.cuh: extra per-chunk aggregates built by K3
+    static constexpr bool OUT8 = false;      // scan_stream.cuh: per-row output staging
+    __host__ __device__ static constexpr int out_shift(int) { return OUT_SHIFT; }
     static constexpr int NIN = 4, NOUT = 2, WMAX = D * D;
     __host__ __device__ static constexpr int in_w(int a) { return a == 2 ? D : D * D; }
     __host__ __device__ static constexpr int out_w(int a) { return a == 0 ? D : D * D; }

@@ -8,7 +8,7 @@ cd "$(dirname "$0")/../parallel-gps_b200/csrc"
 mkdir -p ../lib_var ../build_var/$name
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 pids=()
-for f in filter smoother adjoint; do
+for f in filter smoother adjoint fused; do
   nvcc $ARCH -lineinfo -O3 -std=c++17 -Xcompiler -fPIC "$@" -c -o ../build_var/$name/$f.o $f.cu &
   pids+=($!)
 done

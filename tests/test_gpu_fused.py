@@ -22,25 +22,27 @@ def sym(X):
     return 0.5 * (X + X.transpose(-1, -2))
 
 
-def _check_against_oracle(name, T, seed, nan_frac=0.05, chunk=0):
+def _check_against_oracle(name, T, seed, nan_frac=0.05, chunk=0, fused_reverse=0):
     ops = _ops()
     from pssgp_b200 import _lib
     t, y, cov, ssm = make_problem(name, T, seed=seed, nan_frac=nan_frac)
     P0, Fs, Qs, H, R = [x.clone().requires_grad_(True) for x in ssm]
-    fm, fP, ll = O.pkf((P0, Fs, Qs, H, R), y[:, None], True)
+    fm, fP, ll = O.pkf((P0, Fs, Qs, H, R), y[:, None], True, max_parallel=max(T, 10000))
     g = 0.7
     gP0, gFs, gQs, gH, gR = torch.autograd.grad(g * ll, (P0, Fs, Qs, H, R))
     with torch.no_grad():
-        rsm, rsP = O.pks(ssm, fm.detach(), fP.detach())
+        rsm, rsP = O.pks(ssm, fm.detach(), fP.detach(), max_parallel=max(T, 10000))
     d = lambda x: x.detach().to(DEV).contiguous()
     yd = torch.as_tensor(y).to(DEV)
     h = _lib.handle(torch.cuda.current_device())
     h.set_option("chunk", chunk)
+    h.set_option("fused_reverse", fused_reverse)
     try:
         (fms, fPs, lld), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(
             d(P0), d(Fs), d(Qs), d(H).reshape(-1), d(R).reshape(-1), yd, torch.tensor([g], dtype=torch.float64, device=DEV))
     finally:
         h.set_option("chunk", 0)
+        h.set_option("fused_reverse", 0)
     assert rel_err(fms.cpu(), fm) < TOL and rel_err(fPs.cpu(), fP) < TOL
     assert abs(float(lld) - float(ll)) <= TOL * max(1.0, abs(float(ll)))
     assert rel_err(sms.cpu(), rsm) < TOL and rel_err(sPs.cpu(), rsP) < TOL
@@ -53,8 +55,10 @@ def _check_against_oracle(name, T, seed, nan_frac=0.05, chunk=0):
 
 
 @pytest.mark.parametrize("name", ["matern12", "matern32", "matern52", "m32xm32", "rbf6"])
-@pytest.mark.parametrize("T", [1, 2, 3, 33, 129, 1000, 4097, 20011])
+@pytest.mark.parametrize("T", [1, 2, 3, 33, 129, 1000, 4097, 20011, 400003])
 def test_fused_step_vs_oracle(name, T):
+    if T > 100000 and name != "matern52":
+        pytest.skip("one large case (the two-length main partition) is enough")
     if name == "rbf6" and T > 1000:
         pytest.skip("generic-d path is covered by test_gpu_generic_d.py; here only the fall-through of the fused entry")
     _check_against_oracle(name, T, seed=T + 2)
@@ -63,6 +67,15 @@ def test_fused_step_vs_oracle(name, T):
 @pytest.mark.parametrize("chunk", [2, 4, 8, 64, 258])
 def test_fused_step_chunk_invariance(chunk):
     _check_against_oracle("matern52", 5003, seed=11, chunk=chunk)
+
+
+@pytest.mark.parametrize("name", ["matern12", "matern32", "matern52", "m32xm32"])
+@pytest.mark.parametrize("T", [1, 2, 33, 1000, 20011, 400003])
+def test_fused_reverse_kernel_vs_oracle(name, T):
+    """option fused_reverse = 1: smoother + adjoint recursions in one kernel (per-row output staging)."""
+    if T > 100000 and name != "matern52":
+        pytest.skip("one large case is enough")
+    _check_against_oracle(name, T, seed=T + 5, fused_reverse=1)
 
 
 @pytest.mark.parametrize("variant", ["first", "last", "all", "none"])
