@@ -275,11 +275,15 @@ def main():
         model = StateSpaceGP((t_pin, y_pin), kernels.Matern52(1.0, 1.0), noise_variance=NOISE, parallel=True,
                              max_parallel=2 * n)
 
+        mean_pin = torch.empty((n, 1), dtype=torch.float64).pin_memory()
+        var_pin = torch.empty((n, 1), dtype=torch.float64).pin_memory()
+
         def e2e_step():
             model.data = (t_pin, y_pin)  # H2D of this step's inputs from pinned memory
             ll = model.maximum_log_likelihood_objective()
             grads = torch.autograd.grad(ll, model.trainable_variables)
-            mean, var = model.predict_f(q_pin.numpy())  # numpy in -> numpy out (D2H of the result)
+            # queries from pinned memory, posterior mean / variance read back into pinned memory (D2H of the result)
+            mean, var = model.predict_f(q_pin, out=(mean_pin, var_pin))
             return float(ll), [float(g) for g in grads], mean, var
 
         for _ in range(W):
@@ -292,7 +296,8 @@ def main():
         dt = (time.perf_counter() - t0) / K
         e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * 2 * n + 8 * n),
                "d2h_bytes_per_step": int(8 * 2 * n + 8 * 4), "ms_per_step": dt * 1e3,
-               "api": "StateSpaceGP.data= ; maximum_log_likelihood_objective + autograd.grad ; predict_f(N queries)"}
+               "api": "StateSpaceGP.data= (pinned t, y) ; maximum_log_likelihood_objective + autograd.grad ; "
+                      "predict_f(N pinned queries, out=pinned mean/var)"}
     else:
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "model-level e2e is measured at n_gpus=1"}
@@ -323,8 +328,18 @@ def main():
     if dom is not None:
         avg_s = ktimes[dom][1] / max(ktimes[dom][0], 1) * 1e-3
         achieved = alg_bytes.get(dom, 0) * n / avg_s / 1e9
+        # measured DRAM traffic of that kernel per launch (ncu --set full capture of the same workload, committed
+        # under profiles/); null when the capture does not cover this kernel or this n
+        traffic = None
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            if int(tr.get("n", 0)) == n and dom in tr["kernels"]:
+                traffic = tr["kernels"][dom]["dram_bytes_read"] + tr["kernels"][dom]["dram_bytes_write"]
+        except Exception:
+            pass
         roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                    "frac": achieved / hbm_peak, "traffic": traffic, "alg_bytes_per_launch": alg_bytes.get(dom, 0) * n,
+                    "peak_source": peak_src,
                     "share_of_step": ktimes[dom][1] / sum(v[1] for v in ktimes.values())}
     stage_bytes = s * (12 * d * d + 4 * d + 2)
     step_roof = {"alg_bytes_per_timestep": stage_bytes, "achieved_gbs": stage_bytes * n * world / (ms_dev * 1e-3) / 1e9,

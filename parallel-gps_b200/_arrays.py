@@ -75,6 +75,18 @@ def to_device(x, dtype, device, key=None):
     return src.to(device, non_blocking=True)
 
 
+def to_host_into(t, out):
+    """Device->host read of a result straight into a caller-provided host tensor (pinned for an asynchronous
+    copy at full PCIe speed); returns `out` after the copy has completed."""
+    if not isinstance(out, torch.Tensor) or out.is_cuda:
+        raise TypeError("out must be a host torch tensor")
+    if out.numel() != t.numel() or out.dtype != t.dtype or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {t.dtype} host tensor with {t.numel()} elements")
+    out.view(t.shape).copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return out
+
+
 def to_host(t, out=None):
     """Device->host read of a result (into pinned memory), returned as numpy."""
     nbytes = t.numel() * t.element_size()

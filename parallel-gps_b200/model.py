@@ -126,9 +126,11 @@ class StateSpaceGP:
         dts = time_steps(ts, 0., ts.dtype, ts.device)
         return _LogLikelihood.apply(sde.F, sde.P0, sde.H, R, dts, Y.reshape(-1))
 
-    def predict_f(self, Xnew, full_cov=False, full_output_cov=False):
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False, out=None):
         """model.py:92-111: merge query times as NaN observations, filter + smooth, project with H.
-        Returns (mean[K,1], var[K,1]) — numpy for host inputs, CUDA tensors for device inputs."""
+        Returns (mean[K,1], var[K,1]) — numpy for host inputs, CUDA tensors for device inputs.
+        ``out=(mean_buf, var_buf)``: host torch tensors (pinned for full PCIe speed) that receive the result
+        directly, without the intermediate staging copy of the numpy path; they are returned."""
         ts, ys = self._data
         dtype, dev = ts.dtype, ts.device
         Xd = A.to_device(Xnew, dtype, dev, "Xnew").reshape(-1)
@@ -145,6 +147,8 @@ class StateSpaceGP:
             rm, rP = sms[all_flags], sPs[all_flags]
             mean = rm @ Hd.reshape(-1, 1)
             var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)
+        if out is not None:
+            return A.to_host_into(mean, out[0]), A.to_host_into(var, out[1])
         if A.is_device_tensor(Xnew):
             return mean, var
         return A.to_host(mean, "pred_mean"), A.to_host(var, "pred_var")
