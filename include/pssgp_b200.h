@@ -153,6 +153,20 @@ int pssgp_adjoint_fold(pssgp_handle* h, int dtype, int d, int nshards_after,
                        const void* summaries, void* state_out, void* stream);
 
 /*
+ * Time sharding, fused: pssgp_pkf on one shard (same arguments) that also builds, in the same pass, the chunk
+ * aggregates of the smoother and adjoint scans and writes their shard summaries (layouts as pssgp_pks_summary /
+ * pssgp_pkf_backward_summary) — i.e. pssgp_pkf + pssgp_pks_summary + pssgp_pkf_backward_summary without the two
+ * extra passes over (Fs, Qs, y, fms, fPs).  last_special / Fnext / Qnext as in pssgp_pks.  The pssgp_pks and
+ * pssgp_pkf_backward calls that follow on the same arrays skip their reduce kernels.  If pssgp_pkf_summary ran on
+ * the same (Fs, n) just before, its chunk aggregates are reused (no second filter reduce pass).
+ */
+int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d,
+                             const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,
+                             const void* y, const void* m0, int first_special, int last_special,
+                             const void* Fnext, const void* Qnext,
+                             void* fms, void* fPs, void* ll, void* sm_summary, void* ad_summary, void* stream);
+
+/*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].
  */
 int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d,

@@ -75,6 +75,9 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     fp.ad = {fp.sm.lane_excl + (size_t)SA::NAGG * nChunksPad, fp.sm.warp_excl + (size_t)SA::NAGG * nCta * NW,
              (T*)h->buf[WS_WAGG + KIND_ADJOINT], fp.sm.wstate + (size_t)SA::NSTATE * nCta};
     fp.side_ticket = h->ticket + 1;
+    fp.last_special = 1;
+    fp.Fnext = fp.Qnext = nullptr;
+    fp.sm_summary = fp.ad_summary = nullptr;
 
     // K1: chunk aggregates of the filter + scan over the CTA totals
     {
@@ -138,10 +141,104 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     }
 }
 
+// One shard of a time-sharded series: seeded filter recursion (pssgp_pkf) + chunk aggregates and shard summaries of
+// both reverse scans, left in the workspace for the pssgp_pks / pssgp_pkf_backward calls that follow.
+template <typename T, int D>
+int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
+                            const void* R, const void* y, const void* m0, int first_special, int last_special,
+                            const void* Fnext, const void* Qnext, void* fms, void* fPs, void* ll, void* sm_summary,
+                            void* ad_summary, cudaStream_t st) {
+    using FA = FilterAlg<T, D>;
+    using FF = FusedFwdAlg<T, D>;
+    using SA = SmootherAlg<T, D>;
+    using AA = AdjointAlg<T, D>;
+    constexpr int NW = StreamLayout<FA>::NW;
+    constexpr int LS = StreamLayout<FA>::LS;
+    if constexpr (StreamLayout<FF>::NW != NW || StreamLayout<SA>::NW != NW || StreamLayout<AA>::NW != NW) {
+        return kNotFused;
+    } else {
+    int rc;
+    if ((rc = stream_configure<FA>(h->device))) return rc;
+    if ((rc = stream_configure_apply<FF>(h->device))) return rc;
+    const void* arrs[] = {Fs, Qs, y, fms, fPs};
+    for (const void* a : arrs)
+        if (!aligned16(a)) return set_err(PSSGP_ERR_INVALID, "pkf_with_summaries: arrays must be 16-byte aligned");
+    const StreamPart sp = make_partition<NW, LS>(h, n);
+    const int64_t nCta = sp.nCta;
+    const int64_t nChunksPad = nCta * NW * 32;
+    const bool reuse = h->pending_key[KIND_FILTER] == Fs && h->pending_n[KIND_FILTER] == n &&
+                       h->pending_L[KIND_FILTER] == sp.L;
+    h->pending_key[KIND_FILTER] = nullptr;
+    const int NAGG[3] = {FA::NAGG, SA::NAGG, AA::NAGG};
+    for (int kind = reuse ? 1 : 0; kind < 3; ++kind) {
+        if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
+        if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * NAGG[kind] * (size_t)nCta))) return rc;
+        if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * NAGG[kind] * (size_t)nCta * NW))) return rc;
+    }
+    if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * FA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (AA::NACC + 1) * (size_t)nCta))) return rc;
+    typename FF::Params fp;
+    fp.Fs = (const T*)Fs;
+    fp.Qs = (const T*)Qs;
+    fp.y = (const T*)y;
+    fp.H = (const T*)H;
+    fp.R = (const T*)R;
+    fp.P0 = (const T*)P0;
+    fp.m0 = (const T*)m0;
+    fp.fms = (T*)fms;
+    fp.fPs = (T*)fPs;
+    fp.first_special = first_special;
+    fp.n = n;
+    fp.sm = {(T*)h->buf[WS_LANE + KIND_SMOOTHER], (T*)h->buf[WS_WEXCL + KIND_SMOOTHER],
+             (T*)h->buf[WS_WAGG + KIND_SMOOTHER], (T*)nullptr};
+    fp.ad = {(T*)h->buf[WS_LANE + KIND_ADJOINT], (T*)h->buf[WS_WEXCL + KIND_ADJOINT],
+             (T*)h->buf[WS_WAGG + KIND_ADJOINT], (T*)nullptr};
+    fp.side_ticket = h->ticket + 1;
+    fp.last_special = last_special;
+    fp.Fnext = (const T*)Fnext;
+    fp.Qnext = (const T*)Qnext;
+    fp.sm_summary = (T*)sm_summary;
+    fp.ad_summary = (T*)ad_summary;
+    const typename FA::Params& bp = fp;
+    int nl = 2;
+    if (!reuse) {
+        using Lay = StreamLayout<FA>;
+        PSSGP_LAUNCH(h, FA::name_reduce(), st,
+                     (stream_reduce_kernel<FA><<<(unsigned)nCta, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
+                         bp, sp, nChunksPad, (T*)h->buf[WS_LANE + KIND_FILTER], (T*)h->buf[WS_WEXCL + KIND_FILTER],
+                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1)));
+    } else {
+        // the chunk aggregates are those pssgp_pkf_summary left behind: only the scan over the CTA totals is missing
+        int midThreads = kMidThreads;
+        if (nCta < kMidThreads) midThreads = (int)(((nCta + 31) / 32) * 32);
+        PSSGP_LAUNCH(h, FA::name_mid(), st,
+                     (scan_mid_kernel<FA><<<1, midThreads, 0, st>>>(bp, (const T*)h->buf[WS_WAGG + KIND_FILTER], nCta,
+                                                                   (T*)h->buf[WS_WSTATE], (T*)nullptr)));
+    }
+    launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
+                     (const T*)h->buf[WS_WSTATE], (T*)h->buf[WS_PART], (T*)ll, st);
+    // pssgp_pks (key: fPs) and pssgp_pkf_backward (key: fms) on the same arrays skip their reduce kernels
+    h->pending_key[KIND_SMOOTHER] = fPs;
+    h->pending_key[KIND_ADJOINT] = fms;
+    h->pending_n[KIND_SMOOTHER] = h->pending_n[KIND_ADJOINT] = n;
+    h->pending_L[KIND_SMOOTHER] = h->pending_L[KIND_ADJOINT] = sp.L;
+    return check_launch(h, "pkf_with_summaries", nl);
+    }
+}
+
 static int fused_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
                           const void* H, const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll,
                           void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
     DISPATCH_SMALL(pkfs_grad_impl, h, n, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
+    return kNotFused;
+}
+
+static int with_summaries_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs,
+                                   const void* Qs, const void* H, const void* R, const void* y, const void* m0,
+                                   int first_special, int last_special, const void* Fnext, const void* Qnext, void* fms,
+                                   void* fPs, void* ll, void* sm_summary, void* ad_summary, cudaStream_t st) {
+    DISPATCH_SMALL(pkf_with_summaries_impl, h, n, P0, Fs, Qs, H, R, y, m0, first_special, last_special, Fnext, Qnext, fms,
+                   fPs, ll, sm_summary, ad_summary, st);
     return kNotFused;
 }
 
@@ -167,6 +264,27 @@ int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0
         return rc;
     return pssgp_pkf_backward(h, dtype, n, d, P0, nullptr, Fs, Qs, H, R, y, fms, fPs, g_ll, 1, nullptr, dP0, dFs, dQs,
                               dH, dR, nullptr, stream);
+}
+
+int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs,
+                             const void* Qs, const void* H, const void* R, const void* y, const void* m0,
+                             int first_special, int last_special, const void* Fnext, const void* Qnext, void* fms,
+                             void* fPs, void* ll, void* sm_summary, void* ad_summary, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs || !sm_summary || !ad_summary)
+        return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    if (!last_special && (!Fnext || !Qnext))
+        return set_err(PSSGP_ERR_INVALID, "pkf_with_summaries: Fnext/Qnext required when last_special == 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = with_summaries_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, m0, first_special, last_special, Fnext, Qnext, fms,
+                                 fPs, ll, sm_summary, ad_summary, st);
+    if (rc != kNotFused) return rc;
+    // generic state dimension (or no common partition): filter, then the two summaries from their own reduce passes
+    if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, nullptr, stream))) return rc;
+    if ((rc = pssgp_pks_summary(h, dtype, n, d, Fs, Qs, fms, fPs, last_special, Fnext, Qnext, sm_summary, stream)))
+        return rc;
+    return pssgp_pkf_backward_summary(h, dtype, n, d, P0, m0, Fs, Qs, H, R, y, fms, fPs, first_special, ad_summary, stream);
 }
 
 }  // extern "C"

@@ -13,7 +13,8 @@
 // and the two reverse apply passes share one read of their inputs.  Same arithmetic per element as
 // smoother_small.cuh / adjoint_small.cuh (reference: pssgp/kalman/parallel.py:155-184 for the smoother,
 // TF autodiff of :121-152 for the gradient); only the association order of the chunk aggregates differs.
-// Single shard only (first step and last step are the global ones).
+// pssgp_pkfs_grad runs the three kernels on a whole series; pssgp_pkf_with_summaries runs K2' on one shard of a
+// time-sharded series and leaves the reverse aggregates for pssgp_pks / pssgp_pkf_backward.
 #pragma once
 #include "adjoint_small.cuh"
 #include "filter_small.cuh"
@@ -45,6 +46,14 @@ struct FusedFwdAlg : FilterAlg<T, D> {
         long n;
         SideWs<T> sm, ad;
         unsigned int* side_ticket;
+        // time sharding: the shard's last step is not the global last one: F, Q of the step after it (halo)
+        int last_special;
+        const T* Fnext;
+        const T* Qnext;
+        // non-null: the last CTA writes the shard summaries of both reverse scans instead of scanning the CTA totals
+        // (the states entering this shard from the right are not known yet: pssgp_pks / pssgp_pkf_backward finish)
+        T* sm_summary;
+        T* ad_summary;
     };
 
     struct Carry : Base::Carry {
@@ -205,7 +214,7 @@ struct FusedFwdAlg : FilterAlg<T, D> {
     // from the halo row k_hi, or last_smoothing_element (parallel.py:155-156) at the end of the series.
     PSSGP_DEV static void side_flush(const T* s, long k_hi, const Params& p, Carry& cr) {
         T el[SA::NAGG];
-        if (k_hi >= p.n) {
+        if (k_hi >= p.n && p.last_special) {
 #pragma unroll
             for (int e = 0; e < D * D; ++e) el[SA::oE + e] = T(0);
 #pragma unroll
@@ -214,8 +223,8 @@ struct FusedFwdAlg : FilterAlg<T, D> {
             for (int e = 0; e < NS; ++e) el[SA::oL + e] = s[D + e];
         } else {
             T F[D * D], qf[D * D], Q[NS], FP[D * D], mp[D], Pp[NS];
-            const T* pf = p.Fs + k_hi * (D * D);
-            const T* pq = p.Qs + k_hi * (D * D);
+            const T* pf = k_hi >= p.n ? p.Fnext : p.Fs + k_hi * (D * D);
+            const T* pq = k_hi >= p.n ? p.Qnext : p.Qs + k_hi * (D * D);
 #pragma unroll
             for (int e = 0; e < D * D; ++e) {
                 F[e] = __ldg(pf + e);
@@ -254,15 +263,27 @@ struct FusedFwdAlg : FilterAlg<T, D> {
         if (is_last) {
             __threadfence();
             constexpr int HALF = (NW / 2) * 32;
+            const bool summaries = p.sm_summary != nullptr;
             if (NW >= 2) {
                 if ((int)threadIdx.x < HALF) {
-                    typename SA::Params sp{};
-                    scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, HALF, 1);
+                    if (summaries) {
+                        scan_total_body<SA>(p.sm.wagg, nCta, p.sm_summary, sh_mid_s, (int)threadIdx.x, HALF, 1);
+                    } else {
+                        typename SA::Params sp{};
+                        scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, HALF, 1);
+                    }
                 } else if ((int)threadIdx.x < 2 * HALF) {
-                    typename AA::Params ap{};
-                    scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, (int)threadIdx.x - HALF,
-                                      HALF, 2);
+                    if (summaries) {
+                        scan_total_body<AA>(p.ad.wagg, nCta, p.ad_summary, sh_mid_a, (int)threadIdx.x - HALF, HALF, 2);
+                    } else {
+                        typename AA::Params ap{};
+                        scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, (int)threadIdx.x - HALF,
+                                          HALF, 2);
+                    }
                 }
+            } else if (summaries) {
+                scan_total_body<SA>(p.sm.wagg, nCta, p.sm_summary, sh_mid_s, (int)threadIdx.x, 32, 1);
+                scan_total_body<AA>(p.ad.wagg, nCta, p.ad_summary, sh_mid_a, (int)threadIdx.x, 32, 2);
             } else {
                 typename SA::Params sp{};
                 scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, 32, 1);

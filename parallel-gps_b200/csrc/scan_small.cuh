@@ -157,14 +157,13 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
     scan_mid_body<Alg>(p, wagg, nW, wstate, final_state, sh, (int)threadIdx.x, (int)blockDim.x, 0);
 }
 
-// Single CTA: out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding).
+// out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding), by a group of `nthreads`
+// threads of one CTA (see scan_mid_body for tid / nthreads / bar_id).  sh: (nthreads / 32) * NAGG scalars.
 template <typename Alg>
-__global__ void __launch_bounds__(kMidThreads)
-scan_total_kernel(const typename Alg::scalar* __restrict__ wagg, long nW, typename Alg::scalar* __restrict__ out) {
+__device__ __forceinline__ void scan_total_body(const typename Alg::scalar* wagg, long nW, typename Alg::scalar* out,
+                                                typename Alg::scalar* sh, int tid, int nthreads, int bar_id) {
     using T = typename Alg::scalar;
-    __shared__ T sh[(kMidThreads / 32) * Alg::NAGG];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int nthreads = blockDim.x;
+    const int lane = tid & 31, wid = tid >> 5;
     const long per = (nW + nthreads - 1) / nthreads;
     long i0 = (long)tid * per, i1 = i0 + per;
     if (i0 > nW) i0 = nW;
@@ -174,7 +173,7 @@ scan_total_kernel(const typename Alg::scalar* __restrict__ wagg, long nW, typena
     for (long i = i0; i < i1; ++i) {
         T b[Alg::NAGG], r[Alg::NAGG];
 #pragma unroll
-        for (int e = 0; e < Alg::NAGG; ++e) b[e] = wagg[(long)e * nW + i];
+        for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
         Alg::combine(a, b, r);
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
@@ -196,7 +195,7 @@ scan_total_kernel(const typename Alg::scalar* __restrict__ wagg, long nW, typena
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) sh[wid * Alg::NAGG + e] = a[e];
     }
-    __syncthreads();
+    group_sync(bar_id, nthreads);
     if (tid == 0) {
         const int nwarps = nthreads >> 5;
         for (int w = 1; w < nwarps; ++w) {
@@ -210,6 +209,13 @@ scan_total_kernel(const typename Alg::scalar* __restrict__ wagg, long nW, typena
 #pragma unroll
         for (int e = 0; e < Alg::NAGG; ++e) out[e] = a[e];
     }
+}
+
+template <typename Alg>
+__global__ void __launch_bounds__(kMidThreads)
+scan_total_kernel(const typename Alg::scalar* __restrict__ wagg, long nW, typename Alg::scalar* __restrict__ out) {
+    __shared__ typename Alg::scalar sh[(kMidThreads / 32) * Alg::NAGG];
+    scan_total_body<Alg>(wagg, nW, out, sh, (int)threadIdx.x, (int)blockDim.x, 0);
 }
 
 // One thread: s = init; for i in 0..count-1: s = s o summaries[i*stride ...]; out = Alg::expand(s).

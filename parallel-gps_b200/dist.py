@@ -24,6 +24,7 @@ class TimeShard:
             from . import ops as backend
         self.ops = backend
         self._state_in = None   # m | P entering this shard (from the filter phase)
+        self._rev = None        # (fms, smoother summary, adjoint summary) when the filter pass built them
         self._halo = None       # (Fnext, Qnext)
 
     # ---- collectives ---------------------------------------------------------------------------------
@@ -48,8 +49,12 @@ class TimeShard:
         return self.rank == self.world - 1
 
     # ---- filter --------------------------------------------------------------------------------------
-    def filter(self, P0, Fs, Qs, H, R, y, reduce_ll=True):
+    def filter(self, P0, Fs, Qs, H, R, y, reduce_ll=True, with_reverse_summaries=False):
+        """with_reverse_summaries: the smoother and the gradient will follow on the same arrays — the filter pass
+        also builds their chunk aggregates and shard summaries (C ABI pssgp_pkf_with_summaries), so that
+        smoother_and_grad starts directly with the exchange."""
         d = Fs.shape[1]
+        self._rev = None
         summ = self.ops.pkf_summary(P0, Fs, Qs, H, R, y, self.first)
         msg = torch.cat([summ, Fs[0].reshape(-1), Qs[0].reshape(-1)])
         gathered = self._all_gather(msg)
@@ -65,8 +70,14 @@ class TimeShard:
             st = self.ops.filter_fold(P0, None, gathered[:, :na].contiguous(), self.rank)
             m_in, P_in = st[:d].contiguous(), st[d:].reshape(d, d).contiguous()
         self._state_in = (m_in, P_in)
-        fms, fPs, ll, fin = self.ops.pkf(P_in, Fs, Qs, H, R, y, m0=m_in, first_special=self.first, want_ll=True,
-                                         want_final=False)
+        if with_reverse_summaries and hasattr(self.ops, "pkf_with_summaries"):
+            fms, fPs, ll, s_sm, s_ad = self.ops.pkf_with_summaries(P_in, Fs, Qs, H, R, y, m0=m_in,
+                                                                   first_special=self.first, last_special=self.last,
+                                                                   Fnext=self._halo[0], Qnext=self._halo[1])
+            self._rev = (fms, s_sm, s_ad)
+        else:
+            fms, fPs, ll, fin = self.ops.pkf(P_in, Fs, Qs, H, R, y, m0=m_in, first_special=self.first, want_ll=True,
+                                             want_final=False)
         if reduce_ll:
             ll = self._all_reduce(ll)
         return fms, fPs, ll
@@ -77,12 +88,15 @@ class TimeShard:
         m_in, P_in = self._state_in
         Fn, Qn = self._halo
         parts = []
+        rev = getattr(self, "_rev", None)
+        have = rev is not None and rev[0] is fms   # summaries built by the filter pass for these very arrays
         if want_smoother:
-            s_sm = self.ops.pks_summary(Fs, Qs, fms, fPs, self.last, Fn, Qn)
+            s_sm = rev[1] if have else self.ops.pks_summary(Fs, Qs, fms, fPs, self.last, Fn, Qn)
             parts.append(s_sm)
         if want_grad:
-            s_ad = self.ops.pkf_backward_summary(P_in, m_in, Fs, Qs, H, R, y, fms, fPs, self.first)
+            s_ad = rev[2] if have else self.ops.pkf_backward_summary(P_in, m_in, Fs, Qs, H, R, y, fms, fPs, self.first)
             parts.append(s_ad)
+        self._rev = None
         gathered = self._all_gather(torch.cat(parts))
         after = self.world - 1 - self.rank
         out = {}
@@ -119,6 +133,6 @@ class TimeShard:
     def filter_smoother_grad(self, P0, Fs, Qs, H, R, y, g_ll):
         """One full step: returns (ll, sms, sPs, (dP0, dFs, dQs, dH, dR)); ll and the small gradients are global."""
         Fs, Qs, y = self._aligned(Fs), self._aligned(Qs), self._aligned(y)
-        fms, fPs, ll = self.filter(P0, Fs, Qs, H, R, y, reduce_ll=False)
+        fms, fPs, ll = self.filter(P0, Fs, Qs, H, R, y, reduce_ll=False, with_reverse_summaries=True)
         o = self.smoother_and_grad(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=ll)
         return o["ll"], o["sms"], o["sPs"], (o["dP0"], o["dFs"], o["dQs"], o["dH"], o["dR"])

@@ -133,6 +133,25 @@ def pkf_summary(P0, Fs, Qs, H, R, y, first_special):
     return out
 
 
+def pkf_with_summaries(P0, Fs, Qs, H, R, y, m0=None, first_special=True, last_special=True, Fnext=None, Qnext=None):
+    """C ABI: pssgp_pkf_with_summaries (pkf on one shard + shard summaries of the smoother and adjoint scans).
+    -> fms, fPs, ll, smoother_summary, adjoint_summary."""
+    Fs, Qs, y = _al(Fs), _al(Qs), _al(y)
+    n, d = Fs.shape[0], Fs.shape[1]
+    kw = dict(dtype=Fs.dtype, device=Fs.device)
+    fms = torch.empty((n, d), **kw)
+    fPs = torch.empty((n, d, d), **kw)
+    ll = torch.empty((1,), **kw)
+    s_sm = torch.empty((nagg_smoother(d),), **kw)
+    s_ad = torch.empty((nagg_smoother(d),), **kw)
+    _lib.check(_lib.lib().pssgp_pkf_with_summaries(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs),
+                                                  A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(m0), 1 if first_special else 0,
+                                                  1 if last_special else 0, A.ptr(Fnext), A.ptr(Qnext), A.ptr(fms),
+                                                  A.ptr(fPs), A.ptr(ll), A.ptr(s_sm), A.ptr(s_ad),
+                                                  A.stream_ptr(Fs.device)))
+    return fms, fPs, ll, s_sm, s_ad
+
+
 def filter_fold(P0, m0, summaries, count):
     """summaries: [>=count, NAGG] in rank order. -> m[d] | P[d,d]."""
     d = P0.shape[0]

@@ -115,8 +115,9 @@ def test_world1_summary_reuse_path():
     n0 = h.launch_count()
     out = TimeShard(0, 1).filter_smoother_grad(P0, Fs, Qs, H, R, yd, g)
     torch.cuda.synchronize()
-    # 3 scans x (reduce + total + mid + apply) = 12 launches; without reuse it would be 15
-    assert h.launch_count() - n0 == 12
+    # d <= 4: filter reduce + total, mid + fused apply (builds both reverse aggregates and their summaries),
+    # then (mid + apply) for the smoother and for the adjoint = 8 launches; the unfused path takes 12
+    assert h.launch_count() - n0 == 8
     assert rel_err(out[1].cpu(), sms.cpu()) < 1e-12 and rel_err(out[2].cpu(), sPs.cpu()) < 1e-12
     assert abs(float(out[0]) - float(ll)) <= 1e-12 * abs(float(ll))
 
