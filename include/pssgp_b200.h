@@ -41,7 +41,8 @@ int pssgp_create(pssgp_handle** out, int device);
 int pssgp_destroy(pssgp_handle* h);
 /* Options: "chunk" = time steps per thread-chunk (0 = heuristic); "timing" = 1 brackets every
  * kernel launch with CUDA events on its stream (read back with pssgp_timing_report);
- * "fused_reverse" = 1 makes pssgp_pkfs_grad run the smoother and adjoint recursions in one kernel. */
+ * "fused_reverse" = 1 makes pssgp_pkfs_grad run the smoother and adjoint recursions in one kernel;
+ * "pdl" = 0 turns off programmatic dependent launch between the kernels of pssgp_pkfs_grad (default 1). */
 int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t pssgp_launch_count(const pssgp_handle* h);

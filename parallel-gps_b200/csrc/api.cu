@@ -124,6 +124,8 @@ int pssgp_create(pssgp_handle** out, int device) {
     }
     h->num_sms = sms;
     if (const char* env = getenv("PSSGP_CHUNK")) h->chunk_opt = atoll(env);  // tuning aid: same as option "chunk"
+    h->pdl = 1;
+    if (const char* env = getenv("PSSGP_PDL")) h->pdl = atoi(env) != 0;     // same as option "pdl"
     e = cudaMalloc((void**)&h->ticket, 64);
     if (e == cudaSuccess) e = cudaMemset(h->ticket, 0, 64);
     if (e != cudaSuccess) {
@@ -158,6 +160,10 @@ int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value) {
     if (strcmp(name, "chunk") == 0) {
         if (value < 0 || value > 4096) return set_err(PSSGP_ERR_INVALID, "chunk out of range");
         h->chunk_opt = value;
+        return PSSGP_OK;
+    }
+    if (strcmp(name, "pdl") == 0) {
+        h->pdl = value != 0;
         return PSSGP_OK;
     }
     if (strcmp(name, "fused_reverse") == 0) {

@@ -6,16 +6,36 @@ namespace pssgp {
 
 constexpr int kNotFused = -12345;  // this (dtype, d) has no common partition: run the three scans one after the other
 
+// pdl: launch with programmatic stream serialization (the kernel waits for its predecessor with
+// griddepcontrol.wait before it reads anything, see scan_stream.cuh) so that its CTAs can become resident while the
+// predecessor's last CTA is still scanning the CTA totals.
 template <typename Alg>
 int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPart& sp, const typename Alg::scalar* lane,
                  const typename Alg::scalar* wexcl, const typename Alg::scalar* wstate, typename Alg::scalar* part,
-                 typename Alg::scalar* acc_out, cudaStream_t st) {
+                 typename Alg::scalar* acc_out, cudaStream_t st, bool pdl = false) {
     using Lay = StreamLayout<Alg>;
+    using T = typename Alg::scalar;
     constexpr int NW = Lay::NW;
     const long nChunksPad = (long)sp.nCta * NW * 32;
+    if (pdl && !h->timing) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)sp.nCta);
+        cfg.blockDim = dim3(NW * 32);
+        cfg.dynamicSmemBytes = NW * Lay::WARP_BYTES_APPLY;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, stream_apply_kernel<Alg>, p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket,
+                           acc_out);
+        return PSSGP_OK;
+    }
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
                  (stream_apply_kernel<Alg><<<(unsigned)sp.nCta, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
                      p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out)));
+    (void)sizeof(T);
     return PSSGP_OK;
 }
 
@@ -90,7 +110,7 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     }
     // K2': seeded filter recursion + chunk aggregates and CTA-level scans of both reverse scans
     launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
-                     (const T*)h->buf[WS_WSTATE], part, (T*)ll, st);
+                     (const T*)h->buf[WS_WSTATE], part, (T*)ll, st, h->pdl != 0);
     // K3: smoother and adjoint recursions seeded by the states K2' produced
     typename SA::Params sp_;
     sp_.Fs = (const T*)Fs;
@@ -135,8 +155,8 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
             return check_launch(h, "pkfs_grad", 3);
         }
     }
-    launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st);
-    launch_apply<AA>(h, ap, sp, fp.ad.lane_excl, fp.ad.warp_excl, fp.ad.wstate, part, (T*)dR, st);
+    launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st, h->pdl != 0);
+    launch_apply<AA>(h, ap, sp, fp.ad.lane_excl, fp.ad.warp_excl, fp.ad.wstate, part, (T*)dR, st, h->pdl != 0);
     return check_launch(h, "pkfs_grad", 4);
     }
 }

@@ -85,6 +85,12 @@ PSSGP_DEV void st_shared16(unsigned char* dst, const float* src) {
     *reinterpret_cast<float4*>(dst) = make_float4(src[0], src[1], src[2], src[3]);
 }
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// become resident while its predecessor is still running its (single-CTA) scan tail; it must not touch anything
+// the predecessor produces before pdl_wait().  Both are no-ops for ordinary launches.
+PSSGP_DEV void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PSSGP_DEV void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------------------------------------
 // Compile-time geometry of the per-warp staging areas
 // ---------------------------------------------------------------------------------------------
@@ -643,6 +649,7 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         }
     }
     __shared__ T shw[NW * Alg::NAGG];
+    pdl_launch_dependents();  // the next kernel may start occupying the SMs this kernel's scan tail leaves idle
     PSSGP_PHASE(1);
     cta_scan_publish<Alg, NW, false>(a, lane, wid, (long)blockIdx.x, nCta, nChunksPad, lane_excl, warp_excl, wagg, shw);
     PSSGP_PHASE(2);
@@ -698,6 +705,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
     T acc[NACC1];
 #pragma unroll
     for (int e = 0; e < NACC1; ++e) acc[e] = T(0);
+    pdl_wait();  // everything below reads what the previous kernel of the scan wrote (states, aggregates, moments)
     {
         typename Alg::Ctx ctx;
         Alg::load_ctx(p, ctx);
@@ -796,6 +804,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             }
         }
         cp_async_wait<0>();
+        pdl_launch_dependents();
         if constexpr (Alg::FLUSH) {
             T orow[Alg::NOUT][Alg::WMAX];
             if constexpr (Lay::OUT8) {

@@ -15,6 +15,7 @@ struct pssgp_handle {
     size_t cap[WS_COUNT];
     unsigned int* ticket;
     int64_t chunk_opt;
+    int pdl;            // option "pdl": programmatic dependent launch between the kernels of pkfs_grad
     int fused_reverse;  // option "fused_reverse": pkfs_grad runs smoother + adjoint recursions in one kernel
     int64_t launches;
     // chunk aggregates left in the workspace by a *_summary call (time sharding)
