@@ -154,6 +154,17 @@ int pssgp_adjoint_fold(pssgp_handle* h, int dtype, int d, int nshards_after,
                        const void* summaries, void* state_out, void* stream);
 
 /*
+ * Filter (+ log-likelihood) + RTS smoother of one whole series in one call: pkfs of the reference
+ * (pssgp/kalman/parallel.py:199-201).  For d <= 4 the filter pass also builds the smoother's chunk aggregates
+ * (no second reduce pass).  Outputs fms, fPs, ll (or NULL) as pssgp_pkf, and either sms [n,d] + sPs [n,d,d], or —
+ * proj != NULL, d <= 4 only — proj [n,2] = (H m_k, H P_k H^T) of every smoothed state, which is all that
+ * predict_f keeps (pssgp/model.py:107-111); sms / sPs may then be NULL.
+ */
+int pssgp_pkfs(pssgp_handle* h, int dtype, int64_t n, int d,
+               const void* P0, const void* Fs, const void* Qs, const void* H, const void* R, const void* y,
+               void* fms, void* fPs, void* ll, void* sms, void* sPs, void* proj, void* stream);
+
+/*
  * Time sharding, fused: pssgp_pkf on one shard (same arguments) that also builds, in the same pass, the chunk
  * aggregates of the smoother and adjoint scans and writes their shard summaries (layouts as pssgp_pks_summary /
  * pssgp_pkf_backward_summary) — i.e. pssgp_pkf + pssgp_pks_summary + pssgp_pkf_backward_summary without the two

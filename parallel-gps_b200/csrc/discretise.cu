@@ -329,62 +329,75 @@ discretise_bwd_small_kernel(const T* __restrict__ coef, const T* __restrict__ Pi
 }
 
 // Sums the per-block partials and assembles dF and dPinf.  One block; generic d.
-// coefT holds C_j of G^T (setup kernel called with transpose = 1).
+// coefT holds C_j of G^T (setup kernel called with transpose = 1).  W: NOUT scalars, V: DEG * d * d scalars of
+// global scratch.  Every phase is element-parallel with one barrier between phases (the first version walked the
+// (i, l) terms one after the other with two barriers each: 169 us at d = 3, all of it latency).
 template <typename T>
 __global__ void discretise_bwd_final_kernel(const T* __restrict__ coefT, const T* __restrict__ part, int nparts, int d,
-                                            T* __restrict__ W, T* __restrict__ dF, T* __restrict__ dPinf) {
+                                            T* __restrict__ W, T* __restrict__ V, T* __restrict__ dF,
+                                            T* __restrict__ dPinf) {
     const int DEG = Taylor<T>::DEG;
     const int dd = d * d;
     const int NOUT = (DEG + 1) * dd;
     extern __shared__ unsigned char smem_raw[];
-    T* V = (T*)smem_raw;   // d*d
-    T* V2 = V + dd;        // d*d
-    T* acc = V2 + dd;      // d*d
-    for (int o = threadIdx.x; o < NOUT; o += blockDim.x) {
-        T s = T(0);
-        for (int b = 0; b < nparts; ++b) s += part[(long)b * NOUT + o];
-        W[o] = s;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-        dPinf[e] = W[e];
-        acc[e] = T(0);
+    T* red = (T*)smem_raw;  // blockDim.x scalars
+    // phase 0: W[o] = sum over the partials, G thread groups share the partials of an output (fixed order)
+    const int G = NOUT < (int)blockDim.x ? (int)blockDim.x / NOUT : 1;
+    if (G > 1) {
+        const int g = threadIdx.x / NOUT, o = threadIdx.x - g * NOUT;
+        T sacc = T(0);
+        if (g < G)
+            for (int b = g; b < nparts; b += G) sacc += part[(long)b * NOUT + o];
+        red[threadIdx.x] = sacc;
+        __syncthreads();
+        if ((int)threadIdx.x < NOUT) {
+            T tot = T(0);
+            for (int gg = 0; gg < G; ++gg) tot += red[gg * NOUT + threadIdx.x];
+            W[threadIdx.x] = tot;
+        }
+    } else {
+        for (int o = threadIdx.x; o < NOUT; o += blockDim.x) {
+            T sacc = T(0);
+            for (int b = 0; b < nparts; ++b) sacc += part[(long)b * NOUT + o];
+            W[o] = sacc;
+        }
     }
     __syncthreads();
     const T normF = coefT[0];
     const T inv = normF > T(0) ? T(1) / normF : T(0);
-    // dF = inv * sum_{i>=0} B^i V_i ,  V_i = sum_{l>=0} W_{i+l+1} B^l / (i+l+1)! ... with C_j = B^j / j! available,
-    // use   sum_{p} (1/p!) sum_{i=0}^{p-1} B^i W_p B^(p-1-i)
-    //     = sum_{i,l} [ i! l! / (i+l+1)! ] C_i W_{i+l+1} C_l
-    for (int i = 0; i < DEG; ++i) {
-        // V = sum_l w(i,l) W_{i+l+1} C_l
-        for (int e = threadIdx.x; e < dd; e += blockDim.x) V[e] = T(0);
-        __syncthreads();
+    // dF = inv * sum_{p} (1/p!) sum_{i=0}^{p-1} B^i W_p B^(p-1-i) = inv * sum_i C_i V_i   with C_j = B^j / j! and
+    // V_i = sum_l [ i! l! / (i+l+1)! ] W_{i+l+1} C_l
+    // phase 1: one thread per element of every V_i
+    for (int idx = threadIdx.x; idx < DEG * dd; idx += blockDim.x) {
+        const int i = idx / dd, e = idx - i * dd;
+        const int r = e / d, c = e - r * d;
+        T v = T(0);
         T wgt = T(1) / T(i + 1);  // i! 0! / (i+1)!
         for (int l = 0; i + l + 1 <= DEG; ++l) {
             const T* Wp = W + (size_t)(i + l + 1) * dd;
             const T* Cl = coefT + 8 + (size_t)l * dd;
-            for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-                const int r = e / d, c = e % d;
-                T a1 = T(0);
-                for (int k = 0; k < d; ++k) a1 = fma(Wp[r * d + k], Cl[k * d + c], a1);
-                V2[e] = a1;
-            }
-            __syncthreads();
-            for (int e = threadIdx.x; e < dd; e += blockDim.x) V[e] = fma(wgt, V2[e], V[e]);
-            __syncthreads();
+            T a1 = T(0);
+            for (int k = 0; k < d; ++k) a1 = fma(Wp[r * d + k], Cl[k * d + c], a1);
+            v = fma(wgt, a1, v);
             wgt = wgt * T(l + 1) / T(i + l + 2);  // i!(l+1)!/(i+l+2)!
         }
-        const T* Ci = coefT + 8 + (size_t)i * dd;
-        for (int e = threadIdx.x; e < dd; e += blockDim.x) {
-            const int r = e / d, c = e % d;
-            T a1 = T(0);
-            for (int k = 0; k < d; ++k) a1 = fma(Ci[r * d + k], V[k * d + c], a1);
-            acc[e] += a1;
-        }
-        __syncthreads();
+        V[idx] = v;
     }
-    for (int e = threadIdx.x; e < dd; e += blockDim.x) dF[e] = acc[e] * inv;
+    __syncthreads();
+    // phase 2: one thread per element of dF (and dPinf = W_0)
+    for (int e = threadIdx.x; e < dd; e += blockDim.x) {
+        const int r = e / d, c = e - r * d;
+        T acc = T(0);
+        for (int i = 0; i < DEG; ++i) {
+            const T* Ci = coefT + 8 + (size_t)i * dd;
+            const T* Vi = V + (size_t)i * dd;
+            T a1 = T(0);
+            for (int k = 0; k < d; ++k) a1 = fma(Ci[r * d + k], Vi[k * d + c], a1);
+            acc += a1;
+        }
+        dF[e] = acc * inv;
+        dPinf[e] = W[e];
+    }
 }
 
 constexpr size_t coef_count(int deg, int d) { return 8 + (size_t)(deg + 1) * d * d; }
@@ -426,18 +439,19 @@ int discretise_bwd_impl(pssgp_handle* h, int64_t n, const void* F, const void* P
     int grid = h->num_sms * 4;
     if (grid > ntiles) grid = (int)ntiles;
     if (grid < 1) grid = 1;
-    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + NOUT)))) return rc;
+    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + 2 * NOUT)))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * grid))) return rc;
     T *coef, *coefT;
     if ((rc = setup_coef<T>(h, F, D, 0, &coef, 0, st))) return rc;
     if ((rc = setup_coef<T>(h, F, D, 1, &coefT, cnt, st))) return rc;
     T* W = (T*)h->buf[WS_MISC] + 2 * cnt;
+    T* V = W + NOUT;
     T* part = (T*)h->buf[WS_PART];
     PSSGP_LAUNCH(h, "discretise_bwd", st,
                  (discretise_bwd_small_kernel<T, D><<<grid, TB, 0, st>>>(coef, (const T*)Pinf, (const T*)dts, n,
                                                                         (const T*)Fs, (const T*)dFs, (const T*)dQs, part)));
     PSSGP_LAUNCH(h, "discretise_bwd_final", st,
-                 (discretise_bwd_final_kernel<T><<<1, 256, 3 * D * D * sizeof(T), st>>>(coefT, part, grid, D, W, (T*)dF,
+                 (discretise_bwd_final_kernel<T><<<1, 1024, 1024 * sizeof(T), st>>>(coefT, part, grid, D, W, V, (T*)dF,
                                                                                        (T*)dPinf)));
     return check_launch(h, "discretise_backward", 4);
 }
@@ -639,12 +653,13 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
     const int NOUT = (DEG + 1) * d * d;
     long grid = (long)h->num_sms * 2;
     if (grid > n) grid = n;
-    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + NOUT)))) return rc;
+    if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + 2 * NOUT)))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * grid))) return rc;
     T *coef, *coefT;
     if ((rc = setup_coef<T>(h, F, d, 0, &coef, 0, st))) return rc;
     if ((rc = setup_coef<T>(h, F, d, 1, &coefT, cnt, st))) return rc;
     T* W = (T*)h->buf[WS_MISC] + 2 * cnt;
+    T* V = W + NOUT;
     T* part = (T*)h->buf[WS_PART];
     const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
     const size_t sm = sizeof(T) * 7 * d * d;
@@ -655,8 +670,8 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
                                                                                   n, (const T*)Fs, (const T*)dFs,
                                                                                   (const T*)dQs, part)));
     PSSGP_LAUNCH(h, "discretise_bwd_final", st,
-                 (discretise_bwd_final_kernel<T><<<1, 256, 3 * d * d * sizeof(T), st>>>(coefT, part, (int)grid, d, W,
-                                                                                       (T*)dF, (T*)dPinf)));
+                 (discretise_bwd_final_kernel<T><<<1, 1024, 1024 * sizeof(T), st>>>(coefT, part, (int)grid, d, W, V,
+                                                                                   (T*)dF, (T*)dPinf)));
     return check_launch(h, "discretise_backward", 4);
 }
 

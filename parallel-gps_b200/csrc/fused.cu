@@ -246,10 +246,105 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     }
 }
 
+// Filter (+ log-likelihood) + RTS smoother of one whole series, fused: K1, K2' (filter apply + smoother aggregates
+// and scans), then the seeded smoother recursion writing (sms, sPs) or, when proj != nullptr, only the projection
+// (H m, H P H^T) of every smoothed state.
+template <typename T, int D>
+int pkfs_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,
+              const void* y, void* fms, void* fPs, void* ll, void* sms, void* sPs, void* proj, cudaStream_t st) {
+    using FA = FilterAlg<T, D>;
+    using FF = FusedFwdAlg<T, D, true, false>;
+    using SA = SmootherAlg<T, D>;
+    using SP = SmootherProjAlg<T, D>;
+    constexpr int NW = StreamLayout<FA>::NW;
+    constexpr int LS = StreamLayout<FA>::LS;
+    if constexpr (StreamLayout<FF>::NW != NW || StreamLayout<SA>::NW != NW || StreamLayout<SP>::NW != NW) {
+        return kNotFused;
+    } else {
+    int rc;
+    if ((rc = stream_configure<FA>(h->device))) return rc;
+    if ((rc = stream_configure_apply<FF>(h->device))) return rc;
+    if ((rc = stream_configure<SA>(h->device))) return rc;
+    if ((rc = stream_configure_apply<SP>(h->device))) return rc;
+    const void* arrs[] = {Fs, Qs, y, fms, fPs, sms, sPs, proj};
+    for (const void* a : arrs)
+        if (!aligned16(a)) return set_err(PSSGP_ERR_INVALID, "pkfs: arrays must be 16-byte aligned");
+    const StreamPart sp = make_partition<NW, LS>(h, n);
+    const int64_t nCta = sp.nCta;
+    const int64_t nChunksPad = nCta * NW * 32;
+    h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = nullptr;
+    const int NAGG[2] = {FA::NAGG, SA::NAGG};
+    for (int kind = 0; kind < 2; ++kind) {
+        if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
+        if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * NAGG[kind] * (size_t)nCta))) return rc;
+        if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * NAGG[kind] * (size_t)nCta * NW))) return rc;
+    }
+    if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * FA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_WSTATE_S, sizeof(T) * SA::NSTATE * (size_t)nCta))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * 2 * (size_t)nCta))) return rc;
+    T* part = (T*)h->buf[WS_PART];
+    typename FF::Params fp;
+    fp.Fs = (const T*)Fs;
+    fp.Qs = (const T*)Qs;
+    fp.y = (const T*)y;
+    fp.H = (const T*)H;
+    fp.R = (const T*)R;
+    fp.P0 = (const T*)P0;
+    fp.m0 = nullptr;
+    fp.fms = (T*)fms;
+    fp.fPs = (T*)fPs;
+    fp.first_special = 1;
+    fp.n = n;
+    fp.sm = {(T*)h->buf[WS_LANE + KIND_SMOOTHER], (T*)h->buf[WS_WEXCL + KIND_SMOOTHER],
+             (T*)h->buf[WS_WAGG + KIND_SMOOTHER], (T*)h->buf[WS_WSTATE_S]};
+    fp.ad = {nullptr, nullptr, nullptr, nullptr};
+    fp.side_ticket = h->ticket + 1;
+    fp.last_special = 1;
+    fp.Fnext = fp.Qnext = nullptr;
+    fp.sm_summary = fp.ad_summary = nullptr;
+    {
+        const typename FA::Params& bp = fp;
+        using Lay = StreamLayout<FA>;
+        PSSGP_LAUNCH(h, FA::name_reduce(), st,
+                     (stream_reduce_kernel<FA><<<(unsigned)nCta, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
+                         bp, sp, nChunksPad, (T*)h->buf[WS_LANE + KIND_FILTER], (T*)h->buf[WS_WEXCL + KIND_FILTER],
+                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1)));
+    }
+    launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
+                     (const T*)h->buf[WS_WSTATE], part, (T*)ll, st, h->pdl != 0);
+    typename SP::Params sp_;
+    sp_.Fs = (const T*)Fs;
+    sp_.Qs = (const T*)Qs;
+    sp_.fms = (const T*)fms;
+    sp_.fPs = (const T*)fPs;
+    sp_.sms = (T*)sms;
+    sp_.sPs = (T*)sPs;
+    sp_.n = n;
+    sp_.last_special = 1;
+    sp_.Fnext = sp_.Qnext = sp_.init = nullptr;
+    sp_.H = (const T*)H;
+    sp_.proj = (T*)proj;
+    if (proj != nullptr) {
+        launch_apply<SP>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st, h->pdl != 0);
+    } else {
+        const typename SA::Params& bsp = sp_;
+        launch_apply<SA>(h, bsp, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st, h->pdl != 0);
+    }
+    return check_launch(h, "pkfs", 3);
+    }
+}
+
 static int fused_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
                           const void* H, const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll,
                           void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
     DISPATCH_SMALL(pkfs_grad_impl, h, n, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
+    return kNotFused;
+}
+
+static int pkfs_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+                         const void* H, const void* R, const void* y, void* fms, void* fPs, void* ll, void* sms, void* sPs,
+                         void* proj, cudaStream_t st) {
+    DISPATCH_SMALL(pkfs_impl, h, n, P0, Fs, Qs, H, R, y, fms, fPs, ll, sms, sPs, proj, st);
     return kNotFused;
 }
 
@@ -305,6 +400,22 @@ int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d, const
     if ((rc = pssgp_pks_summary(h, dtype, n, d, Fs, Qs, fms, fPs, last_special, Fnext, Qnext, sm_summary, stream)))
         return rc;
     return pssgp_pkf_backward_summary(h, dtype, n, d, P0, m0, Fs, Qs, H, R, y, fms, fPs, first_special, ad_summary, stream);
+}
+
+int pssgp_pkfs(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+               const void* H, const void* R, const void* y, void* fms, void* fPs, void* ll, void* sms, void* sPs,
+               void* proj, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    if (!proj && (!sms || !sPs)) return set_err(PSSGP_ERR_INVALID, "pkfs: sms and sPs, or proj, must be given");
+    cudaStream_t st = (cudaStream_t)stream;
+    rc = pkfs_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, fms, fPs, ll, sms, sPs, proj, st);
+    if (rc != kNotFused) return rc;
+    if (proj) return set_err(PSSGP_ERR_UNSUPPORTED, "pkfs: projected output is implemented for the fused d <= 4 path only "
+                                                    "(d = %d): pass sms / sPs", d);
+    if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;
+    return pssgp_pks(h, dtype, n, d, Fs, Qs, fms, fPs, 1, nullptr, nullptr, nullptr, sms, sPs, nullptr, stream);
 }
 
 }  // extern "C"

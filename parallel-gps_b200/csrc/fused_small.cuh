@@ -32,7 +32,9 @@ struct SideWs {
     T* wstate;
 };
 
-template <typename T, int D>
+// SM / AD: build the aggregates of the smoother / of the adjoint scan (both for the full step, SM only for pkfs,
+// AD only for a training step without smoother).
+template <typename T, int D, bool SM = true, bool AD = true>
 struct FusedFwdAlg : FilterAlg<T, D> {
     using Base = FilterAlg<T, D>;
     using SA = SmootherAlg<T, D>;
@@ -134,7 +136,7 @@ struct FusedFwdAlg : FilterAlg<T, D> {
         }
         // smoothing element of time k-1 (parallel.py:159-166); the one before the chunk's first row belongs
         // to the previous chunk (its owner builds it from a halo row in side_flush)
-        if (k > cr.k_lo) {
+        if (SM && k > cr.k_lo) {
             T el[SA::NAGG];
             smoother_element(FP, Pp, s, s + D, mp, el);
             push_smoother(cr, el);
@@ -151,7 +153,7 @@ struct FusedFwdAlg : FilterAlg<T, D> {
             is = t_rcp(sv);
         }
         // adjoint element of step k (adjoint_small.cuh element()): x = (Abar, a, B), appended on the later side
-        {
+        if constexpr (AD) {
             T x[AA::NAGG];
             if (first) {
                 AA::identity(x);
@@ -213,6 +215,7 @@ struct FusedFwdAlg : FilterAlg<T, D> {
     // After the chunk's last row (s = filtered moments at k_hi - 1): the smoothing element of time k_hi - 1,
     // from the halo row k_hi, or last_smoothing_element (parallel.py:155-156) at the end of the series.
     PSSGP_DEV static void side_flush(const T* s, long k_hi, const Params& p, Carry& cr) {
+        if constexpr (!SM) return;
         T el[SA::NAGG];
         if (k_hi >= p.n && p.last_special) {
 #pragma unroll
@@ -243,16 +246,18 @@ struct FusedFwdAlg : FilterAlg<T, D> {
     // the two halves of the CTA run them side by side.  All threads of the CTA call this.
     template <int NW>
     PSSGP_DEV static void side_finish(const Params& p, Carry& cr, int lane, int wid, long nCta, long nChunksPad) {
-        __shared__ T shw_s[NW * SA::NAGG];
-        __shared__ T shw_a[NW * AA::NAGG];
+        __shared__ T shw_s[SM ? NW * SA::NAGG : 1];
+        __shared__ T shw_a[AD ? NW * AA::NAGG : 1];
         const long blk_s = nCta - 1 - (long)blockIdx.x;
-        cta_scan_publish<SA, NW, true>(cr.sa, lane, wid, blk_s, nCta, nChunksPad, p.sm.lane_excl, p.sm.warp_excl,
-                                       p.sm.wagg, shw_s);
-        cta_scan_publish<AA, NW, true>(cr.aa, lane, wid, blk_s, nCta, nChunksPad, p.ad.lane_excl, p.ad.warp_excl,
-                                       p.ad.wagg, shw_a);
+        if constexpr (SM)
+            cta_scan_publish<SA, NW, true>(cr.sa, lane, wid, blk_s, nCta, nChunksPad, p.sm.lane_excl, p.sm.warp_excl,
+                                           p.sm.wagg, shw_s);
+        if constexpr (AD)
+            cta_scan_publish<AA, NW, true>(cr.aa, lane, wid, blk_s, nCta, nChunksPad, p.ad.lane_excl, p.ad.warp_excl,
+                                           p.ad.wagg, shw_a);
         __shared__ bool is_last;
-        __shared__ T sh_mid_s[32 * SA::NAGG];
-        __shared__ T sh_mid_a[32 * AA::NAGG];
+        __shared__ T sh_mid_s[SM ? 32 * SA::NAGG : 1];
+        __shared__ T sh_mid_a[AD ? 32 * AA::NAGG : 1];
         __threadfence();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -262,33 +267,31 @@ struct FusedFwdAlg : FilterAlg<T, D> {
         __syncthreads();
         if (is_last) {
             __threadfence();
-            constexpr int HALF = (NW / 2) * 32;
-            const bool summaries = p.sm_summary != nullptr;
-            if (NW >= 2) {
-                if ((int)threadIdx.x < HALF) {
+            // both scans: side by side in the two halves of the CTA (named barriers 1 and 2); one scan: the whole CTA
+            constexpr bool BOTH = SM && AD && NW >= 2;
+            constexpr int GROUP = BOTH ? (NW / 2) * 32 : NW * 32;
+            const bool summaries = p.sm_summary != nullptr || p.ad_summary != nullptr;
+            const int tid = (int)threadIdx.x;
+            if constexpr (SM) {
+                if (tid < GROUP) {
                     if (summaries) {
-                        scan_total_body<SA>(p.sm.wagg, nCta, p.sm_summary, sh_mid_s, (int)threadIdx.x, HALF, 1);
+                        scan_total_body<SA>(p.sm.wagg, nCta, p.sm_summary, sh_mid_s, tid, GROUP, 1);
                     } else {
                         typename SA::Params sp{};
-                        scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, HALF, 1);
-                    }
-                } else if ((int)threadIdx.x < 2 * HALF) {
-                    if (summaries) {
-                        scan_total_body<AA>(p.ad.wagg, nCta, p.ad_summary, sh_mid_a, (int)threadIdx.x - HALF, HALF, 2);
-                    } else {
-                        typename AA::Params ap{};
-                        scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, (int)threadIdx.x - HALF,
-                                          HALF, 2);
+                        scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, tid, GROUP, 1);
                     }
                 }
-            } else if (summaries) {
-                scan_total_body<SA>(p.sm.wagg, nCta, p.sm_summary, sh_mid_s, (int)threadIdx.x, 32, 1);
-                scan_total_body<AA>(p.ad.wagg, nCta, p.ad_summary, sh_mid_a, (int)threadIdx.x, 32, 2);
-            } else {
-                typename SA::Params sp{};
-                scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, (int)threadIdx.x, 32, 1);
-                typename AA::Params ap{};
-                scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, (int)threadIdx.x, 32, 2);
+            }
+            if constexpr (AD) {
+                const int t2 = BOTH ? tid - GROUP : tid;
+                if (t2 >= 0 && t2 < GROUP) {
+                    if (summaries) {
+                        scan_total_body<AA>(p.ad.wagg, nCta, p.ad_summary, sh_mid_a, t2, GROUP, 2);
+                    } else {
+                        typename AA::Params ap{};
+                        scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, t2, GROUP, 2);
+                    }
+                }
             }
             __syncthreads();
             if (threadIdx.x == 0) *p.side_ticket = 0u;

@@ -196,8 +196,8 @@ struct SmootherAlg {
         for (int e = 0; e < NSTATE; ++e) s[e] = p.init ? p.init[e] : T(0);
     }
 
-    PSSGP_DEV static bool step_row(T* s, const Ctx&, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
-                                   const Params& p, T*, Carry& c) {
+    // s = smoothed state at time k+1 -> at time k
+    PSSGP_DEV static void advance(T* s, const T (&in)[NIN][WMAX], long k, const Params& p, Carry& c) {
         if (k == p.n - 1 && p.last_special) {
 #pragma unroll
             for (int i = 0; i < D; ++i) s[i] = in[2][i];
@@ -211,6 +211,11 @@ struct SmootherAlg {
             for (int e = 0; e < NSTATE; ++e) s[e] = s2[e];
         }
         carry_set(c, in);
+    }
+
+    PSSGP_DEV static bool step_row(T* s, const Ctx&, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                   const Params& p, T*, Carry& c) {
+        advance(s, in, k, p, c);
 #pragma unroll
         for (int i = 0; i < D; ++i) out[0][i] = s[i];
 #pragma unroll
@@ -226,6 +231,48 @@ struct SmootherAlg {
     }
 
     PSSGP_DEV static void finish(const Params&, int, T, T*) {}
+};
+
+// RTS smoother that emits only the projection of the smoothed state on the observation row H: proj[k] = (H m_k,
+// H P_k H^T) — what predict_f keeps of (sms, sPs) (pssgp/model.py:107-111), 16 bytes per step instead of
+// 8 d (d + 1).
+template <typename T, int D>
+struct SmootherProjAlg : SmootherAlg<T, D> {
+    using Base = SmootherAlg<T, D>;
+    static const char* name_apply() { return "pks_apply_proj"; }
+    static constexpr int NIN = Base::NIN, NOUT = 1;
+    static constexpr int WMAX = Base::WMAX < 2 ? 2 : Base::WMAX;  // the output row has two values (d = 1: D * D = 1)
+    __host__ __device__ static constexpr int out_w(int) { return 2; }
+    struct Params : Base::Params {
+        const T* H;   // [D]
+        T* proj;      // [n, 2]
+    };
+    __host__ __device__ __forceinline__ static T* out_ptr(const Params& p, int) { return p.proj; }
+    struct Ctx {
+        T h[D];
+    };
+    PSSGP_DEV static void load_ctx(const Params& p, Ctx& c) {
+#pragma unroll
+        for (int i = 0; i < D; ++i) c.h[i] = __ldg(p.H + i);
+    }
+    using Carry = typename Base::Carry;
+    PSSGP_DEV static void carry_init(Carry& c, const Ctx&, long k_lo, long k_hi, const Params& p) {
+        Base::carry_init(c, typename Base::Ctx{}, k_lo, k_hi, p);
+    }
+    PSSGP_DEV static bool step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,
+                                   const Params& p, T*, Carry& c) {
+        T inb[NIN][Base::WMAX];
+#pragma unroll
+        for (int a = 0; a < NIN; ++a)
+#pragma unroll
+            for (int e = 0; e < Base::WMAX; ++e) inb[a][e] = in[a][e];
+        Base::advance(s, inb, k, p, c);
+        T Ph[D];
+        mv_s<T, D>(s + D, cx.h, Ph);
+        out[0][0] = dot<T, D>(cx.h, s);
+        out[0][1] = dot<T, D>(cx.h, Ph);
+        return true;
+    }
 };
 
 }  // namespace pssgp

@@ -91,9 +91,11 @@ def pkfs(model, observations, max_parallel=10000):
     """Filter then smoother (parallel.py:199-201); the filtered moments never leave the device."""
     device, dtype, n, d, P0, Fs, Qs, H, R = _prep_lgssm(model, (observations,))
     dev_model = (P0, Fs, Qs, H.reshape(1, -1), R.reshape(1, 1))
-    y = A.to_device(observations, dtype, device, "y")
-    fms, fPs = pkf(dev_model, y, False, max_parallel)
-    sms, sPs = pks(dev_model, fms, fPs, max_parallel)
+    y = A.to_device(observations, dtype, device, "y").reshape(-1)
+    if y.numel() != n:
+        raise ValueError(f"observations must be [{n},1], got {tuple(observations.shape)}")
+    from .. import ops
+    _, _, _, sms, sPs = ops.pkfs(P0, Fs, Qs, H, R, y)  # C ABI pssgp_pkfs: one fused call
     if _wants_numpy(*model, observations):
         return A.to_host(sms, "sms"), A.to_host(sPs, "sPs")
     return sms, sPs

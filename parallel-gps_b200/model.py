@@ -11,6 +11,7 @@ import numpy as np
 import torch
 
 from . import _arrays as A
+from . import _lib
 from . import config as pssgp_config
 from . import ops
 from .kernels.base import time_steps
@@ -44,16 +45,19 @@ class _LogLikelihood(torch.autograd.Function):
         return back(dF), back(dPinf + dP0), back(dH, hshape), back(dR, rshape), None, None
 
 
-def _merge_sorted(a, b, *args):
-    """model.py:15-55: merge two sorted 1-d device tensors (and companion data) without a sort."""
-    if a.shape[0] < b.shape[0]:
+def _merge_sorted_idx(a, b, *args):
+    """model.py:15-55: merge two sorted 1-d device tensors (and companion data) without a sort.  Also returns the
+    positions of the elements of `a` and of `b` in the merged array.  No boolean mask is materialised and nothing
+    synchronises with the host: the positions of the longer array follow from a second searchsorted
+    (its element i comes after the i elements before it and after every element of the shorter array that is
+    <= it, ties putting the shorter array first exactly like the reference's scatter)."""
+    swapped = a.shape[0] < b.shape[0]
+    if swapped:
         a, b = b, a
         args = tuple((j, i) for i, j in args)
     na, nb = a.shape[0], b.shape[0]
     b_idx = torch.arange(nb, device=a.device) + torch.searchsorted(a, b)
-    is_a = torch.ones(na + nb, dtype=torch.bool, device=a.device)
-    is_a[b_idx] = False
-    a_idx = torch.nonzero(is_a).reshape(-1)
+    a_idx = torch.arange(na, device=a.device) + torch.searchsorted(b, a, right=True)
 
     def inner(u, v):
         c = torch.empty((na + nb,) + tuple(u.shape[1:]), dtype=u.dtype, device=u.device)
@@ -61,7 +65,13 @@ def _merge_sorted(a, b, *args):
         c[a_idx] = u
         return c
 
-    return (inner(a, b),) + tuple(inner(i, j) for i, j in args)
+    merged = (inner(a, b),) + tuple(inner(i, j) for i, j in args)
+    return merged, ((b_idx, a_idx) if swapped else (a_idx, b_idx))
+
+
+def _merge_sorted(a, b, *args):
+    """model.py:15-55 (same returns as the reference)."""
+    return _merge_sorted_idx(a, b, *args)[0]
 
 
 class StateSpaceGP:
@@ -116,7 +126,21 @@ class StateSpaceGP:
     def _make_model(self, ts):
         """model.py:86-90."""
         R = self.noise_variance.value.reshape(1, 1)
+        if not torch.is_grad_enabled():
+            # prediction path: the d x d SDE (balancing + Lyapunov solve on the host) only depends on the
+            # hyper-parameters; keep the one built for the current values
+            from .kernels.base import _get_ssm
+            return _get_ssm(self._cached_sde(), ts, R, 0.)
         return self.kernel.get_ssm(ts, R)
+
+    def _cached_sde(self):
+        key = tuple(float(p.unconstrained_variable) for p in self.kernel.parameters)
+        hit = getattr(self, "_sde_cache", None)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, self.kernel.get_sde())
+            self._sde_cache = hit
+        return hit[1]
 
     def maximum_log_likelihood_objective(self):
         """model.py:113-117; differentiable w.r.t. trainable_variables."""
@@ -136,17 +160,28 @@ class StateSpaceGP:
         Xd = A.to_device(Xnew, dtype, dev, "Xnew").reshape(-1)
         K = Xd.shape[0]
         nan_ys = torch.full((K, ys.shape[1]), float("nan"), dtype=dtype, device=dev)
-        all_ts, all_ys, all_flags = _merge_sorted(ts.reshape(-1), Xd, (ys, nan_ys),
-                                                  (torch.zeros(ts.shape[0], dtype=torch.bool, device=dev),
-                                                   torch.ones(K, dtype=torch.bool, device=dev)))
+        (all_ts, all_ys), (_, q_idx) = _merge_sorted_idx(ts.reshape(-1), Xd, (ys, nan_ys))
         with torch.no_grad():
             ssm = self._make_model(all_ts[:, None])
             Hd, Rd = ssm.H.reshape(-1).contiguous(), ssm.R.reshape(-1).contiguous()
-            fms, fPs, _, _ = ops.pkf(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, all_ys.reshape(-1).contiguous(), want_ll=False)
-            sms, sPs, _ = ops.pks(ssm.Fs, ssm.Qs, fms, fPs)
-            rm, rP = sms[all_flags], sPs[all_flags]
-            mean = rm @ Hd.reshape(-1, 1)
-            var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)
+            yv = all_ys.reshape(-1).contiguous()
+            if ssm.Fs.shape[1] <= ops.SMALL_D:
+                # fused filter + smoother that emits only (H m, H P H^T) of every smoothed state
+                try:
+                    proj = ops.pkfs(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, project=True)[3]
+                except _lib.PssgpError:
+                    proj = None
+            else:
+                proj = None
+            if proj is not None:
+                sel = proj.index_select(0, q_idx)   # rows of the queries (the reference's boolean_mask, model.py:107-108)
+                mean, var = sel[:, 0:1].contiguous(), sel[:, 1:2].contiguous()
+            else:
+                fms, fPs, _, _ = ops.pkf(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, want_ll=False)
+                sms, sPs, _ = ops.pks(ssm.Fs, ssm.Qs, fms, fPs)
+                rm, rP = sms.index_select(0, q_idx), sPs.index_select(0, q_idx)
+                mean = rm @ Hd.reshape(-1, 1)
+                var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)
         if out is not None:
             return A.to_host_into(mean, out[0]), A.to_host_into(var, out[1])
         if A.is_device_tensor(Xnew):

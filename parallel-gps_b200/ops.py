@@ -92,6 +92,28 @@ def pkf_backward(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=None, first_special=Tru
     return dP0, dFs, dQs, dH, dR
 
 
+def pkfs(P0, Fs, Qs, H, R, y, want_ll=False, project=False):
+    """C ABI: pssgp_pkfs (filter + smoother of one whole series, fused for d <= 4).
+    -> fms, fPs, ll (or None), then (sms, sPs), or with project=True proj[n,2] = (H m_k, H P_k H^T) of the smoothed
+    states (d <= 4 only; raises PssgpError otherwise)."""
+    Fs, Qs, y = _al(Fs), _al(Qs), _al(y)
+    n, d = Fs.shape[0], Fs.shape[1]
+    kw = dict(dtype=Fs.dtype, device=Fs.device)
+    fms, fPs = torch.empty((n, d), **kw), torch.empty((n, d, d), **kw)
+    ll = torch.empty((1,), **kw) if want_ll else None
+    sms = sPs = proj = None
+    if project:
+        proj = torch.empty((n, 2), **kw)
+    else:
+        sms, sPs = torch.empty((n, d), **kw), torch.empty((n, d, d), **kw)
+    _lib.check(_lib.lib().pssgp_pkfs(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs), A.ptr(H),
+                                    A.ptr(R), A.ptr(y), A.ptr(fms), A.ptr(fPs), A.ptr(ll), A.ptr(sms), A.ptr(sPs),
+                                    A.ptr(proj), A.stream_ptr(Fs.device)))
+    if project:
+        return fms, fPs, ll, proj
+    return fms, fPs, ll, sms, sPs
+
+
 def pkfs_grad(P0, Fs, Qs, H, R, y, g_ll):
     """C ABI: pssgp_pkfs_grad (filter + log-likelihood + smoother + gradient of one whole series, fused).
     -> (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR)."""

@@ -135,3 +135,34 @@ def test_fused_step_matches_separate_calls_at_bench_size():
     for a, b in zip(g2, ref_g):
         assert rel_err(a.cpu(), b.cpu()) < TOL
     assert torch.equal(sms2[-1], fms2[-1])
+
+
+@pytest.mark.parametrize("name", ["matern12", "matern32", "matern52", "m32xm32"])
+@pytest.mark.parametrize("T", [1, 2, 33, 1000, 20011])
+def test_fused_pkfs_and_projection(name, T):
+    """C ABI pssgp_pkfs: filter + smoother in one call, full outputs and the (H m, H P H^T) projection."""
+    ops = _ops()
+    t, y, cov, ssm = make_problem(name, T, seed=T + 9)
+    with torch.no_grad():
+        fm, fP, ll = O.pkf(ssm, y[:, None], True, max_parallel=max(T, 10000))
+        rsm, rsP = O.pks(ssm, fm, fP, max_parallel=max(T, 10000))
+    d = lambda x: x.detach().to(DEV).contiguous()
+    P0, Fs, Qs, H, R = d(ssm.P0), d(ssm.Fs), d(ssm.Qs), d(ssm.H).reshape(-1), d(ssm.R).reshape(-1)
+    yd = torch.as_tensor(y).to(DEV)
+    fms, fPs, lld, sms, sPs = ops.pkfs(P0, Fs, Qs, H, R, yd, want_ll=True)
+    assert rel_err(fms.cpu(), fm) < TOL and rel_err(fPs.cpu(), fP) < TOL
+    assert abs(float(lld) - float(ll)) <= TOL * max(1.0, abs(float(ll)))
+    assert rel_err(sms.cpu(), rsm) < TOL and rel_err(sPs.cpu(), rsP) < TOL
+    if name == "m32xm32":
+        # d = 4 in FP64: the kernels of the fused path do not share one partition of the time axis (shared-memory
+        # footprints differ), so the projected output is refused loudly and predict_f uses sms / sPs
+        from pssgp_b200 import _lib
+        with pytest.raises(_lib.PssgpError):
+            ops.pkfs(P0, Fs, Qs, H, R, yd, project=True)
+        return
+    proj = ops.pkfs(P0, Fs, Qs, H, R, yd, project=True)[3]
+    h = ssm.H.reshape(-1)
+    ref_mean = rsm @ h
+    ref_var = torch.einsum("i,kij,j->k", h, rsP, h)
+    assert rel_err(proj[:, 0].cpu(), ref_mean) < TOL or float(ref_mean.abs().max()) == 0.0
+    assert rel_err(proj[:, 1].cpu(), ref_var) < TOL
