@@ -166,3 +166,34 @@ def test_fused_pkfs_and_projection(name, T):
     ref_var = torch.einsum("i,kij,j->k", h, rsP, h)
     assert rel_err(proj[:, 0].cpu(), ref_mean) < TOL or float(ref_mean.abs().max()) == 0.0
     assert rel_err(proj[:, 1].cpu(), ref_var) < TOL
+
+
+@pytest.mark.parametrize("name,T", [("matern32", 4000), ("matern52", 20011), ("matern12", 777)])
+@pytest.mark.parametrize("fused_reverse", [0, 1])
+def test_fused_step_fp32(name, T, fused_reverse):
+    """FP32 opt-in mode of the fused step (4 rows per 16-byte-aligned segment instead of 2): tolerance 2e-3
+    relative to ||reference||_inf for the moments and the log-likelihood, 2e-2 for the gradients (float32 eps
+    1.2e-7 amplified by the T-step recursions; the adjoint sums T terms of mixed sign)."""
+    ops = _ops()
+    from pssgp_b200 import _lib
+    t, y, cov, ssm = make_problem(name, T, seed=T + 3)
+    P0, Fs, Qs, H, R = [x.clone().requires_grad_(True) for x in ssm]
+    fm, fP, ll = O.pkf((P0, Fs, Qs, H, R), y[:, None], True, max_parallel=max(T, 10000))
+    gP0, gFs, gQs, gH, gR = torch.autograd.grad(ll, (P0, Fs, Qs, H, R))
+    with torch.no_grad():
+        rsm, rsP = O.pks(ssm, fm.detach(), fP.detach(), max_parallel=max(T, 10000))
+    d = lambda x: x.detach().to(device=DEV, dtype=torch.float32).contiguous()
+    h = _lib.handle(torch.cuda.current_device())
+    h.set_option("fused_reverse", fused_reverse)
+    try:
+        (fms, fPs, lld), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(
+            d(P0), d(Fs), d(Qs), d(H).reshape(-1), d(R).reshape(-1), torch.as_tensor(y, dtype=torch.float32).to(DEV),
+            torch.ones(1, dtype=torch.float32, device=DEV))
+    finally:
+        h.set_option("fused_reverse", 0)
+    assert fms.dtype == torch.float32
+    assert rel_err(fms.cpu(), fm) < 2e-3 and rel_err(fPs.cpu(), fP) < 2e-3
+    assert abs(float(lld) - float(ll)) <= 2e-3 * abs(float(ll))
+    assert rel_err(sms.cpu(), rsm) < 2e-3 and rel_err(sPs.cpu(), rsP) < 2e-3
+    assert rel_err(dFs.cpu(), gFs) < 2e-2 and rel_err(dQs.cpu(), sym(gQs)) < 2e-2
+    assert abs(float(dR) - float(gR)) <= 2e-2 * abs(float(gR))
