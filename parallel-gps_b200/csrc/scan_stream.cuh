@@ -43,6 +43,9 @@
 #ifndef PSSGP_NWCAP
 #define PSSGP_NWCAP 8
 #endif
+#ifndef PSSGP_OUT_POLICY
+#define PSSGP_OUT_POLICY 0  // tuning: 0 = streaming (evict-first) output stores, 1 = default policy, 2 = write-back hint
+#endif
 #ifndef PSSGP_NST
 #define PSSGP_NST 1  // cp.async stages per warp (1: a stage is refilled while its last row is being processed)
 #endif
@@ -205,6 +208,16 @@ __device__ __noinline__ void issue_array_checked(unsigned char* ptr, int g, cons
     }
 }
 
+PSSGP_DEV void st_out16(void* dst, const int4& v) {
+#if PSSGP_OUT_POLICY == 0
+    __stcs(reinterpret_cast<int4*>(dst), v);
+#elif PSSGP_OUT_POLICY == 1
+    *reinterpret_cast<int4*>(dst) = v;
+#else
+    __stwb(reinterpret_cast<int4*>(dst), v);
+#endif
+}
+
 // Mirror of issue_array for an output array: staging slots -> global.
 template <typename T, int W, bool REVERSE>
 PSSGP_DEV void store_array_fast(PieceCursor& pc, int step, const unsigned char* region) {
@@ -214,10 +227,9 @@ PSSGP_DEV void store_array_fast(PieceCursor& pc, int step, const unsigned char* 
         const unsigned char* src = region + pc.soff;
 #pragma unroll
         for (int i = 0; i < IT - 1; ++i)
-            __stcs(reinterpret_cast<int4*>(pc.ptr + (long)i * step), *reinterpret_cast<const int4*>(src + i * GR * PITCH));
+            st_out16(pc.ptr + (long)i * step, *reinterpret_cast<const int4*>(src + i * GR * PITCH));
         if (GR * IT <= 32 || pc.g + GR * (IT - 1) < 32)
-            __stcs(reinterpret_cast<int4*>(pc.ptr + (long)(IT - 1) * step),
-                   *reinterpret_cast<const int4*>(src + (IT - 1) * GR * PITCH));
+            st_out16(pc.ptr + (long)(IT - 1) * step, *reinterpret_cast<const int4*>(src + (IT - 1) * GR * PITCH));
     }
     pc.ptr += REVERSE ? -(long)G::seg_bytes(W) : (long)G::seg_bytes(W);
 }
