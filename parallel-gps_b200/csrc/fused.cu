@@ -12,7 +12,8 @@ constexpr int kNotFused = -12345;  // this (dtype, d) has no common partition: r
 template <typename Alg>
 int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPart& sp, const typename Alg::scalar* lane,
                  const typename Alg::scalar* wexcl, const typename Alg::scalar* wstate, typename Alg::scalar* part,
-                 typename Alg::scalar* acc_out, cudaStream_t st, bool pdl = false) {
+                 typename Alg::scalar* acc_out, cudaStream_t st, bool pdl = false,
+                 const typename Alg::scalar* wprefix = nullptr) {
     using Lay = StreamLayout<Alg>;
     using T = typename Alg::scalar;
     constexpr int NW = Lay::NW;
@@ -29,12 +30,12 @@ int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPar
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         cudaLaunchKernelEx(&cfg, stream_apply_kernel<Alg>, p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket,
-                           acc_out);
+                           acc_out, wprefix);
         return PSSGP_OK;
     }
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
                  (stream_apply_kernel<Alg><<<(unsigned)sp.nCta, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
-                     p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out)));
+                     p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out, wprefix)));
     (void)sizeof(T);
     return PSSGP_OK;
 }
@@ -66,6 +67,7 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
     h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = h->pending_key[KIND_ADJOINT] = nullptr;
+    h->pending_prefix[KIND_FILTER] = h->pending_prefix[KIND_SMOOTHER] = h->pending_prefix[KIND_ADJOINT] = 0;
     // the two reverse scans share one workspace (smoother rows first) so that K3' sees one aggregate / state
     const int NAGG[3] = {FA::NAGG, SA::NAGG + AA::NAGG, AA::NAGG};
     for (int kind = 0; kind < 3; ++kind) {
@@ -106,7 +108,8 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
         PSSGP_LAUNCH(h, FA::name_reduce(), st,
                      (stream_reduce_kernel<FA><<<(unsigned)nCta, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
                          bp, sp, nChunksPad, (T*)h->buf[WS_LANE + KIND_FILTER], (T*)h->buf[WS_WEXCL + KIND_FILTER],
-                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1)));
+                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1,
+                         (T*)nullptr, (T*)nullptr)));
     }
     // K2': seeded filter recursion + chunk aggregates and CTA-level scans of both reverse scans
     launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
@@ -188,13 +191,17 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     const int64_t nChunksPad = nCta * NW * 32;
     const bool reuse = h->pending_key[KIND_FILTER] == Fs && h->pending_n[KIND_FILTER] == n &&
                        h->pending_L[KIND_FILTER] == sp.L;
+    const bool have_prefix = reuse && h->pending_prefix[KIND_FILTER];
     h->pending_key[KIND_FILTER] = nullptr;
+    h->pending_prefix[KIND_FILTER] = 0;
     const int NAGG[3] = {FA::NAGG, SA::NAGG, AA::NAGG};
     for (int kind = reuse ? 1 : 0; kind < 3; ++kind) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
         if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * NAGG[kind] * (size_t)nCta))) return rc;
         if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * NAGG[kind] * (size_t)nCta * NW))) return rc;
     }
+    for (int kind = 1; kind < 3; ++kind)
+        if ((rc = ws_reserve(h, WS_WPREFIX + kind, sizeof(T) * NAGG[kind] * (size_t)nCta))) return rc;
     if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * FA::NSTATE * (size_t)nCta))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (AA::NACC + 1) * (size_t)nCta))) return rc;
     typename FF::Params fp;
@@ -210,9 +217,9 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     fp.first_special = first_special;
     fp.n = n;
     fp.sm = {(T*)h->buf[WS_LANE + KIND_SMOOTHER], (T*)h->buf[WS_WEXCL + KIND_SMOOTHER],
-             (T*)h->buf[WS_WAGG + KIND_SMOOTHER], (T*)nullptr};
+             (T*)h->buf[WS_WAGG + KIND_SMOOTHER], (T*)h->buf[WS_WPREFIX + KIND_SMOOTHER]};
     fp.ad = {(T*)h->buf[WS_LANE + KIND_ADJOINT], (T*)h->buf[WS_WEXCL + KIND_ADJOINT],
-             (T*)h->buf[WS_WAGG + KIND_ADJOINT], (T*)nullptr};
+             (T*)h->buf[WS_WAGG + KIND_ADJOINT], (T*)h->buf[WS_WPREFIX + KIND_ADJOINT]};
     fp.side_ticket = h->ticket + 1;
     fp.last_special = last_special;
     fp.Fnext = (const T*)Fnext;
@@ -220,28 +227,34 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     fp.sm_summary = (T*)sm_summary;
     fp.ad_summary = (T*)ad_summary;
     const typename FA::Params& bp = fp;
-    int nl = 2;
+    int nl = 1;
     if (!reuse) {
         using Lay = StreamLayout<FA>;
         PSSGP_LAUNCH(h, FA::name_reduce(), st,
                      (stream_reduce_kernel<FA><<<(unsigned)nCta, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
                          bp, sp, nChunksPad, (T*)h->buf[WS_LANE + KIND_FILTER], (T*)h->buf[WS_WEXCL + KIND_FILTER],
-                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1)));
-    } else {
+                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1,
+                         (T*)nullptr, (T*)nullptr)));
+        ++nl;
+    } else if (!have_prefix) {
         // the chunk aggregates are those pssgp_pkf_summary left behind: only the scan over the CTA totals is missing
         int midThreads = kMidThreads;
         if (nCta < kMidThreads) midThreads = (int)(((nCta + 31) / 32) * 32);
         PSSGP_LAUNCH(h, FA::name_mid(), st,
                      (scan_mid_kernel<FA><<<1, midThreads, 0, st>>>(bp, (const T*)h->buf[WS_WAGG + KIND_FILTER], nCta,
                                                                    (T*)h->buf[WS_WSTATE], (T*)nullptr)));
+        ++nl;
     }
+    // with prefix aggregates pending, K2' starts from (m0, P0) o prefix[CTA]: no scan over the CTA totals at all
     launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
-                     (const T*)h->buf[WS_WSTATE], (T*)h->buf[WS_PART], (T*)ll, st);
+                     (const T*)h->buf[WS_WSTATE], (T*)h->buf[WS_PART], (T*)ll, st, false,
+                     have_prefix ? (const T*)h->buf[WS_WPREFIX + KIND_FILTER] : (const T*)nullptr);
     // pssgp_pks (key: fPs) and pssgp_pkf_backward (key: fms) on the same arrays skip their reduce kernels
     h->pending_key[KIND_SMOOTHER] = fPs;
     h->pending_key[KIND_ADJOINT] = fms;
     h->pending_n[KIND_SMOOTHER] = h->pending_n[KIND_ADJOINT] = n;
     h->pending_L[KIND_SMOOTHER] = h->pending_L[KIND_ADJOINT] = sp.L;
+    h->pending_prefix[KIND_SMOOTHER] = h->pending_prefix[KIND_ADJOINT] = 1;
     return check_launch(h, "pkf_with_summaries", nl);
     }
 }
@@ -273,6 +286,7 @@ int pkfs_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const 
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
     h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = nullptr;
+    h->pending_prefix[KIND_FILTER] = h->pending_prefix[KIND_SMOOTHER] = 0;
     const int NAGG[2] = {FA::NAGG, SA::NAGG};
     for (int kind = 0; kind < 2; ++kind) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
@@ -308,7 +322,8 @@ int pkfs_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const 
         PSSGP_LAUNCH(h, FA::name_reduce(), st,
                      (stream_reduce_kernel<FA><<<(unsigned)nCta, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
                          bp, sp, nChunksPad, (T*)h->buf[WS_LANE + KIND_FILTER], (T*)h->buf[WS_WEXCL + KIND_FILTER],
-                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1)));
+                         (T*)h->buf[WS_WAGG + KIND_FILTER], (T*)h->buf[WS_WSTATE], (T*)nullptr, h->ticket + 1,
+                         (T*)nullptr, (T*)nullptr)));
     }
     launch_apply<FF>(h, fp, sp, (const T*)h->buf[WS_LANE + KIND_FILTER], (const T*)h->buf[WS_WEXCL + KIND_FILTER],
                      (const T*)h->buf[WS_WSTATE], part, (T*)ll, st, h->pdl != 0);

@@ -52,8 +52,9 @@ struct FusedFwdAlg : FilterAlg<T, D> {
         int last_special;
         const T* Fnext;
         const T* Qnext;
-        // non-null: the last CTA writes the shard summaries of both reverse scans instead of scanning the CTA totals
-        // (the states entering this shard from the right are not known yet: pssgp_pks / pssgp_pkf_backward finish)
+        // non-null: the last CTA writes the shard summaries of both reverse scans and the exclusive prefix aggregate
+        // of every CTA (into sm.wstate / ad.wstate) instead of CTA states (the states entering this shard from the
+        // right are not known yet: pssgp_pks / pssgp_pkf_backward finish with state o prefix)
         T* sm_summary;
         T* ad_summary;
     };
@@ -274,8 +275,8 @@ struct FusedFwdAlg : FilterAlg<T, D> {
             const int tid = (int)threadIdx.x;
             if constexpr (SM) {
                 if (tid < GROUP) {
-                    if (summaries) {
-                        scan_total_body<SA>(p.sm.wagg, nCta, p.sm_summary, sh_mid_s, tid, GROUP, 1);
+                    if (summaries) {  // sm.wstate holds the per-CTA prefix aggregates in this mode
+                        scan_prefix_body<SA>(p.sm.wagg, nCta, p.sm.wstate, p.sm_summary, sh_mid_s, tid, GROUP, 1);
                     } else {
                         typename SA::Params sp{};
                         scan_mid_body<SA>(sp, p.sm.wagg, nCta, p.sm.wstate, (T*)nullptr, sh_mid_s, tid, GROUP, 1);
@@ -286,7 +287,7 @@ struct FusedFwdAlg : FilterAlg<T, D> {
                 const int t2 = BOTH ? tid - GROUP : tid;
                 if (t2 >= 0 && t2 < GROUP) {
                     if (summaries) {
-                        scan_total_body<AA>(p.ad.wagg, nCta, p.ad_summary, sh_mid_a, t2, GROUP, 2);
+                        scan_prefix_body<AA>(p.ad.wagg, nCta, p.ad.wstate, p.ad_summary, sh_mid_a, t2, GROUP, 2);
                     } else {
                         typename AA::Params ap{};
                         scan_mid_body<AA>(ap, p.ad.wagg, nCta, p.ad.wstate, (T*)nullptr, sh_mid_a, t2, GROUP, 2);
@@ -355,6 +356,10 @@ struct FusedRevAlg {
     PSSGP_DEV static void apply(const T* s, const T* a, T* s2) {
         SA::apply(s, a, s2);
         AA::apply(s + SA::NSTATE, a + SA::NAGG, s2 + SA::NSTATE);
+    }
+    PSSGP_DEV static void load_init(const Params& p, T* s) {
+        SA::load_init(p.s, s);
+        AA::load_init(p.a, s + SA::NSTATE);
     }
 
     PSSGP_DEV static int step_row(T* s, const Ctx& cx, const T (&in)[NIN][WMAX], T (&out)[NOUT][WMAX], long k,

@@ -42,8 +42,11 @@ int stream_configure(int device) {
     static unsigned long long done = 0ull;  // one bit per device (the attribute is per device)
     const unsigned long long bit = 1ull << (device & 63);
     if (done & bit) return PSSGP_OK;
-    cudaError_t e = cudaFuncSetAttribute(stream_reduce_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaError_t e = cudaFuncSetAttribute(stream_reduce_kernel<Alg, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          Lay::NW * Lay::WARP_BYTES_REDUCE);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(stream_reduce_kernel<Alg, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 Lay::NW * Lay::WARP_BYTES_REDUCE);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(stream_apply_kernel<Alg>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  Lay::NW * Lay::WARP_BYTES_APPLY);
@@ -124,11 +127,17 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     constexpr int kind = Alg::KIND;
     const bool reuse = (mode == SCAN_FULL && key != nullptr && h->pending_key[kind] == key &&
                         h->pending_n[kind] == n && h->pending_L[kind] == L);
+    // the pending aggregates came with per-CTA prefix aggregates: no scan over the CTA totals is needed (unless
+    // the caller wants the state after the last step, which only that scan produces)
+    const bool have_prefix = reuse && h->pending_prefix[kind] && final_state == nullptr;
     h->pending_key[kind] = nullptr;
+    h->pending_prefix[kind] = 0;
     if (!reuse) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * Alg::NAGG * (size_t)nChunksPad))) return rc;
         if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * Alg::NAGG * (size_t)nW))) return rc;
         if ((rc = ws_reserve(h, WS_WEXCL + kind, sizeof(T) * Alg::NAGG * (size_t)nW * NW))) return rc;
+        if (mode == SCAN_SUMMARY)
+            if ((rc = ws_reserve(h, WS_WPREFIX + kind, sizeof(T) * Alg::NAGG * (size_t)nW))) return rc;
     }
     if ((rc = ws_reserve(h, WS_WSTATE, sizeof(T) * Alg::NSTATE * (size_t)nW))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (Alg::NACC > 0 ? Alg::NACC : 1) * (size_t)nBlocks))) return rc;
@@ -136,14 +145,23 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     T* wagg = (T*)h->buf[WS_WAGG + kind];
     T* wexcl = (T*)h->buf[WS_WEXCL + kind];
     T* wstate = (T*)h->buf[WS_WSTATE];
+    T* wprefix = (T*)h->buf[WS_WPREFIX + kind];
     T* part = (T*)h->buf[WS_PART];
     int nl = 0;
     bool fused_mid = false;
     if (!reuse) {
-        PSSGP_LAUNCH(h, Alg::name_reduce(), st,
-                     (stream_reduce_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
-                         p, sp, nChunksPad, lane, wexcl, wagg, mode == SCAN_FULL ? wstate : nullptr, final_state,
-                         h->ticket + 1)));
+        // SCAN_FULL: the last CTA turns the CTA totals into states; SCAN_SUMMARY: into prefix aggregates + summary
+        if (mode == SCAN_SUMMARY) {
+            PSSGP_LAUNCH(h, Alg::name_reduce(), st,
+                         (stream_reduce_kernel<Alg, true><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
+                             p, sp, nChunksPad, lane, wexcl, wagg, (T*)nullptr, (T*)nullptr, h->ticket + 1, wprefix,
+                             summary)));
+        } else {
+            PSSGP_LAUNCH(h, Alg::name_reduce(), st,
+                         (stream_reduce_kernel<Alg, false><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_REDUCE, st>>>(
+                             p, sp, nChunksPad, lane, wexcl, wagg, wstate, final_state, h->ticket + 1, (T*)nullptr,
+                             (T*)nullptr)));
+        }
         ++nl;
         fused_mid = (mode == SCAN_FULL);
     }
@@ -151,19 +169,20 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     if (nW < kMidThreads) midThreads = (int)(((nW + 31) / 32) * 32);
     if (midThreads < 32) midThreads = 32;
     if (mode == SCAN_SUMMARY) {
-        PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_total_kernel<Alg><<<1, midThreads, 0, st>>>(wagg, nW, summary)));
         h->pending_key[kind] = key;
         h->pending_n[kind] = n;
         h->pending_L[kind] = L;
-        return check_launch(h, "scan summary", nl + 1);
+        h->pending_prefix[kind] = 1;
+        return check_launch(h, "scan summary", nl);
     }
-    if (!fused_mid) {
+    if (!fused_mid && !have_prefix) {
         PSSGP_LAUNCH(h, Alg::name_mid(), st, (scan_mid_kernel<Alg><<<1, midThreads, 0, st>>>(p, wagg, nW, wstate, final_state)));
         ++nl;
     }
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
                  (stream_apply_kernel<Alg><<<(unsigned)nBlocks, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
-                     p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out)));
+                     p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out,
+                     have_prefix ? (const T*)wprefix : (const T*)nullptr)));
     return check_launch(h, "scan", nl + 1);
 }
 

@@ -157,6 +157,124 @@ scan_mid_kernel(typename Alg::Params p, const typename Alg::scalar* __restrict__
     scan_mid_body<Alg>(p, wagg, nW, wstate, final_state, sh, (int)threadIdx.x, (int)blockDim.x, 0);
 }
 
+// Time sharding: like scan_mid_body, but the state entering the shard is not known yet (it depends on the other
+// shards' summaries), so what is produced is the exclusive prefix AGGREGATE of every CTA, wprefix[e*nW + w] =
+// wagg[0] o ... o wagg[w-1] (identity for w = 0), plus the shard summary total_out = wagg[0] o ... o wagg[nW-1].
+// The apply kernel then starts from  state_in o wprefix[w]  (stream_apply_kernel, wprefix != nullptr).
+template <typename Alg>
+__device__ __forceinline__ void scan_prefix_body(const typename Alg::scalar* wagg, long nW, typename Alg::scalar* wprefix,
+                                                 typename Alg::scalar* total_out, typename Alg::scalar* sh, int tid,
+                                                 int nthreads, int bar_id) {
+    using T = typename Alg::scalar;
+    const int lane = tid & 31, wid = tid >> 5;
+    const long per = (nW + nthreads - 1) / nthreads;
+    long i0 = (long)tid * per, i1 = i0 + per;
+    if (i0 > nW) i0 = nW;
+    if (i1 > nW) i1 = nW;
+    T a[Alg::NAGG];
+    Alg::identity(a);
+    for (long i = i0; i < i1; ++i) {
+        T b[Alg::NAGG], r[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
+        if (i == i0) {
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) a[e] = b[e];
+        } else {
+            Alg::combine(a, b, r);
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
+        }
+    }
+    const int nwarps = nthreads >> 5;
+    int logw = 0;
+    while ((1 << logw) < nwarps) ++logw;
+    T ex[Alg::NAGG];  // lane-exclusive within the warp
+#pragma unroll 1
+    for (int lvl = 0;; ++lvl) {
+        if (lvl == 5) {
+            if (lane == 31) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) sh[e * 32 + wid] = a[e];
+            }
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) ex[e] = shfl_up_t(a[e], 1);
+            group_sync(bar_id, nthreads);
+            if (wid != 0) break;
+            if (lane < nwarps) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) a[e] = sh[e * 32 + lane];
+            } else {
+                Alg::identity(a);
+            }
+        }
+        if (lvl == 5 + logw) break;
+        const int off = 1 << (lvl < 5 ? lvl : lvl - 5);
+        T o[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) o[e] = shfl_up_t(a[e], off);
+        if (lane >= off && (lvl < 5 || lane < nwarps)) {
+            T r[Alg::NAGG];
+            Alg::combine(o, a, r);
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) a[e] = r[e];
+        }
+    }
+    if (wid == 0) {
+        // exclusive over warps (the value of lane 0 is never used)
+        T wx[Alg::NAGG];
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) wx[e] = shfl_up_t(a[e], 1);
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) sh[e * 32 + lane] = wx[e];
+    }
+    group_sync(bar_id, nthreads);
+    // g = (prefix of the earlier warps) o (prefix of the earlier lanes), then item by item
+    T g[Alg::NAGG];
+    Alg::identity(g);
+    bool have = false;
+    const long nsteps = 2 + (i1 - i0);
+#pragma unroll 1
+    for (long j = 0; j < nsteps; ++j) {
+        T b[Alg::NAGG];
+        bool act;
+        if (j == 0) {
+            act = wid > 0;
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) b[e] = sh[e * 32 + wid];
+        } else if (j == 1) {
+            act = lane > 0;
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) b[e] = ex[e];
+        } else {
+            const long i = i0 + (j - 2);
+#pragma unroll
+            for (int e = 0; e < Alg::NAGG; ++e) wprefix[(long)e * nW + i] = g[e];
+            act = (i + 1 < i1) || (i1 == nW);  // the aggregate after the last item of all is the shard summary
+            if (act) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) b[e] = __ldcg(wagg + (long)e * nW + i);
+            }
+        }
+        if (act) {
+            if (!have) {
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) g[e] = b[e];
+                have = true;
+            } else {
+                T r[Alg::NAGG];
+                Alg::combine(g, b, r);
+#pragma unroll
+                for (int e = 0; e < Alg::NAGG; ++e) g[e] = r[e];
+            }
+        }
+    }
+    if (total_out != nullptr && i1 == nW && i0 < nW) {
+#pragma unroll
+        for (int e = 0; e < Alg::NAGG; ++e) total_out[e] = g[e];
+    }
+}
+
 // out[NAGG] = wagg[0] o wagg[1] o ... o wagg[nW-1]  (shard summary for time sharding), by a group of `nthreads`
 // threads of one CTA (see scan_mid_body for tid / nthreads / bar_id).  sh: (nthreads / 32) * NAGG scalars.
 template <typename Alg>

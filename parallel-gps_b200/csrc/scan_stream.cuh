@@ -595,12 +595,16 @@ PSSGP_DEV void cta_scan_publish(const typename Alg::scalar (&a_in)[Alg::NAGG], i
 // ---------------------------------------------------------------------------------------------
 // K1: chunk aggregates, warp-exclusive prefixes, CTA-exclusive warp prefixes, CTA totals
 // ---------------------------------------------------------------------------------------------
-template <typename Alg>
+// PREFIX = false: the last CTA turns the CTA totals into the states entering the CTAs (wstate; nullptr: none);
+// PREFIX = true (time sharding): into per-CTA prefix aggregates + the shard summary (scan_prefix_body).  Two
+// instantiations, so that the single-shard kernel does not carry the code of the other tail.
+template <typename Alg, bool PREFIX = false>
 __global__ void __launch_bounds__(StreamLayout<Alg>::NW * 32)
 stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                      typename Alg::scalar* __restrict__ lane_excl, typename Alg::scalar* __restrict__ warp_excl,
                      typename Alg::scalar* __restrict__ wagg, typename Alg::scalar* wstate,
-                     typename Alg::scalar* final_state, unsigned int* ticket) {
+                     typename Alg::scalar* final_state, unsigned int* ticket, typename Alg::scalar* wprefix,
+                     typename Alg::scalar* total_out) {
     using T = typename Alg::scalar;
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
@@ -667,7 +671,7 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
     PSSGP_PHASE(2);
     // K2 folded into K1: the CTA that finishes last scans the CTA totals (wstate == nullptr: the caller runs
     // scan_mid_kernel / scan_total_kernel itself)
-    if (wstate != nullptr) {
+    if (PREFIX || wstate != nullptr) {
         __shared__ bool is_last;
         __shared__ T sh_mid[32 * Alg::NAGG];
         __threadfence();
@@ -680,7 +684,10 @@ stream_reduce_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         PSSGP_PHASE(3);
         if (is_last) {
             __threadfence();
-            scan_mid_body<Alg>(p, wagg, nCta, wstate, final_state, sh_mid, (int)threadIdx.x, (int)blockDim.x, 0);
+            if constexpr (PREFIX)
+                scan_prefix_body<Alg>(wagg, nCta, wprefix, total_out, sh_mid, (int)threadIdx.x, (int)blockDim.x, 0);
+            else
+                scan_mid_body<Alg>(p, wagg, nCta, wstate, final_state, sh_mid, (int)threadIdx.x, (int)blockDim.x, 0);
             if (threadIdx.x == 0) *ticket = 0u;
             __syncthreads();
             PSSGP_PHASE(7);
@@ -698,7 +705,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
                     const typename Alg::scalar* __restrict__ warp_excl,
                     const typename Alg::scalar* __restrict__ wstate,
                     typename Alg::scalar* __restrict__ acc_part, unsigned int* __restrict__ ticket,
-                    typename Alg::scalar* __restrict__ acc_out) {
+                    typename Alg::scalar* __restrict__ acc_out, const typename Alg::scalar* __restrict__ wprefix) {
     using T = typename Alg::scalar;
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
@@ -735,26 +742,39 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
         const bool mine = wg.k_lo < n;
         T st8[Alg::NSTATE];
         {
-            // state entering this chunk = CTA state o warp prefix o lane prefix, on temporaries (see cta_scan_publish)
+            // state entering this chunk = CTA state o warp prefix o lane prefix, on temporaries; one rolled loop so
+            // that the kernel carries ONE inlined copy of apply (cold instruction fetch, see scan_mid_body).
+            // Time sharding (wprefix != nullptr): the CTA state is (state entering the shard) o (prefix of this CTA).
             T sl[Alg::NSTATE];
+            if (wprefix != nullptr) {
+                Alg::load_init(p, sl);
+            } else {
 #pragma unroll
-            for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = wstate[(long)e * nCta + blockIdx.x];
-            if (wid != 0) {
-                T ex[Alg::NAGG], s2[Alg::NSTATE];
-                const long gw = (long)blockIdx.x * NW + wid;
-#pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) ex[e] = warp_excl[(long)e * (nCta * NW) + gw];
-                Alg::apply(sl, ex, s2);
-#pragma unroll
-                for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = s2[e];
+                for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = wstate[(long)e * nCta + blockIdx.x];
             }
-            if (lane != 0 && mine) {
-                T ex[Alg::NAGG], s2[Alg::NSTATE];
+#pragma unroll 1
+            for (int j = 0; j < 3; ++j) {
+                const typename Alg::scalar* src;
+                long stride, idx;
+                bool act;
+                if (j == 0) {
+                    act = wprefix != nullptr && blockIdx.x != 0;
+                    src = wprefix, stride = nCta, idx = blockIdx.x;
+                } else if (j == 1) {
+                    act = wid != 0;
+                    src = warp_excl, stride = nCta * NW, idx = (long)blockIdx.x * NW + wid;
+                } else {
+                    act = lane != 0 && mine;
+                    src = lane_excl, stride = nChunksPad, idx = wg.lc;
+                }
+                if (act) {
+                    T ex[Alg::NAGG], s2[Alg::NSTATE];
 #pragma unroll
-                for (int e = 0; e < Alg::NAGG; ++e) ex[e] = lane_excl[(long)e * nChunksPad + wg.lc];
-                Alg::apply(sl, ex, s2);
+                    for (int e = 0; e < Alg::NAGG; ++e) ex[e] = src[(long)e * stride + idx];
+                    Alg::apply(sl, ex, s2);
 #pragma unroll
-                for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = s2[e];
+                    for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = s2[e];
+                }
             }
 #pragma unroll
             for (int e = 0; e < Alg::NSTATE; ++e) st8[e] = sl[e];

@@ -5,7 +5,7 @@
 
 // chunk-aggregate slots exist once per scan kind (filter / smoother / adjoint) so that several
 // *_summary calls can be pending at the same time.
-enum { WS_LANE = 0, WS_WAGG = 3, WS_WEXCL = 6, WS_WSTATE = 9, WS_PART, WS_MISC, WS_GEN0, WS_GEN1, WS_GEN2, WS_GEN3, WS_WSTATE_S, WS_WSTATE_A, WS_COUNT };
+enum { WS_LANE = 0, WS_WAGG = 3, WS_WEXCL = 6, WS_WSTATE = 9, WS_PART, WS_MISC, WS_GEN0, WS_GEN1, WS_GEN2, WS_GEN3, WS_WSTATE_S, WS_WSTATE_A, WS_WPREFIX, WS_WPREFIX1, WS_WPREFIX2, WS_COUNT };
 enum { KIND_FILTER = 0, KIND_SMOOTHER = 1, KIND_ADJOINT = 2 };
 
 struct pssgp_handle {
@@ -22,6 +22,9 @@ struct pssgp_handle {
     const void* pending_key[3];
     int64_t pending_n[3];
     int pending_L[3];
+    // the pending aggregates come with the exclusive prefix aggregate of every CTA (WS_WPREFIX + kind): the full
+    // call needs no scan over the CTA totals, only state o prefix in the prologue of its apply kernel
+    int pending_prefix[3];
     // optional per-kernel CUDA-event timing (option "timing" = 1)
     int timing;
     int n_rec, cap_rec;

@@ -115,9 +115,10 @@ def test_world1_summary_reuse_path():
     n0 = h.launch_count()
     out = TimeShard(0, 1).filter_smoother_grad(P0, Fs, Qs, H, R, yd, g)
     torch.cuda.synchronize()
-    # d <= 4: filter reduce + total, mid + fused apply (builds both reverse aggregates and their summaries),
-    # then (mid + apply) for the smoother and for the adjoint = 8 launches; the unfused path takes 12
-    assert h.launch_count() - n0 == 8
+    # d <= 4: filter reduce (its last CTA leaves the summary and per-CTA prefix aggregates), fused apply (builds both
+    # reverse aggregates, their summaries and prefix aggregates), smoother apply, adjoint apply = 4 launches; the
+    # unfused path with separate total / mid kernels takes 12
+    assert h.launch_count() - n0 == 4
     assert rel_err(out[1].cpu(), sms.cpu()) < 1e-12 and rel_err(out[2].cpu(), sPs.cpu()) < 1e-12
     assert abs(float(out[0]) - float(ll)) <= 1e-12 * abs(float(ll))
 
