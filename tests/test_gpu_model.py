@@ -104,3 +104,42 @@ def test_noise_variance_gradient_and_training_loss():
     assert abs(float(loss) + float(o_ll)) <= 1e-9 * abs(float(o_ll))
     for a, b in zip(g, o_g):
         assert abs(float(a) + float(b)) <= 1e-9 * max(abs(float(x)) for x in o_g)
+
+
+def test_grid_log_likelihood_matches_oracle():
+    """BASELINE configs[4] (batch of hyper-parameter settings, sum kernel Matern52 + RBF order 6, d = 9): the grid
+    evaluation equals the oracle's StateSpaceGP log-likelihood setting by setting; and a 2-way split of the grid
+    (rank 0 and rank 1 evaluated one after the other with an in-process all-gather) equals the unsplit result."""
+    pkg()
+    from pssgp_b200 import kernels as PK
+    from pssgp_b200.batch import grid_log_likelihood, shard_indices
+    rng = np.random.RandomState(5)
+    t = np.sort(rng.rand(400)) * 4.0
+    y = O.obs_noise(O.sinu(t), 0.1, 2)
+    grid = [(l1, l2) for l1 in (0.3, 1.0, 3.0) for l2 in (0.5, 2.0)]
+    mk_p = lambda l1, l2: PK.Matern52(1.0, l1) + PK.RBF(1.0, l2, order=6, balancing_iter=5)
+    mk_o = lambda l1, l2: O.Matern52(1.0, l1) + O.RBF(1.0, l2, order=6, balancing_iter=5)
+    ll = grid_log_likelihood(mk_p, grid, (t[:, None], y[:, None]), 0.1)
+    for i, s in enumerate(grid):
+        with torch.no_grad():
+            ref = O.StateSpaceGP((torch.as_tensor(t[:, None]), torch.as_tensor(y[:, None])), mk_o(*s), noise_variance=0.1,
+                                 parallel=True, max_parallel=1000).maximum_log_likelihood_objective()
+        assert abs(float(ll[i]) - float(ref)) <= 1e-7 * abs(float(ref)), (i, s)
+
+    class TwoRanks:  # rank r's all_gather sees the other rank's vector computed beforehand
+        def __init__(self):
+            self.vecs = {}
+
+        def all_gather_into_tensor(self, out, vec, group=None):
+            self.vecs[self.rank] = vec.clone()
+            other = self.vecs.get(1 - self.rank, torch.full_like(vec, float("nan")))
+            parts = [self.vecs[0] if self.rank == 0 else other, other if self.rank == 0 else self.vecs[1]]
+            out.copy_(torch.cat(parts))
+
+    fake = TwoRanks()
+    fake.rank = 1
+    grid_log_likelihood(mk_p, grid, (t[:, None], y[:, None]), 0.1, rank=1, world=2, dist=fake)
+    fake.rank = 0
+    split = grid_log_likelihood(mk_p, grid, (t[:, None], y[:, None]), 0.1, rank=0, world=2, dist=fake)
+    assert torch.equal(split, ll)
+    assert shard_indices(7, 1, 3) == [1, 4] and shard_indices(6, 0, 2) == [0, 2, 4]
