@@ -124,6 +124,7 @@ int pssgp_create(pssgp_handle** out, int device) {
     }
     h->num_sms = sms;
     if (const char* env = getenv("PSSGP_CHUNK")) h->chunk_opt = atoll(env);  // tuning aid: same as option "chunk"
+    if (const char* env = getenv("PSSGP_FUSED_REVERSE")) h->fused_reverse = atoi(env) != 0;  // same as the option
     h->pdl = 1;
     if (const char* env = getenv("PSSGP_PDL")) h->pdl = atoi(env) != 0;     // same as option "pdl"
     e = cudaMalloc((void**)&h->ticket, 64);
