@@ -44,7 +44,7 @@
 #define PSSGP_NWCAP 8
 #endif
 #ifndef PSSGP_OUT_POLICY
-#define PSSGP_OUT_POLICY 0  // tuning: 0 = streaming (evict-first) output stores, 1 = default policy, 2 = write-back hint
+#define PSSGP_OUT_POLICY 0  // tuning: 0 = streaming (evict-first) output stores, 1 = default policy, 2 = write-back hint, 3 = write-through
 #endif
 #ifndef PSSGP_NST
 #define PSSGP_NST 1  // cp.async stages per warp (1: a stage is refilled while its last row is being processed)
@@ -213,8 +213,10 @@ PSSGP_DEV void st_out16(void* dst, const int4& v) {
     __stcs(reinterpret_cast<int4*>(dst), v);
 #elif PSSGP_OUT_POLICY == 1
     *reinterpret_cast<int4*>(dst) = v;
-#else
+#elif PSSGP_OUT_POLICY == 2
     __stwb(reinterpret_cast<int4*>(dst), v);
+#else
+    __stwt(reinterpret_cast<int4*>(dst), v);
 #endif
 }
 
