@@ -310,6 +310,7 @@ struct FusedRevAlg {
     using SA = SmootherAlg<T, D>;
     using AA = AdjointAlg<T, D>;
     static const char* name_apply() { return "pks_bwd_apply_fused"; }
+    static constexpr int KIND = KIND_ADJOINT;
     static constexpr int NS = nsym(D);
     static constexpr int NAGG = SA::NAGG + AA::NAGG;
     static constexpr int NSTATE = SA::NSTATE + AA::NSTATE;

@@ -46,6 +46,9 @@
 #ifndef PSSGP_OUT_POLICY
 #define PSSGP_OUT_POLICY 0  // tuning: 0 = streaming (evict-first) output stores, 1 = default policy, 2 = write-back hint, 3 = write-through
 #endif
+#ifndef PSSGP_FETCH_AHEAD_KINDS
+#define PSSGP_FETCH_AHEAD_KINDS 2  // bit mask over KIND_FILTER (1) / KIND_SMOOTHER (2) / KIND_ADJOINT (4), apply kernels
+#endif
 #ifndef PSSGP_NST
 #define PSSGP_NST 1  // cp.async stages per warp (1: a stage is refilled while its last row is being processed)
 #endif
@@ -713,6 +716,9 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
     constexpr int NW = Lay::NW, NST = Lay::NST, LS = Lay::LS;
     constexpr int NACC1 = Alg::NACC > 0 ? Alg::NACC : 1;
     constexpr int ROW_UNROLL = Lay::OUT8 ? 1 : LS;  // OUT8: one rolled copy of the row body (run-time row index)
+    // FETCH_AHEAD (macro PSSGP_FETCH_AHEAD_KINDS, bit per Alg::KIND): all LS rows of a stage go to registers at once
+    // and the stage is refilled before the first of them is processed: the copy has LS rows of arithmetic to land
+    constexpr bool FETCH_AHEAD = !Lay::OUT8 && !Alg::HAS_SIDE && ((PSSGP_FETCH_AHEAD_KINDS >> Alg::KIND) & 1) != 0;
     const long nCta = sp.nCta;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -790,14 +796,31 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             cp_async_wait<NST - 1>();
             __syncwarp();
             const long k0 = wg.k_lo + (long)(Alg::REVERSE ? (nsub - 1 - s) : s) * LS;
+            T rows_all[FETCH_AHEAD ? LS : 1][Alg::NIN][Alg::WMAX];
+            if constexpr (FETCH_AHEAD) {
+#pragma unroll
+                for (int rr = 0; rr < LS; ++rr)
+                    stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, Alg::REVERSE ? (LS - 1 - rr) : rr, rows_all[rr]);
+                __syncwarp();
+                if (s + NST < nsub) in.issue(p, n, L, wg.fast, wsm_addr + st * Lay::STAGE_BYTES);
+                cp_async_commit();
+            }
 #pragma unroll ROW_UNROLL
             for (int rr = 0; rr < LS; ++rr) {
                 const int r = Alg::REVERSE ? (LS - 1 - rr) : rr;
                 const long k = k0 + r;
                 T row[Alg::NIN][Alg::WMAX];
-                if constexpr (Lay::OUT8) stream_fetch_row_rt<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
-                else stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
-                if (rr == LS - 1) {
+                if constexpr (FETCH_AHEAD) {
+#pragma unroll
+                    for (int a = 0; a < Alg::NIN; ++a)
+#pragma unroll
+                        for (int e = 0; e < Alg::WMAX; ++e) row[a][e] = rows_all[rr][a][e];
+                } else if constexpr (Lay::OUT8) {
+                    stream_fetch_row_rt<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
+                } else {
+                    stream_fetch_row<Alg>(wsm + st * Lay::STAGE_BYTES, lane, r, row);
+                }
+                if (!FETCH_AHEAD && rr == LS - 1) {
                     // the stage is drained: hand it back to the copy engine before the last row's arithmetic
                     __syncwarp();
                     if (s + NST < nsub) in.issue(p, n, L, wg.fast, wsm_addr + st * Lay::STAGE_BYTES);
