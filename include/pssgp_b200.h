@@ -179,6 +179,15 @@ int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d,
                              void* fms, void* fPs, void* ll, void* sm_summary, void* ad_summary, void* stream);
 
 /*
+ * Time sharding without fold launches (d <= 4): registers the summaries of the shards that FOLLOW this one (rank
+ * order, `stride` scalars between consecutive summaries, e.g. rows of an all-gather buffer) for the next pssgp_pks
+ * (kind = 1, smoother summaries) or pssgp_pkf_backward (kind = 2, adjoint summaries) on this handle: that call
+ * folds them (last to first) onto its initial state inside its own kernels, as pssgp_smoother_fold /
+ * pssgp_adjoint_fold followed by init / adj_init would, and `init` / `adj_init` may be NULL.  count = 0 clears.
+ */
+int pssgp_set_fold(pssgp_handle* h, int kind, const void* summaries, int count, int64_t stride);
+
+/*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].
  */
 int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d,

@@ -39,6 +39,12 @@ int pkf_bwd_impl(pssgp_handle* h, int64_t n, const void* P0, const void* m0, con
                  int first_special, const void* init, void* dP0, void* dFs, void* dQs, void* dH, void* dR,
                  void* first_state, cudaStream_t st) {
     auto p = adjoint_params<T, D>(n, P0, m0, Fs, Qs, H, R, y, fms, fPs, g_ll, first_special, init, dP0, dFs, dQs, dH, dR);
+    // summaries registered with pssgp_set_fold: folded onto the initial state inside the scan's own kernels
+    p.fold = (const T*)h->fold_ptr[KIND_ADJOINT];
+    p.fold_count = h->fold_count[KIND_ADJOINT];
+    p.fold_stride = (long)h->fold_stride[KIND_ADJOINT];
+    h->fold_ptr[KIND_ADJOINT] = nullptr;
+    h->fold_count[KIND_ADJOINT] = 0;
     return run_scan<AdjointAlg<T, D>>(h, p, n, (T*)dR, (T*)first_state, st, SCAN_FULL, nullptr, dFs ? fms : nullptr);
 }
 
@@ -73,6 +79,8 @@ int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d, const void*
     if (rc) return rc;
     if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs || !g_ll || !dFs || !dQs || !dH || !dR)
         return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    if (h->fold_count[KIND_ADJOINT] > 0 && d > 4)
+        return set_err(PSSGP_ERR_UNSUPPORTED, "pssgp_set_fold is implemented for d <= 4: use pssgp_adjoint_fold");
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_SMALL(pkf_bwd_impl, h, n, P0, m0, Fs, Qs, H, R, y, fms, fPs, g_ll, first_special, adj_init, dP0, dFs, dQs,
                    dH, dR, adj_first, st);

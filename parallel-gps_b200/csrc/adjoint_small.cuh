@@ -63,6 +63,11 @@ struct AdjointAlg {
         T* first_state;   // unused here (returned through final_state of the framework)
         long n;
         int first_special;
+        // time sharding: summaries (Abar, a, B) of the shards that follow, in rank order, fold_stride scalars apart;
+        // folded (last to first) onto `init` (zeros if null) by load_init instead of by pssgp_adjoint_fold
+        const T* fold = nullptr;
+        int fold_count = 0;
+        long fold_stride = 0;
     };
 
     PSSGP_DEV static void identity(T* a) {
@@ -282,6 +287,15 @@ struct AdjointAlg {
     PSSGP_DEV static void load_init(const Params& p, T* s) {
 #pragma unroll
         for (int e = 0; e < NSTATE; ++e) s[e] = p.init ? p.init[e] : T(0);
+#pragma unroll 1
+        for (int i = p.fold_count - 1; i >= 0; --i) {
+            T b[NAGG], s2[NSTATE];
+#pragma unroll
+            for (int e = 0; e < NAGG; ++e) b[e] = p.fold[(long)i * p.fold_stride + e];
+            apply(s, b, s2);
+#pragma unroll
+            for (int e = 0; e < NSTATE; ++e) s[e] = s2[e];
+        }
     }
 
     // Adjoint of the measurement update given (mp, Pp, u, s, r): in (dm+, dP+) -> out (dmp, dPp),

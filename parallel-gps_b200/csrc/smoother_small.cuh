@@ -51,6 +51,11 @@ struct SmootherAlg {
         const T* Fnext;     // [D, D] F of time n (halo) when !last_special
         const T* Qnext;     // [D, D]
         const T* init;      // [NSTATE] smoothed state at time n when !last_special
+        // time sharding: summaries (E, g, L) of the shards that follow, in rank order, fold_stride scalars apart;
+        // folded (last to first) onto `init` (zeros if null) by load_init instead of by pssgp_smoother_fold
+        const T* fold = nullptr;
+        int fold_count = 0;
+        long fold_stride = 0;
     };
 
     PSSGP_DEV static void identity(T* a) {
@@ -194,6 +199,15 @@ struct SmootherAlg {
     PSSGP_DEV static void load_init(const Params& p, T* s) {
 #pragma unroll
         for (int e = 0; e < NSTATE; ++e) s[e] = p.init ? p.init[e] : T(0);
+#pragma unroll 1
+        for (int i = p.fold_count - 1; i >= 0; --i) {
+            T b[NAGG], s2[NSTATE];
+#pragma unroll
+            for (int e = 0; e < NAGG; ++e) b[e] = p.fold[(long)i * p.fold_stride + e];
+            apply(s, b, s2);
+#pragma unroll
+            for (int e = 0; e < NSTATE; ++e) s[e] = s2[e];
+        }
     }
 
     // s = smoothed state at time k+1 -> at time k

@@ -25,6 +25,11 @@ struct pssgp_handle {
     // the pending aggregates come with the exclusive prefix aggregate of every CTA (WS_WPREFIX + kind): the full
     // call needs no scan over the CTA totals, only state o prefix in the prologue of its apply kernel
     int pending_prefix[3];
+    // shard summaries to fold onto the initial state of the next scan of each kind (pssgp_set_fold): the fold then
+    // runs inside that scan's kernels instead of in a launch of its own
+    const void* fold_ptr[3];
+    int fold_count[3];
+    int64_t fold_stride[3];
     // optional per-kernel CUDA-event timing (option "timing" = 1)
     int timing;
     int n_rec, cap_rec;

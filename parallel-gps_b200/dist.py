@@ -104,7 +104,11 @@ class TimeShard:
         if want_smoother:
             na = s_sm.numel()
             init = None
-            if after > 0:
+            fused_fold = d <= getattr(self.ops, "SMALL_D", 0) and hasattr(self.ops, "set_fold")
+            if after > 0 and fused_fold:
+                # the fold runs inside the smoother's own kernels, straight from the rows of the gather buffer
+                self.ops.set_fold(1, gathered[self.rank + 1:, off:off + na], after)
+            elif after > 0:
                 init = self.ops.smoother_fold(gathered[self.rank + 1:, off:off + na].contiguous(), after, d)
             sms, sPs, _ = self.ops.pks(Fs, Qs, fms, fPs, last_special=self.last, Fnext=Fn, Qnext=Qn, init=init)
             out["sms"], out["sPs"] = sms, sPs
@@ -112,7 +116,10 @@ class TimeShard:
         if want_grad:
             na = s_ad.numel()
             adj = None
-            if after > 0:
+            fused_fold = d <= getattr(self.ops, "SMALL_D", 0) and hasattr(self.ops, "set_fold")
+            if after > 0 and fused_fold:
+                self.ops.set_fold(2, gathered[self.rank + 1:, off:off + na], after)
+            elif after > 0:
                 adj = self.ops.adjoint_fold(gathered[self.rank + 1:, off:off + na].contiguous(), after, d)
             dP0, dFs, dQs, dH, dR = self.ops.pkf_backward(P_in, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=m_in,
                                                           first_special=self.first, adj_init=adj)
