@@ -197,3 +197,51 @@ def test_fused_step_fp32(name, T, fused_reverse):
     assert rel_err(sms.cpu(), rsm) < 2e-3 and rel_err(sPs.cpu(), rsP) < 2e-3
     assert rel_err(dFs.cpu(), gFs) < 2e-2 and rel_err(dQs.cpu(), sym(gQs)) < 2e-2
     assert abs(float(dR) - float(gR)) <= 2e-2 * abs(float(gR))
+
+
+def test_fused_step_beyond_2gb_arrays():
+    """N = 3.2e7 at d = 3: Fs, Qs, fPs, sPs, dFs, dQs are 2.3 GB each, so every byte offset past the first 2^31
+    exercises the 64-bit address arithmetic of the streaming kernels.  Checked against the three separate scans
+    (same kernels, different partition bookkeeping) and through size-independent identities: the smoothed state
+    equals the filtered one at the last step, smoothed variances never exceed filtered ones, and the
+    log-likelihood of the whole equals the sum over two halves seeded with the filtered state at the cut."""
+    ops = _ops()
+    if torch.cuda.get_device_properties(0).total_memory < 60e9:
+        pytest.skip("needs ~35 GB of device memory")
+    from pssgp_b200 import kernels
+    n = 32_000_000
+    rng = np.random.RandomState(12)
+    dts = torch.as_tensor(0.004 * rng.uniform(0.5, 1.5, size=n)).to(DEV)
+    t = torch.cumsum(dts, 0)
+    y = torch.sin(np.pi * t) + 0.3 * torch.as_tensor(rng.standard_normal(n)).to(DEV)
+    y[::97] = float("nan")
+    with torch.no_grad():
+        sde = kernels.Matern52(1.0, 1.0).get_sde()
+    F, Pinf, H = sde.F.to(DEV).contiguous(), sde.P0.to(DEV).contiguous(), sde.H.to(DEV).reshape(-1).contiguous()
+    R = torch.tensor([0.1], dtype=torch.float64, device=DEV)
+    g1 = torch.ones(1, dtype=torch.float64, device=DEV)
+    Fs, Qs = ops.discretise(F, Pinf, dts)
+    (fms, fPs, ll), (sms, sPs), grads = ops.pkfs_grad(Pinf, Fs, Qs, H, R, y, g1)
+    assert torch.isfinite(ll).all() and torch.isfinite(sms).all() and torch.isfinite(grads[1]).all()
+    assert torch.equal(sms[-1], fms[-1])
+    assert bool((sPs[:, 0, 0] <= fPs[:, 0, 0] * (1 + 1e-12) + 1e-15).all())
+    # separate scans on the same data
+    fms2, fPs2, ll2, _ = ops.pkf(Pinf, Fs, Qs, H, R, y)
+    assert float((fms2 - fms).abs().max()) <= 1e-12 * float(fms.abs().max())
+    assert abs(float(ll2) - float(ll)) <= 1e-12 * abs(float(ll))
+    del fms2, fPs2
+    sms2, sPs2, _ = ops.pks(Fs, Qs, fms, fPs)
+    assert float((sms2 - sms).abs().max()) <= 1e-9 * float(sms.abs().max())
+    assert float((sPs2 - sPs).abs().max()) <= 1e-9 * float(sPs.abs().max())
+    del sms2, sPs2
+    ref_g = ops.pkf_backward(Pinf, Fs, Qs, H, R, y, fms, fPs, g1)
+    for a, b in zip(grads, ref_g):
+        assert float((a - b).abs().max()) <= 1e-9 * max(float(b.abs().max()), 1e-300)
+    del ref_g
+    # split at the middle: second half seeded with the filtered state at the cut
+    h = n // 2
+    _, _, ll_a, fin = ops.pkf(Pinf, Fs[:h], Qs[:h], H, R, y[:h], want_final=True)
+    d = 3
+    _, _, ll_b, _ = ops.pkf(fin[d:].reshape(d, d).contiguous(), Fs[h:], Qs[h:], H, R, y[h:], m0=fin[:d].contiguous(),
+                            first_special=False)
+    assert abs(float(ll_a) + float(ll_b) - float(ll)) <= 1e-10 * abs(float(ll))
