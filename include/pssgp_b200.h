@@ -179,13 +179,17 @@ int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d,
                              void* fms, void* fPs, void* ll, void* sm_summary, void* ad_summary, void* stream);
 
 /*
- * Time sharding without fold launches (d <= 4): registers the summaries of the shards that FOLLOW this one (rank
- * order, `stride` scalars between consecutive summaries, e.g. rows of an all-gather buffer) for the next pssgp_pks
- * (kind = 1, smoother summaries) or pssgp_pkf_backward (kind = 2, adjoint summaries) on this handle: that call
- * folds them (last to first) onto its initial state inside its own kernels, as pssgp_smoother_fold /
- * pssgp_adjoint_fold followed by init / adj_init would, and `init` / `adj_init` may be NULL.  count = 0 clears.
+ * Time sharding without fold launches (d <= 4): registers shard summaries (rank order, `stride` scalars between
+ * consecutive summaries, e.g. rows of an all-gather buffer) for the next scan of that kind on this handle, which
+ * folds them onto its initial state inside its own kernels:
+ *   kind = 0  filter summaries of the shards BEFORE this one, for pssgp_pkf_with_summaries (which must follow
+ *             pssgp_pkf_summary on the same arrays; P0 / m0 are then the global prior); state_out (m [d] | P [d,d],
+ *             may be NULL) receives the folded state entering the shard, e.g. for pssgp_pkf_backward's P0 / m0;
+ *   kind = 1  smoother summaries of the shards AFTER this one, for pssgp_pks (init may be NULL);
+ *   kind = 2  adjoint summaries of the shards AFTER this one, for pssgp_pkf_backward (adj_init may be NULL).
+ * Equivalent to pssgp_filter_fold / pssgp_smoother_fold / pssgp_adjoint_fold + passing their result.  count = 0 clears.
  */
-int pssgp_set_fold(pssgp_handle* h, int kind, const void* summaries, int count, int64_t stride);
+int pssgp_set_fold(pssgp_handle* h, int kind, const void* summaries, int count, int64_t stride, void* state_out);
 
 /*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].

@@ -39,7 +39,7 @@ SIGNATURES = {
                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_pkfs_grad": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                _vp, _vp, _vp, _vp, _vp]),
-    "pssgp_set_fold": (_int, [_vp, _int, _vp, _int, _i64]),
+    "pssgp_set_fold": (_int, [_vp, _int, _vp, _int, _i64, _vp]),
     "pssgp_pkfs": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_pkf_with_summaries": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _int, _vp, _vp,
                                         _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -174,13 +174,14 @@ int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value) {
     return set_err(PSSGP_ERR_INVALID, "unknown option '%s'", name);
 }
 
-int pssgp_set_fold(pssgp_handle* h, int kind, const void* summaries, int count, int64_t stride) {
+int pssgp_set_fold(pssgp_handle* h, int kind, const void* summaries, int count, int64_t stride, void* state_out) {
     if (!h) return set_err(PSSGP_ERR_INVALID, "null handle");
-    if (kind != KIND_SMOOTHER && kind != KIND_ADJOINT) return set_err(PSSGP_ERR_INVALID, "set_fold: kind must be 1 or 2");
+    if (kind < KIND_FILTER || kind > KIND_ADJOINT) return set_err(PSSGP_ERR_INVALID, "set_fold: kind must be 0, 1 or 2");
     if (count < 0 || (count > 0 && !summaries)) return set_err(PSSGP_ERR_INVALID, "set_fold: bad argument");
     h->fold_ptr[kind] = count > 0 ? summaries : nullptr;
     h->fold_count[kind] = count;
     h->fold_stride[kind] = stride;
+    if (kind == KIND_FILTER) h->fold_state_out = count > 0 ? state_out : nullptr;
     return PSSGP_OK;
 }
 

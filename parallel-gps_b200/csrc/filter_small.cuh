@@ -49,6 +49,11 @@ struct FilterAlg {
         T* fms;        // [n, D]
         T* fPs;        // [n, D, D]
         int first_special;  // 1: logical step 0 is the global first step (parallel.py:13-43 semantics)
+        // time sharding: summaries (A, b, C, J, eta) of the shards BEFORE this one, in rank order, fold_stride scalars
+        // apart; folded (first to last) onto (m0, P0) by load_init instead of by pssgp_filter_fold
+        const T* fold = nullptr;
+        int fold_count = 0;
+        long fold_stride = 0;
     };
 
     PSSGP_DEV static void identity(T* a) {
@@ -260,6 +265,15 @@ struct FilterAlg {
         for (int i = 0; i < D; ++i)
 #pragma unroll
             for (int j = 0; j <= i; ++j) s[D + sidx(i, j)] = T(0.5) * (p.P0[i * D + j] + p.P0[j * D + i]);
+#pragma unroll 1
+        for (int i = 0; i < p.fold_count; ++i) {
+            T b[NAGG], s2[NSTATE];
+#pragma unroll
+            for (int e = 0; e < NAGG; ++e) b[e] = p.fold[(long)i * p.fold_stride + e];
+            apply(s, b, s2);
+#pragma unroll
+            for (int e = 0; e < NSTATE; ++e) s[e] = s2[e];
+        }
     }
 
     // Seeded Kalman step k: s=(m,P) filtered at k-1 -> filtered at k; emits fms/fPs, accumulates ll.

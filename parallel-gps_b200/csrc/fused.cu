@@ -226,6 +226,21 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     fp.Qnext = (const T*)Qnext;
     fp.sm_summary = (T*)sm_summary;
     fp.ad_summary = (T*)ad_summary;
+    // filter summaries of the previous shards registered with pssgp_set_fold: folded onto (m0, P0) in K2' itself
+    if (h->fold_count[KIND_FILTER] > 0) {
+        if (!have_prefix) {
+            h->fold_count[KIND_FILTER] = 0;
+            h->fold_ptr[KIND_FILTER] = nullptr;
+            return set_err(PSSGP_ERR_INVALID, "pkf_with_summaries: pssgp_set_fold(kind 0) needs the aggregates of a "
+                                              "pssgp_pkf_summary call on the same arrays");
+        }
+        fp.fold = (const T*)h->fold_ptr[KIND_FILTER];
+        fp.fold_count = h->fold_count[KIND_FILTER];
+        fp.fold_stride = (long)h->fold_stride[KIND_FILTER];
+        fp.state_in_out = (T*)h->fold_state_out;
+        h->fold_count[KIND_FILTER] = 0;
+        h->fold_ptr[KIND_FILTER] = nullptr;
+    }
     const typename FA::Params& bp = fp;
     int nl = 1;
     if (!reuse) {
@@ -363,6 +378,26 @@ static int pkfs_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const voi
     return kNotFused;
 }
 
+// d <= 4 without a common partition (pkf_with_summaries falls back to separate scans): the registered filter fold is
+// done by the one-thread fold kernel, reading the summaries at their stride.
+template <typename T, int D>
+int filter_fold_strided_impl(pssgp_handle* h, int count, const void* P0, const void* m0, const void* summaries,
+                             long stride, void* state_out, cudaStream_t st) {
+    typename FilterAlg<T, D>::Params p;
+    p.Fs = p.Qs = p.y = p.H = p.R = nullptr;
+    p.P0 = (const T*)P0;
+    p.m0 = (const T*)m0;
+    p.fms = p.fPs = nullptr;
+    p.first_special = 0;
+    return run_fold<FilterAlg<T, D>>(h, p, (const T*)summaries, count, stride, (T*)state_out, st);
+}
+
+static int filter_fold_strided_dispatch(pssgp_handle* h, int dtype, int d, int count, const void* P0, const void* m0,
+                                        const void* summaries, long stride, void* state_out, cudaStream_t st) {
+    DISPATCH_SMALL(filter_fold_strided_impl, h, count, P0, m0, summaries, stride, state_out, st);
+    return set_err(PSSGP_ERR_UNSUPPORTED, "pssgp_set_fold is implemented for d <= 4 (d = %d)", d);
+}
+
 static int with_summaries_dispatch(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs,
                                    const void* Qs, const void* H, const void* R, const void* y, const void* m0,
                                    int first_special, int last_special, const void* Fnext, const void* Qnext, void* fms,
@@ -411,6 +446,23 @@ int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d, const
                                  fPs, ll, sm_summary, ad_summary, st);
     if (rc != kNotFused) return rc;
     // generic state dimension (or no common partition): filter, then the two summaries from their own reduce passes
+    if (h->fold_count[KIND_FILTER] > 0) {
+        // a registered filter fold: done here explicitly; the folded state replaces (m0, P0)
+        const int cnt = h->fold_count[KIND_FILTER];
+        const void* sums = h->fold_ptr[KIND_FILTER];
+        const long stride = (long)h->fold_stride[KIND_FILTER];
+        void* out = h->fold_state_out;
+        h->fold_count[KIND_FILTER] = 0;
+        h->fold_ptr[KIND_FILTER] = nullptr;
+        const size_t esz = dtype == PSSGP_F64 ? 8 : 4;
+        if (!out) {
+            if ((rc = ws_reserve(h, WS_GEN3, esz * (size_t)(d + d * d)))) return rc;
+            out = h->buf[WS_GEN3];
+        }
+        if ((rc = filter_fold_strided_dispatch(h, dtype, d, cnt, P0, m0, sums, stride, out, st))) return rc;
+        m0 = out;
+        P0 = (const char*)out + esz * (size_t)d;
+    }
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, nullptr, stream))) return rc;
     if ((rc = pssgp_pks_summary(h, dtype, n, d, Fs, Qs, fms, fPs, last_special, Fnext, Qnext, sm_summary, stream)))
         return rc;

@@ -57,7 +57,14 @@ struct FusedFwdAlg : FilterAlg<T, D> {
         // right are not known yet: pssgp_pks / pssgp_pkf_backward finish with state o prefix)
         T* sm_summary;
         T* ad_summary;
+        // non-null (with Base::fold): receives the folded state entering the shard, m [D] | P [D, D], for the calls
+        // that need it afterwards (pssgp_pkf_backward's P0 / m0)
+        T* state_in_out = nullptr;
     };
+    // called by every thread of the apply kernel with the state entering the shard (time sharding, prefix mode)
+    PSSGP_DEV static void publish_init(const Params& p, const T* s) {
+        if (p.state_in_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) Base::expand_state(s, p.state_in_out);
+    }
 
     struct Carry : Base::Carry {
         T sa[SA::NAGG];   // e_{k_lo} o ... (smoother elements of this chunk appended so far)

@@ -756,6 +756,7 @@ stream_apply_kernel(typename Alg::Params p, StreamPart sp, long nChunksPad,
             T sl[Alg::NSTATE];
             if (wprefix != nullptr) {
                 Alg::load_init(p, sl);
+                if constexpr (Alg::HAS_SIDE) Alg::publish_init(p, sl);
             } else {
 #pragma unroll
                 for (int e = 0; e < Alg::NSTATE; ++e) sl[e] = wstate[(long)e * nCta + blockIdx.x];

@@ -30,6 +30,7 @@ struct pssgp_handle {
     const void* fold_ptr[3];
     int fold_count[3];
     int64_t fold_stride[3];
+    void* fold_state_out;  // kind 0 only: where the folded state entering the shard is written
     // optional per-kernel CUDA-event timing (option "timing" = 1)
     int timing;
     int n_rec, cap_rec;

@@ -64,14 +64,25 @@ class TimeShard:
             self._halo = (nxt[na:na + d * d].reshape(d, d).contiguous(), nxt[na + d * d:].reshape(d, d).contiguous())
         else:
             self._halo = (None, None)
+        fused = with_reverse_summaries and hasattr(self.ops, "pkf_with_summaries")
+        fused_fold = fused and d <= getattr(self.ops, "SMALL_D", 0) and hasattr(self.ops, "set_fold")
         if self.first:
             m_in, P_in = None, P0
+            m0_arg, P0_arg = None, P0
+        elif fused_fold:
+            # the summaries of the previous shards are folded onto the prior inside the fused kernel, straight from
+            # the rows of the gather buffer; the folded state (needed again by the adjoint) lands in `st`
+            st = torch.empty((d + d * d,), dtype=Fs.dtype, device=Fs.device)
+            self.ops.set_fold(0, gathered[:self.rank, :na], self.rank, state_out=st)
+            m_in, P_in = st[:d], st[d:].reshape(d, d)
+            m0_arg, P0_arg = None, P0
         else:
             st = self.ops.filter_fold(P0, None, gathered[:, :na].contiguous(), self.rank)
             m_in, P_in = st[:d].contiguous(), st[d:].reshape(d, d).contiguous()
+            m0_arg, P0_arg = m_in, P_in
         self._state_in = (m_in, P_in)
-        if with_reverse_summaries and hasattr(self.ops, "pkf_with_summaries"):
-            fms, fPs, ll, s_sm, s_ad = self.ops.pkf_with_summaries(P_in, Fs, Qs, H, R, y, m0=m_in,
+        if fused:
+            fms, fPs, ll, s_sm, s_ad = self.ops.pkf_with_summaries(P0_arg, Fs, Qs, H, R, y, m0=m0_arg,
                                                                    first_special=self.first, last_special=self.last,
                                                                    Fnext=self._halo[0], Qnext=self._halo[1])
             self._rev = (fms, s_sm, s_ad)

@@ -192,14 +192,15 @@ def pks_summary(Fs, Qs, fms, fPs, last_special, Fnext=None, Qnext=None):
     return out
 
 
-def set_fold(kind, summaries, count):
-    """C ABI: pssgp_set_fold.  kind: 1 = smoother, 2 = adjoint.  summaries: [count, NAGG] view (rows may be strided,
-    e.g. a column block of the all-gather buffer; rows in rank order) of the shards that follow this one.  The next
-    pks / pkf_backward on this device's handle folds them onto its initial state inside its own kernels (d <= 4)."""
+def set_fold(kind, summaries, count, state_out=None):
+    """C ABI: pssgp_set_fold.  kind: 0 = filter (summaries of the shards before this one, consumed by
+    pkf_with_summaries; state_out [d + d*d] receives the folded state entering the shard), 1 = smoother, 2 = adjoint
+    (summaries of the shards after this one, consumed by pks / pkf_backward).  summaries: [count, NAGG] view in rank
+    order (rows may be strided, e.g. a column block of the all-gather buffer).  d <= 4 only."""
     if count > 0 and (summaries.dim() != 2 or summaries.stride(1) != 1):
         raise ValueError("summaries must be a 2-d view with unit stride along the last axis")
     _lib.check(_lib.lib().pssgp_set_fold(_h(summaries).ptr, int(kind), A.ptr(summaries) if count > 0 else None, int(count),
-                                         int(summaries.stride(0)) if count > 0 else 0))
+                                         int(summaries.stride(0)) if count > 0 else 0, A.ptr(state_out)))
 
 
 def smoother_fold(summaries, count, d):
