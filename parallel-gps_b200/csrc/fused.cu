@@ -15,7 +15,6 @@ int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPar
                  typename Alg::scalar* acc_out, cudaStream_t st, bool pdl = false,
                  const typename Alg::scalar* wprefix = nullptr) {
     using Lay = StreamLayout<Alg>;
-    using T = typename Alg::scalar;
     constexpr int NW = Lay::NW;
     const long nChunksPad = (long)sp.nCta * NW * 32;
     if (pdl && !h->timing) {
@@ -36,7 +35,6 @@ int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPar
     PSSGP_LAUNCH(h, Alg::name_apply(), st,
                  (stream_apply_kernel<Alg><<<(unsigned)sp.nCta, NW * 32, NW * Lay::WARP_BYTES_APPLY, st>>>(
                      p, sp, nChunksPad, lane, wexcl, wstate, part, h->ticket, acc_out, wprefix)));
-    (void)sizeof(T);
     return PSSGP_OK;
 }
 

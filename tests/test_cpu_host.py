@@ -176,3 +176,25 @@ def test_merge_sorted_matches_argsort():
     a = torch.linspace(0, 1, 5, dtype=torch.float64)
     t, f = _merge_sorted(a, a.clone(), (torch.zeros(5, dtype=torch.bool), torch.ones(5, dtype=torch.bool)))
     assert torch.all(t[1:] >= t[:-1]) and int(f.sum()) == 5
+
+
+def test_merge_sorted_idx_positions_and_batch_sharding():
+    """The sync-free merge returns where each input element went (used by predict_f to pick the query rows without a
+    boolean mask, pssgp/model.py:107-108), for both argument orders; grid settings shard round-robin."""
+    pkg()
+    from pssgp_b200.batch import shard_indices
+    from pssgp_b200.model import _merge_sorted_idx
+    rng = np.random.RandomState(3)
+    for na, nb in ((12, 5), (5, 12), (6, 6), (1, 4)):
+        a = torch.as_tensor(np.sort(rng.rand(na)))
+        b = torch.as_tensor(np.sort(rng.rand(nb)))
+        (t,), (ia, ib) = _merge_sorted_idx(a, b)
+        assert torch.equal(t[ia], a) and torch.equal(t[ib], b)
+        assert sorted(ia.tolist() + ib.tolist()) == list(range(na + nb))
+        assert torch.all(t[1:] >= t[:-1])
+    # ties: the shorter array goes first (searchsorted side='left' in the reference's scatter)
+    a = torch.tensor([0.0, 1.0, 2.0, 3.0], dtype=torch.float64)
+    b = torch.tensor([1.0, 3.0], dtype=torch.float64)
+    (t,), (ia, ib) = _merge_sorted_idx(a, b)
+    assert ib.tolist() == [1, 4] and ia.tolist() == [0, 2, 3, 5]
+    assert [shard_indices(10, r, 4) for r in range(4)] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
