@@ -90,7 +90,6 @@ def pks(lgssm, ms, Ps, max_parallel=10000):
 def pkfs(model, observations, max_parallel=10000):
     """Filter then smoother (parallel.py:199-201); the filtered moments never leave the device."""
     device, dtype, n, d, P0, Fs, Qs, H, R = _prep_lgssm(model, (observations,))
-    dev_model = (P0, Fs, Qs, H.reshape(1, -1), R.reshape(1, 1))
     y = A.to_device(observations, dtype, device, "y").reshape(-1)
     if y.numel() != n:
         raise ValueError(f"observations must be [{n},1], got {tuple(observations.shape)}")
