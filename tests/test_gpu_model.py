@@ -143,3 +143,37 @@ def test_grid_log_likelihood_matches_oracle():
     split = grid_log_likelihood(mk_p, grid, (t[:, None], y[:, None]), 0.1, rank=0, world=2, dist=fake)
     assert torch.equal(split, ll)
     assert shard_indices(7, 1, 3) == [1, 4] and shard_indices(6, 0, 2) == [0, 2, 4]
+
+
+def test_config0_toy_sinusoid_from_the_golden_fixture():
+    """BASELINE configs[0]: Matern32 StateSpaceGP(parallel=True), float64, the reference's toy sinusoid at N = 1,000
+    (data produced by the reference's own pssgp.toymodels, committed as tests/golden/toy_sinusoid_n1000.npz), noise
+    0.1: log-likelihood and predict_f at the 1,000 training times themselves (duplicate times after the merge: steps
+    with dt = 0) against the oracle's StateSpaceGP and the dense GP."""
+    import os
+    from util import ROOT
+    pkg()
+    from pssgp_b200 import kernels as PK
+    from pssgp_b200.model import StateSpaceGP
+    g = np.load(os.path.join(ROOT, "tests", "golden", "toy_sinusoid_n1000.npz"))
+    t, y = g["t"], g["y"]
+    q = t.copy()[:, None]
+    oss = O.StateSpaceGP((t, y), O.Matern32(1., 1.), 0.1, parallel=True, max_parallel=2000)
+    with torch.no_grad():
+        o_ll = oss.maximum_log_likelihood_objective()
+        o_mean, o_var = oss.predict_f(q)
+        gp = O.GPR((t, y), O.Matern32(1., 1.), 0.1)
+        gp_ll = gp.maximum_log_likelihood_objective()
+        gp_mean, gp_var = gp.predict_f(q)
+    ss = StateSpaceGP((t[:, None], y[:, None]), PK.Matern32(1., 1.), 0.1, parallel=True, max_parallel=2000)
+    with torch.no_grad():
+        ll = ss.maximum_log_likelihood_objective()
+    mean, var = ss.predict_f(q)
+    assert mean.shape == (1000, 1) and var.shape == (1000, 1)
+    assert abs(float(ll) - float(o_ll)) <= 1e-9 * abs(float(o_ll))
+    assert np.max(np.abs(mean[:, 0] - o_mean.numpy().reshape(-1))) <= 1e-9 * float(o_mean.abs().max())
+    assert np.max(np.abs(var[:, 0] - o_var.numpy().reshape(-1))) <= 1e-9 * float(o_var.abs().max())
+    # the reference's own contract (tests/test_gp_vs_kfs.py: Matern tolerances 1e-6) against the dense GP
+    np.testing.assert_allclose(float(ll), float(gp_ll), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(mean[:, 0], gp_mean.numpy().reshape(-1), rtol=1e-6, atol=1e-6)
+    np.testing.assert_allclose(var[:, 0], gp_var.numpy().reshape(-1), rtol=1e-6, atol=1e-6)
