@@ -27,17 +27,30 @@ def torch_dtype(x):
 
 
 class _Staging:
-    """Reusable pinned host buffers so numpy callers do not pay cudaHostAlloc on every call."""
+    """Reusable pinned host buffers so numpy callers do not pay cudaHostAlloc on every call.
+
+    A buffer is handed to an asynchronous H2D / D2H copy; the CUDA event recorded right after that copy was
+    enqueued (``mark``) is waited for before the buffer is given out again (``get``), so a second call with the
+    same key never overwrites bytes a still-queued DMA is going to read."""
 
     def __init__(self):
         self._bufs = {}
+        self._events = {}
 
     def get(self, key, nbytes):
+        ev = self._events.pop(key, None)
+        if ev is not None:
+            ev.synchronize()
         buf = self._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
             self._bufs[key] = buf
         return buf
+
+    def mark(self, key, device):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(device))
+        self._events[key] = ev
 
 
 _staging = _Staging()
@@ -69,9 +82,17 @@ def to_device(x, dtype, device, key=None):
         return torch.empty(src.shape, dtype=dtype, device=device)
     if not src.is_pinned():
         nbytes = src.numel() * src.element_size()
-        stage = _staging.get(key if key is not None else id(x), nbytes)[:nbytes].view(dtype).view(src.shape)
+        if key is None:
+            # no reusable slot was named: a fresh pinned tensor (torch's caching host allocator keeps the block
+            # alive until the copy that uses it has run)
+            stage = torch.empty(src.shape, dtype=dtype, pin_memory=True)
+            stage.copy_(src)
+            return stage.to(device, non_blocking=True)
+        stage = _staging.get(key, nbytes)[:nbytes].view(dtype).view(src.shape)
         stage.copy_(src)
-        src = stage
+        out = stage.to(device, non_blocking=True)
+        _staging.mark(key, device)
+        return out
     return src.to(device, non_blocking=True)
 
 

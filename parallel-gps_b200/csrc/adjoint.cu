@@ -43,9 +43,9 @@ int pkf_bwd_impl(pssgp_handle* h, int64_t n, const void* P0, const void* m0, con
     p.fold = (const T*)h->fold_ptr[KIND_ADJOINT];
     p.fold_count = h->fold_count[KIND_ADJOINT];
     p.fold_stride = (long)h->fold_stride[KIND_ADJOINT];
-    h->fold_ptr[KIND_ADJOINT] = nullptr;
-    h->fold_count[KIND_ADJOINT] = 0;
-    return run_scan<AdjointAlg<T, D>>(h, p, n, (T*)dR, (T*)first_state, st, SCAN_FULL, nullptr, dFs ? fms : nullptr);
+    fold_clear(h, KIND_ADJOINT);
+    return run_scan<AdjointAlg<T, D>>(h, p, n, (T*)dR, (T*)first_state, st, SCAN_FULL, nullptr,
+                                      dFs ? adjoint_sig(sizeof(T), D, n, Fs, Qs, y, H, R, fms, fPs, first_special) : 0);
 }
 
 template <typename T, int D>
@@ -54,7 +54,8 @@ int pkf_bwd_summary_impl(pssgp_handle* h, int64_t n, const void* P0, const void*
                          int first_special, void* summary, cudaStream_t st) {
     auto p = adjoint_params<T, D>(n, P0, m0, Fs, Qs, H, R, y, fms, fPs, nullptr, first_special, nullptr, nullptr,
                                   nullptr, nullptr, nullptr, nullptr);
-    return run_scan<AdjointAlg<T, D>>(h, p, n, nullptr, nullptr, st, SCAN_SUMMARY, (T*)summary, fms);
+    return run_scan<AdjointAlg<T, D>>(h, p, n, nullptr, nullptr, st, SCAN_SUMMARY, (T*)summary,
+                                      adjoint_sig(sizeof(T), D, n, Fs, Qs, y, H, R, fms, fPs, first_special));
 }
 
 template <typename T, int D>
@@ -76,11 +77,15 @@ int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d, const void*
                        const void* g_ll, int first_special, const void* adj_init, void* dP0, void* dFs, void* dQs,
                        void* dH, void* dR, void* adj_first, void* stream) {
     int rc = check_common(h, dtype, n, d);
-    if (rc) return rc;
-    if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs || !g_ll || !dFs || !dQs || !dH || !dR)
-        return set_err(PSSGP_ERR_INVALID, "null pointer argument");
-    if (h->fold_count[KIND_ADJOINT] > 0 && d > 4)
+    const bool have_fold = h && h->fold_count[KIND_ADJOINT] > 0;
+    const bool null_arg = !P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs || !g_ll || !dFs || !dQs || !dH || !dR;
+    if (rc || null_arg || (have_fold && d > 4)) {
+        // a registered fold is consumed by this call whether it succeeds or not (never left armed for a later scan)
+        if (h) fold_clear(h, KIND_ADJOINT);
+        if (rc) return rc;
+        if (null_arg) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
         return set_err(PSSGP_ERR_UNSUPPORTED, "pssgp_set_fold is implemented for d <= 4: use pssgp_adjoint_fold");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_SMALL(pkf_bwd_impl, h, n, P0, m0, Fs, Qs, H, R, y, fms, fPs, g_ll, first_special, adj_init, dP0, dFs, dQs,
                    dH, dR, adj_first, st);

@@ -708,6 +708,8 @@ int pssgp_discretise(pssgp_handle* h, int dtype, int64_t n, int d, const void* F
     cudaSetDevice(h->device);
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype != PSSGP_F64 && dtype != PSSGP_F32) return set_err(PSSGP_ERR_INVALID, "bad dtype %d", dtype);
+    // Fs / Qs are about to be overwritten: chunk aggregates built from them (pending *_summary calls) are stale
+    for (int kind = 0; kind < 3; ++kind) pending_clear(h, kind);
     DISPATCH_SMALL(discretise_impl, h, n, F, Pinf, dts, Fs, Qs, st);
     if (d > 64) return set_err(PSSGP_ERR_UNSUPPORTED, "discretise: state dimension %d > 64", d);
     if (dtype == PSSGP_F64) return discretise_generic_impl<double>(h, n, d, F, Pinf, dts, Fs, Qs, st);

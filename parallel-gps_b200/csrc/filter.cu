@@ -27,14 +27,16 @@ int pkf_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const v
              const void* R, const void* y, const void* m0, int first_special, void* fms, void* fPs, void* ll,
              void* final_state, cudaStream_t st) {
     auto p = filter_params<T, D>(P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs);
-    return run_scan<FilterAlg<T, D>>(h, p, n, (T*)ll, (T*)final_state, st, SCAN_FULL, nullptr, Fs);
+    return run_scan<FilterAlg<T, D>>(h, p, n, (T*)ll, (T*)final_state, st, SCAN_FULL, nullptr,
+                                     filter_sig(sizeof(T), D, n, Fs, Qs, y, H, R, first_special));
 }
 
 template <typename T, int D>
 int pkf_summary_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
                      const void* R, const void* y, int first_special, void* summary, cudaStream_t st) {
     auto p = filter_params<T, D>(P0, Fs, Qs, H, R, y, nullptr, first_special, nullptr, nullptr);
-    return run_scan<FilterAlg<T, D>>(h, p, n, nullptr, nullptr, st, SCAN_SUMMARY, (T*)summary, Fs);
+    return run_scan<FilterAlg<T, D>>(h, p, n, nullptr, nullptr, st, SCAN_SUMMARY, (T*)summary,
+                                     filter_sig(sizeof(T), D, n, Fs, Qs, y, H, R, first_special));
 }
 
 template <typename T, int D>
@@ -57,6 +59,9 @@ int pssgp_pkf(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, cons
     if (rc) return rc;
     if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
     cudaStream_t st = (cudaStream_t)stream;
+    // fms / fPs are about to be overwritten: reverse-scan aggregates built from them are stale
+    pending_clear(h, KIND_SMOOTHER);
+    pending_clear(h, KIND_ADJOINT);
     DISPATCH_SMALL(pkf_impl, h, n, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, final_state, st);
     return pkf_generic(h, dtype, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, final_state, nullptr, st);
 }

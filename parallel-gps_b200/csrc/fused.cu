@@ -64,8 +64,7 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     const StreamPart sp = make_partition<NW, LS>(h, n);
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
-    h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = h->pending_key[KIND_ADJOINT] = nullptr;
-    h->pending_prefix[KIND_FILTER] = h->pending_prefix[KIND_SMOOTHER] = h->pending_prefix[KIND_ADJOINT] = 0;
+    for (int kind = 0; kind < 3; ++kind) pending_clear(h, kind);
     // the two reverse scans share one workspace (smoother rows first) so that K3' sees one aggregate / state
     const int NAGG[3] = {FA::NAGG, SA::NAGG + AA::NAGG, AA::NAGG};
     for (int kind = 0; kind < 3; ++kind) {
@@ -187,11 +186,10 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     const StreamPart sp = make_partition<NW, LS>(h, n);
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
-    const bool reuse = h->pending_key[KIND_FILTER] == Fs && h->pending_n[KIND_FILTER] == n &&
-                       h->pending_L[KIND_FILTER] == sp.L;
+    const bool reuse = h->pending_key[KIND_FILTER] == filter_sig(sizeof(T), D, n, Fs, Qs, y, H, R, first_special) &&
+                       h->pending_n[KIND_FILTER] == n && h->pending_L[KIND_FILTER] == sp.L;
     const bool have_prefix = reuse && h->pending_prefix[KIND_FILTER];
-    h->pending_key[KIND_FILTER] = nullptr;
-    h->pending_prefix[KIND_FILTER] = 0;
+    for (int kind = 0; kind < 3; ++kind) pending_clear(h, kind);
     const int NAGG[3] = {FA::NAGG, SA::NAGG, AA::NAGG};
     for (int kind = reuse ? 1 : 0; kind < 3; ++kind) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;
@@ -227,8 +225,7 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
     // filter summaries of the previous shards registered with pssgp_set_fold: folded onto (m0, P0) in K2' itself
     if (h->fold_count[KIND_FILTER] > 0) {
         if (!have_prefix) {
-            h->fold_count[KIND_FILTER] = 0;
-            h->fold_ptr[KIND_FILTER] = nullptr;
+            fold_clear(h, KIND_FILTER);
             return set_err(PSSGP_ERR_INVALID, "pkf_with_summaries: pssgp_set_fold(kind 0) needs the aggregates of a "
                                               "pssgp_pkf_summary call on the same arrays");
         }
@@ -263,8 +260,8 @@ int pkf_with_summaries_impl(pssgp_handle* h, int64_t n, const void* P0, const vo
                      (const T*)h->buf[WS_WSTATE], (T*)h->buf[WS_PART], (T*)ll, st, false,
                      have_prefix ? (const T*)h->buf[WS_WPREFIX + KIND_FILTER] : (const T*)nullptr);
     // pssgp_pks (key: fPs) and pssgp_pkf_backward (key: fms) on the same arrays skip their reduce kernels
-    h->pending_key[KIND_SMOOTHER] = fPs;
-    h->pending_key[KIND_ADJOINT] = fms;
+    h->pending_key[KIND_SMOOTHER] = smoother_sig(sizeof(T), D, n, Fs, Qs, fms, fPs, last_special, Fnext, Qnext);
+    h->pending_key[KIND_ADJOINT] = adjoint_sig(sizeof(T), D, n, Fs, Qs, y, H, R, fms, fPs, first_special);
     h->pending_n[KIND_SMOOTHER] = h->pending_n[KIND_ADJOINT] = n;
     h->pending_L[KIND_SMOOTHER] = h->pending_L[KIND_ADJOINT] = sp.L;
     h->pending_prefix[KIND_SMOOTHER] = h->pending_prefix[KIND_ADJOINT] = 1;
@@ -298,8 +295,7 @@ int pkfs_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const 
     const StreamPart sp = make_partition<NW, LS>(h, n);
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
-    h->pending_key[KIND_FILTER] = h->pending_key[KIND_SMOOTHER] = nullptr;
-    h->pending_prefix[KIND_FILTER] = h->pending_prefix[KIND_SMOOTHER] = 0;
+    for (int kind = 0; kind < 3; ++kind) pending_clear(h, kind);
     const int NAGG[2] = {FA::NAGG, SA::NAGG};
     for (int kind = 0; kind < 2; ++kind) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * NAGG[kind] * (size_t)nChunksPad))) return rc;

@@ -203,7 +203,7 @@ int pick_chunk_generic(const pssgp_handle* h, int64_t n, int d) {
 
 template <class G>
 int run_generic(pssgp_handle* h, typename G::Params p, int64_t n, int d, int nacc, typename G::scalar* acc_out,
-                typename G::scalar* final_state, typename G::scalar* summary, const void* key, cudaStream_t st) {
+                typename G::scalar* final_state, typename G::scalar* summary, uint64_t key, cudaStream_t st) {
     using T = typename G::scalar;
     const int NA = G::nagg(d), NS = G::nstate(d), NWK = G::nwork(d) + kScratch + 8;
     const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
@@ -236,9 +236,9 @@ int run_generic(pssgp_handle* h, typename G::Params p, int64_t n, int d, int nac
         tot += (size_t)cnt[l];
     }
     constexpr int kind = G::KIND;
-    const bool reuse = (summary == nullptr && key != nullptr && h->pending_key[kind] == key && h->pending_n[kind] == n &&
+    const bool reuse = (summary == nullptr && key != 0 && h->pending_key[kind] == key && h->pending_n[kind] == n &&
                         h->pending_L[kind] == L);
-    h->pending_key[kind] = nullptr;
+    pending_clear(h, kind);
     if (!reuse) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * tot * NA))) return rc;
     }
@@ -344,7 +344,8 @@ int pkf_generic_t(pssgp_handle* h, int64_t n, int d, const void* P0, const void*
     p.Fs = (const T*)Fs; p.Qs = (const T*)Qs; p.y = (const T*)y; p.H = (const T*)H; p.R = (const T*)R;
     p.P0 = (const T*)P0; p.m0 = (const T*)m0; p.fms = (T*)fms; p.fPs = (T*)fPs;
     p.n = n; p.d = d; p.first_special = first_special;
-    return run_generic<GFilter<T>>(h, p, n, d, summary ? 0 : 1, (T*)ll, (T*)final_state, (T*)summary, Fs, st);
+    return run_generic<GFilter<T>>(h, p, n, d, summary ? 0 : 1, (T*)ll, (T*)final_state, (T*)summary,
+                                   filter_sig(sizeof(T), d, n, Fs, Qs, y, H, R, first_special), st);
 }
 
 int pkf_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
@@ -377,7 +378,8 @@ int pks_generic_t(pssgp_handle* h, int64_t n, int d, const void* Fs, const void*
     p.Fs = (const T*)Fs; p.Qs = (const T*)Qs; p.fms = (const T*)fms; p.fPs = (const T*)fPs;
     p.sms = (T*)sms; p.sPs = (T*)sPs; p.n = n; p.d = d; p.last_special = last_special;
     p.Fnext = (const T*)Fnext; p.Qnext = (const T*)Qnext; p.init = (const T*)init;
-    return run_generic<GSmoother<T>>(h, p, n, d, 0, nullptr, (T*)first_state, (T*)summary, fPs, st);
+    return run_generic<GSmoother<T>>(h, p, n, d, 0, nullptr, (T*)first_state, (T*)summary,
+                                     smoother_sig(sizeof(T), d, n, Fs, Qs, fms, fPs, last_special, Fnext, Qnext), st);
 }
 
 int pks_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* Fs, const void* Qs, const void* fms,
@@ -413,7 +415,8 @@ int pkf_bwd_generic_t(pssgp_handle* h, int64_t n, int d, const void* P0, const v
     p.P0 = (const T*)P0; p.m0 = (const T*)m0; p.fms = (const T*)fms; p.fPs = (const T*)fPs; p.g = (const T*)g_ll;
     p.init = (const T*)adj_init; p.dFs = (T*)dFs; p.dQs = (T*)dQs; p.dP0 = (T*)dP0; p.dH = (T*)dH; p.dR = (T*)dR;
     p.n = n; p.d = d; p.first_special = first_special;
-    return run_generic<GAdjoint<T>>(h, p, n, d, summary ? 0 : 1 + d, (T*)dR, (T*)adj_first, (T*)summary, fms, st);
+    return run_generic<GAdjoint<T>>(h, p, n, d, summary ? 0 : 1 + d, (T*)dR, (T*)adj_first, (T*)summary,
+                                    adjoint_sig(sizeof(T), d, n, Fs, Qs, y, H, R, fms, fPs, first_special), st);
 }
 
 int pkf_bwd_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* m0, const void* Fs,

@@ -107,7 +107,7 @@ StreamPart make_partition(const pssgp_handle* h, int64_t n) {
 template <typename Alg>
 int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::scalar* acc_out,
              typename Alg::scalar* final_state, cudaStream_t st, int mode = SCAN_FULL,
-             typename Alg::scalar* summary = nullptr, const void* key = nullptr) {
+             typename Alg::scalar* summary = nullptr, uint64_t key = 0) {
     using T = typename Alg::scalar;
     using Lay = StreamLayout<Alg>;
     constexpr int NW = Lay::NW;
@@ -125,13 +125,12 @@ int run_scan(pssgp_handle* h, typename Alg::Params p, int64_t n, typename Alg::s
     const int64_t nW = nBlocks;  // one aggregate per CTA of K1
     const int64_t nChunksPad = nBlocks * NW * 32;
     constexpr int kind = Alg::KIND;
-    const bool reuse = (mode == SCAN_FULL && key != nullptr && h->pending_key[kind] == key &&
+    const bool reuse = (mode == SCAN_FULL && key != 0 && h->pending_key[kind] == key &&
                         h->pending_n[kind] == n && h->pending_L[kind] == L);
     // the pending aggregates came with per-CTA prefix aggregates: no scan over the CTA totals is needed (unless
     // the caller wants the state after the last step, which only that scan produces)
     const bool have_prefix = reuse && h->pending_prefix[kind] && final_state == nullptr;
-    h->pending_key[kind] = nullptr;
-    h->pending_prefix[kind] = 0;
+    pending_clear(h, kind);
     if (!reuse) {
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * Alg::NAGG * (size_t)nChunksPad))) return rc;
         if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * Alg::NAGG * (size_t)nW))) return rc;

@@ -32,16 +32,17 @@ int pks_impl(pssgp_handle* h, int64_t n, const void* Fs, const void* Qs, const v
     p.fold = (const T*)h->fold_ptr[KIND_SMOOTHER];
     p.fold_count = h->fold_count[KIND_SMOOTHER];
     p.fold_stride = (long)h->fold_stride[KIND_SMOOTHER];
-    h->fold_ptr[KIND_SMOOTHER] = nullptr;
-    h->fold_count[KIND_SMOOTHER] = 0;
-    return run_scan<SmootherAlg<T, D>>(h, p, n, nullptr, (T*)first_state, st, SCAN_FULL, nullptr, fPs);
+    fold_clear(h, KIND_SMOOTHER);
+    return run_scan<SmootherAlg<T, D>>(h, p, n, nullptr, (T*)first_state, st, SCAN_FULL, nullptr,
+                                       smoother_sig(sizeof(T), D, n, Fs, Qs, fms, fPs, last_special, Fnext, Qnext));
 }
 
 template <typename T, int D>
 int pks_summary_impl(pssgp_handle* h, int64_t n, const void* Fs, const void* Qs, const void* fms, const void* fPs,
                      int last_special, const void* Fnext, const void* Qnext, void* summary, cudaStream_t st) {
     auto p = smoother_params<T, D>(n, Fs, Qs, fms, fPs, last_special, Fnext, Qnext, nullptr, nullptr, nullptr);
-    return run_scan<SmootherAlg<T, D>>(h, p, n, nullptr, nullptr, st, SCAN_SUMMARY, (T*)summary, fPs);
+    return run_scan<SmootherAlg<T, D>>(h, p, n, nullptr, nullptr, st, SCAN_SUMMARY, (T*)summary,
+                                       smoother_sig(sizeof(T), D, n, Fs, Qs, fms, fPs, last_special, Fnext, Qnext));
 }
 
 template <typename T, int D>
@@ -62,12 +63,17 @@ int pssgp_pks(pssgp_handle* h, int dtype, int64_t n, int d, const void* Fs, cons
               const void* fPs, int last_special, const void* Fnext, const void* Qnext, const void* init, void* sms,
               void* sPs, void* first_state, void* stream) {
     int rc = check_common(h, dtype, n, d);
-    if (rc) return rc;
-    if (!Fs || !Qs || !fms || !fPs || !sms || !sPs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
-    if (!last_special && (!Fnext || !Qnext || (!init && h->fold_count[KIND_SMOOTHER] == 0)))
+    const bool have_fold = h && h->fold_count[KIND_SMOOTHER] > 0;
+    if (rc || !Fs || !Qs || !fms || !fPs || !sms || !sPs || (!last_special && (!Fnext || !Qnext || (!init && !have_fold))) ||
+        (have_fold && d > 4)) {
+        // a registered fold is consumed by this call whether it succeeds or not (never left armed for a later scan)
+        if (h) fold_clear(h, KIND_SMOOTHER);
+        if (rc) return rc;
+        if (!Fs || !Qs || !fms || !fPs || !sms || !sPs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+        if (have_fold && d > 4)
+            return set_err(PSSGP_ERR_UNSUPPORTED, "pssgp_set_fold is implemented for d <= 4: use pssgp_smoother_fold");
         return set_err(PSSGP_ERR_INVALID, "pks: Fnext/Qnext and init (or pssgp_set_fold) required when last_special == 0");
-    if (h->fold_count[KIND_SMOOTHER] > 0 && d > 4)
-        return set_err(PSSGP_ERR_UNSUPPORTED, "pssgp_set_fold is implemented for d <= 4: use pssgp_smoother_fold");
+    }
     cudaStream_t st = (cudaStream_t)stream;
     DISPATCH_SMALL(pks_impl, h, n, Fs, Qs, fms, fPs, last_special, Fnext, Qnext, init, sms, sPs, first_state, st);
     return pks_generic(h, dtype, n, d, Fs, Qs, fms, fPs, last_special, Fnext, Qnext, init, sms, sPs, first_state,

@@ -19,7 +19,10 @@ struct pssgp_handle {
     int fused_reverse;  // option "fused_reverse": pkfs_grad runs smoother + adjoint recursions in one kernel
     int64_t launches;
     // chunk aggregates left in the workspace by a *_summary call (time sharding)
-    const void* pending_key[3];
+    // pending_key = signature (dtype size, d, n, every input pointer, the first/last flags) of the call that built
+    // them, 0 = none; a consumer must present the same signature.  Calls that overwrite arrays the aggregates were
+    // built from (fms / fPs, Fs / Qs) clear the keys of the kinds concerned on entry.
+    uint64_t pending_key[3];
     int64_t pending_n[3];
     int pending_L[3];
     // the pending aggregates come with the exclusive prefix aggregate of every CTA (WS_WPREFIX + kind): the full
@@ -44,6 +47,38 @@ struct pssgp_timing_rec {
 };
 
 namespace pssgp {
+inline uint64_t sig_val(const void* p) { return (uint64_t)(uintptr_t)p; }
+inline uint64_t sig_val(long long v) { return (uint64_t)v; }
+inline uint64_t sig_val(long v) { return (uint64_t)v; }
+inline uint64_t sig_val(int v) { return (uint64_t)(long long)v; }
+inline uint64_t sig_val(unsigned long v) { return (uint64_t)v; }
+template <typename... A> inline uint64_t make_sig(A... a) {
+    uint64_t s = 0x243f6a8885a308d3ull;
+    ((s ^= sig_val(a) + 0x9e3779b97f4a7c15ull + (s << 6) + (s >> 2)), ...);
+    return s ? s : 1;
+}
+// signatures of the three kinds of chunk aggregates (same argument lists on the producing and the consuming side)
+inline uint64_t filter_sig(size_t esz, int d, long long n, const void* Fs, const void* Qs, const void* y, const void* H,
+                           const void* R, int first_special) {
+    return make_sig(0, esz, d, n, Fs, Qs, y, H, R, first_special != 0);
+}
+inline uint64_t smoother_sig(size_t esz, int d, long long n, const void* Fs, const void* Qs, const void* fms,
+                             const void* fPs, int last_special, const void* Fnext, const void* Qnext) {
+    return make_sig(1, esz, d, n, Fs, Qs, fms, fPs, last_special != 0, last_special ? nullptr : Fnext,
+                    last_special ? nullptr : Qnext);
+}
+inline uint64_t adjoint_sig(size_t esz, int d, long long n, const void* Fs, const void* Qs, const void* y, const void* H,
+                            const void* R, const void* fms, const void* fPs, int first_special) {
+    return make_sig(2, esz, d, n, Fs, Qs, y, H, R, fms, fPs, first_special != 0);
+}
+inline void pending_clear(pssgp_handle* h, int kind) {
+    h->pending_key[kind] = 0;
+    h->pending_prefix[kind] = 0;
+}
+inline void fold_clear(pssgp_handle* h, int kind) {
+    h->fold_ptr[kind] = nullptr;
+    h->fold_count[kind] = 0;
+}
 int set_err(int code, const char* fmt, ...);
 int ws_reserve(pssgp_handle* h, int slot, size_t bytes);
 int check_launch(pssgp_handle* h, const char* what, int nlaunches);
