@@ -1,6 +1,8 @@
 // C ABI: pssgp_pkfs_grad — filter + log-likelihood + smoother + gradient in one call (see include/pssgp_b200.h).
 #include "fused_small.cuh"
 #include "scan_run.cuh"
+#include "generic_algebras.cuh"
+#include "mid_host.h"
 
 namespace pssgp {
 
@@ -417,6 +419,11 @@ int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0
     cudaStream_t st = (cudaStream_t)stream;
     rc = fused_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
     if (rc != kNotFused) return rc;
+    if (dtype == PSSGP_F64 && mid::supported(d) && !h->force_generic)
+        return mid::pkfs_grad_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
+                                       (const double*)R, (const double*)y, (const double*)g_ll, (double*)fms, (double*)fPs,
+                                       (double*)ll, (double*)sms, (double*)sPs, (double*)dP0, (double*)dFs, (double*)dQs,
+                                       (double*)dH, (double*)dR, st);
     // generic state dimension (or no common partition): the three scans one after the other
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;
     if ((rc = pssgp_pks(h, dtype, n, d, Fs, Qs, fms, fPs, 1, nullptr, nullptr, nullptr, sms, sPs, nullptr, stream)))
@@ -473,6 +480,10 @@ int pssgp_pkfs(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, con
     cudaStream_t st = (cudaStream_t)stream;
     rc = pkfs_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, fms, fPs, ll, sms, sPs, proj, st);
     if (rc != kNotFused) return rc;
+    if (!proj && dtype == PSSGP_F64 && mid::supported(d) && !h->force_generic)
+        return mid::pkfs_grad_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
+                                       (const double*)R, (const double*)y, nullptr, (double*)fms, (double*)fPs, (double*)ll,
+                                       (double*)sms, (double*)sPs, nullptr, nullptr, nullptr, nullptr, nullptr, st);
     if (proj) return set_err(PSSGP_ERR_UNSUPPORTED, "pkfs: projected output is implemented for the fused d <= 4 path only "
                                                     "(d = %d): pass sms / sPs", d);
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;

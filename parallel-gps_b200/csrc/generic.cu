@@ -11,6 +11,7 @@
 // The generic associative operator (with its d x d solve) is evaluated ~N/L * (1 + 1/Gf + ...) times only.
 #include "generic_algebras.cuh"
 #include "scan_run.cuh"
+#include "mid_host.h"
 
 namespace pssgp {
 
@@ -201,40 +202,108 @@ int pick_chunk_generic(const pssgp_handle* h, int64_t n, int d) {
     return L;
 }
 
+// Level sizes of the fan-out hierarchy over cnt0 level-0 aggregates.
+struct HierLevels {
+    int64_t cnt[kMaxLevels];
+    size_t off[kMaxLevels];
+    int nl;
+    size_t tot;
+};
+static HierLevels hier_levels(int64_t cnt0, int Gf) {
+    HierLevels hl;
+    hl.nl = 0;
+    hl.cnt[hl.nl++] = cnt0;
+    while (hl.cnt[hl.nl - 1] > kTopMax && hl.nl < kMaxLevels) {
+        hl.cnt[hl.nl] = (hl.cnt[hl.nl - 1] + Gf - 1) / Gf;
+        ++hl.nl;
+    }
+    hl.tot = 0;
+    for (int l = 0; l < hl.nl; ++l) {
+        hl.off[l] = hl.tot;
+        hl.tot += (size_t)hl.cnt[l];
+    }
+    return hl;
+}
+constexpr int kGf = 16;
+size_t hier_total(int64_t cnt0) { return hier_levels(cnt0, kGf).tot; }
+
+template <class G> int hier_configure(int d) {
+    using T = typename G::scalar;
+    const int NA = G::nagg(d), NS = G::nstate(d), NWK = G::nwork(d) + kScratch + 8;
+    const size_t sm_up = sizeof(T) * (size_t)(3 * NA + NWK);
+    const size_t sm_top = sm_up > sizeof(T) * (size_t)(NA + 2 * NS + NWK) ? sm_up : sizeof(T) * (size_t)(NA + 2 * NS + NWK);
+    const size_t sm_down = sizeof(T) * (size_t)(NA + 2 * NS + NWK);
+    if (sm_top > 227 * 1024)
+        return set_err(PSSGP_ERR_UNSUPPORTED, "state dimension %d needs %zu B of shared memory per CTA (max 232448)", d, sm_top);
+    int rc;
+    if ((rc = set_smem(g_up_kernel<G>, sm_up))) return rc;
+    if ((rc = set_smem(g_top_kernel<G>, sm_top))) return rc;
+    if ((rc = set_smem(g_down_kernel<G>, sm_down))) return rc;
+    return PSSGP_OK;
+}
+
+// Hierarchy over the level-0 aggregates aggs[0 .. cnt0) (the buffers have room for hier_total(cnt0) entries):
+// up-sweep (unless `have_up`: the upper levels are still valid), then either the shard summary (summary != nullptr)
+// or the top walk + down-sweep that leaves the state entering every level-0 aggregate in states[0 .. cnt0).
+template <class G>
+int run_hierarchy(pssgp_handle* h, const typename G::Params& p, int d, int64_t cnt0, typename G::scalar* aggs,
+                  typename G::scalar* states, typename G::scalar* final_state, typename G::scalar* summary, bool have_up,
+                  cudaStream_t st, int* launches) {
+    using T = typename G::scalar;
+    const int NA = G::nagg(d), NS = G::nstate(d), NWK = G::nwork(d) + kScratch + 8;
+    const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
+    const int Gf = kGf;
+    const size_t sm_up = sizeof(T) * (size_t)(3 * NA + NWK);
+    const size_t sm_top = sm_up > sizeof(T) * (size_t)(NA + 2 * NS + NWK) ? sm_up : sizeof(T) * (size_t)(NA + 2 * NS + NWK);
+    const size_t sm_down = sizeof(T) * (size_t)(NA + 2 * NS + NWK);
+    int rc;
+    if ((rc = hier_configure<G>(d))) return rc;
+    const HierLevels hl = hier_levels(cnt0, Gf);
+    const int nl = hl.nl;
+    if (!have_up) {
+        for (int l = 0; l + 1 < nl; ++l) {
+            PSSGP_LAUNCH(h, G::name(1), st,
+                         (g_up_kernel<G><<<(unsigned)hl.cnt[l + 1], nt, sm_up, st>>>(d, aggs + hl.off[l] * NA, hl.cnt[l], Gf,
+                                                                                      aggs + hl.off[l + 1] * NA)));
+            ++*launches;
+        }
+    }
+    if (summary != nullptr) {
+        PSSGP_LAUNCH(h, G::name(2), st,
+                     (g_top_kernel<G><<<1, nt, sm_top, st>>>(p, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], nullptr, nullptr,
+                                                            summary)));
+        ++*launches;
+        return PSSGP_OK;
+    }
+    PSSGP_LAUNCH(h, G::name(2), st,
+                 (g_top_kernel<G><<<1, nt, sm_top, st>>>(p, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1],
+                                                        states + hl.off[nl - 1] * NS, final_state, nullptr)));
+    ++*launches;
+    for (int l = nl - 2; l >= 0; --l) {
+        PSSGP_LAUNCH(h, G::name(3), st,
+                     (g_down_kernel<G><<<(unsigned)hl.cnt[l + 1], nt, sm_down, st>>>(d, aggs + hl.off[l] * NA, hl.cnt[l], Gf,
+                                                                                     states + hl.off[l + 1] * NS,
+                                                                                     states + hl.off[l] * NS)));
+        ++*launches;
+    }
+    return PSSGP_OK;
+}
+
 template <class G>
 int run_generic(pssgp_handle* h, typename G::Params p, int64_t n, int d, int nacc, typename G::scalar* acc_out,
                 typename G::scalar* final_state, typename G::scalar* summary, uint64_t key, cudaStream_t st) {
     using T = typename G::scalar;
     const int NA = G::nagg(d), NS = G::nstate(d), NWK = G::nwork(d) + kScratch + 8;
     const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
-    const int Gf = 16;
     const int L = pick_chunk_generic(h, n, d);
     const size_t sm_reduce = sizeof(T) * (size_t)(NA + NWK);
-    const size_t sm_up = sizeof(T) * (size_t)(3 * NA + NWK);
-    const size_t sm_top = sm_up > sizeof(T) * (size_t)(NA + 2 * NS + NWK) ? sm_up : sizeof(T) * (size_t)(NA + 2 * NS + NWK);
-    const size_t sm_down = sizeof(T) * (size_t)(NA + 2 * NS + NWK);
     const size_t sm_apply = sizeof(T) * (size_t)(NS + NWK);
-    if (sm_up > 227 * 1024)
-        return set_err(PSSGP_ERR_UNSUPPORTED, "state dimension %d needs %zu B of shared memory per CTA (max 232448)", d, sm_up);
     int rc;
+    if ((rc = hier_configure<G>(d))) return rc;
     if ((rc = set_smem(g_reduce_kernel<G>, sm_reduce))) return rc;
-    if ((rc = set_smem(g_up_kernel<G>, sm_up))) return rc;
-    if ((rc = set_smem(g_top_kernel<G>, sm_top))) return rc;
-    if ((rc = set_smem(g_down_kernel<G>, sm_down))) return rc;
     if ((rc = set_smem(g_apply_kernel<G>, sm_apply))) return rc;
-    // level sizes
-    int64_t cnt[kMaxLevels];
-    int nl = 0;
-    cnt[nl++] = (n + L - 1) / L;
-    while (cnt[nl - 1] > kTopMax && nl < kMaxLevels) {
-        cnt[nl] = (cnt[nl - 1] + Gf - 1) / Gf;
-        ++nl;
-    }
-    size_t tot = 0, off[kMaxLevels];
-    for (int l = 0; l < nl; ++l) {
-        off[l] = tot;
-        tot += (size_t)cnt[l];
-    }
+    const int64_t cnt0 = (n + L - 1) / L;
+    const size_t tot = hier_total(cnt0);
     constexpr int kind = G::KIND;
     const bool reuse = (summary == nullptr && key != 0 && h->pending_key[kind] == key && h->pending_n[kind] == n &&
                         h->pending_L[kind] == L);
@@ -243,46 +312,27 @@ int run_generic(pssgp_handle* h, typename G::Params p, int64_t n, int d, int nac
         if ((rc = ws_reserve(h, WS_LANE + kind, sizeof(T) * tot * NA))) return rc;
     }
     if ((rc = ws_reserve(h, WS_WAGG + kind, sizeof(T) * tot * NS))) return rc;
-    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)cnt[0] * (nacc > 0 ? nacc : 1)))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)cnt0 * (nacc > 0 ? nacc : 1)))) return rc;
     T* aggs = (T*)h->buf[WS_LANE + kind];
     T* states = (T*)h->buf[WS_WAGG + kind];
     T* part = (T*)h->buf[WS_PART];
     int launches = 0;
     if (!reuse) {
-        PSSGP_LAUNCH(h, G::name(0), st, (g_reduce_kernel<G><<<(unsigned)cnt[0], nt, sm_reduce, st>>>(p, n, L, aggs)));
+        PSSGP_LAUNCH(h, G::name(0), st, (g_reduce_kernel<G><<<(unsigned)cnt0, nt, sm_reduce, st>>>(p, n, L, aggs)));
         ++launches;
-        for (int l = 0; l + 1 < nl; ++l) {
-            PSSGP_LAUNCH(h, G::name(1), st,
-                         (g_up_kernel<G><<<(unsigned)cnt[l + 1], nt, sm_up, st>>>(d, aggs + off[l] * NA, cnt[l], Gf,
-                                                                                   aggs + off[l + 1] * NA)));
-            ++launches;
-        }
     }
+    if ((rc = run_hierarchy<G>(h, p, d, cnt0, aggs, states, final_state, summary, reuse, st, &launches))) return rc;
     if (summary != nullptr) {
-        PSSGP_LAUNCH(h, G::name(2), st,
-                     (g_top_kernel<G><<<1, nt, sm_top, st>>>(p, aggs + off[nl - 1] * NA, cnt[nl - 1], nullptr, nullptr,
-                                                            summary)));
         h->pending_key[kind] = key;
         h->pending_n[kind] = n;
         h->pending_L[kind] = L;
-        return check_launch(h, "generic summary", launches + 1);
-    }
-    PSSGP_LAUNCH(h, G::name(2), st,
-                 (g_top_kernel<G><<<1, nt, sm_top, st>>>(p, aggs + off[nl - 1] * NA, cnt[nl - 1],
-                                                        states + off[nl - 1] * NS, final_state, nullptr)));
-    ++launches;
-    for (int l = nl - 2; l >= 0; --l) {
-        PSSGP_LAUNCH(h, G::name(3), st,
-                     (g_down_kernel<G><<<(unsigned)cnt[l + 1], nt, sm_down, st>>>(d, aggs + off[l] * NA, cnt[l], Gf,
-                                                                                  states + off[l + 1] * NS,
-                                                                                  states + off[l] * NS)));
-        ++launches;
+        return check_launch(h, "generic summary", launches);
     }
     PSSGP_LAUNCH(h, G::name(4), st,
-                 (g_apply_kernel<G><<<(unsigned)cnt[0], nt, sm_apply, st>>>(p, n, L, states, nacc, part)));
+                 (g_apply_kernel<G><<<(unsigned)cnt0, nt, sm_apply, st>>>(p, n, L, states, nacc, part)));
     ++launches;
     if (nacc > 0) {
-        PSSGP_LAUNCH(h, "g_finish", st, (g_finish_kernel<G><<<1, 256, 0, st>>>(p, part, cnt[0], nacc, acc_out)));
+        PSSGP_LAUNCH(h, "g_finish", st, (g_finish_kernel<G><<<1, 256, 0, st>>>(p, part, cnt0, nacc, acc_out)));
         ++launches;
     }
     return check_launch(h, "generic scan", launches);
@@ -351,6 +401,10 @@ int pkf_generic_t(pssgp_handle* h, int64_t n, int d, const void* P0, const void*
 int pkf_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
                 const void* H, const void* R, const void* y, const void* m0, int first_special, void* fms, void* fPs,
                 void* ll, void* final_state, void* summary, cudaStream_t st) {
+    if (dtype == PSSGP_F64 && mid::supported(d) && !h->force_generic)
+        return mid::pkf_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
+                                 (const double*)R, (const double*)y, (const double*)m0, first_special, (double*)fms,
+                                 (double*)fPs, (double*)ll, (double*)final_state, (double*)summary, st);
     if (dtype == PSSGP_F64)
         return pkf_generic_t<double>(h, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, final_state, summary, st);
     return pkf_generic_t<float>(h, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, final_state, summary, st);
@@ -424,6 +478,12 @@ int pkf_bwd_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0
                     const void* g_ll, int first_special, const void* adj_init, void* dP0, void* dFs, void* dQs,
                     void* dH, void* dR, void* adj_first, void* summary, cudaStream_t st) {
     if (d > 64) return set_err(PSSGP_ERR_UNSUPPORTED, "pkf_backward: state dimension %d > 64", d);
+    if (dtype == PSSGP_F64 && mid::supported(d) && !h->force_generic && summary == nullptr && adj_init == nullptr &&
+        adj_first == nullptr)
+        return mid::pkf_backward_dispatch(d, h, n, (const double*)P0, (const double*)m0, (const double*)Fs,
+                                          (const double*)Qs, (const double*)H, (const double*)R, (const double*)y,
+                                          (const double*)fms, (const double*)fPs, (const double*)g_ll, first_special,
+                                          (double*)dP0, (double*)dFs, (double*)dQs, (double*)dH, (double*)dR, st);
     if (dtype == PSSGP_F64)
         return pkf_bwd_generic_t<double>(h, n, d, P0, m0, Fs, Qs, H, R, y, fms, fPs, g_ll, first_special, adj_init, dP0,
                                          dFs, dQs, dH, dR, adj_first, summary, st);
@@ -444,6 +504,25 @@ int adjoint_fold_generic(pssgp_handle* h, int dtype, int d, int count, const voi
                          cudaStream_t st) {
     if (dtype == PSSGP_F64) return adjoint_fold_t<double>(h, d, count, summaries, state_out, st);
     return adjoint_fold_t<float>(h, d, count, summaries, state_out, st);
+}
+
+// Hierarchy / finish entry points used by the warp-level d > 4 kernels (mid_inst.cu, one translation unit per d).
+int hier_filter_f64(pssgp_handle* h, const GFilter<double>::Params& p, int d, int64_t cnt0, double* aggs, double* states,
+                    double* final_state, double* summary, bool have_up, cudaStream_t st, int* launches) {
+    return run_hierarchy<GFilter<double>>(h, p, d, cnt0, aggs, states, final_state, summary, have_up, st, launches);
+}
+int hier_rev_f64(pssgp_handle* h, const GRev<double>::Params& p, int d, int64_t cnt0, double* aggs, double* states,
+                 double* final_state, double* summary, bool have_up, cudaStream_t st, int* launches) {
+    return run_hierarchy<GRev<double>>(h, p, d, cnt0, aggs, states, final_state, summary, have_up, st, launches);
+}
+int finish_filter_f64(pssgp_handle* h, const GFilter<double>::Params& p, const double* part, int64_t nparts, double* ll,
+                      cudaStream_t st) {
+    PSSGP_LAUNCH(h, "g_finish", st, (g_finish_kernel<GFilter<double>><<<1, 256, 0, st>>>(p, part, nparts, 1, ll)));
+    return PSSGP_OK;
+}
+int finish_rev_f64(pssgp_handle* h, const GRev<double>::Params& p, const double* part, int64_t nparts, cudaStream_t st) {
+    PSSGP_LAUNCH(h, "g_finish", st, (g_finish_kernel<GRev<double>><<<1, 256, 0, st>>>(p, part, nparts, 1 + p.d, p.dR)));
+    return PSSGP_OK;
 }
 
 }  // namespace pssgp

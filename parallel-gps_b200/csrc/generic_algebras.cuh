@@ -741,4 +741,114 @@ struct GAdjoint {
     }
 };
 
+// ------------------------------------------------------------------------------------------------
+// Combined reverse scan of the fused d > 4 step (mid.cuh): the log-likelihood adjoint (dm, dP) and the
+// solve-free (modified Bryson-Frazier) form of the RTS smoother (lam, Lam) propagate backwards through the SAME
+// transition matrices Abar_k = (I - K_k H) F_k:
+//     dm'  = Abar^T dm  + a          dP'  = Abar^T dP  Abar + sym((Abar^T dm) a^T) + Ba
+//     lam' = Abar^T lam - a          Lam' = Abar^T Lam Abar + Bm
+// with a = F^T H^T r/S, Ba = (r^2/S^2 - 1/S)/2 * F^T H^T H F, Bm = F^T H^T H F / S per observed step (a missing
+// observation: Abar = F, a = Ba = Bm = 0).  Smoothed moments: sm_k = m_k - P_k lam_k, sP_k = P_k - P_k Lam_k P_k
+// (equal to pssgp/kalman/parallel.py:155-196 in exact arithmetic; no d x d solve per step).
+// aggregate: Abar[dd] | Ba[dd] | Bm[dd] | a[d] ; state: dm[d] | lam[d] | dP[dd] | Lam[dd]
+// Only the hierarchy over chunk aggregates runs through this CTA-cooperative algebra; the per-step work is in the
+// warp-level kernels of mid.cuh.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct GRev {
+    using scalar = T;
+    static constexpr int KIND = KIND_ADJOINT;
+    static constexpr int NACC = -1;  // run-time: 1 + d
+    static const char* name(int i) {
+        static const char* n[] = {"mrev_reduce", "mrev_up", "mrev_top", "mrev_down", "mrev_apply"};
+        return n[i];
+    }
+    struct Params {
+        const T* Fs; const T* Qs; const T* y; const T* H; const T* R; const T* P0; const T* m0;
+        const T* fms; const T* fPs; const T* g; const T* init;
+        T* sms; T* sPs; T* dFs; T* dQs; T* dP0; T* dH; T* dR;
+        long n; int d; int first_special;
+    };
+    __host__ __device__ static int nagg(int d) { return 3 * d * d + d; }
+    __host__ __device__ static int nstate(int d) { return 2 * d * d + 2 * d; }
+    __host__ __device__ static int nwork(int d) { return 2 * d * d + 2 * d + 16; }
+
+    __device__ static void identity(const Coop& c, int d, T* a) {
+        co_fill(c, nagg(d), a, T(0));
+        c.sync();
+        for (int i = c.tid; i < d; i += c.nt) a[i * d + i] = T(1);
+        c.sync();
+    }
+
+    // x1 later in time (first in scan order), x2 earlier: out = "x1, then x2"
+    __device__ static void combine(const Coop& c, int d, const T* x1, const T* x2, T* out, T* w, const GScratch<T>&) {
+        const int dd = d * d;
+        const T *A1 = x1, *Ba1 = x1 + dd, *Bm1 = x1 + 2 * dd, *a1 = x1 + 3 * dd;
+        const T *A2 = x2, *Ba2 = x2 + dd, *Bm2 = x2 + 2 * dd, *a2 = x2 + 3 * dd;
+        T *Ao = out, *Bao = out + dd, *Bmo = out + 2 * dd, *ao = out + 3 * dd, *T1 = w, *T2 = w + dd, *t = w + 2 * dd;
+        co_mm(c, d, d, d, A1, d, 1, A2, d, 1, Ao, d, (const T*)nullptr, T(1));
+        co_mm(c, d, d, d, Ba1, d, 1, A2, d, 1, T1, d, (const T*)nullptr, T(1));
+        co_mm(c, d, d, d, Bm1, d, 1, A2, d, 1, T2, d, (const T*)nullptr, T(1));
+        co_mv(c, d, d, A2, 1, d, a1, t, (const T*)nullptr, T(1));
+        c.sync();
+        for (int idx = c.tid; idx < dd; idx += c.nt) {
+            const int i = idx / d, j = idx - i * d;
+            T acc = Ba2[idx] + T(0.5) * (t[i] * a2[j] + t[j] * a2[i]);
+            T acm = Bm2[idx];
+            for (int k = 0; k < d; ++k) {
+                acc = fma(A2[k * d + i], T1[k * d + j], acc);
+                acm = fma(A2[k * d + i], T2[k * d + j], acm);
+            }
+            Bao[idx] = acc;
+            Bmo[idx] = acm;
+        }
+        for (int i = c.tid; i < d; i += c.nt) ao[i] = t[i] + a2[i];
+        c.sync();
+    }
+
+    __device__ static void apply(const Coop& c, int d, const T* s, const T* x, T* s2, T* w, const GScratch<T>&) {
+        const int dd = d * d;
+        const T *Ab = x, *Ba = x + dd, *Bm = x + 2 * dd, *a = x + 3 * dd;
+        const T *dm = s, *lam = s + d, *dP = s + 2 * d, *Lam = s + 2 * d + dd;
+        T *T1 = w, *T2 = w + dd, *t = w + 2 * dd, *tl = t + d;
+        co_mv(c, d, d, Ab, 1, d, dm, t, (const T*)nullptr, T(1));
+        co_mv(c, d, d, Ab, 1, d, lam, tl, (const T*)nullptr, T(1));
+        co_mm(c, d, d, d, dP, d, 1, Ab, d, 1, T1, d, (const T*)nullptr, T(1));
+        co_mm(c, d, d, d, Lam, d, 1, Ab, d, 1, T2, d, (const T*)nullptr, T(1));
+        c.sync();
+        for (int idx = c.tid; idx < dd; idx += c.nt) {
+            const int i = idx / d, j = idx - i * d;
+            T acc = Ba[idx] + T(0.5) * (t[i] * a[j] + t[j] * a[i]);
+            T acm = Bm[idx];
+            for (int k = 0; k < d; ++k) {
+                acc = fma(Ab[k * d + i], T1[k * d + j], acc);
+                acm = fma(Ab[k * d + i], T2[k * d + j], acm);
+            }
+            s2[2 * d + idx] = acc;
+            s2[2 * d + dd + idx] = acm;
+        }
+        for (int i = c.tid; i < d; i += c.nt) {
+            s2[i] = t[i] + a[i];
+            s2[d + i] = tl[i] - a[i];
+        }
+        c.sync();
+    }
+
+    __device__ static void load_init(const Coop& c, const Params& p, T* s) {
+        const int d = p.d;
+        if (!p.init) co_fill(c, nstate(d), s, T(0));
+        else co_copy(c, nstate(d), p.init, s);
+        c.sync();
+    }
+    __device__ static void expand_state(const Coop& c, int d, const T* s, T* out) { co_copy(c, nstate(d), s, out); }
+    __device__ static void finish(const Params& p, int e, T tot, T*) {
+        const T gl = p.g ? p.g[0] : T(1);
+        if (e == 0) {
+            if (p.dR) p.dR[0] = gl * tot;
+        } else if (p.dH) {
+            p.dH[e - 1] = gl * tot;
+        }
+    }
+};
+
 }  // namespace pssgp

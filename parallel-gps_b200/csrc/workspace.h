@@ -16,6 +16,7 @@ struct pssgp_handle {
     unsigned int* ticket;
     int64_t chunk_opt;
     int pdl;            // option "pdl": programmatic dependent launch between the kernels of pkfs_grad
+    int force_generic;  // option "force_generic": d > 4 runs the CTA-cooperative kernels of generic.cu (tuning / tests)
     int fused_reverse;  // option "fused_reverse": pkfs_grad runs smoother + adjoint recursions in one kernel
     int64_t launches;
     // chunk aggregates left in the workspace by a *_summary call (time sharding)
