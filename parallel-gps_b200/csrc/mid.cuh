@@ -152,6 +152,16 @@ template <class G, class Fn> MDEV void vsweep(const Grp& g, Fn fn) {
 template <class G> MDEV void load_mat(const Grp& g, double* dst, const double* src) {
     sweep<G>(g, [&](int i, int j, int idx) { cp8(dst + i * G::LD + j, src + idx); });
 }
+// M <- (M + M^T) / 2 in place (every unordered pair is handled by one thread)
+template <class G> MDEV void sym_inplace(const Grp& g, double* M) {
+    sweep<G>(g, [&](int i, int j, int) {
+        if (j > i) {
+            const double v = 0.5 * (M[i * G::LD + j] + M[j * G::LD + i]);
+            M[i * G::LD + j] = v;
+            M[j * G::LD + i] = v;
+        }
+    });
+}
 template <class G> MDEV void load_vec(const Grp& g, double* dst, const double* src) {
     vsweep<G>(g, [&](int i) { cp8(dst + i, src + i); });
 }
@@ -240,7 +250,8 @@ k1_filter_reduce(Params p, int L, long nchunks, double* __restrict__ aggs) {
         const double yk = ynext;
         if (i + 1 < nrows) ynext = p.y[k + 1];
         const double* F = ring + (i % NSLOT) * 2 * MSZ;
-        const double* Q = F + MSZ;
+        double* Q = ring + (i % NSLOT) * 2 * MSZ + MSZ;
+        sym_inplace<G>(g, Q);
         const bool first = (k == 0 && p.first_special);
         if (!first) {
             mm<G, false, false>(g, F, A, A2);
@@ -372,9 +383,10 @@ k2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, do
         const double yk = ynext;
         if (i + 1 < nrows) ynext = p.y[k + 1];
         const bool obs = !isnan(yk);
-        const double* sl = ring + (i % NSLOT) * K::SLOT;
+        double* sl = ring + (i % NSLOT) * K::SLOT;
         const double* F = sl;
-        const double* Q = sl + MSZ;
+        double* Q = sl + MSZ;
+        sym_inplace<G>(g, Q);
         const double* Pc = STORED ? sl + 2 * MSZ : P;
         const double* mc = STORED ? sl + 3 * MSZ : m;
         const bool first = (k == 0 && p.first_special);
@@ -555,9 +567,10 @@ k3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, do
         const double yk = ynext;
         if (j + 1 < nrows) ynext = p.y[k - 1];
         const bool obs = !isnan(yk);
-        const double* sl = slot(k);
+        double* sl = slot(k);
         const double* F = sl;
-        const double* Q = sl + MSZ;
+        double* Q = sl + MSZ;
+        sym_inplace<G>(g, Q);
         const double* Pk = sl + 2 * MSZ;
         const double* mk = sl + 3 * MSZ;
         const double* slp = slot(k - 1);

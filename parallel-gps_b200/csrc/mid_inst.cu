@@ -1,5 +1,7 @@
 // Explicit instantiation of the warp-level d > 4 path for ONE state dimension (compile with -DMID_D=<D>).
 #include "mid.cuh"
+#include "mid_frag.cuh"
+#include "mid_hier.cuh"
 #include "mid_host.h"
 
 #ifndef MID_D
@@ -13,6 +15,106 @@ template <class Kern> static int set_smem_attr(Kern kernel, size_t bytes) {
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
     if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "cudaFuncSetAttribute(%zu): %s", bytes, cudaGetErrorString(e));
     return PSSGP_OK;
+}
+
+
+// Kernel family per state dimension: fragment-resident (registers, one warp per chunk) up to D = 16, shared-memory
+// tiles with groups of warps above.  Option "mid_smem" forces the shared-memory family (tests / tuning).
+template <int D> constexpr bool has_frag() { return D <= 16; }
+
+template <int D> static int k1_groups(bool fr) {
+    if constexpr (has_frag<D>()) if (fr) return frag::FK1<D>::WPC;
+    return K1<D, default_wg<D>()>::GPC;
+}
+template <int D, bool REV, bool STORED> static int k2_groups(bool fr) {
+    if constexpr (has_frag<D>()) if (fr) return frag::FK2<D, REV, STORED>::WPC;
+    return K2<D, default_wg<D>(), REV, STORED>::GPC;
+}
+template <int D, bool SMOOTH, bool ADJ> static int k3_groups(bool fr) {
+    if constexpr (has_frag<D>()) if (fr) return frag::FK3<D, SMOOTH, ADJ>::WPC;
+    return K3<D, default_wg<D>(), SMOOTH, ADJ>::GPC;
+}
+
+template <int D> static int launch_k1(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, double* aggs, cudaStream_t st) {
+    int rc;
+    if constexpr (has_frag<D>()) {
+        if (fr) {
+            using KA = frag::FK1<D>;
+            if ((rc = set_smem_attr(frag::fk1_filter_reduce<D>, KA::SMEM))) return rc;
+            const unsigned grid = (unsigned)((nchunks + KA::WPC - 1) / KA::WPC);
+            PSSGP_LAUNCH(h, "mid_filter_reduce", st, (frag::fk1_filter_reduce<D><<<grid, KA::WPC * 32, KA::SMEM, st>>>(p, L, nchunks, aggs)));
+            return PSSGP_OK;
+        }
+    }
+    constexpr int WG = default_wg<D>();
+    using KA = K1<D, WG>;
+    if ((rc = set_smem_attr(k1_filter_reduce<D, WG>, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8))) return rc;
+    const unsigned grid = (unsigned)((nchunks + KA::GPC - 1) / KA::GPC);
+    PSSGP_LAUNCH(h, "mid_filter_reduce", st,
+                 (k1_filter_reduce<D, WG><<<grid, KA::GPC * WG * 32, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8, st>>>(p, L, nchunks, aggs)));
+    return PSSGP_OK;
+}
+
+template <int D, bool REV, bool STORED>
+static int launch_k2(pssgp_handle* h, bool fr, const char* name, const Params& p, int L, int64_t nchunks, const double* fstates,
+                     double* part, double* raggs, cudaStream_t st) {
+    int rc;
+    if constexpr (has_frag<D>()) {
+        if (fr) {
+            using KB = frag::FK2<D, REV, STORED>;
+            if ((rc = set_smem_attr(frag::fk2_forward<D, REV, STORED>, KB::SMEM))) return rc;
+            const unsigned grid = (unsigned)((nchunks + KB::WPC - 1) / KB::WPC);
+            PSSGP_LAUNCH(h, name, st,
+                         (frag::fk2_forward<D, REV, STORED><<<grid, KB::WPC * 32, KB::SMEM, st>>>(p, L, nchunks, fstates, part, raggs)));
+            return PSSGP_OK;
+        }
+    }
+    constexpr int WG = default_wg<D>();
+    using KB = K2<D, WG, REV, STORED>;
+    if ((rc = set_smem_attr(k2_forward<D, WG, REV, STORED>, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8))) return rc;
+    const unsigned grid = (unsigned)((nchunks + KB::GPC - 1) / KB::GPC);
+    PSSGP_LAUNCH(h, name, st,
+                 (k2_forward<D, WG, REV, STORED><<<grid, KB::GPC * WG * 32, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8, st>>>(
+                     p, L, nchunks, fstates, part, raggs)));
+    return PSSGP_OK;
+}
+
+template <int D, bool SMOOTH, bool ADJ>
+static int launch_k3(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, const double* rstates, double* part,
+                     cudaStream_t st) {
+    int rc;
+    if constexpr (has_frag<D>()) {
+        if (fr) {
+            using KC = frag::FK3<D, SMOOTH, ADJ>;
+            if ((rc = set_smem_attr(frag::fk3_reverse<D, SMOOTH, ADJ>, KC::SMEM))) return rc;
+            const unsigned grid = (unsigned)((nchunks + KC::WPC - 1) / KC::WPC);
+            PSSGP_LAUNCH(h, "mid_reverse", st,
+                         (frag::fk3_reverse<D, SMOOTH, ADJ><<<grid, KC::WPC * 32, KC::SMEM, st>>>(p, L, nchunks, rstates, part)));
+            return PSSGP_OK;
+        }
+    }
+    constexpr int WG = default_wg<D>();
+    using KC = K3<D, WG, SMOOTH, ADJ>;
+    if ((rc = set_smem_attr(k3_reverse<D, WG, SMOOTH, ADJ>, (size_t)KC::GPC * KC::GROUP_DOUBLES * 8))) return rc;
+    const unsigned grid = (unsigned)((nchunks + KC::GPC - 1) / KC::GPC);
+    PSSGP_LAUNCH(h, "mid_reverse", st,
+                 (k3_reverse<D, WG, SMOOTH, ADJ><<<grid, KC::GPC * WG * 32, (size_t)KC::GPC * KC::GROUP_DOUBLES * 8, st>>>(
+                     p, L, nchunks, rstates, part)));
+    return PSSGP_OK;
+}
+
+template <int D>
+static int hier_filter(pssgp_handle* h, const Params& p, int64_t nchunks, double* aggs, double* states, double* final_state,
+                       double* summary, bool have_up, cudaStream_t st, int* launches) {
+    static const char* const names[3] = {"mhier_filter_up", "mhier_filter_top", "mhier_filter_down"};
+    const typename hier::FilterH<D>::Init in = {p.P0, p.m0};
+    return hier::run<hier::FilterH<D>>(h, in, nchunks, aggs, states, final_state, summary, have_up, names, st, launches);
+}
+template <int D>
+static int hier_rev(pssgp_handle* h, int64_t nchunks, double* raggs, double* rstates, cudaStream_t st, int* launches) {
+    static const char* const names[3] = {"mhier_rev_up", "mhier_rev_top", "mhier_rev_down"};
+    const typename hier::RevH<D>::Init in = {nullptr};
+    return hier::run<hier::RevH<D>>(h, in, nchunks, raggs, rstates, nullptr, nullptr, false, names, st, launches);
 }
 
 // chunk length: one resident wave of groups of the most shared-memory-hungry kernel of the call
@@ -52,17 +154,14 @@ template <int D>
 int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H, const double* R,
         const double* y, const double* m0, int first_special, double* fms, double* fPs, double* ll, double* final_state,
         double* summary, cudaStream_t st) {
-    constexpr int WG = default_wg<D>();
-    using KA = K1<D, WG>;
-    using KB = K2<D, WG, false, false>;
+    const bool fr = has_frag<D>() && !h->mid_smem;
     int rc;
-    if ((rc = set_smem_attr(k1_filter_reduce<D, WG>, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8))) return rc;
-    if ((rc = set_smem_attr(k2_forward<D, WG, false, false>, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8))) return rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
     p.fms = fms; p.fPs = fPs;
-    const int L = pick_len(h, n, KB::GPC < KA::GPC ? KB::GPC : KA::GPC);
+    const int g1 = k1_groups<D>(fr), g2 = k2_groups<D, false, false>(fr);
+    const int L = pick_len(h, n, g2 < g1 ? g2 : g1);
     const int64_t nchunks = (n + L - 1) / L;
-    const size_t tot = hier_total(nchunks);
+    const size_t tot = hier::total(nchunks);
     const int NA = 3 * D * D + 2 * D, NS = D + D * D;
     const uint64_t key = filter_sig(8, D, n, Fs, Qs, y, H, R, first_special);
     const bool reuse = (summary == nullptr && h->pending_key[KIND_FILTER] == key && h->pending_n[KIND_FILTER] == n &&
@@ -77,27 +176,19 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
     if (!reuse) {
-        const unsigned grid = (unsigned)((nchunks + KA::GPC - 1) / KA::GPC);
-        PSSGP_LAUNCH(h, "mid_filter_reduce", st,
-                     (k1_filter_reduce<D, WG><<<grid, KA::GPC * WG * 32, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8, st>>>(
-                         p, L, nchunks, aggs)));
+        if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st))) return rc;
         ++launches;
     }
     const GFilter<double>::Params gp = gfilter_params(p, D);
-    if ((rc = hier_filter_f64(h, gp, D, nchunks, aggs, states, final_state, summary, reuse, st, &launches))) return rc;
+    if ((rc = hier_filter<D>(h, p, nchunks, aggs, states, final_state, summary, reuse, st, &launches))) return rc;
     if (summary != nullptr) {
         h->pending_key[KIND_FILTER] = key;
         h->pending_n[KIND_FILTER] = n;
         h->pending_L[KIND_FILTER] = L;
         return check_launch(h, "mid pkf summary", launches);
     }
-    {
-        const unsigned grid = (unsigned)((nchunks + KB::GPC - 1) / KB::GPC);
-        PSSGP_LAUNCH(h, "mid_forward", st,
-                     (k2_forward<D, WG, false, false><<<grid, KB::GPC * WG * 32, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8, st>>>(
-                         p, L, nchunks, states, part, nullptr)));
-        ++launches;
-    }
+    if ((rc = launch_k2<D, false, false>(h, fr, "mid_forward", p, L, nchunks, states, part, nullptr, st))) return rc;
+    ++launches;
     if (ll != nullptr) {
         finish_filter_f64(h, gp, part, nchunks, ll, st);
         ++launches;
@@ -107,18 +198,12 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
 
 // reverse part shared by pkfs_grad and pkf_backward: hierarchy over the reverse aggregates + K3 + finish
 template <int D, bool SMOOTH, bool ADJ>
-static int run_reverse(pssgp_handle* h, const Params& p, int L, int64_t nchunks, double* raggs, double* rstates,
+static int run_reverse(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, double* raggs, double* rstates,
                        double* part, double* dH, double* dR, cudaStream_t st, int* launches) {
-    constexpr int WG = default_wg<D>();
-    using KC = K3<D, WG, SMOOTH, ADJ>;
     int rc;
-    if ((rc = set_smem_attr(k3_reverse<D, WG, SMOOTH, ADJ>, (size_t)KC::GPC * KC::GROUP_DOUBLES * 8))) return rc;
     const GRev<double>::Params rp = grev_params(p, D, dH, dR);
-    if ((rc = hier_rev_f64(h, rp, D, nchunks, raggs, rstates, nullptr, nullptr, false, st, launches))) return rc;
-    const unsigned grid = (unsigned)((nchunks + KC::GPC - 1) / KC::GPC);
-    PSSGP_LAUNCH(h, "mid_reverse", st,
-                 (k3_reverse<D, WG, SMOOTH, ADJ><<<grid, KC::GPC * WG * 32, (size_t)KC::GPC * KC::GROUP_DOUBLES * 8, st>>>(
-                     p, L, nchunks, rstates, part)));
+    if ((rc = hier_rev<D>(h, nchunks, raggs, rstates, st, launches))) return rc;
+    if ((rc = launch_k3<D, SMOOTH, ADJ>(h, fr, p, L, nchunks, rstates, part, st))) return rc;
     ++*launches;
     if (ADJ) {
         finish_rev_f64(h, rp, part, nchunks, st);
@@ -131,23 +216,18 @@ template <int D>
 int pkfs_grad(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H,
               const double* R, const double* y, const double* g_ll, double* fms, double* fPs, double* ll, double* sms,
               double* sPs, double* dP0, double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st) {
-    constexpr int WG = default_wg<D>();
-    using KA = K1<D, WG>;
-    using KB = K2<D, WG, true, false>;
-    using KC = K3<D, WG, true, true>;
+    const bool fr = has_frag<D>() && !h->mid_smem;
     const bool smooth = sms != nullptr, adj = dFs != nullptr;
     int rc;
-    if ((rc = set_smem_attr(k1_filter_reduce<D, WG>, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8))) return rc;
-    if ((rc = set_smem_attr(k2_forward<D, WG, true, false>, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8))) return rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, nullptr, 1);
     p.fms = fms; p.fPs = fPs; p.fms_in = fms; p.fPs_in = fPs; p.g = g_ll;
     p.sms = sms; p.sPs = sPs; p.dFs = dFs; p.dQs = dQs; p.dP0 = dP0;
-    int gpc = KC::GPC;
-    if (KB::GPC < gpc) gpc = KB::GPC;
-    if (KA::GPC < gpc) gpc = KA::GPC;
+    int gpc = k3_groups<D, true, true>(fr);
+    if (k2_groups<D, true, false>(fr) < gpc) gpc = k2_groups<D, true, false>(fr);
+    if (k1_groups<D>(fr) < gpc) gpc = k1_groups<D>(fr);
     const int L = pick_len(h, n, gpc);
     const int64_t nchunks = (n + L - 1) / L;
-    const size_t tot = hier_total(nchunks);
+    const size_t tot = hier::total(nchunks);
     const int NAF = 3 * D * D + 2 * D, NSF = D + D * D, NAR = 3 * D * D + D, NSR = 2 * D * D + 2 * D;
     for (int kind = 0; kind < 3; ++kind) pending_clear(h, kind);
     if ((rc = ws_reserve(h, WS_LANE + KIND_FILTER, sizeof(double) * tot * NAF))) return rc;
@@ -161,29 +241,19 @@ int pkfs_grad(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, co
     double* rstates = (double*)h->buf[WS_WAGG + KIND_ADJOINT];
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
-    {
-        const unsigned grid = (unsigned)((nchunks + KA::GPC - 1) / KA::GPC);
-        PSSGP_LAUNCH(h, "mid_filter_reduce", st,
-                     (k1_filter_reduce<D, WG><<<grid, KA::GPC * WG * 32, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8, st>>>(
-                         p, L, nchunks, aggs)));
-        ++launches;
-    }
+    if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st))) return rc;
+    ++launches;
     const GFilter<double>::Params gp = gfilter_params(p, D);
-    if ((rc = hier_filter_f64(h, gp, D, nchunks, aggs, states, nullptr, nullptr, false, st, &launches))) return rc;
-    {
-        const unsigned grid = (unsigned)((nchunks + KB::GPC - 1) / KB::GPC);
-        PSSGP_LAUNCH(h, "mid_forward_rev", st,
-                     (k2_forward<D, WG, true, false><<<grid, KB::GPC * WG * 32, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8, st>>>(
-                         p, L, nchunks, states, part, raggs)));
-        ++launches;
-    }
+    if ((rc = hier_filter<D>(h, p, nchunks, aggs, states, nullptr, nullptr, false, st, &launches))) return rc;
+    if ((rc = launch_k2<D, true, false>(h, fr, "mid_forward_rev", p, L, nchunks, states, part, raggs, st))) return rc;
+    ++launches;
     if (ll != nullptr) {
         finish_filter_f64(h, gp, part, nchunks, ll, st);
         ++launches;
     }
-    if (smooth && adj) rc = run_reverse<D, true, true>(h, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
-    else if (smooth) rc = run_reverse<D, true, false>(h, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
-    else rc = run_reverse<D, false, true>(h, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
+    if (smooth && adj) rc = run_reverse<D, true, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
+    else if (smooth) rc = run_reverse<D, true, false>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
+    else rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
     if (rc) return rc;
     return check_launch(h, "mid pkfs_grad", launches);
 }
@@ -193,16 +263,14 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
                  const double* H, const double* R, const double* y, const double* fms, const double* fPs,
                  const double* g_ll, int first_special, double* dP0, double* dFs, double* dQs, double* dH, double* dR,
                  cudaStream_t st) {
-    constexpr int WG = default_wg<D>();
-    using KB = K2<D, WG, true, true>;
-    using KC = K3<D, WG, false, true>;
+    const bool fr = has_frag<D>() && !h->mid_smem;
     int rc;
-    if ((rc = set_smem_attr(k2_forward<D, WG, true, true>, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8))) return rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
     p.fms_in = fms; p.fPs_in = fPs; p.g = g_ll; p.dFs = dFs; p.dQs = dQs; p.dP0 = dP0;
-    const int L = pick_len(h, n, KB::GPC < KC::GPC ? KB::GPC : KC::GPC);
+    const int g2 = k2_groups<D, true, true>(fr), g3 = k3_groups<D, false, true>(fr);
+    const int L = pick_len(h, n, g2 < g3 ? g2 : g3);
     const int64_t nchunks = (n + L - 1) / L;
-    const size_t tot = hier_total(nchunks);
+    const size_t tot = hier::total(nchunks);
     const int NAR = 3 * D * D + D, NSR = 2 * D * D + 2 * D;
     pending_clear(h, KIND_ADJOINT);
     if ((rc = ws_reserve(h, WS_LANE + KIND_ADJOINT, sizeof(double) * tot * NAR))) return rc;
@@ -212,14 +280,9 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
     double* rstates = (double*)h->buf[WS_WAGG + KIND_ADJOINT];
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
-    {
-        const unsigned grid = (unsigned)((nchunks + KB::GPC - 1) / KB::GPC);
-        PSSGP_LAUNCH(h, "mid_forward_stored", st,
-                     (k2_forward<D, WG, true, true><<<grid, KB::GPC * WG * 32, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8, st>>>(
-                         p, L, nchunks, nullptr, nullptr, raggs)));
-        ++launches;
-    }
-    if ((rc = run_reverse<D, false, true>(h, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches))) return rc;
+    if ((rc = launch_k2<D, true, true>(h, fr, "mid_forward_stored", p, L, nchunks, nullptr, nullptr, raggs, st))) return rc;
+    ++launches;
+    if ((rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches))) return rc;
     return check_launch(h, "mid pkf_backward", launches);
 }
 

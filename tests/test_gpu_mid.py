@@ -31,7 +31,7 @@ def oracle_all(ssm, y, T, g):
     return fm.detach(), fP.detach(), ll.detach(), sm, sP, grads
 
 
-def check(name, tol, T, seed, chunk=0):
+def check(name, tol, T, seed, chunk=0, smem=0):
     pkg()
     from pssgp_b200 import _lib, ops
     span = 40.0 if name.startswith("qp") else 4.0
@@ -47,12 +47,14 @@ def check(name, tol, T, seed, chunk=0):
     yd = torch.as_tensor(y).to(DEV)
     h = _lib.handle(0)
     h.set_option("chunk", chunk)
+    h.set_option("mid_smem", smem)   # 1: shared-memory tile kernels also for d <= 16 (default there: fragment-resident)
     try:
         (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(
             P0, Fs, Qs, H, R, yd, torch.tensor([g], dtype=torch.float64, device=DEV))
         f2, fP2, ll2, s2, sP2 = ops.pkfs(P0, Fs, Qs, H, R, yd, want_ll=True)
     finally:
         h.set_option("chunk", 0)
+        h.set_option("mid_smem", 0)
     assert rel_err(fms.cpu(), rfm) < tol and rel_err(fPs.cpu(), rfP) < tol
     assert abs(float(ll) - float(rll)) <= tol * max(1.0, abs(float(rll)))
     assert rel_err(sms.cpu(), rsm) < tol and rel_err(sPs.cpu(), rsP) < tol
@@ -67,13 +69,19 @@ def check(name, tol, T, seed, chunk=0):
     assert rel_err(s2.cpu(), rsm) < tol and rel_err(sP2.cpu(), rsP) < tol
 
 
+@pytest.mark.parametrize("smem", [0, 1])
 @pytest.mark.parametrize("name,tol", CASES)
 @pytest.mark.parametrize("T", [1, 2, 17, 300, 2051])
-def test_fused_step_vs_oracle(name, tol, T):
-    check(name, tol, T, seed=T)
+def test_fused_step_vs_oracle(name, tol, T, smem):
+    if smem and name == "qp5":
+        pytest.skip("d > 16 always runs the shared-memory family")
+    check(name, tol, T, seed=T, smem=smem)
 
 
+@pytest.mark.parametrize("smem", [0, 1])
 @pytest.mark.parametrize("name,tol", CASES)
 @pytest.mark.parametrize("chunk", [1, 3, 16, 700])
-def test_fused_step_chunk_invariance(name, tol, chunk):
-    check(name, tol, 1200, seed=9, chunk=chunk)
+def test_fused_step_chunk_invariance(name, tol, chunk, smem):
+    if smem and name == "qp5":
+        pytest.skip("d > 16 always runs the shared-memory family")
+    check(name, tol, 1200, seed=9, chunk=chunk, smem=smem)
