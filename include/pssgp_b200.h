@@ -192,6 +192,33 @@ int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d,
 int pssgp_set_fold(pssgp_handle* h, int kind, const void* summaries, int count, int64_t stride, void* state_out);
 
 /*
+ * Time sharding for 5 <= d <= 32 (FP64): the smoother (modified Bryson-Frazier form, equal to
+ * pssgp/kalman/parallel.py:155-196 in exact arithmetic) and the log-likelihood adjoint run as ONE combined reverse
+ * scan, so a shard exchanges one reverse summary  Abar[d,d] | Ba[d,d] | Bm[d,d] | a[d]  (3 d^2 + d values) and
+ * one state  dm[d] | lam[d] | dP[d,d] | Lam[d,d]  (2 d^2 + 2 d values):
+ *   pssgp_pkf_summary   -> all-gather -> pssgp_filter_fold                     (filter summaries, as for any d)
+ *   pssgp_shard_forward    filter of the shard seeded by the folded state (m0, P0; rank 0: the prior, first_special)
+ *                          + rev_summary of the shard; fms, fPs, ll as pssgp_pkf
+ *   all-gather rev_summary -> pssgp_rev_fold(nshards_after, summaries of the FOLLOWING shards in rank order,
+ *                          stride scalars apart) -> state entering this shard from above (not on the last rank)
+ *   pssgp_shard_reverse    sms, sPs (pssgp_pks outputs; may be NULL) and dP0, dFs, dQs, dH, dR (pssgp_pkf_backward
+ *                          outputs; dFs NULL: no gradient) of the shard; rev_init = the folded state or NULL.
+ * The chunk aggregates pssgp_pkf_summary / pssgp_shard_forward leave in the workspace are reused by the call that
+ * follows on the same arrays.
+ */
+int pssgp_shard_forward(pssgp_handle* h, int dtype, int64_t n, int d,
+                        const void* P0, const void* Fs, const void* Qs, const void* H, const void* R, const void* y,
+                        const void* m0, int first_special,
+                        void* fms, void* fPs, void* ll, void* rev_summary, void* stream);
+int pssgp_rev_fold(pssgp_handle* h, int dtype, int d, int nshards_after, const void* summaries, int64_t stride,
+                   void* state_out, void* stream);
+int pssgp_shard_reverse(pssgp_handle* h, int dtype, int64_t n, int d,
+                        const void* P0, const void* m0, const void* Fs, const void* Qs, const void* H, const void* R,
+                        const void* y, const void* fms, const void* fPs, const void* g_ll, int first_special,
+                        const void* rev_init,
+                        void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream);
+
+/*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].
  */
 int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d,

@@ -46,6 +46,10 @@ SIGNATURES = {
     "pssgp_pkf_backward_summary": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int,
                                           _vp, _vp]),
     "pssgp_adjoint_fold": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp]),
+    "pssgp_shard_forward": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp, _vp]),
+    "pssgp_rev_fold": (_int, [_vp, _int, _int, _int, _vp, _i64, _vp, _vp]),
+    "pssgp_shard_reverse": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _int, _vp,
+                                   _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_discretise_backward": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 

@@ -470,6 +470,50 @@ int pssgp_pkf_with_summaries(pssgp_handle* h, int dtype, int64_t n, int d, const
     return pssgp_pkf_backward_summary(h, dtype, n, d, P0, m0, Fs, Qs, H, R, y, fms, fPs, first_special, ad_summary, stream);
 }
 
+int pssgp_shard_forward(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
+                        const void* H, const void* R, const void* y, const void* m0, int first_special, void* fms,
+                        void* fPs, void* ll, void* rev_summary, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs || !rev_summary)
+        return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    if (dtype != PSSGP_F64 || !mid::supported(d))
+        return set_err(PSSGP_ERR_UNSUPPORTED, "shard_forward: FP64 and 5 <= d <= 32 (d = %d); d <= 4 uses "
+                                              "pssgp_pkf_with_summaries", d);
+    return mid::shard_forward_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
+                                       (const double*)R, (const double*)y, (const double*)m0, first_special, (double*)fms,
+                                       (double*)fPs, (double*)ll, (double*)rev_summary, (cudaStream_t)stream);
+}
+
+int pssgp_rev_fold(pssgp_handle* h, int dtype, int d, int nshards_after, const void* summaries, int64_t stride,
+                   void* state_out, void* stream) {
+    int rc = check_common(h, dtype, 1, d);
+    if (rc) return rc;
+    if (!state_out || nshards_after < 1 || !summaries) return set_err(PSSGP_ERR_INVALID, "rev_fold: bad argument");
+    if (dtype != PSSGP_F64 || !mid::supported(d))
+        return set_err(PSSGP_ERR_UNSUPPORTED, "rev_fold: FP64 and 5 <= d <= 32 (d = %d)", d);
+    return mid::rev_fold_dispatch(d, h, (const double*)summaries, nshards_after, stride, (double*)state_out,
+                                  (cudaStream_t)stream);
+}
+
+int pssgp_shard_reverse(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* m0, const void* Fs,
+                        const void* Qs, const void* H, const void* R, const void* y, const void* fms, const void* fPs,
+                        const void* g_ll, int first_special, const void* rev_init, void* sms, void* sPs, void* dP0,
+                        void* dFs, void* dQs, void* dH, void* dR, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !fms || !fPs) return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    if ((!sms || !sPs) && !dFs) return set_err(PSSGP_ERR_INVALID, "shard_reverse: nothing to compute");
+    if (dFs && (!g_ll || !dQs || !dH || !dR)) return set_err(PSSGP_ERR_INVALID, "shard_reverse: null gradient argument");
+    if (dtype != PSSGP_F64 || !mid::supported(d))
+        return set_err(PSSGP_ERR_UNSUPPORTED, "shard_reverse: FP64 and 5 <= d <= 32 (d = %d)", d);
+    return mid::shard_reverse_dispatch(d, h, n, (const double*)P0, (const double*)m0, (const double*)Fs, (const double*)Qs,
+                                       (const double*)H, (const double*)R, (const double*)y, (const double*)fms,
+                                       (const double*)fPs, (const double*)g_ll, first_special, (const double*)rev_init,
+                                       (double*)sms, (double*)sPs, (double*)dP0, (double*)dFs, (double*)dQs, (double*)dH,
+                                       (double*)dR, (cudaStream_t)stream);
+}
+
 int pssgp_pkfs(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, const void* Fs, const void* Qs,
                const void* H, const void* R, const void* y, void* fms, void* fPs, void* ll, void* sms, void* sPs,
                void* proj, void* stream) {

@@ -23,6 +23,16 @@ namespace mid {
                                         const double*, const double*, int, double*, double*, double*, double*, double*,   \
                                         cudaStream_t);
 MID_FOR_EACH_D(MID_DECL)
+#define MID_DECL2(D)                                                                                                       \
+    extern template int shard_forward<D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*, \
+                                         const double*, const double*, const double*, int, double*, double*, double*,      \
+                                         double*, cudaStream_t);                                                            \
+    extern template int shard_reverse<D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*, \
+                                         const double*, const double*, const double*, const double*, const double*,         \
+                                         const double*, int, const double*, double*, double*, double*, double*, double*,    \
+                                         double*, double*, cudaStream_t);                                                   \
+    extern template int rev_fold<D>(pssgp_handle*, const double*, int, int64_t, double*, cudaStream_t);
+MID_FOR_EACH_D(MID_DECL2)
 
 bool supported(int d) { return d >= 5 && d <= 32; }
 
@@ -59,6 +69,44 @@ int pkf_backward_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, c
 #define MID_CASE(D)                                                                                                 \
     case D:                                                                                                         \
         return pkf_backward<D>(h, n, P0, m0, Fs, Qs, H, R, y, fms, fPs, g_ll, first_special, dP0, dFs, dQs, dH, dR, st);
+        MID_FOR_EACH_D(MID_CASE)
+#undef MID_CASE
+    }
+    return set_err(PSSGP_ERR_UNSUPPORTED, "mid path: state dimension %d", d);
+}
+
+int shard_forward_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs,
+                           const double* H, const double* R, const double* y, const double* m0, int first_special,
+                           double* fms, double* fPs, double* ll, double* rev_summary, cudaStream_t st) {
+    switch (d) {
+#define MID_CASE(D) \
+    case D: return shard_forward<D>(h, n, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, rev_summary, st);
+        MID_FOR_EACH_D(MID_CASE)
+#undef MID_CASE
+    }
+    return set_err(PSSGP_ERR_UNSUPPORTED, "mid path: state dimension %d", d);
+}
+
+int shard_reverse_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, const double* m0, const double* Fs,
+                           const double* Qs, const double* H, const double* R, const double* y, const double* fms,
+                           const double* fPs, const double* g_ll, int first_special, const double* rev_init, double* sms,
+                           double* sPs, double* dP0, double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st) {
+    switch (d) {
+#define MID_CASE(D)                                                                                                     \
+    case D:                                                                                                             \
+        return shard_reverse<D>(h, n, P0, m0, Fs, Qs, H, R, y, fms, fPs, g_ll, first_special, rev_init, sms, sPs, dP0, dFs, \
+                                dQs, dH, dR, st);
+        MID_FOR_EACH_D(MID_CASE)
+#undef MID_CASE
+    }
+    return set_err(PSSGP_ERR_UNSUPPORTED, "mid path: state dimension %d", d);
+}
+
+int rev_fold_dispatch(int d, pssgp_handle* h, const double* summaries, int count, int64_t stride, double* state_out,
+                      cudaStream_t st) {
+    switch (d) {
+#define MID_CASE(D) \
+    case D: return rev_fold<D>(h, summaries, count, stride, state_out, st);
         MID_FOR_EACH_D(MID_CASE)
 #undef MID_CASE
     }

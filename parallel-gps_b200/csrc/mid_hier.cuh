@@ -371,10 +371,12 @@ __global__ void __launch_bounds__(256) hier_up_kernel(const double* __restrict__
 
 // top level (single warp): walk the n aggregates from the initial state -> states[i] = state entering aggregate i,
 // final_state = state after all; or (summary != nullptr) reduce them to one aggregate.
+// `stride` = distance in doubles between consecutive aggregates in scan order (negative: a gathered buffer of shard
+// summaries in rank order walked from the last rank down).  states may be nullptr (fold: only final_state wanted).
 template <class H>
 __global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, const double* __restrict__ aggs, long n,
-                                                      double* __restrict__ states, double* __restrict__ final_state,
-                                                      double* __restrict__ summary) {
+                                                      long stride, double* __restrict__ states,
+                                                      double* __restrict__ final_state, double* __restrict__ summary) {
     extern __shared__ __align__(16) double smem[];
     constexpr int PW = top_warp_doubles<H>();
     const Grp g = warp_grp();
@@ -385,12 +387,12 @@ __global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, con
         typename H::AggRegs rg;
         rg.fetch(g, aggs);
         rg.put(g, a);
-        if (n > 1) rg.fetch(g, aggs + H::NAGG_G);
+        if (n > 1) rg.fetch(g, aggs + stride);
 #pragma unroll 1
         for (long i = 1; i < n; ++i) {
             rg.put(g, b);
             __syncwarp();
-            if (i + 1 < n) rg.fetch(g, aggs + (i + 1) * H::NAGG_G);
+            if (i + 1 < n) rg.fetch(g, aggs + (i + 1) * stride);
             H::combine(g, a, b, o, w);
             double* t = a;
             a = o;
@@ -403,14 +405,14 @@ __global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, con
     double *a = smem, *s = smem + H::AGG, *s2 = s + H::STATE, *w = s2 + H::STATE;
     H::init_state(g, s, init);
     typename H::AggRegs rg;
-    rg.fetch(g, aggs);
+    if (n > 0) rg.fetch(g, aggs);
     __syncwarp();
 #pragma unroll 1
     for (long i = 0; i < n; ++i) {
-        H::store_state(g, states + i * H::NSTATE_G, s);
+        if (states != nullptr) H::store_state(g, states + i * H::NSTATE_G, s);
         rg.put(g, a);
         __syncwarp();
-        if (i + 1 < n) rg.fetch(g, aggs + (i + 1) * H::NAGG_G);
+        if (i + 1 < n) rg.fetch(g, aggs + (i + 1) * stride);
         H::apply(g, s, a, s2, w);
         double* t = s;
         s = s2;
@@ -502,13 +504,13 @@ int run(pssgp_handle* h, const typename H::Init& init, int64_t cnt0, double* agg
     }
     if (summary != nullptr) {
         PSSGP_LAUNCH(h, names[1], st,
-                     (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], nullptr,
-                                                                        nullptr, summary)));
+                     (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], (long)NA,
+                                                                        nullptr, nullptr, summary)));
         ++*launches;
         return PSSGP_OK;
     }
     PSSGP_LAUNCH(h, names[1], st,
-                 (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1],
+                 (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], (long)NA,
                                                                     states + hl.off[nl - 1] * NS, final_state, nullptr)));
     ++*launches;
     for (int l = nl - 2; l >= 0; --l) {
@@ -519,6 +521,19 @@ int run(pssgp_handle* h, const typename H::Init& init, int64_t cnt0, double* agg
                                                                                       states + hl.off[l] * NS)));
         ++*launches;
     }
+    return PSSGP_OK;
+}
+
+// state_out = init o summaries[0] o summaries[stride] o ... (count of them): fold of gathered shard summaries
+template <class H>
+int fold(pssgp_handle* h, const typename H::Init& init, const double* summaries, int count, long stride, double* state_out,
+         const char* name, cudaStream_t st) {
+    constexpr int PWT = top_warp_doubles<H>();
+    cudaError_t e = cudaFuncSetAttribute(hier_top_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, PWT * 8);
+    if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "cudaFuncSetAttribute(hierarchy): %s", cudaGetErrorString(e));
+    PSSGP_LAUNCH(h, name, st,
+                 (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, summaries, (long)count, stride, nullptr, state_out,
+                                                                    nullptr)));
     return PSSGP_OK;
 }
 

@@ -26,7 +26,28 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
                  const double* g_ll, int first_special, double* dP0, double* dFs, double* dQs, double* dH, double* dR,
                  cudaStream_t st);
 
+template <int D>
+int shard_forward(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H,
+                  const double* R, const double* y, const double* m0, int first_special, double* fms, double* fPs,
+                  double* ll, double* rev_summary, cudaStream_t st);
+template <int D>
+int shard_reverse(pssgp_handle* h, int64_t n, const double* P0, const double* m0, const double* Fs, const double* Qs,
+                  const double* H, const double* R, const double* y, const double* fms, const double* fPs,
+                  const double* g_ll, int first_special, const double* rev_init, double* sms, double* sPs, double* dP0,
+                  double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st);
+template <int D>
+int rev_fold(pssgp_handle* h, const double* summaries, int count, int64_t stride, double* state_out, cudaStream_t st);
+
 bool supported(int d);
+int shard_forward_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs,
+                           const double* H, const double* R, const double* y, const double* m0, int first_special,
+                           double* fms, double* fPs, double* ll, double* rev_summary, cudaStream_t st);
+int shard_reverse_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, const double* m0, const double* Fs,
+                           const double* Qs, const double* H, const double* R, const double* y, const double* fms,
+                           const double* fPs, const double* g_ll, int first_special, const double* rev_init, double* sms,
+                           double* sPs, double* dP0, double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st);
+int rev_fold_dispatch(int d, pssgp_handle* h, const double* summaries, int count, int64_t stride, double* state_out,
+                      cudaStream_t st);
 int pkf_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H,
                  const double* R, const double* y, const double* m0, int first_special, double* fms, double* fPs,
                  double* ll, double* final_state, double* summary, cudaStream_t st);

@@ -111,10 +111,11 @@ static int hier_filter(pssgp_handle* h, const Params& p, int64_t nchunks, double
     return hier::run<hier::FilterH<D>>(h, in, nchunks, aggs, states, final_state, summary, have_up, names, st, launches);
 }
 template <int D>
-static int hier_rev(pssgp_handle* h, int64_t nchunks, double* raggs, double* rstates, cudaStream_t st, int* launches) {
+static int hier_rev(pssgp_handle* h, int64_t nchunks, double* raggs, double* rstates, const double* init, double* summary,
+                    bool have_up, cudaStream_t st, int* launches) {
     static const char* const names[3] = {"mhier_rev_up", "mhier_rev_top", "mhier_rev_down"};
-    const typename hier::RevH<D>::Init in = {nullptr};
-    return hier::run<hier::RevH<D>>(h, in, nchunks, raggs, rstates, nullptr, nullptr, false, names, st, launches);
+    const typename hier::RevH<D>::Init in = {init};
+    return hier::run<hier::RevH<D>>(h, in, nchunks, raggs, rstates, nullptr, summary, have_up, names, st, launches);
 }
 
 // chunk length: one resident wave of groups of the most shared-memory-hungry kernel of the call
@@ -199,10 +200,11 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
 // reverse part shared by pkfs_grad and pkf_backward: hierarchy over the reverse aggregates + K3 + finish
 template <int D, bool SMOOTH, bool ADJ>
 static int run_reverse(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, double* raggs, double* rstates,
-                       double* part, double* dH, double* dR, cudaStream_t st, int* launches) {
+                       double* part, double* dH, double* dR, cudaStream_t st, int* launches, const double* rev_init = nullptr,
+                       bool have_up = false) {
     int rc;
     const GRev<double>::Params rp = grev_params(p, D, dH, dR);
-    if ((rc = hier_rev<D>(h, nchunks, raggs, rstates, st, launches))) return rc;
+    if ((rc = hier_rev<D>(h, nchunks, raggs, rstates, rev_init, nullptr, have_up, st, launches))) return rc;
     if ((rc = launch_k3<D, SMOOTH, ADJ>(h, fr, p, L, nchunks, rstates, part, st))) return rc;
     ++*launches;
     if (ADJ) {
@@ -286,6 +288,113 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
     return check_launch(h, "mid pkf_backward", launches);
 }
 
+
+// ---- time sharding: one contiguous shard of the series per GPU ------------------------------------------------
+// forward phase of one shard: filter seeded by (m0, P0) = filtered state entering the shard (rank 0: the prior,
+// first_special = 1), + the shard summary of the combined reverse scan.  If pssgp_pkf_summary ran on the same arrays
+// just before, its chunk aggregates are reused (no second reduce pass).
+template <int D>
+int shard_forward(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H,
+                  const double* R, const double* y, const double* m0, int first_special, double* fms, double* fPs,
+                  double* ll, double* rev_summary, cudaStream_t st) {
+    const bool fr = has_frag<D>() && !h->mid_smem;
+    int rc;
+    Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
+    p.fms = fms; p.fPs = fPs; p.fms_in = fms; p.fPs_in = fPs;
+    int gpc = k3_groups<D, true, true>(fr);
+    if (k2_groups<D, true, false>(fr) < gpc) gpc = k2_groups<D, true, false>(fr);
+    if (k1_groups<D>(fr) < gpc) gpc = k1_groups<D>(fr);
+    const int L = pick_len(h, n, gpc);
+    const int64_t nchunks = (n + L - 1) / L;
+    const size_t tot = hier::total(nchunks);
+    const int NAF = 3 * D * D + 2 * D, NSF = D + D * D, NAR = 3 * D * D + D, NSR = 2 * D * D + 2 * D;
+    const uint64_t key = filter_sig(8, D, n, Fs, Qs, y, H, R, first_special);
+    const bool reuse = (h->pending_key[KIND_FILTER] == key && h->pending_n[KIND_FILTER] == n && h->pending_L[KIND_FILTER] == L);
+    for (int kind = 0; kind < 3; ++kind) pending_clear(h, kind);
+    if (!reuse)
+        if ((rc = ws_reserve(h, WS_LANE + KIND_FILTER, sizeof(double) * tot * NAF))) return rc;
+    if ((rc = ws_reserve(h, WS_WAGG + KIND_FILTER, sizeof(double) * tot * NSF))) return rc;
+    if ((rc = ws_reserve(h, WS_LANE + KIND_ADJOINT, sizeof(double) * tot * NAR))) return rc;
+    if ((rc = ws_reserve(h, WS_WAGG + KIND_ADJOINT, sizeof(double) * tot * NSR))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(double) * (size_t)nchunks * (1 + D)))) return rc;
+    double* aggs = (double*)h->buf[WS_LANE + KIND_FILTER];
+    double* states = (double*)h->buf[WS_WAGG + KIND_FILTER];
+    double* raggs = (double*)h->buf[WS_LANE + KIND_ADJOINT];
+    double* rstates = (double*)h->buf[WS_WAGG + KIND_ADJOINT];
+    double* part = (double*)h->buf[WS_PART];
+    int launches = 0;
+    if (!reuse) {
+        if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st))) return rc;
+        ++launches;
+    }
+    const GFilter<double>::Params gp = gfilter_params(p, D);
+    if ((rc = hier_filter<D>(h, p, nchunks, aggs, states, nullptr, nullptr, reuse, st, &launches))) return rc;
+    if ((rc = launch_k2<D, true, false>(h, fr, "mid_forward_rev", p, L, nchunks, states, part, raggs, st))) return rc;
+    ++launches;
+    if (ll != nullptr) {
+        finish_filter_f64(h, gp, part, nchunks, ll, st);
+        ++launches;
+    }
+    if ((rc = hier_rev<D>(h, nchunks, raggs, rstates, nullptr, rev_summary, false, st, &launches))) return rc;
+    h->pending_key[KIND_ADJOINT] = adjoint_sig(8, D, n, Fs, Qs, y, H, R, fms, fPs, first_special);
+    h->pending_n[KIND_ADJOINT] = n;
+    h->pending_L[KIND_ADJOINT] = L;
+    return check_launch(h, "mid shard_forward", launches);
+}
+
+// reverse phase of one shard: smoother (sms != nullptr) and gradient (dFs != nullptr) seeded by rev_init = state of
+// the combined reverse scan entering the shard from the following shards (nullptr on the last rank).
+template <int D>
+int shard_reverse(pssgp_handle* h, int64_t n, const double* P0, const double* m0, const double* Fs, const double* Qs,
+                  const double* H, const double* R, const double* y, const double* fms, const double* fPs,
+                  const double* g_ll, int first_special, const double* rev_init, double* sms, double* sPs, double* dP0,
+                  double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st) {
+    const bool fr = has_frag<D>() && !h->mid_smem;
+    const bool smooth = sms != nullptr, adj = dFs != nullptr;
+    int rc;
+    Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
+    p.fms_in = fms; p.fPs_in = fPs; p.g = g_ll; p.sms = sms; p.sPs = sPs; p.dFs = dFs; p.dQs = dQs; p.dP0 = dP0;
+    int gpc = k3_groups<D, true, true>(fr);
+    if (k2_groups<D, true, false>(fr) < gpc) gpc = k2_groups<D, true, false>(fr);
+    if (k1_groups<D>(fr) < gpc) gpc = k1_groups<D>(fr);
+    const int L = pick_len(h, n, gpc);
+    const int64_t nchunks = (n + L - 1) / L;
+    const size_t tot = hier::total(nchunks);
+    const int NAR = 3 * D * D + D, NSR = 2 * D * D + 2 * D;
+    const uint64_t key = adjoint_sig(8, D, n, Fs, Qs, y, H, R, fms, fPs, first_special);
+    const bool reuse = (h->pending_key[KIND_ADJOINT] == key && h->pending_n[KIND_ADJOINT] == n && h->pending_L[KIND_ADJOINT] == L);
+    pending_clear(h, KIND_ADJOINT);
+    if (!reuse)
+        if ((rc = ws_reserve(h, WS_LANE + KIND_ADJOINT, sizeof(double) * tot * NAR))) return rc;
+    if ((rc = ws_reserve(h, WS_WAGG + KIND_ADJOINT, sizeof(double) * tot * NSR))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(double) * (size_t)nchunks * (1 + D)))) return rc;
+    double* raggs = (double*)h->buf[WS_LANE + KIND_ADJOINT];
+    double* rstates = (double*)h->buf[WS_WAGG + KIND_ADJOINT];
+    double* part = (double*)h->buf[WS_PART];
+    int launches = 0;
+    if (!reuse) {
+        // no aggregates left by shard_forward for these arrays: rebuild them from the stored moments
+        if ((rc = launch_k2<D, true, true>(h, fr, "mid_forward_stored", p, L, nchunks, nullptr, nullptr, raggs, st))) return rc;
+        ++launches;
+    }
+    if (smooth && adj) rc = run_reverse<D, true, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, rev_init, reuse);
+    else if (smooth) rc = run_reverse<D, true, false>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, rev_init, reuse);
+    else rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, rev_init, reuse);
+    if (rc) return rc;
+    return check_launch(h, "mid shard_reverse", launches);
+}
+
+// folds the reverse-scan summaries of the `count` FOLLOWING shards (rank order, `stride` doubles apart) into the state
+// entering this shard: state = 0 o summary[count-1] o ... o summary[0]
+template <int D>
+int rev_fold(pssgp_handle* h, const double* summaries, int count, int64_t stride, double* state_out, cudaStream_t st) {
+    const typename hier::RevH<D>::Init in = {nullptr};
+    int rc = hier::fold<hier::RevH<D>>(h, in, summaries + (int64_t)(count - 1) * stride, count, -(long)stride, state_out,
+                                       "mhier_rev_fold", st);
+    if (rc) return rc;
+    return check_launch(h, "mid rev_fold", 1);
+}
+
 template int pkf<MID_D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*, const double*,
                         const double*, const double*, int, double*, double*, double*, double*, double*, cudaStream_t);
 template int pkfs_grad<MID_D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*,
@@ -294,6 +403,15 @@ template int pkfs_grad<MID_D>(pssgp_handle*, int64_t, const double*, const doubl
 template int pkf_backward<MID_D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*,
                                  const double*, const double*, const double*, const double*, const double*, const double*,
                                  int, double*, double*, double*, double*, double*, cudaStream_t);
+
+template int shard_forward<MID_D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*,
+                                  const double*, const double*, const double*, int, double*, double*, double*, double*,
+                                  cudaStream_t);
+template int shard_reverse<MID_D>(pssgp_handle*, int64_t, const double*, const double*, const double*, const double*,
+                                  const double*, const double*, const double*, const double*, const double*, const double*,
+                                  int, const double*, double*, double*, double*, double*, double*, double*, double*,
+                                  cudaStream_t);
+template int rev_fold<MID_D>(pssgp_handle*, const double*, int, int64_t, double*, cudaStream_t);
 
 }  // namespace mid
 }  // namespace pssgp

@@ -148,9 +148,33 @@ class TimeShard:
         # boundary.  Done once here so that the summary and the full call see the same pointer (workspace reuse).
         return t if t is None or not t.is_cuda or t.data_ptr() % 16 == 0 else t.clone()
 
+    def _step_combined_reverse(self, P0, Fs, Qs, H, R, y, g_ll):
+        """5 <= d <= 32: filter summaries -> all-gather -> seeded filter + reverse summary (pssgp_shard_forward) ->
+        all-gather -> fold -> combined reverse scan (pssgp_shard_reverse) -> all-reduce of the small gradients."""
+        d = Fs.shape[1]
+        ops = self.ops
+        summ = ops.pkf_summary(P0, Fs, Qs, H, R, y, self.first)
+        gathered = self._all_gather(summ)
+        if self.first:
+            m_in, P_in = None, P0
+        else:
+            st = ops.filter_fold(P0, None, gathered.contiguous(), self.rank)
+            m_in, P_in = st[:d].contiguous(), st[d:].reshape(d, d).contiguous()
+        fms, fPs, ll, rsum = ops.shard_forward(P_in, Fs, Qs, H, R, y, m0=m_in, first_special=self.first)
+        rg = self._all_gather(rsum)
+        after = self.world - 1 - self.rank
+        rev_init = ops.rev_fold(rg[self.rank + 1:], after, d) if after > 0 else None
+        (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.shard_reverse(P_in, Fs, Qs, H, R, y, fms, fPs, g_ll, m0=m_in,
+                                                               first_special=self.first, rev_init=rev_init)
+        red = self._all_reduce(torch.cat([dH.reshape(-1), dR.reshape(-1), dP0.reshape(-1), ll.reshape(-1)]))
+        return red[d + 1 + d * d:], sms, sPs, (red[d + 1:d + 1 + d * d].reshape(d, d), dFs, dQs, red[:d], red[d:d + 1])
+
     def filter_smoother_grad(self, P0, Fs, Qs, H, R, y, g_ll):
         """One full step: returns (ll, sms, sPs, (dP0, dFs, dQs, dH, dR)); ll and the small gradients are global."""
         Fs, Qs, y = self._aligned(Fs), self._aligned(Qs), self._aligned(y)
+        has = getattr(self.ops, "has_combined_reverse", None)
+        if has is not None and has(Fs.shape[1], Fs.dtype):
+            return self._step_combined_reverse(P0, Fs, Qs, H, R, y, g_ll)
         fms, fPs, ll = self.filter(P0, Fs, Qs, H, R, y, reduce_ll=False, with_reverse_summaries=True)
         o = self.smoother_and_grad(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=ll)
         return o["ll"], o["sms"], o["sPs"], (o["dP0"], o["dFs"], o["dQs"], o["dH"], o["dR"])

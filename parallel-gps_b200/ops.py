@@ -226,3 +226,68 @@ def adjoint_fold(summaries, count, d):
     _lib.check(_lib.lib().pssgp_adjoint_fold(_h(summaries).ptr, A.dtype_code(summaries), d, int(count),
                                             A.ptr(summaries), A.ptr(out), A.stream_ptr(summaries.device)))
     return out
+
+
+# ---- time sharding for 5 <= d <= 32: combined reverse scan (smoother in MBF form + log-likelihood adjoint) ----
+MID_D_MAX = 32
+
+
+def has_combined_reverse(d, dtype=torch.float64):
+    """True where pssgp_shard_forward / pssgp_rev_fold / pssgp_shard_reverse are implemented."""
+    return SMALL_D < d <= MID_D_MAX and dtype == torch.float64
+
+
+def nagg_rev(d):
+    """length of a combined reverse-scan shard summary  Abar | Ba | Bm | a."""
+    return 3 * d * d + d
+
+
+def nstate_rev(d):
+    """length of a combined reverse-scan state  dm | lam | dP | Lam."""
+    return 2 * d * d + 2 * d
+
+
+def shard_forward(P0, Fs, Qs, H, R, y, m0=None, first_special=True):
+    """C ABI: pssgp_shard_forward. -> fms, fPs, ll, rev_summary."""
+    Fs, Qs, y = _al(Fs), _al(Qs), _al(y)
+    n, d = Fs.shape[0], Fs.shape[1]
+    kw = dict(dtype=Fs.dtype, device=Fs.device)
+    fms, fPs = torch.empty((n, d), **kw), torch.empty((n, d, d), **kw)
+    ll = torch.empty((1,), **kw)
+    summ = torch.empty((nagg_rev(d),), **kw)
+    _lib.check(_lib.lib().pssgp_shard_forward(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(Fs), A.ptr(Qs), A.ptr(H),
+                                             A.ptr(R), A.ptr(y), A.ptr(m0), 1 if first_special else 0, A.ptr(fms),
+                                             A.ptr(fPs), A.ptr(ll), A.ptr(summ), A.stream_ptr(Fs.device)))
+    return fms, fPs, ll, summ
+
+
+def rev_fold(summaries, count, d):
+    """summaries: [count, nagg_rev(d)] view of the FOLLOWING shards in rank order (rows may be strided).
+    -> state entering this shard from above (dm | lam | dP | Lam)."""
+    if summaries.dim() != 2 or summaries.stride(1) != 1:
+        raise ValueError("summaries must be a 2-d view with unit stride along the last axis")
+    out = torch.empty((nstate_rev(d),), dtype=summaries.dtype, device=summaries.device)
+    _lib.check(_lib.lib().pssgp_rev_fold(_h(summaries).ptr, A.dtype_code(summaries), d, int(count), A.ptr(summaries),
+                                        int(summaries.stride(0)), A.ptr(out), A.stream_ptr(summaries.device)))
+    return out
+
+
+def shard_reverse(P0, Fs, Qs, H, R, y, fms, fPs, g_ll=None, m0=None, first_special=True, rev_init=None,
+                  want_smoother=True, want_grad=True):
+    """C ABI: pssgp_shard_reverse. -> (sms, sPs) or None, (dP0, dFs, dQs, dH, dR) or None."""
+    Fs, Qs, y, fms, fPs = _al(Fs), _al(Qs), _al(y), _al(fms), _al(fPs)
+    n, d = Fs.shape[0], Fs.shape[1]
+    kw = dict(dtype=Fs.dtype, device=Fs.device)
+    sms = sPs = dP0 = dFs = dQs = dH = dR = None
+    if want_smoother:
+        sms, sPs = torch.empty((n, d), **kw), torch.empty((n, d, d), **kw)
+    if want_grad:
+        dP0 = torch.zeros((d, d), **kw)
+        dFs, dQs = torch.empty((n, d, d), **kw), torch.empty((n, d, d), **kw)
+        dH, dR = torch.empty((d,), **kw), torch.empty((1,), **kw)
+    _lib.check(_lib.lib().pssgp_shard_reverse(_h(Fs).ptr, A.dtype_code(Fs), n, d, A.ptr(P0), A.ptr(m0), A.ptr(Fs), A.ptr(Qs),
+                                             A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(fms), A.ptr(fPs), A.ptr(g_ll),
+                                             1 if first_special else 0, A.ptr(rev_init), A.ptr(sms), A.ptr(sPs),
+                                             A.ptr(dP0), A.ptr(dFs), A.ptr(dQs), A.ptr(dH), A.ptr(dR),
+                                             A.stream_ptr(Fs.device)))
+    return ((sms, sPs) if want_smoother else None), ((dP0, dFs, dQs, dH, dR) if want_grad else None)

@@ -47,7 +47,8 @@ class FakeDist:
 
 @pytest.mark.parametrize("name,T,G", [("matern32", 1000, 2), ("matern52", 5003, 3), ("matern52", 40, 4),
                                       ("m32xm32", 2000, 2), ("matern12", 513, 8),
-                                      ("rbf6", 900, 3), ("m52+rbf6", 700, 2)])
+                                      ("rbf6", 900, 3), ("m52+rbf6", 700, 2), ("rbf6", 5000, 8), ("qp3", 1500, 4),
+                                      ("qp5", 600, 2)])
 def test_sharded_equals_unsharded(name, T, G):
     pkg()
     from pssgp_b200 import ops
@@ -85,7 +86,7 @@ def test_sharded_equals_unsharded(name, T, G):
     for th in threads:
         th.join()
     assert not errors, errors
-    tol = 1e-9
+    tol = 1e-7 if name.startswith("qp") else 1e-9
     cat = lambda i: torch.cat([results[r][i] for r in range(G)])
     assert rel_err(cat(1).cpu(), sms.cpu()) < tol and rel_err(cat(2).cpu(), sPs.cpu()) < tol
     for r in range(G):
