@@ -19,6 +19,13 @@ noise 0.1, FP64, N = 1e6 irregular time steps per GPU: dt_k = 0.004 * U(0.5, 1.5
   inside the timed region (library option "timing"); algorithmic bytes per DESIGN.md.
 * ``cpu_baseline``: the CPU oracle (restated reference: pkf + autograd gradient + pks in TFP's
   scan order, torch-CPU on all host cores) on the same workload (rank 0, N = 1 only).
+* ``configs``: the other BASELINE.json configurations measured in the same run (few steps each, same timing
+  rules): configs[2] RBF order 6 (d = 6), N = 1e7 TOTAL, time-sharded over --gpus (strong scaling); configs[3]
+  quasi-periodic Periodic(order 5) x Matern32 (d = 24), N = 1e6, single GPU; configs[4] Matern52 + RBF6 (d = 9),
+  1.25e7 steps per GPU (N = 1e8 on 8 GPUs) and the log-likelihood over a 32 x 32 grid of hyper-parameter settings
+  (batch-sharded over --gpus).  Each entry carries its own roofline and a bounded oracle-port cpu_baseline.
+* ``sharded_check`` (--gpus > 1): max relative error of the time-sharded step against the unsharded step of the
+  same series computed on every rank (ll, smoothed moments, gradients), d = 3 and d = 6.
 * ``--impl reference``: only the CPU arm (the reference's TF stack is not installable here; the
   oracle port is the stand-in), same metric/config.
 """
@@ -56,6 +63,44 @@ def make_series(n, seed_offset=0):
     miss = np.random.RandomState(7 + seed_offset).choice(n, size=n // 100, replace=False)
     y[miss] = np.nan
     return t, y
+
+
+def make_series_sunspot(n, seed=666):
+    """monthly sampling (28..31 days cycling like calendar months, in years), an 11-year
+    quasi-cycle + noise of variance 10 (sunspot/common.py:24), 1 % missing."""
+    months = np.array([31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31], dtype=np.float64) / 365.25
+    t = np.cumsum(np.resize(months, n))
+    rng = np.random.RandomState(seed)
+    y = 50.0 + 40.0 * np.sin(2 * np.pi * t / 11.0) * (1 + 0.3 * np.sin(2 * np.pi * t / 80.0)) + np.sqrt(10.0) * rng.randn(n)
+    y[rng.choice(n, size=n // 100, replace=False)] = np.nan
+    return t, y
+
+
+def make_series_weekly(n, seed=42):
+    """weekly sampling with +-1 day jitter (in years), seasonal cycle + trend, noise 0.05."""
+    rng = np.random.RandomState(seed)
+    t = np.cumsum(1.0 / 52.0 + rng.uniform(-1.0, 1.0, size=n) / 365.25)
+    y = 0.02 * t + np.sin(2 * np.pi * t) + 0.3 * np.sin(4 * np.pi * t) + np.sqrt(0.05) * rng.randn(n)
+    y[rng.choice(n, size=n // 100, replace=False)] = np.nan
+    return t, y
+
+
+# the other BASELINE.json configurations (name -> kernel factory on a kernels module, noise, series, sizes)
+def extra_configs(world):
+    return {
+        "rbf6_n1e7_time_sharded": dict(
+            baseline_config=2, kern=lambda K: K.RBF(1.0, 1.0, order=6, balancing_iter=5), noise=10.0,
+            series=make_series_sunspot, n_total=10_000_000, scaling="strong",
+            what="RBF order 6 balancing_iter 5 (sunspots-shaped), N = 1e7 total, time-sharded over n_gpus"),
+        "qp5_n1e6": dict(
+            baseline_config=3, kern=lambda K: K.Periodic(K.SquaredExponential(5.0, 1.0), period=1.0, order=5) * K.Matern32(0.1, 50.0),
+            noise=0.05, series=make_series_weekly, n_total=1_000_000, scaling="single-gpu",
+            what="Periodic(SE(5,1), period 1, order 5) x Matern32(0.1, 50) (CO2-shaped, d = 24), N = 1e6, FP64, 1 GPU"),
+        "m52rbf6_n1p25e7_per_gpu": dict(
+            baseline_config=4, kern=lambda K: K.Matern52(1.0, 1.0) + K.RBF(1.0, 1.0, order=6, balancing_iter=5), noise=NOISE,
+            series=make_series, n_total=12_500_000 * world, scaling="weak",
+            what="Matern52 + RBF order 6 (d = 9), 1.25e7 steps per GPU time-sharded (N = 1e8 on 8 GPUs)"),
+    }
 
 
 class ClockSampler:
@@ -123,6 +168,10 @@ def cpu_reference_arm(steps, warmup, sample_n):
     """Times the CPU restatement of the reference path (oracle port) with all host threads."""
     import torch
     import __graft_entry__ as entry
+    try:
+        torch.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
+    except Exception:
+        pass
     O = entry.import_oracle()
     t, y = make_series(sample_n)
     cov = O.Matern52(1.0, 1.0)
@@ -159,6 +208,189 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def time_steps_on_device(step, W, K, barrier, dist, dev, torch):
+    for _ in range(W):
+        out = step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(K):
+        out = step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1) / K
+    if dist is not None:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt)
+    del out
+    return ms
+
+
+def shard_lgssm(cfg, world, rank, dev, torch, kernels, ops):
+    """Synthetic series of the config, this rank's contiguous shard discretised on the device."""
+    n_total = cfg["n_total"]
+    n = n_total // world
+    t_host, y_host = cfg["series"](n_total)
+    lo, hi = rank * n, (rank + 1) * n
+    with torch.no_grad():
+        sde = cfg["kern"](kernels).get_sde()
+    F, Pinf = sde.F.to(dev).contiguous(), sde.P0.to(dev).contiguous()
+    H = sde.H.to(dev).reshape(-1).contiguous()
+    R = torch.tensor([cfg["noise"]], dtype=torch.float64, device=dev)
+    t_dev = torch.as_tensor(t_host[lo:hi]).to(dev)
+    t_prev = 0.0 if lo == 0 else float(t_host[lo - 1])
+    dts = t_dev - torch.cat([torch.tensor([t_prev], dtype=torch.float64, device=dev), t_dev[:-1]])
+    y_dev = torch.as_tensor(y_host[lo:hi]).to(dev)
+    Fs, Qs = ops.discretise(F, Pinf, dts)
+    return n, Pinf, Fs, Qs, H, R, y_dev, (t_host, y_host)
+
+
+def oracle_sample_baseline(cfg, sample_n):
+    """Oracle-port CPU baseline of one config on its first sample_n time steps (all host threads)."""
+    import torch
+    import __graft_entry__ as entry
+    O = entry.import_oracle()
+    t, y = cfg["series"](sample_n)
+    cov = cfg["kern"](O)
+    with torch.no_grad():
+        ssm = cov.get_ssm(t[:, None], torch.tensor([[cfg["noise"]]], dtype=torch.float64))
+    t0 = time.perf_counter()
+    oracle_step(O, torch, ssm, y, sample_n)
+    dt = time.perf_counter() - t0
+    return {"value": sample_n / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"first {sample_n} time steps of the workload once ({dt:.1f} s): oracle port (pkf + autograd gradient "
+                      f"+ pks in TFP scan order, torch-CPU)"}
+
+
+def run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels, ops, pdist, h, hbm_peak, fp64_peak, W, K,
+                     with_cpu):
+    if cfg["scaling"] == "single-gpu" and world > 1:
+        return {"skipped": "single-GPU configuration: measured at n_gpus = 1"}
+    n, Pinf, Fs, Qs, H, R, y_dev, _ = shard_lgssm(cfg, world, rank, dev, torch, kernels, ops)
+    d = Fs.shape[1]
+    g_ll = torch.ones(1, dtype=torch.float64, device=dev)
+    shard = pdist.TimeShard(rank, world, dist) if world > 1 else None
+
+    def step():
+        if shard is None:
+            return ops.pkfs_grad(Pinf, Fs, Qs, H, R, y_dev, g_ll)
+        return shard.filter_smoother_grad(Pinf, Fs, Qs, H, R, y_dev, g_ll)
+
+    ms = time_steps_on_device(step, W, K, barrier, dist, dev, torch)
+    h.set_option("timing", 1)
+    h.timing_report()
+    for _ in range(2):
+        out = step()
+    barrier()
+    kt = h.timing_report()
+    h.set_option("timing", 0)
+    del out
+    n_total = n * world
+    alg = 8 * (12 * d * d + 4 * d + 2)
+    gbs = alg * n_total / (ms * 1e-3) / 1e9
+    flops = 30.0 * d ** 3  # useful flops of this implementation per time step: 15 d x d products (K1 3, K2 3, K3 9)
+    tfl = flops * n_total / (ms * 1e-3) / 1e12
+    entry = {
+        "baseline_config": cfg["baseline_config"], "workload": cfg["what"], "state_dim": d, "dtype": "f64",
+        "n_total": n_total, "n_per_gpu": n, "n_gpus": world, "scaling": cfg["scaling"], "steps": K, "warmup": W,
+        "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": UNIT,
+        "roofline": {"bound": "hbm" if d <= 9 else "fp64", "alg_bytes_per_timestep": alg, "achieved_gbs": gbs,
+                     "hbm_peak_gbs": hbm_peak * world, "frac_of_hbm_peak": gbs / (hbm_peak * world),
+                     "useful_flops_per_timestep": flops, "achieved_tflops": tfl, "fp64_peak_tflops": fp64_peak * world,
+                     "frac_of_fp64_peak": tfl / (fp64_peak * world),
+                     "fp64_peak_source": "DMMA m8n8k4 full-chip rate measured with scripts/sm_probe.cu (profiles/r02_sm_probe.txt)"},
+        "kernels": {k: {"launches": c // 2, "avg_us": 1e3 * t / max(c, 1)} for k, (c, t) in kt.items()},
+    }
+    del Fs, Qs, y_dev
+    torch.cuda.empty_cache()
+    if with_cpu and rank == 0 and world == 1:
+        try:
+            entry["cpu_baseline"] = oracle_sample_baseline(cfg, 20_000 if d > 9 else 50_000)
+        except Exception as e:  # pragma: no cover
+            entry["cpu_baseline"] = {"error": repr(e)}
+    return entry
+
+
+def run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, W):
+    """configs[4]b: log-likelihood over a 32 x 32 grid of (Matern52 lengthscale, RBF lengthscale) in [0.1, 10],
+    Matern52 + RBF6 (d = 9), N = 1e5, batch-sharded over the ranks (no data-path collective)."""
+    from pssgp_b200 import batch
+    n = 100_000
+    t_host, y_host = make_series(n)
+    ls = np.logspace(-1, 1, 32)
+    settings = [(a, b) for a in ls for b in ls]
+    mk = lambda a, b: kernels.Matern52(1.0, float(a)) + kernels.RBF(1.0, float(b), order=6, balancing_iter=5)
+    data = (torch.as_tensor(t_host[:, None]).to(dev), torch.as_tensor(y_host[:, None]).to(dev))
+    batch.grid_log_likelihood(mk, settings[:8 * world], data, NOISE, rank=rank, world=world, dist=dist, device=dev)  # warm-up
+    barrier()
+    t0 = time.perf_counter()
+    ll = batch.grid_log_likelihood(mk, settings, data, NOISE, rank=rank, world=world, dist=dist, device=dev)
+    barrier()
+    dt = time.perf_counter() - t0
+    if dist is not None:
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt)
+    return {"baseline_config": 4, "workload": "grid log-likelihood, 32 x 32 settings of Matern52 + RBF6 (d = 9), N = 1e5, "
+                                              "batch-sharded over n_gpus", "settings": len(settings), "n": n,
+            "seconds": dt, "value": len(settings) / dt, "unit": "settings/s", "timesteps_per_s": len(settings) * n / dt,
+            "n_gpus": world, "finite": bool(torch.isfinite(ll).all()), "ll_max": float(ll.max()),
+            "argmax_setting": [float(x) for x in settings[int(ll.argmax())]]}
+
+
+def sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist):
+    """Time-sharded step against the unsharded step of the same series (computed on every rank), d = 3 and d = 6."""
+    out = {}
+    for name, mk, n_rank in (("matern52_d3", lambda: kernels.Matern52(1.0, 1.0), 60_000),
+                             ("rbf6_d6", lambda: kernels.RBF(1.0, 1.0, order=6, balancing_iter=5), 20_000)):
+        n_total = n_rank * world
+        t_host, y_host = make_series(n_total, seed_offset=5)
+        with torch.no_grad():
+            sde = mk().get_sde()
+        F, Pinf = sde.F.to(dev).contiguous(), sde.P0.to(dev).contiguous()
+        H = sde.H.to(dev).reshape(-1).contiguous()
+        R = torch.tensor([NOISE], dtype=torch.float64, device=dev)
+        t_dev = torch.as_tensor(t_host).to(dev)
+        dts = t_dev - torch.cat([torch.zeros(1, dtype=torch.float64, device=dev), t_dev[:-1]])
+        y_dev = torch.as_tensor(y_host).to(dev)
+        Fs, Qs = ops.discretise(F, Pinf, dts)
+        g = torch.full((1,), 1.1, dtype=torch.float64, device=dev)
+        (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(Pinf, Fs, Qs, H, R, y_dev, g)
+        lo, hi = rank * n_rank, (rank + 1) * n_rank
+        sh = pdist.TimeShard(rank, world, dist)
+        ll2, sms2, sPs2, (dP02, dFs2, dQs2, dH2, dR2) = sh.filter_smoother_grad(
+            Pinf, Fs[lo:hi].contiguous(), Qs[lo:hi].contiguous(), H, R, y_dev[lo:hi].contiguous(), g)
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
+        errs = torch.tensor([rel(ll2, ll), rel(sms2, sms[lo:hi]), rel(sPs2, sPs[lo:hi]), rel(dFs2, dFs[lo:hi]),
+                             rel(dQs2, dQs[lo:hi]), rel(dP02, dP0), rel(dH2, dH), rel(dR2, dR)], dtype=torch.float64, device=dev)
+        dist.all_reduce(errs, op=dist.ReduceOp.MAX)
+        names = ["ll", "sms", "sPs", "dFs", "dQs", "dP0", "dH", "dR"]
+        out[name] = {"n_total": n_total, "max_rel_err": float(errs.max()), "per_output": dict(zip(names, [float(e) for e in errs]))}
+    out["max_rel_err"] = max(v["max_rel_err"] for v in out.values())
+    return out
+
+
+def sequential_numba_baseline(sample_n=200_000):
+    """numba-JIT sequential kf + ks (pssgp/kalman/sequential.py restated), ONE host core."""
+    import torch
+    import __graft_entry__ as entry
+    O = entry.import_oracle()
+    import seq_numba
+    t, y = make_series(sample_n)
+    with torch.no_grad():
+        ssm = O.Matern52(1.0, 1.0).get_ssm(t[:, None], torch.tensor([[NOISE]], dtype=torch.float64))
+    P0, Fs, Qs, H, R = [np.ascontiguousarray(x.numpy()) for x in ssm]
+    seq_numba.kfs(P0, Fs[:1000], Qs[:1000], H, R, y[:1000])  # JIT compile
+    t0 = time.perf_counter()
+    seq_numba.kfs(P0, Fs, Qs, H, R, y)
+    dt = time.perf_counter() - t0
+    return {"value": sample_n / dt, "unit": "filter+smoother timesteps/s", "cores": 1, "kind": "port",
+            "sample": f"first {sample_n} time steps of the workload, sequential kf + ks (numba-JIT restatement of "
+                      f"pssgp/kalman/sequential.py:11-73), no gradient (the reference obtains it by TF autodiff)"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -167,6 +399,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=N_PER_GPU, help="time steps per GPU (default: the BASELINE workload)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (configs[2..4])")
+    ap.add_argument("--only", default=None, help="comma-separated names of the extra configs to run")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -302,6 +536,39 @@ def main():
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                "note": "model-level e2e is measured at n_gpus=1"}
 
+    # ---- the other BASELINE configurations + the sharded-vs-unsharded check (all ranks take part) ----------
+    peaks_all = {}
+    try:
+        peaks_all = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_all = float(peaks_all.get("hbm_gbs", 6650.0))
+    FP64_PEAK_TFLOPS = 37.1  # DMMA full-chip rate, scripts/sm_probe.cu on this pool's B200 (profiles/r02_sm_probe.txt)
+    del Fs, Qs, out
+    torch.cuda.empty_cache()
+    extras, check = {}, None
+    if not args.no_extra:
+        Kx, Wx = max(2, min(K, 3)), 3
+        for name, cfg in extra_configs(world).items():
+            if args.only and name not in args.only.split(","):
+                continue
+            try:
+                extras[name] = run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels, ops, pdist, h,
+                                                hbm_all, FP64_PEAK_TFLOPS, Wx, Kx, not args.no_cpu_baseline)
+            except Exception as e:  # keep the headline line alive
+                extras[name] = {"error": repr(e)}
+                torch.cuda.empty_cache()
+        if not args.only or "grid_1024" in args.only.split(","):
+            try:
+                extras["grid_1024"] = run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, Wx)
+            except Exception as e:
+                extras["grid_1024"] = {"error": repr(e)}
+        if world > 1:
+            try:
+                check = sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist)
+            except Exception as e:
+                check = {"error": repr(e)}
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -353,6 +620,10 @@ def main():
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"the full workload once ({sample_n} time steps, {dt:.1f} s): oracle port = torch-CPU "
                          f"restatement of the reference's pkf + autograd gradient + pks; TF reference not installable"}
+        try:
+            cpu["sequential_kf_ks"] = sequential_numba_baseline()
+        except Exception as e:  # pragma: no cover
+            cpu["sequential_kf_ks"] = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
@@ -365,6 +636,7 @@ def main():
                    "parallelism": "time-sharded x%d" % world if world > 1 else "single GPU"},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "step_roofline": step_roof,
         "kernels": per_kernel, "ms_per_step_with_kernel_events": ms_instrumented, "cpu_baseline": cpu, "clocks": clock_info,
+        "configs": extras, "sharded_check": check,
     }
     print(json.dumps(line))
     if dist is not None:

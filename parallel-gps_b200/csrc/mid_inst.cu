@@ -121,10 +121,13 @@ static int hier_rev(pssgp_handle* h, int64_t nchunks, double* raggs, double* rst
 // chunk length: one resident wave of groups of the most shared-memory-hungry kernel of the call
 static int pick_len(const pssgp_handle* h, int64_t n, int gpc) {
     if (h->chunk_opt > 0) return (int)h->chunk_opt;
+    // whole waves of `slots` resident groups, chunks of at most kMaxLen steps: every wave is full (a last partial wave
+    // would cost as much as a full one)
+    constexpr int64_t kMaxLen = 4096;
     const int64_t slots = (int64_t)(h->num_sms > 0 ? h->num_sms : 1) * gpc;
-    int64_t L = (n + slots - 1) / slots;
+    const int64_t waves = (n + slots * kMaxLen - 1) / (slots * kMaxLen);
+    int64_t L = (n + slots * waves - 1) / (slots * waves);
     if (L < 16) L = 16;
-    if (L > 4096) L = 4096;
     return (int)L;
 }
 
