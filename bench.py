@@ -45,6 +45,7 @@ sys.path.insert(0, ROOT)
 
 N_PER_GPU = 1_000_000
 NOISE = 0.1
+print_line = lambda obj: print(json.dumps(obj))
 METRIC = "filter+smoother+grad timesteps/s"
 UNIT = "timesteps/s"
 
@@ -205,7 +206,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    print_line(line)
 
 
 def time_steps_on_device(step, W, K, barrier, dist, dev, torch):
@@ -402,6 +403,13 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the other BASELINE configs (configs[2..4])")
     ap.add_argument("--only", default=None, help="comma-separated names of the extra configs to run")
     args = ap.parse_args()
+    # exactly ONE line on stdout (the JSON): anything a library prints on fd 1 meanwhile (NCCL's version banner) goes to
+    # stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    global print_line
+    print_line = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
     if args.impl == "reference":
         run_reference(args)
         return
@@ -638,7 +646,7 @@ def main():
         "kernels": per_kernel, "ms_per_step_with_kernel_events": ms_instrumented, "cpu_baseline": cpu, "clocks": clock_info,
         "configs": extras, "sharded_check": check,
     }
-    print(json.dumps(line))
+    print_line(line)
     if dist is not None:
         dist.destroy_process_group()
 
