@@ -266,13 +266,13 @@ def oracle_sample_baseline(cfg, sample_n):
 
 
 def run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels, ops, pdist, h, hbm_peak, fp64_peak, W, K,
-                     with_cpu):
+                     with_cpu, xchg=None):
     if cfg["scaling"] == "single-gpu" and world > 1:
         return {"skipped": "single-GPU configuration: measured at n_gpus = 1"}
     n, Pinf, Fs, Qs, H, R, y_dev, _ = shard_lgssm(cfg, world, rank, dev, torch, kernels, ops)
     d = Fs.shape[1]
     g_ll = torch.ones(1, dtype=torch.float64, device=dev)
-    shard = pdist.TimeShard(rank, world, dist) if world > 1 else None
+    shard = pdist.TimeShard(rank, world, dist, exchange=xchg) if world > 1 else None
 
     def step():
         if shard is None:
@@ -341,7 +341,7 @@ def run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, W):
             "argmax_setting": [float(x) for x in settings[int(ll.argmax())]]}
 
 
-def sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist):
+def sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist, xchg=None):
     """Time-sharded step against the unsharded step of the same series (computed on every rank), d = 3 and d = 6."""
     out = {}
     for name, mk, n_rank in (("matern52_d3", lambda: kernels.Matern52(1.0, 1.0), 60_000),
@@ -360,7 +360,7 @@ def sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist):
         g = torch.full((1,), 1.1, dtype=torch.float64, device=dev)
         (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(Pinf, Fs, Qs, H, R, y_dev, g)
         lo, hi = rank * n_rank, (rank + 1) * n_rank
-        sh = pdist.TimeShard(rank, world, dist)
+        sh = pdist.TimeShard(rank, world, dist, exchange=xchg)
         ll2, sms2, sPs2, (dP02, dFs2, dQs2, dH2, dR2) = sh.filter_smoother_grad(
             Pinf, Fs[lo:hi].contiguous(), Qs[lo:hi].contiguous(), H, R, y_dev[lo:hi].contiguous(), g)
         rel = lambda a, b: float((a - b).abs().max() / b.abs().max().clamp_min(1e-300))
@@ -453,7 +453,20 @@ def main():
     y_dev = torch.as_tensor(y_host[lo:hi]).to(dev)
     Fs, Qs = ops.discretise(F, Pinf, dts)
     g_ll = torch.ones(1, dtype=torch.float64, device=dev)
-    shard = pdist.TimeShard(rank, world, dist) if world > 1 else None
+    xchg, xchg_kind = None, "none"
+    if world > 1:
+        xchg_kind = "nccl collectives"
+        if os.environ.get("PSSGP_EXCHANGE", "peer") == "peer":
+            try:
+                xchg = pdist.PeerExchange(rank, world, dist, dev)
+                xchg_kind = "NVLink peer stores (pssgp_peer_exchange)"
+            except Exception as e:  # symmetric memory unavailable: NCCL collectives
+                print(f"[bench] peer exchange unavailable ({e!r}); using NCCL collectives", file=sys.stderr)
+        ok = torch.tensor([1.0 if xchg is not None else 0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            xchg, xchg_kind = None, "nccl collectives"
+    shard = pdist.TimeShard(rank, world, dist, exchange=xchg) if world > 1 else None
     h = _lib.handle(local_rank)
 
     def device_step():
@@ -472,6 +485,39 @@ def main():
     for _ in range(W):
         out = device_step()
     barrier()
+    # time sharding with the peer exchange is kernels only (no NCCL call, no host synchronisation): the whole step is
+    # captured once and replayed as ONE CUDA graph launch, which takes the per-launch host work of the ~20 small
+    # operations around the three exchanges off the critical path of every rank
+    graphed = False
+    eager_step = device_step
+    if shard is not None and xchg is not None and os.environ.get("PSSGP_GRAPH", "1") == "1":
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    out = eager_step()
+            torch.cuda.current_stream(dev).wait_stream(side)
+            barrier()
+            graph = torch.cuda.CUDAGraph()
+            lc0 = h.launch_count()
+            with torch.cuda.graph(graph, stream=side):
+                graph_out = eager_step()
+            graph_launches = h.launch_count() - lc0   # kernels of this library recorded into the graph
+            ok = torch.tensor([1.0], device=dev)
+        except Exception as e:
+            print(f"[bench] CUDA-graph capture of the sharded step failed ({e!r}); eager launches", file=sys.stderr)
+            ok = torch.tensor([0.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 1.0:
+            graphed = True
+
+            def device_step():
+                graph.replay()
+                return graph_out
+            for _ in range(W):
+                out = device_step()
+            barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -484,7 +530,8 @@ def main():
     e1.record()
     barrier()
     ms_dev = e0.elapsed_time(e1) / K
-    launches = (h.launch_count() - launches0) // max(K, 1)
+    launches = graph_launches if graphed else (h.launch_count() - launches0) // max(K, 1)
+    device_step = eager_step   # the per-kernel event pass below needs eager launches
     # the same K steps once more with a CUDA-event pair around every kernel launch (library option "timing"):
     # per-kernel durations for the roofline; kept out of the loop above because every event record costs
     # a few microseconds of stream time
@@ -501,6 +548,7 @@ def main():
     ktimes = h.timing_report()
     h.set_option("timing", 0)
     clock_info = clocks.stop() if rank == 0 else None
+    xchg_fail = xchg.failures() if xchg is not None else 0
     if dist is not None:
         tt = torch.tensor([ms_dev], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -562,7 +610,7 @@ def main():
                 continue
             try:
                 extras[name] = run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels, ops, pdist, h,
-                                                hbm_all, FP64_PEAK_TFLOPS, Wx, Kx, not args.no_cpu_baseline)
+                                                hbm_all, FP64_PEAK_TFLOPS, Wx, Kx, not args.no_cpu_baseline, xchg)
             except Exception as e:  # keep the headline line alive
                 extras[name] = {"error": repr(e)}
                 torch.cuda.empty_cache()
@@ -573,7 +621,8 @@ def main():
                 extras["grid_1024"] = {"error": repr(e)}
         if world > 1:
             try:
-                check = sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist)
+                check = sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist, xchg)
+                check["exchange"] = xchg_kind
             except Exception as e:
                 check = {"error": repr(e)}
 
@@ -641,7 +690,8 @@ def main():
                                "FP64, log-lik + gradient + RTS smoother (configs[1])",
                    "n_per_gpu": n, "state_dim": d, "l2_policy": "inputs larger than L2 (Fs+Qs+y = 152 MB, "
                    "plus 96+96+144 MB of outputs per step; L2 = 126 MB)",
-                   "parallelism": "time-sharded x%d" % world if world > 1 else "single GPU"},
+                   "parallelism": "time-sharded x%d" % world if world > 1 else "single GPU", "exchange": xchg_kind,
+                   "cuda_graph": graphed, "exchange_failures": xchg_fail},
         "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "step_roofline": step_roof,
         "kernels": per_kernel, "ms_per_step_with_kernel_events": ms_instrumented, "cpu_baseline": cpu, "clocks": clock_info,
         "configs": extras, "sharded_check": check,

@@ -219,6 +219,23 @@ int pssgp_shard_reverse(pssgp_handle* h, int dtype, int64_t n, int d,
                         void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream);
 
 /*
+ * All-gather of one small message per rank over NVLink peer memory (time sharding; replaces the latency-bound NCCL
+ * all-gather of shard summaries the SURVEY.md §8e design calls for).  peer_bufs[j] / peer_flags[j] (HOST arrays of
+ * `world` device pointers) are rank j's copy of a symmetric buffer mapped into this process (torch symmetric memory or
+ * cudaIpc): doubles and 64-bit flags respectively.  The kernel stores msg [nvals doubles] into row `rank`
+ * (row_stride doubles per row) at slot_offset doubles of EVERY rank's buffer, publishes a sequence number in flag
+ * flag_offset + rank of every rank, and waits until the flags flag_offset + j of its own buffer show that every rank's
+ * row has landed: afterwards rows 0 .. world-1 of the local slot hold all messages.  seq_counter: one 64-bit device
+ * counter per slot in local memory, zero-initialised, owned by the caller (incremented by the kernel: no host-side
+ * state, the launch is CUDA-graph replayable).  err_counter: 64-bit device counter incremented when a wait gives up after
+ * ~10 s (a peer never published its row): the caller checks it instead of the GPU hanging.  Every rank must issue the same sequence of exchanges; a slot may be
+ * reused once every rank has issued a later exchange.  FP64 messages (reinterpret other payloads).
+ */
+int pssgp_peer_exchange(pssgp_handle* h, const void* msg, int64_t nvals, void* const* peer_bufs, void* const* peer_flags,
+                        int world, int rank, int64_t slot_offset, int64_t row_stride, int64_t flag_offset,
+                        void* seq_counter, void* err_counter, void* stream);
+
+/*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].
  */
 int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d,

@@ -14,12 +14,76 @@ The reference has no multi-device code; this is the §8(e) desi
 object providing the per-shard operations (default: pssgp_b200.ops = CUDA); tests substitute a CPU
 implementation to exercise the exchange logic under gloo.
 """
+import ctypes
+
 import torch
 
 
+class PeerExchange:
+    """All-gather / all-reduce of the shard summaries through a symmetric buffer over NVLink peer memory (C ABI
+    ``pssgp_peer_exchange``): one small kernel per exchange stores this rank's message into every peer's buffer and
+    waits on release / acquire flags.  No NCCL call on the data path; nothing synchronises with the host.
+
+    ``torch.distributed._symmetric_memory`` provides the peer-mapped allocation (the process group is only used for
+    the one-time rendezvous).  Every rank must issue the same sequence of exchanges; a slot is reused after NSLOTS
+    exchanges, each of which synchronises all ranks."""
+    NSLOTS = 8
+
+    def __init__(self, rank, world, dist, device, row_doubles=4096, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.rank, self.world, self.row = int(rank), int(world), int(row_doubles)
+        self.device = torch.device(device)
+        nd = self.NSLOTS * self.world * self.row
+        nf = self.NSLOTS * self.world
+        self.buf = symm_mem.empty(nd + nf, dtype=torch.float64, device=self.device)
+        self.buf.zero_()
+        grp = group if group is not None else dist.group.WORLD
+        self.hdl = symm_mem.rendezvous(self.buf, grp)
+        ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self._peer_bufs = (ctypes.c_void_p * self.world)(*ptrs)
+        self._peer_flags = (ctypes.c_void_p * self.world)(*[p + 8 * nd for p in ptrs])
+        self.seq = torch.zeros(self.NSLOTS + 1, dtype=torch.int64, device=self.device)  # [NSLOTS] = give-up counter
+        self.count = 0
+        self._lib = _lib
+        torch.cuda.synchronize(self.device)
+        dist.barrier(group=group)   # every rank's buffer and flags are zero before the first remote store
+
+    def all_gather(self, vec):
+        """vec: contiguous float64 device vector (same length on every rank, <= row_doubles).
+        -> [world, len] view of the local slot (rows strided by row_doubles; valid until NSLOTS exchanges later)."""
+        from . import _arrays as A
+        vec = vec.contiguous().reshape(-1)
+        if vec.dtype != torch.float64:
+            raise TypeError("PeerExchange carries float64 messages")
+        n = vec.numel()
+        if n > self.row:
+            raise ValueError(f"message of {n} values exceeds the slot row ({self.row})")
+        slot = self.count % self.NSLOTS
+        self.count += 1
+        h = self._lib.handle(self.device.index)
+        self._lib.check(self._lib.lib().pssgp_peer_exchange(
+            h.ptr, A.ptr(vec), n, self._peer_bufs, self._peer_flags, self.world, self.rank, slot * self.world * self.row,
+            self.row, slot * self.world, self.seq.data_ptr() + 8 * slot, self.seq.data_ptr() + 8 * self.NSLOTS,
+            A.stream_ptr(self.device)))
+        lo = slot * self.world * self.row
+        return self.buf[lo:lo + self.world * self.row].view(self.world, self.row)[:, :n]
+
+    def failures(self):
+        """Number of waits that gave up (synchronises with the device); 0 on a healthy run."""
+        return int(self.seq[self.NSLOTS].item())
+
+    def all_reduce_sum(self, vec):
+        """In-place sum over ranks (rows added in rank order on every rank: deterministic and identical everywhere)."""
+        g = self.all_gather(vec)
+        vec.copy_(g.sum(0).reshape(vec.shape))
+        return vec
+
+
 class TimeShard:
-    def __init__(self, rank, world, dist=None, backend=None, group=None):
+    def __init__(self, rank, world, dist=None, backend=None, group=None, exchange=None):
         self.rank, self.world, self.dist, self.group = int(rank), int(world), dist, group
+        self.xchg = exchange   # PeerExchange (NVLink peer stores) or None (torch.distributed collectives)
         if backend is None:
             from . import ops as backend
         self.ops = backend
@@ -31,12 +95,16 @@ class TimeShard:
     def _all_gather(self, vec):
         if self.world == 1:
             return vec.reshape(1, -1)
+        if self.xchg is not None:
+            return self.xchg.all_gather(vec)
         out = torch.empty((self.world * vec.numel(),), dtype=vec.dtype, device=vec.device)
         self.dist.all_gather_into_tensor(out, vec.contiguous().reshape(-1), group=self.group)
         return out.reshape(self.world, vec.numel())
 
     def _all_reduce(self, vec):
         if self.world > 1:
+            if self.xchg is not None:
+                return self.xchg.all_reduce_sum(vec)
             self.dist.all_reduce(vec, group=self.group)
         return vec
 

@@ -24,11 +24,15 @@ def main():
     with torch.no_grad():
         rfm, rfP, rll = O.pkf(ssm, y[:, None], True)
         rsm, rsP = O.pks(ssm, rfm, rfP)
-    if backend == "nccl":
+    xchg = None
+    if backend in ("nccl", "peer"):
         torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
         dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
         dist.init_process_group("nccl", device_id=dev)
         ops = None
+        if backend == "peer":
+            from pssgp_b200.dist import PeerExchange
+            xchg = PeerExchange(rank, world, dist, dev)
     else:
         dev = torch.device("cpu")
         dist.init_process_group("gloo")
@@ -37,10 +41,16 @@ def main():
     P0, H, R = to(ssm.P0), to(ssm.H).reshape(-1), to(ssm.R).reshape(-1)
     Fs, Qs = to(ssm.Fs[lo:hi]), to(ssm.Qs[lo:hi])
     yd = torch.as_tensor(y[lo:hi]).to(dev)
-    sh = TimeShard(rank, world, dist, backend=ops)
+    sh = TimeShard(rank, world, dist, backend=ops, exchange=xchg)
     fms, fPs, ll = sh.filter(P0, Fs, Qs, H, R, yd)
     g = torch.ones(1, dtype=torch.float64, device=dev)
-    o = sh.smoother_and_grad(P0, Fs, Qs, H, R, yd, fms, fPs, g, want_grad=(backend == "nccl"))
+    o = sh.smoother_and_grad(P0, Fs, Qs, H, R, yd, fms, fPs, g, want_grad=(backend != "gloo"))
+    if backend == "peer":
+        # several steps back to back: slots and sequence numbers wrap around
+        for _ in range(5):
+            ll5, sms5, sPs5, _ = sh.filter_smoother_grad(P0, Fs, Qs, H, R, yd, g)
+        o["sms"], o["sPs"] = sms5, sPs5
+        ll = ll5
     ok = (rel_err(fms.cpu(), rfm[lo:hi]) < 1e-9 and rel_err(fPs.cpu(), rfP[lo:hi]) < 1e-9
           and abs(float(ll) - float(rll)) <= 1e-9 * abs(float(rll))
           and rel_err(o["sms"].cpu(), rsm[lo:hi]) < 1e-9 and rel_err(o["sPs"].cpu(), rsP[lo:hi]) < 1e-9)
