@@ -167,6 +167,10 @@ int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value) {
         h->pdl = value != 0;
         return PSSGP_OK;
     }
+    if (strcmp(name, "mid_warps") == 0) {
+        h->mid_warps = (int)value;
+        return PSSGP_OK;
+    }
     if (strcmp(name, "mid_smem") == 0) {
         h->mid_smem = value != 0;
         return PSSGP_OK;

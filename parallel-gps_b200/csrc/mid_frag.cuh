@@ -383,10 +383,15 @@ template <int MT> MDEV Mat<MT> msub(const Mat<MT>& a, const Mat<MT>& b) {
 }
 
 template <int D> constexpr int frag_nslot() { return D <= 8 ? 4 : 3; }
+// warps per CTA: as many as the ring slots of a CTA fit in shared memory, at most `cap` (the launch bound; the option
+// "mid_warps" lowers it at run time)
 template <int D> constexpr int frag_warps(int slot_doubles, int cap) {
     const int fit = (200 * 1024) / (frag_nslot<D>() * slot_doubles * 8);
     return fit > cap ? cap : (fit < 1 ? 1 : fit);
 }
+#ifndef PSSGP_FRAG_CAP_SMALL
+#define PSSGP_FRAG_CAP_SMALL 24
+#endif
 
 // ------------------------------------------------------------------------------------------------
 // K1: chunk aggregates of the filter.  Tracks At = A^T, C, J (CF), b, eta (VR).
@@ -395,8 +400,9 @@ template <int D> struct FK1 {
     using G = FGeo<D>;
     static constexpr int NSLOT = frag_nslot<D>();
     static constexpr int SLOT = 2 * G::MSZ;  // F | Q
-    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? 16 : 8);
-    static constexpr size_t SMEM = (size_t)WPC * NSLOT * SLOT * 8;
+    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? PSSGP_FRAG_CAP_SMALL : 12);
+    static constexpr size_t WARP_SMEM = (size_t)NSLOT * SLOT * 8;
+    static constexpr size_t SMEM = (size_t)WPC * WARP_SMEM;
 };
 
 template <int D>
@@ -406,7 +412,7 @@ __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, 
     constexpr int MT = G::MT, MSZ = G::MSZ, NSLOT = K::NSLOT, DD = G::DD;
     extern __shared__ __align__(16) double smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
-    const long chunk = (long)blockIdx.x * K::WPC + wid;
+    const long chunk = (long)blockIdx.x * (blockDim.x >> 5) + wid;
     if (chunk >= nchunks) return;
     double* ring = smem + (size_t)wid * NSLOT * K::SLOT;
     for (int i = lane; i < NSLOT * K::SLOT; i += 32) ring[i] = 0.0;
@@ -501,8 +507,9 @@ template <int D, bool REV, bool STORED> struct FK2 {
     static constexpr int NSLOT = frag_nslot<D>();
     static constexpr int NM = 2 + (STORED ? 1 : 0);  // F | Q | P_{k-1}
     static constexpr int SLOT = NM * G::MSZ + (STORED ? G::DP : 0);
-    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? 16 : 8);
-    static constexpr size_t SMEM = (size_t)WPC * NSLOT * SLOT * 8;
+    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? PSSGP_FRAG_CAP_SMALL : 12);
+    static constexpr size_t WARP_SMEM = (size_t)NSLOT * SLOT * 8;
+    static constexpr size_t SMEM = (size_t)WPC * WARP_SMEM;
 };
 
 template <int D, bool REV, bool STORED>
@@ -515,7 +522,7 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
     constexpr int O_P = 2 * MSZ, O_M = 3 * MSZ;
     extern __shared__ __align__(16) double smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
-    const long chunk = (long)blockIdx.x * K::WPC + wid;
+    const long chunk = (long)blockIdx.x * (blockDim.x >> 5) + wid;
     if (chunk >= nchunks) return;
     double* ring = smem + (size_t)wid * NSLOT * K::SLOT;
     for (int i = lane; i < NSLOT * K::SLOT; i += 32) ring[i] = 0.0;
@@ -683,8 +690,9 @@ template <int D, bool SMOOTH, bool ADJ> struct FK3 {
     using G = FGeo<D>;
     static constexpr int NSLOT = frag_nslot<D>() < 3 ? 3 : frag_nslot<D>();
     static constexpr int SLOT = 3 * G::MSZ + G::DP;  // F | Q | fP | fm
-    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? 16 : 6);
-    static constexpr size_t SMEM = (size_t)WPC * NSLOT * SLOT * 8;
+    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? PSSGP_FRAG_CAP_SMALL : 10);
+    static constexpr size_t WARP_SMEM = (size_t)NSLOT * SLOT * 8;
+    static constexpr size_t SMEM = (size_t)WPC * WARP_SMEM;
 };
 
 template <int D, bool SMOOTH, bool ADJ>
@@ -696,7 +704,7 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
     constexpr int O_P = 2 * MSZ, O_M = 3 * MSZ;
     extern __shared__ __align__(16) double smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
-    const long chunk = (long)blockIdx.x * K::WPC + wid;
+    const long chunk = (long)blockIdx.x * (blockDim.x >> 5) + wid;
     if (chunk >= nchunks) return;
     double* ring = smem + (size_t)wid * NSLOT * K::SLOT;
     for (int i = lane; i < NSLOT * K::SLOT; i += 32) ring[i] = 0.0;

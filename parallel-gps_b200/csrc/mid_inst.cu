@@ -22,16 +22,23 @@ template <class Kern> static int set_smem_attr(Kern kernel, size_t bytes) {
 // tiles with groups of warps above.  Option "mid_smem" forces the shared-memory family (tests / tuning).
 template <int D> constexpr bool has_frag() { return D <= 16; }
 
+static thread_local int g_mid_warps = 0;  // option "mid_warps" of the handle in use (0 = compile-time default)
+// measured (scripts/sweep_mid_warps.py, N = 1e6): d = 6 gains up to the 24 warps that fit; d = 9 / d = 16 are fastest with 8
+static int cap_warps(int wpc) {
+    const int lim = g_mid_warps > 0 ? g_mid_warps : (MID_D > 8 ? 8 : 1000);
+    return lim < wpc ? lim : wpc;
+}
+
 template <int D> static int k1_groups(bool fr) {
-    if constexpr (has_frag<D>()) if (fr) return frag::FK1<D>::WPC;
+    if constexpr (has_frag<D>()) if (fr) return cap_warps(frag::FK1<D>::WPC);
     return K1<D, default_wg<D>()>::GPC;
 }
 template <int D, bool REV, bool STORED> static int k2_groups(bool fr) {
-    if constexpr (has_frag<D>()) if (fr) return frag::FK2<D, REV, STORED>::WPC;
+    if constexpr (has_frag<D>()) if (fr) return cap_warps(frag::FK2<D, REV, STORED>::WPC);
     return K2<D, default_wg<D>(), REV, STORED>::GPC;
 }
 template <int D, bool SMOOTH, bool ADJ> static int k3_groups(bool fr) {
-    if constexpr (has_frag<D>()) if (fr) return frag::FK3<D, SMOOTH, ADJ>::WPC;
+    if constexpr (has_frag<D>()) if (fr) return cap_warps(frag::FK3<D, SMOOTH, ADJ>::WPC);
     return K3<D, default_wg<D>(), SMOOTH, ADJ>::GPC;
 }
 
@@ -41,8 +48,9 @@ template <int D> static int launch_k1(pssgp_handle* h, bool fr, const Params& p,
         if (fr) {
             using KA = frag::FK1<D>;
             if ((rc = set_smem_attr(frag::fk1_filter_reduce<D>, KA::SMEM))) return rc;
-            const unsigned grid = (unsigned)((nchunks + KA::WPC - 1) / KA::WPC);
-            PSSGP_LAUNCH(h, "mid_filter_reduce", st, (frag::fk1_filter_reduce<D><<<grid, KA::WPC * 32, KA::SMEM, st>>>(p, L, nchunks, aggs)));
+            const int wpc = cap_warps(KA::WPC);
+            const unsigned grid = (unsigned)((nchunks + wpc - 1) / wpc);
+            PSSGP_LAUNCH(h, "mid_filter_reduce", st, (frag::fk1_filter_reduce<D><<<grid, wpc * 32, wpc * KA::WARP_SMEM, st>>>(p, L, nchunks, aggs)));
             return PSSGP_OK;
         }
     }
@@ -63,9 +71,10 @@ static int launch_k2(pssgp_handle* h, bool fr, const char* name, const Params& p
         if (fr) {
             using KB = frag::FK2<D, REV, STORED>;
             if ((rc = set_smem_attr(frag::fk2_forward<D, REV, STORED>, KB::SMEM))) return rc;
-            const unsigned grid = (unsigned)((nchunks + KB::WPC - 1) / KB::WPC);
+            const int wpc = cap_warps(KB::WPC);
+            const unsigned grid = (unsigned)((nchunks + wpc - 1) / wpc);
             PSSGP_LAUNCH(h, name, st,
-                         (frag::fk2_forward<D, REV, STORED><<<grid, KB::WPC * 32, KB::SMEM, st>>>(p, L, nchunks, fstates, part, raggs)));
+                         (frag::fk2_forward<D, REV, STORED><<<grid, wpc * 32, wpc * KB::WARP_SMEM, st>>>(p, L, nchunks, fstates, part, raggs)));
             return PSSGP_OK;
         }
     }
@@ -87,9 +96,10 @@ static int launch_k3(pssgp_handle* h, bool fr, const Params& p, int L, int64_t n
         if (fr) {
             using KC = frag::FK3<D, SMOOTH, ADJ>;
             if ((rc = set_smem_attr(frag::fk3_reverse<D, SMOOTH, ADJ>, KC::SMEM))) return rc;
-            const unsigned grid = (unsigned)((nchunks + KC::WPC - 1) / KC::WPC);
+            const int wpc = cap_warps(KC::WPC);
+            const unsigned grid = (unsigned)((nchunks + wpc - 1) / wpc);
             PSSGP_LAUNCH(h, "mid_reverse", st,
-                         (frag::fk3_reverse<D, SMOOTH, ADJ><<<grid, KC::WPC * 32, KC::SMEM, st>>>(p, L, nchunks, rstates, part)));
+                         (frag::fk3_reverse<D, SMOOTH, ADJ><<<grid, wpc * 32, wpc * KC::WARP_SMEM, st>>>(p, L, nchunks, rstates, part)));
             return PSSGP_OK;
         }
     }
@@ -158,6 +168,7 @@ template <int D>
 int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H, const double* R,
         const double* y, const double* m0, int first_special, double* fms, double* fPs, double* ll, double* final_state,
         double* summary, cudaStream_t st) {
+    g_mid_warps = h->mid_warps;
     const bool fr = has_frag<D>() && !h->mid_smem;
     int rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
@@ -221,6 +232,7 @@ template <int D>
 int pkfs_grad(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H,
               const double* R, const double* y, const double* g_ll, double* fms, double* fPs, double* ll, double* sms,
               double* sPs, double* dP0, double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st) {
+    g_mid_warps = h->mid_warps;
     const bool fr = has_frag<D>() && !h->mid_smem;
     const bool smooth = sms != nullptr, adj = dFs != nullptr;
     int rc;
@@ -268,6 +280,7 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
                  const double* H, const double* R, const double* y, const double* fms, const double* fPs,
                  const double* g_ll, int first_special, double* dP0, double* dFs, double* dQs, double* dH, double* dR,
                  cudaStream_t st) {
+    g_mid_warps = h->mid_warps;
     const bool fr = has_frag<D>() && !h->mid_smem;
     int rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
@@ -300,6 +313,7 @@ template <int D>
 int shard_forward(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs, const double* H,
                   const double* R, const double* y, const double* m0, int first_special, double* fms, double* fPs,
                   double* ll, double* rev_summary, cudaStream_t st) {
+    g_mid_warps = h->mid_warps;
     const bool fr = has_frag<D>() && !h->mid_smem;
     int rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
@@ -352,6 +366,7 @@ int shard_reverse(pssgp_handle* h, int64_t n, const double* P0, const double* m0
                   const double* H, const double* R, const double* y, const double* fms, const double* fPs,
                   const double* g_ll, int first_special, const double* rev_init, double* sms, double* sPs, double* dP0,
                   double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st) {
+    g_mid_warps = h->mid_warps;
     const bool fr = has_frag<D>() && !h->mid_smem;
     const bool smooth = sms != nullptr, adj = dFs != nullptr;
     int rc;

@@ -16,6 +16,7 @@ struct pssgp_handle {
     unsigned int* ticket;
     int64_t chunk_opt;
     int pdl;            // option "pdl": programmatic dependent launch between the kernels of pkfs_grad
+    int mid_warps;      // option "mid_warps": cap on the warps per CTA of the fragment-resident d > 4 kernels (0 = default)
     int mid_smem;       // option "mid_smem": 5 <= d <= 16 runs the shared-memory tile kernels instead of the fragment-resident ones
     int force_generic;  // option "force_generic": d > 4 runs the CTA-cooperative kernels of generic.cu (tuning / tests)
     int fused_reverse;  // option "fused_reverse": pkfs_grad runs smoother + adjoint recursions in one kernel
