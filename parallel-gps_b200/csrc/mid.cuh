@@ -211,7 +211,7 @@ k1_filter_reduce(Params p, int L, long nchunks, double* __restrict__ aggs) {
     constexpr int MSZ = G::MSZ, DP = G::DP, LD = G::LD, NSLOT = K::NSLOT, DD = G::DD;
     extern __shared__ __align__(16) double smem[];
     const int gi = threadIdx.x / G::NT;
-    const long chunk = (long)blockIdx.x * K::GPC + gi;
+    const long chunk = (long)blockIdx.x * (blockDim.x / G::NT) + gi;  // groups per CTA: run-time (<= K::GPC)
     if (chunk >= nchunks) return;
     const Grp g = make_grp<G>(gi);
     double* S = smem + (size_t)gi * K::GROUP_DOUBLES;
@@ -329,7 +329,7 @@ k2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, do
     constexpr int MSZ = G::MSZ, DP = G::DP, LD = G::LD, NSLOT = K::NSLOT, DD = G::DD;
     extern __shared__ __align__(16) double smem[];
     const int gi = threadIdx.x / G::NT;
-    const long chunk = (long)blockIdx.x * K::GPC + gi;
+    const long chunk = (long)blockIdx.x * (blockDim.x / G::NT) + gi;  // groups per CTA: run-time (<= K::GPC)
     if (chunk >= nchunks) return;
     const Grp g = make_grp<G>(gi);
     double* S = smem + (size_t)gi * K::GROUP_DOUBLES;
@@ -502,7 +502,7 @@ k3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, do
     constexpr int MSZ = G::MSZ, DP = G::DP, LD = G::LD, NSLOT = K::NSLOT, DD = G::DD;
     extern __shared__ __align__(16) double smem[];
     const int gi = threadIdx.x / G::NT;
-    const long chunk = (long)blockIdx.x * K::GPC + gi;
+    const long chunk = (long)blockIdx.x * (blockDim.x / G::NT) + gi;  // groups per CTA: run-time (<= K::GPC)
     if (chunk >= nchunks) return;
     const Grp g = make_grp<G>(gi);
     double* S = smem + (size_t)gi * K::GROUP_DOUBLES;

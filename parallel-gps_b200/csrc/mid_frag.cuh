@@ -42,21 +42,39 @@ template <int MT> MDEV void mzero(Mat<MT>& m) {
         for (int b = 0; b < MT; ++b) m.v[a][b][0] = m.v[a][b][1] = 0.0;
 }
 
+// Operand of a product that still sits in a ring slot (tile-major): fragments are loaded inside the product loop, so
+// an input matrix never occupies registers for longer than one DMMA (MT = 3: a matrix is 36 registers per thread).
+template <int MT> struct SMat {
+    const double* p;
+    int r, c;
+    bool tr;  // fragments of the TRANSPOSE of the stored matrix
+    MDEV double get(int a, int b, int s) const {
+        return tr ? p[(b * MT + a) * 64 + (2 * c + s) * 8 + r] : p[(a * MT + b) * 64 + r * 8 + 2 * c + s];
+    }
+};
+template <int MT> MDEV double oget(const Mat<MT>& m, int a, int b, int s) { return m.v[a][b][s]; }
+template <int MT> MDEV double oget(const SMat<MT>& m, int a, int b, int s) { return m.get(a, b, s); }
+
 // acc += X S^T.  KD = number of valid columns of X and S (the state dimension): k-steps whose four columns
 // 8 kt + 2c + s all lie in the zero padding are skipped (d = 9: 3 DMMAs per output tile instead of 4).
-template <int MT, int KD = 8 * MT> MDEV void mmT(Mat<MT>& acc, const Mat<MT>& X, const Mat<MT>& S) {
+template <int MT, int KD, class XO, class SO> MDEV void mmT(Mat<MT>& acc, const XO& X, const SO& S) {
 #pragma unroll
     for (int kt = 0; kt < MT; ++kt)
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
             if (8 * kt + s >= KD) continue;
+            double xa[MT], sb[MT];
+#pragma unroll
+            for (int mt = 0; mt < MT; ++mt) xa[mt] = oget<MT>(X, mt, kt, s);
+#pragma unroll
+            for (int nt = 0; nt < MT; ++nt) sb[nt] = oget<MT>(S, nt, kt, s);
 #pragma unroll
             for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-                for (int nt = 0; nt < MT; ++nt) dmma(acc.v[mt][nt], X.v[mt][kt][s], S.v[nt][kt][s]);
+                for (int nt = 0; nt < MT; ++nt) dmma(acc.v[mt][nt], xa[mt], sb[nt]);
         }
 }
-template <int MT, int KD = 8 * MT> MDEV Mat<MT> mulT(const Mat<MT>& X, const Mat<MT>& S) {
+template <int MT, int KD, class XO, class SO> MDEV Mat<MT> mulT(const XO& X, const SO& S) {
     Mat<MT> acc;
     mzero(acc);
     mmT<MT, KD>(acc, X, S);
@@ -80,16 +98,16 @@ template <int MT, int NQ> MDEV void rank_update(Mat<MT>& acc, const VecR<MT> (&x
     }
 }
 
-// y = M v : M in CF, v in VP -> VR
-template <int MT> MDEV VecR<MT> mv(const Mat<MT>& M, const VecP<MT>& v) {
+// y = M v : M in CF (registers or ring slot), v in VP -> VR
+template <int MT, class MO> MDEV VecR<MT> mv(const MO& M, const VecP<MT>& v) {
     VecR<MT> y;
 #pragma unroll
     for (int mt = 0; mt < MT; ++mt) {
         double s = 0.0;
 #pragma unroll
         for (int nt = 0; nt < MT; ++nt) {
-            s = fma(M.v[mt][nt][0], v.v[nt][0], s);
-            s = fma(M.v[mt][nt][1], v.v[nt][1], s);
+            s = fma(oget<MT>(M, mt, nt, 0), v.v[nt][0], s);
+            s = fma(oget<MT>(M, mt, nt, 1), v.v[nt][1], s);
         }
         s += __shfl_xor_sync(FULL, s, 1);
         s += __shfl_xor_sync(FULL, s, 2);
@@ -197,6 +215,18 @@ template <int MT> MDEV Mat<MT> ld_sym(const double* slot, int r, int c) {
         }
     return m;
 }
+// input operand: held in registers when a matrix is small (MT <= 2), read from the slot on use otherwise
+template <int MT, bool LAZY = (MT >= 3)> struct InOp;
+template <int MT> struct InOp<MT, false> {
+    using type = Mat<MT>;
+    MDEV static type make(const double* slot, bool tr, int r, int c) { return tr ? ld_matT<MT>(slot, r, c) : ld_mat<MT>(slot, r, c); }
+};
+template <int MT> struct InOp<MT, true> {
+    using type = SMat<MT>;
+    MDEV static type make(const double* slot, bool tr, int r, int c) { return SMat<MT>{slot, r, c, tr}; }
+};
+template <int MT> MDEV typename InOp<MT>::type in_op(const double* slot, bool tr, int r, int c) { return InOp<MT>::make(slot, tr, r, c); }
+
 template <int MT> MDEV VecR<MT> ld_vr(const double* v, int r) {
     VecR<MT> y;
 #pragma unroll
@@ -454,18 +484,18 @@ __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, 
         const double yk = ynext;
         if (i + 1 < nrows) ynext = p.y[k + 1];
         const double* sl = ring + (i % NSLOT) * K::SLOT;
-        const bool first = (k == 0 && p.first_special);
-        // the first step of the global series is an update without propagation: F := I, Q := 0
-        const Mat<MT> F = first ? identity_cf<MT>(r, c) : ld_mat<MT>(sl, r, c);
-        Mat<MT> Cn = ld_sym<MT>(sl + MSZ, r, c);
-        if (first) mzero(Cn);
-        At = mulT<MT, D>(At, F);                   // (F A)^T = A^T F^T
-        {
-            const Mat<MT> T2 = mulT<MT, D>(F, C);  // F C   (C symmetric)
-            mmT<MT, D>(Cn, T2, F);                 // F C F^T + Q
+        // the first step of the global series is an update without propagation (parallel.py:24-30)
+        if (!(k == 0 && p.first_special)) {
+            const auto F = in_op<MT>(sl, false, r, c);
+            Mat<MT> Cn = ld_sym<MT>(sl + MSZ, r, c);
+            At = mulT<MT, D>(At, F);                   // (F A)^T = A^T F^T
+            {
+                const Mat<MT> T2 = mulT<MT, D>(F, C);  // F C   (C symmetric)
+                mmT<MT, D>(Cn, T2, F);                 // F C F^T + Q
+            }
+            C = Cn;
+            b = mv(F, vr2vp(b, c));
         }
-        C = Cn;
-        b = mv(F, vr2vp(b, c));
         const bool obs = !isnan(yk);
         const VecR<MT> u = mv(C, hP);
         const VecR<MT> w = mv(At, hP);      // A^T h
@@ -592,7 +622,7 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
         if (i + 1 < nrows) ynext = p.y[k + 1];
         const bool obs = !isnan(yk);
         const double* sl = ring + (i % NSLOT) * K::SLOT;
-        const Mat<MT> F = ld_mat<MT>(sl, r, c);
+        const auto F = in_op<MT>(sl, false, r, c);
         if constexpr (STORED) {
             P = ld_mat<MT>(sl + O_P, r, c);
             m = ld_vr<MT>(sl + O_M, r);
@@ -638,7 +668,7 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
         }
         if constexpr (REV) {
             // append step k on the later side of the chunk's reverse aggregate (nothing for the global first step)
-            const Mat<MT> Ft = ld_matT<MT>(sl, r, c);
+            const auto Ft = in_op<MT>(sl, true, r, c);
             const VecR<MT> w = mv(Ft, hP);                 // F^T h
             const VecR<MT> t = mv(Abt, vr2vp(w, c));       // Abar_old^T w
             const double isr = first ? 0.0 : is, eisr = first ? 0.0 : eis;
@@ -765,18 +795,25 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
         const double* slp = slot(k - 1);
         if constexpr (SMOOTH) {
             // sm_k = m_k - P_k lam_k ; sP_k = P_k - P_k Lam_k P_k   (state entering from above)
-            const Mat<MT> Pk = ld_mat<MT>(sl + O_P, r, c);
+            const auto Pk = in_op<MT>(sl + O_P, false, r, c);
             const Mat<MT> Zt = mulT<MT, D>(Pk, Lam);  // P_k Lam = (Lam P_k)^T
-            const Mat<MT> PZ = mulT<MT, D>(Pk, Zt);   // P_k (Lam P_k)
-            gst_mat<D, MT>(p.sPs + k * DD, msub(Pk, PZ), 1.0, sp);
+            Mat<MT> PZ = mulT<MT, D>(Pk, Zt);         // P_k (Lam P_k)
+#pragma unroll
+            for (int a = 0; a < MT; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < MT; ++b2) {
+                    PZ.v[a][b2][0] = oget<MT>(Pk, a, b2, 0) - PZ.v[a][b2][0];
+                    PZ.v[a][b2][1] = oget<MT>(Pk, a, b2, 1) - PZ.v[a][b2][1];
+                }
+            gst_mat<D, MT>(p.sPs + k * DD, PZ, 1.0, sp);
             const VecR<MT> v1 = mv(Pk, vr2vp(lam, c));
             const VecR<MT> mk = ld_vr<MT>(sl + O_M, r);
             gst_vr<D, MT>(p.sms + k * D, vaxpy(-1.0, v1, mk), r, c);
         }
         // forward quantities of step k
-        const Mat<MT> F = ld_mat<MT>(sl, r, c);
-        const Mat<MT> Ft = ld_matT<MT>(sl, r, c);
-        const Mat<MT> Pprev = ld_mat<MT>(slp + O_P, r, c);
+        const auto F = in_op<MT>(sl, false, r, c);
+        const auto Ft = in_op<MT>(sl, true, r, c);
+        const auto Pprev = in_op<MT>(slp + O_P, false, r, c);
         const VecR<MT> mprev = ld_vr<MT>(slp + O_M, r);
         Mat<MT> Pp = ld_sym<MT>(sl + MSZ, r, c);
         {

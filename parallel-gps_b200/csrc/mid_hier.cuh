@@ -13,14 +13,18 @@ namespace pssgp {
 namespace mid {
 namespace hier {
 
-constexpr int GF = 8;        // fan-in of a hierarchy level
-constexpr int TOPMAX = 8;    // aggregates the top warp walks sequentially
+constexpr int GF = 4;        // fan-in of a hierarchy level (short sequential chains: the nodes are latency-bound)
+constexpr int TOPMAX = 4;    // aggregates the top group walks sequentially
+// warps that cooperate on one node of the hierarchy (one warp up to d = 16; the d^3 work of larger d is spread over 4)
+template <int D> constexpr int hier_wg() { return D <= 16 ? 1 : 4; }
 
 // [M | B] (D x (D + NR), pitch WP) -> [. | M^-1 B]   (columns of M are not cleaned up)
-template <int D, int NR, int WP> MDEV void wsolve(int lane, double* W) {
-    constexpr int NC = D + NR;
+template <class G, int NR, int WP> MDEV void wsolve(const Grp& g, double* W) {
+    constexpr int D = G::D, NC = D + NR, NT = G::NT;
+    const int lane = g.lane;
 #pragma unroll 1
     for (int col = 0; col < D; ++col) {
+        // every warp of the group finds the pivot row on its own (same data, same answer)
         double v = (lane >= col && lane < D) ? fabs(W[lane * WP + col]) : -1.0;
         int idx = lane;
 #pragma unroll
@@ -34,22 +38,22 @@ template <int D, int NR, int WP> MDEV void wsolve(int lane, double* W) {
         }
         const int p = idx;
         const double inv = 1.0 / W[p * WP + col];
-        __syncwarp();
+        gsync<G::WG>(g);
 #pragma unroll 1
-        for (int j = col + lane; j < NC; j += 32) {
+        for (int j = col + g.tid; j < NC; j += NT) {
             const double a = W[col * WP + j], b = W[p * WP + j];
             W[p * WP + j] = a;
             W[col * WP + j] = b * inv;
         }
-        __syncwarp();
+        gsync<G::WG>(g);
 #pragma unroll 1
-        for (int j = col + 1 + lane; j < NC; j += 32) {
+        for (int j = col + 1 + g.tid; j < NC; j += NT) {
             const double pj = W[col * WP + j];
 #pragma unroll(D <= 16 ? D : 8)
             for (int i = 0; i < D; ++i)
                 if (i != col) W[i * WP + j] = fma(-W[i * WP + col], pj, W[i * WP + j]);
         }
-        __syncwarp();
+        gsync<G::WG>(g);
     }
 }
 
@@ -65,16 +69,16 @@ template <class G> MDEV void gstore_mat(const Grp& g, double* dst, const double*
 }
 // A dense d x d matrix / d vector staged in registers: every global load is issued before the first use.
 template <class G> struct MatRegs {
-    static constexpr int NQ = (G::DD + 31) / 32;
+    static constexpr int NQ = (G::DD + G::NT - 1) / G::NT;
     double v[NQ];
     MDEV void fetch(const Grp& g, const double* src) {
 #pragma unroll
-        for (int q = 0; q < NQ; ++q) v[q] = (g.lane + 32 * q < G::DD) ? __ldg(src + g.lane + 32 * q) : 0.0;
+        for (int q = 0; q < NQ; ++q) v[q] = (g.tid + G::NT * q < G::DD) ? __ldg(src + g.tid + G::NT * q) : 0.0;
     }
     MDEV void put(const Grp& g, double* dst) const {
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
-            const int idx = g.lane + 32 * q;
+            const int idx = g.tid + G::NT * q;
             if (idx < G::DD) {
                 const int i = idx / G::D, j = idx - i * G::D;
                 dst[i * G::LD + j] = v[q];
@@ -84,9 +88,9 @@ template <class G> struct MatRegs {
 };
 template <class G> struct VecRegs {
     double v;
-    MDEV void fetch(const Grp& g, const double* src) { v = g.lane < G::D ? __ldg(src + g.lane) : 0.0; }
+    MDEV void fetch(const Grp& g, const double* src) { v = g.tid < G::D ? __ldg(src + g.tid) : 0.0; }
     MDEV void put(const Grp& g, double* dst) const {
-        if (g.lane < G::D) dst[g.lane] = v;
+        if (g.tid < G::D) dst[g.tid] = v;
     }
 };
 template <class G> MDEV void gload_vec(const Grp& g, double* dst, const double* src) {
@@ -100,7 +104,7 @@ template <class G> MDEV void gstore_vec(const Grp& g, double* dst, const double*
 // Filter.  aggregate (smem): A | C | J | b | eta ; state: P | m
 // ---------------------------------------------------------------------------------------------------------------
 template <int D> struct FilterH {
-    using G = Geo<D, 1>;
+    using G = Geo<D, hier_wg<D>()>;
     static constexpr int MSZ = G::MSZ, DP = G::DP, LD = G::LD, DD = G::DD;
     static constexpr int AGG = 3 * MSZ + 2 * DP;      // smem doubles
     static constexpr int STATE = MSZ + DP;
@@ -158,34 +162,34 @@ template <int D> struct FilterH {
         mm<G, false, false>(g, C1, J2, T1);      // C1 J2
         mm<G, false, true>(g, C1, A2, T2);       // C1 A2^T
         mv<G, false>(g, C1, e2, v1, b1);         // b1 + C1 eta2
-        __syncwarp();
+        gsync<G::WG>(g);
         sweep<G>(g, [&](int i, int j, int) {
             W[i * WP + j] = T1[i * LD + j] + (i == j ? 1.0 : 0.0);
             W[i * WP + D + j] = A1[i * LD + j];
             W[i * WP + 2 * D + 1 + j] = T2[i * LD + j];
         });
         vsweep<G>(g, [&](int i) { W[i * WP + 2 * D] = v1[i]; });
-        __syncwarp();
-        wsolve<D, 2 * D + 1, WP>(g.lane, W);
+        gsync<G::WG>(g);
+        wsolve<G, 2 * D + 1, WP>(g, W);
         sweep<G>(g, [&](int i, int j, int) {
             T1[i * LD + j] = W[i * WP + D + j];            // ZA = M^-1 A1
             T2[i * LD + j] = W[i * WP + 2 * D + 1 + j];    // ZC = M^-1 C1 A2^T
         });
         vsweep<G>(g, [&](int i) { zb[i] = W[i * WP + 2 * D]; });
-        __syncwarp();
+        gsync<G::WG>(g);
         mm<G, false, false>(g, A2, T1, Ao);      // A = A2 ZA
         mm<G, false, false>(g, A2, T2, X1);      // A2 ZC
         mm<G, false, false>(g, J2, T1, T3);      // J2 ZA
         mv<G, false>(g, A2, zb, bo, b2);         // b = A2 zb + b2
         mv<G, false>(g, J2, zb, v2);             // J2 zb
-        __syncwarp();
+        gsync<G::WG>(g);
         vsweep<G>(g, [&](int i) { v1[i] = e2[i] - v2[i]; });
         mm<G, true, false>(g, A1, T3, X2);       // A1^T J2 ZA
         sym_add<G>(g, X1, C2, Co);               // C = sym(A2 ZC) + C2
-        __syncwarp();
+        gsync<G::WG>(g);
         mv<G, true>(g, A1, v1, eo, e1);          // eta = A1^T (eta2 - J2 zb) + eta1
         sym_add<G>(g, X2, J1, Jo);               // J = sym(A1^T J2 ZA) + J1
-        __syncwarp();
+        gsync<G::WG>(g);
     }
 
     // s2 = s o a   (s, s2 distinct)
@@ -197,22 +201,22 @@ template <int D> struct FilterH {
         mm<G, false, false>(g, P, J, T1);        // P J
         mm<G, false, true>(g, P, A, T2);         // P A^T
         mv<G, false>(g, P, eta, v1, m);          // m + P eta
-        __syncwarp();
+        gsync<G::WG>(g);
         sweep<G>(g, [&](int i, int j, int) {
             W[i * WP + j] = T1[i * LD + j] + (i == j ? 1.0 : 0.0);
             W[i * WP + D + 1 + j] = T2[i * LD + j];
         });
         vsweep<G>(g, [&](int i) { W[i * WP + D] = v1[i]; });
-        __syncwarp();
-        wsolve<D, D + 1, WP>(g.lane, W);
+        gsync<G::WG>(g);
+        wsolve<G, D + 1, WP>(g, W);
         sweep<G>(g, [&](int i, int j, int) { T2[i * LD + j] = W[i * WP + D + 1 + j]; });
         vsweep<G>(g, [&](int i) { zb[i] = W[i * WP + D]; });
-        __syncwarp();
+        gsync<G::WG>(g);
         mm<G, false, false>(g, A, T2, X1);       // A Z
         mv<G, false>(g, A, zb, s2 + MSZ, b);     // m' = A z + b
-        __syncwarp();
+        gsync<G::WG>(g);
         sym_add<G>(g, X1, C, s2);                // P' = sym(A Z) + C
-        __syncwarp();
+        gsync<G::WG>(g);
     }
 };
 
@@ -220,7 +224,7 @@ template <int D> struct FilterH {
 // Combined reverse scan (GRev).  aggregate (smem): Ab | Ba | Bm | a ; state: dP | Lam | dm | lam
 // ---------------------------------------------------------------------------------------------------------------
 template <int D> struct RevH {
-    using G = Geo<D, 1>;
+    using G = Geo<D, hier_wg<D>()>;
     static constexpr int MSZ = G::MSZ, DP = G::DP, LD = G::LD, DD = G::DD;
     static constexpr int AGG = 3 * MSZ + DP;
     static constexpr int STATE = 2 * MSZ + 2 * DP;
@@ -278,17 +282,17 @@ template <int D> struct RevH {
         mm<G, false, false>(g, Ba1, A2, T1);
         mm<G, false, false>(g, Bm1, A2, T2);
         mv<G, true>(g, A2, a1, t);               // A2^T a1
-        __syncwarp();
+        gsync<G::WG>(g);
         mm<G, true, false>(g, A2, T1, X1);       // A2^T Ba1 A2
         mm<G, true, false>(g, A2, T2, X2);       // A2^T Bm1 A2
-        __syncwarp();
+        gsync<G::WG>(g);
         sweep<G>(g, [&](int i, int j, int) {
             const int q = i * LD + j;
             Bao[q] = Ba2[q] + 0.5 * (t[i] * a2[j] + t[j] * a2[i]) + 0.5 * (X1[q] + X1[j * LD + i]);
             Bmo[q] = Bm2[q] + 0.5 * (X2[q] + X2[j * LD + i]);
         });
         vsweep<G>(g, [&](int i) { ao[i] = t[i] + a2[i]; });
-        __syncwarp();
+        gsync<G::WG>(g);
     }
 
     MDEV static void apply(const Grp& g, const double* s, const double* x, double* s2, double* w) {
@@ -299,10 +303,10 @@ template <int D> struct RevH {
         mm<G, false, false>(g, Lam, Ab, T2);
         mv<G, true>(g, Ab, dm, t);
         mv<G, true>(g, Ab, lam, tl);
-        __syncwarp();
+        gsync<G::WG>(g);
         mm<G, true, false>(g, Ab, T1, X1);
         mm<G, true, false>(g, Ab, T2, X2);
-        __syncwarp();
+        gsync<G::WG>(g);
         sweep<G>(g, [&](int i, int j, int) {
             const int q = i * LD + j;
             s2[q] = Ba[q] + 0.5 * (t[i] * a[j] + t[j] * a[i]) + 0.5 * (X1[q] + X1[j * LD + i]);
@@ -312,7 +316,7 @@ template <int D> struct RevH {
             s2[2 * MSZ + i] = t[i] + a[i];
             s2[2 * MSZ + DP + i] = tl[i] - a[i];
         });
-        __syncwarp();
+        gsync<G::WG>(g);
     }
 };
 
@@ -321,33 +325,26 @@ template <class H> __host__ __device__ constexpr int walk_warp_doubles() { retur
 template <class H> __host__ __device__ constexpr int top_warp_doubles() {
     return up_warp_doubles<H>() > walk_warp_doubles<H>() ? up_warp_doubles<H>() : walk_warp_doubles<H>();
 }
-template <class H> constexpr int warps_per_cta(int per_warp_doubles) {
+// groups per CTA
+template <class H> __host__ __device__ constexpr int warps_per_cta(int per_warp_doubles) {
     const int fit = (200 * 1024) / (per_warp_doubles * 8);
-    return fit > 8 ? 8 : (fit < 1 ? 1 : fit);
-}
-
-MDEV Grp warp_grp() {
-    Grp g;
-    g.lane = threadIdx.x & 31;
-    g.tid = g.lane;
-    g.r = g.lane >> 2;
-    g.c = g.lane & 3;
-    g.wig = 0;
-    g.bar = 0;
-    return g;
+    const int cap = 32 / H::G::WG < 8 ? 32 / H::G::WG : 8;
+    return fit > cap ? cap : (fit < 1 ? 1 : fit);
 }
 
 // level l -> l + 1: one warp per group of GF aggregates
 template <class H>
-__global__ void __launch_bounds__(256) hier_up_kernel(const double* __restrict__ in, long nin, double* __restrict__ out, long nout) {
+__global__ void __launch_bounds__(warps_per_cta<H>(up_warp_doubles<H>()) * H::G::NT) hier_up_kernel(const double* __restrict__ in, long nin, double* __restrict__ out, long nout) {
+    using G = typename H::G;
     extern __shared__ __align__(16) double smem[];
     constexpr int PW = up_warp_doubles<H>();
-    const long grp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int gi = threadIdx.x / G::NT;
+    const long grp = (long)blockIdx.x * (blockDim.x / G::NT) + gi;
     if (grp >= nout) return;
-    const Grp g = warp_grp();
-    double* S = smem + (size_t)(threadIdx.x >> 5) * PW;
-    for (int i = g.lane; i < PW; i += 32) S[i] = 0.0;
-    __syncwarp();
+    const Grp g = make_grp<G>(gi);
+    double* S = smem + (size_t)gi * PW;
+    for (int i = g.tid; i < PW; i += G::NT) S[i] = 0.0;
+    gsync<G::WG>(g);
     double *a = S, *b = S + H::AGG, *o = S + 2 * H::AGG, *w = S + 3 * H::AGG;
     const long i0 = grp * GF;
     const long i1 = (i0 + GF < nin) ? i0 + GF : nin;
@@ -358,14 +355,14 @@ __global__ void __launch_bounds__(256) hier_up_kernel(const double* __restrict__
 #pragma unroll 1
     for (long i = i0 + 1; i < i1; ++i) {
         rg.put(g, b);
-        __syncwarp();
+        gsync<G::WG>(g);
         if (i + 1 < i1) rg.fetch(g, in + (i + 1) * H::NAGG_G);  // in flight while this pair is combined
         H::combine(g, a, b, o, w);
         double* t = a;
         a = o;
         o = t;
     }
-    __syncwarp();
+    gsync<G::WG>(g);
     H::store_agg(g, out + grp * H::NAGG_G, a);
 }
 
@@ -374,14 +371,15 @@ __global__ void __launch_bounds__(256) hier_up_kernel(const double* __restrict__
 // `stride` = distance in doubles between consecutive aggregates in scan order (negative: a gathered buffer of shard
 // summaries in rank order walked from the last rank down).  states may be nullptr (fold: only final_state wanted).
 template <class H>
-__global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, const double* __restrict__ aggs, long n,
-                                                      long stride, double* __restrict__ states,
-                                                      double* __restrict__ final_state, double* __restrict__ summary) {
+__global__ void __launch_bounds__(H::G::NT) hier_top_kernel(typename H::Init init, const double* __restrict__ aggs, long n,
+                                                       long stride, double* __restrict__ states,
+                                                       double* __restrict__ final_state, double* __restrict__ summary) {
+    using G = typename H::G;
     extern __shared__ __align__(16) double smem[];
     constexpr int PW = top_warp_doubles<H>();
-    const Grp g = warp_grp();
-    for (int i = g.lane; i < PW; i += 32) smem[i] = 0.0;
-    __syncwarp();
+    const Grp g = make_grp<G>(0);
+    for (int i = g.tid; i < PW; i += G::NT) smem[i] = 0.0;
+    gsync<G::WG>(g);
     if (summary != nullptr) {
         double *a = smem, *b = smem + H::AGG, *o = smem + 2 * H::AGG, *w = smem + 3 * H::AGG;
         typename H::AggRegs rg;
@@ -391,14 +389,14 @@ __global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, con
 #pragma unroll 1
         for (long i = 1; i < n; ++i) {
             rg.put(g, b);
-            __syncwarp();
+            gsync<G::WG>(g);
             if (i + 1 < n) rg.fetch(g, aggs + (i + 1) * stride);
             H::combine(g, a, b, o, w);
             double* t = a;
             a = o;
             o = t;
         }
-        __syncwarp();
+        gsync<G::WG>(g);
         H::store_agg(g, summary, a);
         return;
     }
@@ -406,12 +404,12 @@ __global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, con
     H::init_state(g, s, init);
     typename H::AggRegs rg;
     if (n > 0) rg.fetch(g, aggs);
-    __syncwarp();
+    gsync<G::WG>(g);
 #pragma unroll 1
     for (long i = 0; i < n; ++i) {
         if (states != nullptr) H::store_state(g, states + i * H::NSTATE_G, s);
         rg.put(g, a);
-        __syncwarp();
+        gsync<G::WG>(g);
         if (i + 1 < n) rg.fetch(g, aggs + (i + 1) * stride);
         H::apply(g, s, a, s2, w);
         double* t = s;
@@ -423,30 +421,32 @@ __global__ void __launch_bounds__(32) hier_top_kernel(typename H::Init init, con
 
 // level l + 1 -> l: one warp per group turns the group-entry state into the entry state of every member
 template <class H>
-__global__ void __launch_bounds__(256) hier_down_kernel(const double* __restrict__ aggs, long n,
-                                                        const double* __restrict__ gstates, long ngroups,
-                                                        double* __restrict__ states) {
+__global__ void __launch_bounds__(warps_per_cta<H>(walk_warp_doubles<H>()) * H::G::NT) hier_down_kernel(const double* __restrict__ aggs, long n,
+                                                         const double* __restrict__ gstates, long ngroups,
+                                                         double* __restrict__ states) {
+    using G = typename H::G;
     extern __shared__ __align__(16) double smem[];
     constexpr int PW = walk_warp_doubles<H>();
-    const long grp = (long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int gi = threadIdx.x / G::NT;
+    const long grp = (long)blockIdx.x * (blockDim.x / G::NT) + gi;
     if (grp >= ngroups) return;
-    const Grp g = warp_grp();
-    double* S = smem + (size_t)(threadIdx.x >> 5) * PW;
-    for (int i = g.lane; i < PW; i += 32) S[i] = 0.0;
-    __syncwarp();
+    const Grp g = make_grp<G>(gi);
+    double* S = smem + (size_t)gi * PW;
+    for (int i = g.tid; i < PW; i += G::NT) S[i] = 0.0;
+    gsync<G::WG>(g);
     double *a = S, *s = S + H::AGG, *s2 = s + H::STATE, *w = s2 + H::STATE;
     const long i0 = grp * GF;
     const long i1 = (i0 + GF < n) ? i0 + GF : n;
     typename H::AggRegs rg;
     if (i0 + 1 < i1) rg.fetch(g, aggs + i0 * H::NAGG_G);
     H::load_state(g, s, gstates + grp * H::NSTATE_G);
-    __syncwarp();
+    gsync<G::WG>(g);
 #pragma unroll 1
     for (long i = i0; i < i1; ++i) {
         H::store_state(g, states + i * H::NSTATE_G, s);
         if (i + 1 < i1) {
             rg.put(g, a);
-            __syncwarp();
+            gsync<G::WG>(g);
             if (i + 2 < i1) rg.fetch(g, aggs + (i + 1) * H::NAGG_G);
             H::apply(g, s, a, s2, w);
             double* t = s;
@@ -497,26 +497,26 @@ int run(pssgp_handle* h, const typename H::Init& init, int64_t cnt0, double* agg
         for (int l = 0; l + 1 < nl; ++l) {
             const unsigned grid = (unsigned)((hl.cnt[l + 1] + WU - 1) / WU);
             PSSGP_LAUNCH(h, names[0], st,
-                         (hier_up_kernel<H><<<grid, WU * 32, (size_t)WU * PWU * 8, st>>>(aggs + hl.off[l] * NA, hl.cnt[l],
+                         (hier_up_kernel<H><<<grid, WU * H::G::NT, (size_t)WU * PWU * 8, st>>>(aggs + hl.off[l] * NA, hl.cnt[l],
                                                                                         aggs + hl.off[l + 1] * NA, hl.cnt[l + 1])));
             ++*launches;
         }
     }
     if (summary != nullptr) {
         PSSGP_LAUNCH(h, names[1], st,
-                     (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], (long)NA,
+                     (hier_top_kernel<H><<<1, H::G::NT, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], (long)NA,
                                                                         nullptr, nullptr, summary)));
         ++*launches;
         return PSSGP_OK;
     }
     PSSGP_LAUNCH(h, names[1], st,
-                 (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], (long)NA,
+                 (hier_top_kernel<H><<<1, H::G::NT, (size_t)PWT * 8, st>>>(init, aggs + hl.off[nl - 1] * NA, hl.cnt[nl - 1], (long)NA,
                                                                     states + hl.off[nl - 1] * NS, final_state, nullptr)));
     ++*launches;
     for (int l = nl - 2; l >= 0; --l) {
         const unsigned grid = (unsigned)((hl.cnt[l + 1] + WD - 1) / WD);
         PSSGP_LAUNCH(h, names[2], st,
-                     (hier_down_kernel<H><<<grid, WD * 32, (size_t)WD * PWD * 8, st>>>(aggs + hl.off[l] * NA, hl.cnt[l],
+                     (hier_down_kernel<H><<<grid, WD * H::G::NT, (size_t)WD * PWD * 8, st>>>(aggs + hl.off[l] * NA, hl.cnt[l],
                                                                                       states + hl.off[l + 1] * NS, hl.cnt[l + 1],
                                                                                       states + hl.off[l] * NS)));
         ++*launches;
@@ -532,7 +532,7 @@ int fold(pssgp_handle* h, const typename H::Init& init, const double* summaries,
     cudaError_t e = cudaFuncSetAttribute(hier_top_kernel<H>, cudaFuncAttributeMaxDynamicSharedMemorySize, PWT * 8);
     if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "cudaFuncSetAttribute(hierarchy): %s", cudaGetErrorString(e));
     PSSGP_LAUNCH(h, name, st,
-                 (hier_top_kernel<H><<<1, 32, (size_t)PWT * 8, st>>>(init, summaries, (long)count, stride, nullptr, state_out,
+                 (hier_top_kernel<H><<<1, H::G::NT, (size_t)PWT * 8, st>>>(init, summaries, (long)count, stride, nullptr, state_out,
                                                                     nullptr)));
     return PSSGP_OK;
 }

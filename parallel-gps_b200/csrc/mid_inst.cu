@@ -20,7 +20,7 @@ template <class Kern> static int set_smem_attr(Kern kernel, size_t bytes) {
 
 // Kernel family per state dimension: fragment-resident (registers, one warp per chunk) up to D = 16, shared-memory
 // tiles with groups of warps above.  Option "mid_smem" forces the shared-memory family (tests / tuning).
-template <int D> constexpr bool has_frag() { return D <= 16; }
+template <int D> constexpr bool has_frag() { return D <= 24; }
 
 static thread_local int g_mid_warps = 0;  // option "mid_warps" of the handle in use (0 = compile-time default)
 // measured (scripts/sweep_mid_warps.py, N = 1e6): d = 6 gains up to the 24 warps that fit; d = 9 / d = 16 are fastest with 8
@@ -42,13 +42,16 @@ template <int D, bool SMOOTH, bool ADJ> static int k3_groups(bool fr) {
     return K3<D, default_wg<D>(), SMOOTH, ADJ>::GPC;
 }
 
-template <int D> static int launch_k1(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, double* aggs, cudaStream_t st) {
+// gpc: groups (chunks) per CTA shared by the kernels of one call — the chunk count is sized for ONE resident wave of
+// num_sms * gpc chunks, so every kernel launches num_sms CTAs (a kernel that could pack more groups per CTA would
+// otherwise leave SMs idle)
+template <int D> static int launch_k1(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, double* aggs, cudaStream_t st, int gpc) {
     int rc;
     if constexpr (has_frag<D>()) {
         if (fr) {
             using KA = frag::FK1<D>;
             if ((rc = set_smem_attr(frag::fk1_filter_reduce<D>, KA::SMEM))) return rc;
-            const int wpc = cap_warps(KA::WPC);
+            const int wpc = gpc < cap_warps(KA::WPC) ? gpc : cap_warps(KA::WPC);
             const unsigned grid = (unsigned)((nchunks + wpc - 1) / wpc);
             PSSGP_LAUNCH(h, "mid_filter_reduce", st, (frag::fk1_filter_reduce<D><<<grid, wpc * 32, wpc * KA::WARP_SMEM, st>>>(p, L, nchunks, aggs)));
             return PSSGP_OK;
@@ -57,21 +60,22 @@ template <int D> static int launch_k1(pssgp_handle* h, bool fr, const Params& p,
     constexpr int WG = default_wg<D>();
     using KA = K1<D, WG>;
     if ((rc = set_smem_attr(k1_filter_reduce<D, WG>, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8))) return rc;
-    const unsigned grid = (unsigned)((nchunks + KA::GPC - 1) / KA::GPC);
+    const int gp = gpc < KA::GPC ? gpc : KA::GPC;
+    const unsigned grid = (unsigned)((nchunks + gp - 1) / gp);
     PSSGP_LAUNCH(h, "mid_filter_reduce", st,
-                 (k1_filter_reduce<D, WG><<<grid, KA::GPC * WG * 32, (size_t)KA::GPC * KA::GROUP_DOUBLES * 8, st>>>(p, L, nchunks, aggs)));
+                 (k1_filter_reduce<D, WG><<<grid, gp * WG * 32, (size_t)gp * KA::GROUP_DOUBLES * 8, st>>>(p, L, nchunks, aggs)));
     return PSSGP_OK;
 }
 
 template <int D, bool REV, bool STORED>
 static int launch_k2(pssgp_handle* h, bool fr, const char* name, const Params& p, int L, int64_t nchunks, const double* fstates,
-                     double* part, double* raggs, cudaStream_t st) {
+                     double* part, double* raggs, cudaStream_t st, int gpc) {
     int rc;
     if constexpr (has_frag<D>()) {
         if (fr) {
             using KB = frag::FK2<D, REV, STORED>;
             if ((rc = set_smem_attr(frag::fk2_forward<D, REV, STORED>, KB::SMEM))) return rc;
-            const int wpc = cap_warps(KB::WPC);
+            const int wpc = gpc < cap_warps(KB::WPC) ? gpc : cap_warps(KB::WPC);
             const unsigned grid = (unsigned)((nchunks + wpc - 1) / wpc);
             PSSGP_LAUNCH(h, name, st,
                          (frag::fk2_forward<D, REV, STORED><<<grid, wpc * 32, wpc * KB::WARP_SMEM, st>>>(p, L, nchunks, fstates, part, raggs)));
@@ -81,22 +85,23 @@ static int launch_k2(pssgp_handle* h, bool fr, const char* name, const Params& p
     constexpr int WG = default_wg<D>();
     using KB = K2<D, WG, REV, STORED>;
     if ((rc = set_smem_attr(k2_forward<D, WG, REV, STORED>, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8))) return rc;
-    const unsigned grid = (unsigned)((nchunks + KB::GPC - 1) / KB::GPC);
+    const int gp = gpc < KB::GPC ? gpc : KB::GPC;
+    const unsigned grid = (unsigned)((nchunks + gp - 1) / gp);
     PSSGP_LAUNCH(h, name, st,
-                 (k2_forward<D, WG, REV, STORED><<<grid, KB::GPC * WG * 32, (size_t)KB::GPC * KB::GROUP_DOUBLES * 8, st>>>(
+                 (k2_forward<D, WG, REV, STORED><<<grid, gp * WG * 32, (size_t)gp * KB::GROUP_DOUBLES * 8, st>>>(
                      p, L, nchunks, fstates, part, raggs)));
     return PSSGP_OK;
 }
 
 template <int D, bool SMOOTH, bool ADJ>
 static int launch_k3(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, const double* rstates, double* part,
-                     cudaStream_t st) {
+                     cudaStream_t st, int gpc) {
     int rc;
     if constexpr (has_frag<D>()) {
         if (fr) {
             using KC = frag::FK3<D, SMOOTH, ADJ>;
             if ((rc = set_smem_attr(frag::fk3_reverse<D, SMOOTH, ADJ>, KC::SMEM))) return rc;
-            const int wpc = cap_warps(KC::WPC);
+            const int wpc = gpc < cap_warps(KC::WPC) ? gpc : cap_warps(KC::WPC);
             const unsigned grid = (unsigned)((nchunks + wpc - 1) / wpc);
             PSSGP_LAUNCH(h, "mid_reverse", st,
                          (frag::fk3_reverse<D, SMOOTH, ADJ><<<grid, wpc * 32, wpc * KC::WARP_SMEM, st>>>(p, L, nchunks, rstates, part)));
@@ -106,9 +111,10 @@ static int launch_k3(pssgp_handle* h, bool fr, const Params& p, int L, int64_t n
     constexpr int WG = default_wg<D>();
     using KC = K3<D, WG, SMOOTH, ADJ>;
     if ((rc = set_smem_attr(k3_reverse<D, WG, SMOOTH, ADJ>, (size_t)KC::GPC * KC::GROUP_DOUBLES * 8))) return rc;
-    const unsigned grid = (unsigned)((nchunks + KC::GPC - 1) / KC::GPC);
+    const int gp = gpc < KC::GPC ? gpc : KC::GPC;
+    const unsigned grid = (unsigned)((nchunks + gp - 1) / gp);
     PSSGP_LAUNCH(h, "mid_reverse", st,
-                 (k3_reverse<D, WG, SMOOTH, ADJ><<<grid, KC::GPC * WG * 32, (size_t)KC::GPC * KC::GROUP_DOUBLES * 8, st>>>(
+                 (k3_reverse<D, WG, SMOOTH, ADJ><<<grid, gp * WG * 32, (size_t)gp * KC::GROUP_DOUBLES * 8, st>>>(
                      p, L, nchunks, rstates, part)));
     return PSSGP_OK;
 }
@@ -174,7 +180,8 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
     p.fms = fms; p.fPs = fPs;
     const int g1 = k1_groups<D>(fr), g2 = k2_groups<D, false, false>(fr);
-    const int L = pick_len(h, n, g2 < g1 ? g2 : g1);
+    const int gpc = g2 < g1 ? g2 : g1;
+    const int L = pick_len(h, n, gpc);
     const int64_t nchunks = (n + L - 1) / L;
     const size_t tot = hier::total(nchunks);
     const int NA = 3 * D * D + 2 * D, NS = D + D * D;
@@ -191,7 +198,7 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
     if (!reuse) {
-        if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st))) return rc;
+        if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st, gpc))) return rc;
         ++launches;
     }
     const GFilter<double>::Params gp = gfilter_params(p, D);
@@ -202,7 +209,7 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
         h->pending_L[KIND_FILTER] = L;
         return check_launch(h, "mid pkf summary", launches);
     }
-    if ((rc = launch_k2<D, false, false>(h, fr, "mid_forward", p, L, nchunks, states, part, nullptr, st))) return rc;
+    if ((rc = launch_k2<D, false, false>(h, fr, "mid_forward", p, L, nchunks, states, part, nullptr, st, gpc))) return rc;
     ++launches;
     if (ll != nullptr) {
         finish_filter_f64(h, gp, part, nchunks, ll, st);
@@ -214,12 +221,12 @@ int pkf(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const do
 // reverse part shared by pkfs_grad and pkf_backward: hierarchy over the reverse aggregates + K3 + finish
 template <int D, bool SMOOTH, bool ADJ>
 static int run_reverse(pssgp_handle* h, bool fr, const Params& p, int L, int64_t nchunks, double* raggs, double* rstates,
-                       double* part, double* dH, double* dR, cudaStream_t st, int* launches, const double* rev_init = nullptr,
-                       bool have_up = false) {
+                       double* part, double* dH, double* dR, cudaStream_t st, int* launches, int gpc,
+                       const double* rev_init = nullptr, bool have_up = false) {
     int rc;
     const GRev<double>::Params rp = grev_params(p, D, dH, dR);
     if ((rc = hier_rev<D>(h, nchunks, raggs, rstates, rev_init, nullptr, have_up, st, launches))) return rc;
-    if ((rc = launch_k3<D, SMOOTH, ADJ>(h, fr, p, L, nchunks, rstates, part, st))) return rc;
+    if ((rc = launch_k3<D, SMOOTH, ADJ>(h, fr, p, L, nchunks, rstates, part, st, gpc))) return rc;
     ++*launches;
     if (ADJ) {
         finish_rev_f64(h, rp, part, nchunks, st);
@@ -258,19 +265,19 @@ int pkfs_grad(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, co
     double* rstates = (double*)h->buf[WS_WAGG + KIND_ADJOINT];
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
-    if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st))) return rc;
+    if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st, gpc))) return rc;
     ++launches;
     const GFilter<double>::Params gp = gfilter_params(p, D);
     if ((rc = hier_filter<D>(h, p, nchunks, aggs, states, nullptr, nullptr, false, st, &launches))) return rc;
-    if ((rc = launch_k2<D, true, false>(h, fr, "mid_forward_rev", p, L, nchunks, states, part, raggs, st))) return rc;
+    if ((rc = launch_k2<D, true, false>(h, fr, "mid_forward_rev", p, L, nchunks, states, part, raggs, st, gpc))) return rc;
     ++launches;
     if (ll != nullptr) {
         finish_filter_f64(h, gp, part, nchunks, ll, st);
         ++launches;
     }
-    if (smooth && adj) rc = run_reverse<D, true, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
-    else if (smooth) rc = run_reverse<D, true, false>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
-    else rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches);
+    if (smooth && adj) rc = run_reverse<D, true, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc);
+    else if (smooth) rc = run_reverse<D, true, false>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc);
+    else rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc);
     if (rc) return rc;
     return check_launch(h, "mid pkfs_grad", launches);
 }
@@ -286,7 +293,8 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
     Params p = base_params(n, P0, Fs, Qs, H, R, y, m0, first_special);
     p.fms_in = fms; p.fPs_in = fPs; p.g = g_ll; p.dFs = dFs; p.dQs = dQs; p.dP0 = dP0;
     const int g2 = k2_groups<D, true, true>(fr), g3 = k3_groups<D, false, true>(fr);
-    const int L = pick_len(h, n, g2 < g3 ? g2 : g3);
+    const int gpc = g2 < g3 ? g2 : g3;
+    const int L = pick_len(h, n, gpc);
     const int64_t nchunks = (n + L - 1) / L;
     const size_t tot = hier::total(nchunks);
     const int NAR = 3 * D * D + D, NSR = 2 * D * D + 2 * D;
@@ -298,9 +306,9 @@ int pkf_backward(pssgp_handle* h, int64_t n, const double* P0, const double* m0,
     double* rstates = (double*)h->buf[WS_WAGG + KIND_ADJOINT];
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
-    if ((rc = launch_k2<D, true, true>(h, fr, "mid_forward_stored", p, L, nchunks, nullptr, nullptr, raggs, st))) return rc;
+    if ((rc = launch_k2<D, true, true>(h, fr, "mid_forward_stored", p, L, nchunks, nullptr, nullptr, raggs, st, gpc))) return rc;
     ++launches;
-    if ((rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches))) return rc;
+    if ((rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc))) return rc;
     return check_launch(h, "mid pkf_backward", launches);
 }
 
@@ -341,12 +349,12 @@ int shard_forward(pssgp_handle* h, int64_t n, const double* P0, const double* Fs
     double* part = (double*)h->buf[WS_PART];
     int launches = 0;
     if (!reuse) {
-        if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st))) return rc;
+        if ((rc = launch_k1<D>(h, fr, p, L, nchunks, aggs, st, gpc))) return rc;
         ++launches;
     }
     const GFilter<double>::Params gp = gfilter_params(p, D);
     if ((rc = hier_filter<D>(h, p, nchunks, aggs, states, nullptr, nullptr, reuse, st, &launches))) return rc;
-    if ((rc = launch_k2<D, true, false>(h, fr, "mid_forward_rev", p, L, nchunks, states, part, raggs, st))) return rc;
+    if ((rc = launch_k2<D, true, false>(h, fr, "mid_forward_rev", p, L, nchunks, states, part, raggs, st, gpc))) return rc;
     ++launches;
     if (ll != nullptr) {
         finish_filter_f64(h, gp, part, nchunks, ll, st);
@@ -392,12 +400,12 @@ int shard_reverse(pssgp_handle* h, int64_t n, const double* P0, const double* m0
     int launches = 0;
     if (!reuse) {
         // no aggregates left by shard_forward for these arrays: rebuild them from the stored moments
-        if ((rc = launch_k2<D, true, true>(h, fr, "mid_forward_stored", p, L, nchunks, nullptr, nullptr, raggs, st))) return rc;
+        if ((rc = launch_k2<D, true, true>(h, fr, "mid_forward_stored", p, L, nchunks, nullptr, nullptr, raggs, st, gpc))) return rc;
         ++launches;
     }
-    if (smooth && adj) rc = run_reverse<D, true, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, rev_init, reuse);
-    else if (smooth) rc = run_reverse<D, true, false>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, rev_init, reuse);
-    else rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, rev_init, reuse);
+    if (smooth && adj) rc = run_reverse<D, true, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc, rev_init, reuse);
+    else if (smooth) rc = run_reverse<D, true, false>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc, rev_init, reuse);
+    else rc = run_reverse<D, false, true>(h, fr, p, L, nchunks, raggs, rstates, part, dH, dR, st, &launches, gpc, rev_init, reuse);
     if (rc) return rc;
     return check_launch(h, "mid shard_reverse", launches);
 }
