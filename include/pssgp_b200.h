@@ -115,7 +115,10 @@ int pssgp_pkf_backward(pssgp_handle* h, int dtype, int64_t n, int d,
  * pkfs (pssgp/kalman/parallel.py:199-201) + TF-autodiff training step of the reference with the three
  * scans sharing their passes over (Fs, Qs, y): for d <= 4 the forward filter pass also builds the chunk
  * aggregates of both reverse scans, so the LGSSM is read three times instead of six
- * (csrc/fused_small.cuh).  Other state dimensions run the three scans one after the other.  m0 = 0.
+ * (csrc/fused_small.cuh); 5 <= d <= 32 in FP64 runs the warp-level DMMA kernels of csrc/mid.cuh / mid_frag.cuh
+ * (smoother in modified Bryson-Frazier form sharing one reverse scan with the adjoint).  Other cases run the three
+ * scans one after the other.  m0 = 0.  sms = sPs = NULL: no smoother (filter + log-likelihood + gradient: the training
+ * step).
  */
 int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d,
                     const void* P0, const void* Fs, const void* Qs, const void* H, const void* R,

@@ -68,8 +68,18 @@ def pick_device(*xs):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def from_dlpack(x):
+    """Zero-copy view of any DLPack producer (an object with ``__dlpack__`` — TensorFlow via
+    ``tf.experimental.dlpack``, CuPy, JAX, numpy — or a raw DLPack capsule) as a torch tensor."""
+    return torch.from_dlpack(x)
+
+
 def to_device(x, dtype, device, key=None):
-    """Returns a contiguous CUDA tensor of `dtype` on `device` (async H2D from pinned memory for host data)."""
+    """Returns a contiguous CUDA tensor of `dtype` on `device` (async H2D from pinned memory for host data).
+    Accepts torch tensors, numpy arrays / array-likes, and any DLPack producer (zero-copy when the producer's memory
+    already lives on `device` in the right dtype: the north star's "zero-copy DLPack views of TF tensors")."""
+    if not isinstance(x, (torch.Tensor, np.ndarray)) and (hasattr(x, "__dlpack__") or type(x).__name__ == "PyCapsule"):
+        x = from_dlpack(x)
     if isinstance(x, torch.Tensor):
         if x.is_cuda:
             t = x.detach().to(device=device, dtype=dtype).contiguous()

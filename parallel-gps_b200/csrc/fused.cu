@@ -40,12 +40,14 @@ int launch_apply(pssgp_handle* h, const typename Alg::Params& p, const StreamPar
     return PSSGP_OK;
 }
 
-template <typename T, int D>
-int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
-                   const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll, void* sms, void* sPs,
-                   void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
+// SMOOTH = false: filter + log-likelihood + gradient only (sms / sPs not produced, the smoother's chunk aggregates
+// are not built): the training step of StateSpaceGP.maximum_log_likelihood_objective.
+template <typename T, int D, bool SMOOTH>
+int pkfs_grad_impl_t(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
+                     const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll, void* sms, void* sPs,
+                     void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
     using FA = FilterAlg<T, D>;
-    using FF = FusedFwdAlg<T, D>;
+    using FF = FusedFwdAlg<T, D, SMOOTH, true>;
     using SA = SmootherAlg<T, D>;
     using AA = AdjointAlg<T, D>;
     using FR = FusedRevAlg<T, D>;
@@ -62,7 +64,7 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     if ((rc = stream_configure<AA>(h->device))) return rc;
     const void* arrs[] = {Fs, Qs, y, fms, fPs, sms, sPs, dFs, dQs};
     for (const void* a : arrs)
-        if (!aligned16(a)) return set_err(PSSGP_ERR_INVALID, "pkfs_grad: arrays must be 16-byte aligned");
+        if (a != nullptr && !aligned16(a)) return set_err(PSSGP_ERR_INVALID, "pkfs_grad: arrays must be 16-byte aligned");
     const StreamPart sp = make_partition<NW, LS>(h, n);
     const int64_t nCta = sp.nCta;
     const int64_t nChunksPad = nCta * NW * 32;
@@ -144,7 +146,7 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
     ap.first_state = nullptr;
     ap.n = n;
     ap.first_special = 1;
-    if constexpr (StreamLayout<FR>::NW == NW) {
+    if constexpr (SMOOTH && StreamLayout<FR>::NW == NW) {
         // option "fused_reverse": one kernel for both reverse recursions (one read of F, Q, y, fms, fPs instead of
         // two).  Off by default: at d = 3 / FP64 the fused kernel is issue-bound at 254 registers per thread and
         // takes longer (198 us) than the two separate ones (80 + 98 us); see DESIGN.md.
@@ -157,10 +159,20 @@ int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, c
             return check_launch(h, "pkfs_grad", 3);
         }
     }
-    launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st, h->pdl != 0);
+    if constexpr (SMOOTH)
+        launch_apply<SA>(h, sp_, sp, fp.sm.lane_excl, fp.sm.warp_excl, fp.sm.wstate, part, (T*)nullptr, st, h->pdl != 0);
     launch_apply<AA>(h, ap, sp, fp.ad.lane_excl, fp.ad.warp_excl, fp.ad.wstate, part, (T*)dR, st, h->pdl != 0);
-    return check_launch(h, "pkfs_grad", 4);
+    return check_launch(h, "pkfs_grad", SMOOTH ? 4 : 3);
     }
+}
+
+template <typename T, int D>
+int pkfs_grad_impl(pssgp_handle* h, int64_t n, const void* P0, const void* Fs, const void* Qs, const void* H,
+                   const void* R, const void* y, const void* g_ll, void* fms, void* fPs, void* ll, void* sms, void* sPs,
+                   void* dP0, void* dFs, void* dQs, void* dH, void* dR, cudaStream_t st) {
+    if (sms != nullptr)
+        return pkfs_grad_impl_t<T, D, true>(h, n, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
+    return pkfs_grad_impl_t<T, D, false>(h, n, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
 }
 
 // One shard of a time-sharded series: seeded filter recursion (pssgp_pkf) + chunk aggregates and shard summaries of
@@ -414,8 +426,9 @@ int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0
                     void* sms, void* sPs, void* dP0, void* dFs, void* dQs, void* dH, void* dR, void* stream) {
     int rc = check_common(h, dtype, n, d);
     if (rc) return rc;
-    if (!P0 || !Fs || !Qs || !H || !R || !y || !g_ll || !fms || !fPs || !sms || !sPs || !dP0 || !dFs || !dQs || !dH || !dR)
+    if (!P0 || !Fs || !Qs || !H || !R || !y || !g_ll || !fms || !fPs || !dP0 || !dFs || !dQs || !dH || !dR)
         return set_err(PSSGP_ERR_INVALID, "null pointer argument");
+    if ((sms == nullptr) != (sPs == nullptr)) return set_err(PSSGP_ERR_INVALID, "pkfs_grad: sms and sPs go together");
     cudaStream_t st = (cudaStream_t)stream;
     rc = fused_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, g_ll, fms, fPs, ll, sms, sPs, dP0, dFs, dQs, dH, dR, st);
     if (rc != kNotFused) return rc;
@@ -426,8 +439,9 @@ int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0
                                        (double*)dH, (double*)dR, st);
     // generic state dimension (or no common partition): the three scans one after the other
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;
-    if ((rc = pssgp_pks(h, dtype, n, d, Fs, Qs, fms, fPs, 1, nullptr, nullptr, nullptr, sms, sPs, nullptr, stream)))
-        return rc;
+    if (sms != nullptr)
+        if ((rc = pssgp_pks(h, dtype, n, d, Fs, Qs, fms, fPs, 1, nullptr, nullptr, nullptr, sms, sPs, nullptr, stream)))
+            return rc;
     return pssgp_pkf_backward(h, dtype, n, d, P0, nullptr, Fs, Qs, H, R, y, fms, fPs, g_ll, 1, nullptr, dP0, dFs, dQs,
                               dH, dR, nullptr, stream);
 }

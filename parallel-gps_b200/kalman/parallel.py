@@ -20,8 +20,16 @@ from .. import _lib
 __all__ = ["pkf", "pks", "pkfs"]
 
 
+def _dl(x):
+    """DLPack producers (TF / CuPy / JAX tensors, raw capsules) become zero-copy torch views; the rest is untouched."""
+    import numpy as np
+    if not isinstance(x, (torch.Tensor, np.ndarray)) and (hasattr(x, "__dlpack__") or type(x).__name__ == "PyCapsule"):
+        return A.from_dlpack(x)
+    return x
+
+
 def _prep_lgssm(lgssm, extra=()):
-    P0, Fs, Qs, H, R = lgssm
+    P0, Fs, Qs, H, R = (_dl(v) for v in lgssm)
     device = A.pick_device(P0, Fs, Qs, H, R, *extra)
     dtype = A.torch_dtype(Fs)
     P0d = A.to_device(P0, dtype, device, "P0")
@@ -49,6 +57,7 @@ def _wants_numpy(*xs):
 
 def pkf(lgssm, observations, return_loglikelihood=False, max_parallel=10000):
     """Parallel Kalman filter (parallel.py:121-152). Returns (fms[T,d], fPs[T,d,d][, ll])."""
+    lgssm, observations = tuple(_dl(v) for v in lgssm), _dl(observations)
     device, dtype, n, d, P0, Fs, Qs, H, R = _prep_lgssm(lgssm, (observations,))
     y = A.to_device(observations, dtype, device, "y").reshape(-1)
     if y.numel() != n:
@@ -72,6 +81,7 @@ def pkf(lgssm, observations, return_loglikelihood=False, max_parallel=10000):
 
 def pks(lgssm, ms, Ps, max_parallel=10000):
     """Parallel RTS smoother (parallel.py:187-196). Returns (sms[T,d], sPs[T,d,d])."""
+    lgssm, ms, Ps = tuple(_dl(v) for v in lgssm), _dl(ms), _dl(Ps)
     device, dtype, n, d, P0, Fs, Qs, H, R = _prep_lgssm(lgssm, (ms, Ps))
     msd = A.to_device(ms, dtype, device, "ms")
     Psd = A.to_device(Ps, dtype, device, "Ps")
@@ -89,6 +99,7 @@ def pks(lgssm, ms, Ps, max_parallel=10000):
 
 def pkfs(model, observations, max_parallel=10000):
     """Filter then smoother (parallel.py:199-201); the filtered moments never leave the device."""
+    model, observations = tuple(_dl(v) for v in model), _dl(observations)
     device, dtype, n, d, P0, Fs, Qs, H, R = _prep_lgssm(model, (observations,))
     y = A.to_device(observations, dtype, device, "y").reshape(-1)
     if y.numel() != n:

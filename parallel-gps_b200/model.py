@@ -29,20 +29,30 @@ class _LogLikelihood(torch.autograd.Function):
         Hd = H.detach().to(device=device, dtype=dtype).reshape(-1).contiguous()
         Rd = R.detach().to(device=device, dtype=dtype).reshape(-1).contiguous()
         Fs, Qs = ops.discretise(Fd, Pd, dts)
-        fms, fPs, ll, _ = ops.pkf(Pd, Fs, Qs, Hd, Rd, y)
-        ctx.save_for_backward(Fd, Pd, Hd, Rd, dts, y, Fs, Qs, fms, fPs)
         ctx.host = (F.device, F.dtype, tuple(H.shape), tuple(R.shape))
+        if any(ctx.needs_input_grad[:4]):
+            # training step: the fused filter + adjoint call (C ABI pssgp_pkfs_grad without smoother) with unit upstream
+            # gradient, then the discretisation adjoint; backward() only scales (the gradient is linear in g).  One pass
+            # over (Fs, Qs, y) fewer than pkf followed by pkf_backward, and nothing of size N is kept for backward.
+            one = torch.ones(1, dtype=dtype, device=device)
+            (fms, fPs, ll), _, (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(Pd, Fs, Qs, Hd, Rd, y, one, want_smoother=False)
+            dF, dPinf = ops.discretise_backward(Fd, Pd, dts, Fs, dFs, dQs)
+            ctx.save_for_backward(dF, dPinf + dP0, dH, dR)
+        else:
+            fms, fPs, ll, _ = ops.pkf(Pd, Fs, Qs, Hd, Rd, y)
         return ll[0].to(device=F.device, dtype=F.dtype)
 
     @staticmethod
     def backward(ctx, g):
-        Fd, Pd, Hd, Rd, dts, y, Fs, Qs, fms, fPs = ctx.saved_tensors
+        dF, dPinf, dH, dR = ctx.saved_tensors
         hdev, hdt, hshape, rshape = ctx.host
-        gd = g.detach().to(device=dts.device, dtype=dts.dtype).reshape(1).contiguous()
-        dP0, dFs, dQs, dH, dR = ops.pkf_backward(Pd, Fs, Qs, Hd, Rd, y, fms, fPs, gd)
-        dF, dPinf = ops.discretise_backward(Fd, Pd, dts, Fs, dFs, dQs)
-        back = lambda t, shape=None: (t.reshape(shape) if shape else t).to(device=hdev, dtype=hdt)
-        return back(dF), back(dPinf + dP0), back(dH, hshape), back(dR, rshape), None, None
+        # one small device -> host copy for the four d x d sized gradients
+        d = dF.shape[0]
+        packed = torch.cat([dF.reshape(-1), dPinf.reshape(-1), dH.reshape(-1), dR.reshape(-1)]).to(device=hdev, dtype=hdt)
+        packed = packed * g.detach().to(device=hdev, dtype=hdt)
+        gF, gP = packed[:d * d].reshape(d, d), packed[d * d:2 * d * d].reshape(d, d)
+        gH, gR = packed[2 * d * d:2 * d * d + d].reshape(hshape), packed[2 * d * d + d:].reshape(rshape)
+        return gF, gP, gH, gR, None, None
 
 
 def _merge_sorted_idx(a, b, *args):
@@ -75,10 +85,20 @@ def _merge_sorted(a, b, *args):
 
 
 class StateSpaceGP:
-    """model.py:58-117.  ``parallel=False`` selects the same CUDA kernels run as one sequential chunk."""
+    """model.py:58-117.  Both ``parallel`` values run the temporally-parallel CUDA path: the reference's sequential
+    ``kf`` / ``ks`` (pssgp/kalman/sequential.py, selected there by ``parallel=False``) compute the same quantities to
+    rounding and exist here only as the test comparator (oracle/).  ``parallel=False`` therefore warns once instead of
+    silently pretending to be sequential.  ``max_parallel`` (depth cap of TFP's recursion) is accepted and unused."""
+
+    _warned_sequential = False
 
     def __init__(self, data, kernel, noise_variance=1.0, parallel=False, max_parallel=10000, device=None):
         A.require_cuda()
+        if not parallel and not StateSpaceGP._warned_sequential:
+            import warnings
+            warnings.warn("pssgp_b200.StateSpaceGP(parallel=False): there is no sequential CUDA mode; the parallel-scan "
+                          "kernels are used (identical results to rounding)", stacklevel=2)
+            StateSpaceGP._warned_sequential = True
         self.noise_variance = Parameter(noise_variance, name="noise_variance")
         self.kernel = kernel
         self.parallel = parallel
@@ -134,7 +154,7 @@ class StateSpaceGP:
         return self.kernel.get_ssm(ts, R)
 
     def _cached_sde(self):
-        key = tuple(float(p.unconstrained_variable) for p in self.kernel.parameters)
+        key = tuple(tuple(p.unconstrained_variable.detach().reshape(-1).tolist()) for p in self.kernel.parameters)
         hit = getattr(self, "_sde_cache", None)
         if hit is None or hit[0] != key:
             with torch.no_grad():
@@ -165,20 +185,14 @@ class StateSpaceGP:
             ssm = self._make_model(all_ts[:, None])
             Hd, Rd = ssm.H.reshape(-1).contiguous(), ssm.R.reshape(-1).contiguous()
             yv = all_ys.reshape(-1).contiguous()
-            if ssm.Fs.shape[1] <= ops.SMALL_D:
+            if ops.has_projection(ssm.Fs.shape[1], dtype):
                 # fused filter + smoother that emits only (H m, H P H^T) of every smoothed state
-                try:
-                    proj = ops.pkfs(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, project=True)[3]
-                except _lib.PssgpError:
-                    proj = None
-            else:
-                proj = None
-            if proj is not None:
+                proj = ops.pkfs(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, project=True)[3]
                 sel = proj.index_select(0, q_idx)   # rows of the queries (the reference's boolean_mask, model.py:107-108)
                 mean, var = sel[:, 0:1].contiguous(), sel[:, 1:2].contiguous()
             else:
-                fms, fPs, _, _ = ops.pkf(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, want_ll=False)
-                sms, sPs, _ = ops.pks(ssm.Fs, ssm.Qs, fms, fPs)
+                # fused filter + smoother (pssgp_pkfs): the warp-level DMMA kernels for 5 <= d <= 32
+                sms, sPs = ops.pkfs(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv)[3:5]
                 rm, rP = sms.index_select(0, q_idx), sPs.index_select(0, q_idx)
                 mean = rm @ Hd.reshape(-1, 1)
                 var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)

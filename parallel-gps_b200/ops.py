@@ -114,14 +114,22 @@ def pkfs(P0, Fs, Qs, H, R, y, want_ll=False, project=False):
     return fms, fPs, ll, sms, sPs
 
 
-def pkfs_grad(P0, Fs, Qs, H, R, y, g_ll):
+def has_projection(d, dtype):
+    """pssgp_pkfs can emit (H m, H P H^T) of the smoothed states directly (fused d <= 4 kernels with a common
+    partition: every d <= 3, and d = 4 in FP32)."""
+    return d <= 3 or (d == 4 and dtype == torch.float32)
+
+
+def pkfs_grad(P0, Fs, Qs, H, R, y, g_ll, want_smoother=True):
     """C ABI: pssgp_pkfs_grad (filter + log-likelihood + smoother + gradient of one whole series, fused).
-    -> (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR)."""
+    -> (fms, fPs, ll), (sms, sPs) or None, (dP0, dFs, dQs, dH, dR)."""
     Fs, Qs, y = _al(Fs), _al(Qs), _al(y)
     n, d = Fs.shape[0], Fs.shape[1]
     kw = dict(dtype=Fs.dtype, device=Fs.device)
-    fms, sms = torch.empty((n, d), **kw), torch.empty((n, d), **kw)
-    fPs, sPs, dFs, dQs = (torch.empty((n, d, d), **kw) for _ in range(4))
+    fms = torch.empty((n, d), **kw)
+    fPs, dFs, dQs = (torch.empty((n, d, d), **kw) for _ in range(3))
+    sms = torch.empty((n, d), **kw) if want_smoother else None
+    sPs = torch.empty((n, d, d), **kw) if want_smoother else None
     ll, dR = torch.empty((1,), **kw), torch.empty((1,), **kw)
     dP0 = torch.zeros((d, d), **kw)
     dH = torch.empty((d,), **kw)
@@ -129,7 +137,7 @@ def pkfs_grad(P0, Fs, Qs, H, R, y, g_ll):
                                          A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(g_ll), A.ptr(fms), A.ptr(fPs), A.ptr(ll),
                                          A.ptr(sms), A.ptr(sPs), A.ptr(dP0), A.ptr(dFs), A.ptr(dQs), A.ptr(dH),
                                          A.ptr(dR), A.stream_ptr(Fs.device)))
-    return (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR)
+    return (fms, fPs, ll), ((sms, sPs) if want_smoother else None), (dP0, dFs, dQs, dH, dR)
 
 
 # ---- time sharding (one contiguous shard per GPU) --------------------------------------------------------
