@@ -198,3 +198,32 @@ def test_merge_sorted_idx_positions_and_batch_sharding():
     (t,), (ia, ib) = _merge_sorted_idx(a, b)
     assert ib.tolist() == [1, 4] and ia.tolist() == [0, 2, 3, 5]
     assert [shard_indices(10, r, 4) for r in range(4)] == [[0, 4, 8], [1, 5, 9], [2, 6], [3, 7]]
+
+
+def test_dlpack_producers_are_recognised_on_the_host_side():
+    """_arrays.from_dlpack / the DLPack branch of the host API accept any __dlpack__ producer and raw capsules
+    (CPU producers here; the zero-copy device case is tests/test_gpu_dlpack.py)."""
+    import numpy as np
+    import torch
+    from torch.utils.dlpack import to_dlpack
+    pkg()
+    from pssgp_b200 import _arrays as A
+    from pssgp_b200.kalman.parallel import _dl
+
+    class Producer:
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, stream=None):
+            return self._t.__dlpack__()
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    x = torch.arange(12, dtype=torch.float64).reshape(3, 4)
+    for obj in (Producer(x), to_dlpack(x)):
+        v = _dl(obj)
+        assert isinstance(v, torch.Tensor) and v.data_ptr() == x.data_ptr() and torch.equal(v, x)
+    a = np.arange(5.0)
+    assert _dl(a) is a and _dl(x) is x          # numpy arrays and torch tensors pass through untouched
+    assert torch.equal(A.from_dlpack(Producer(x)), x)

@@ -166,3 +166,23 @@ def test_stationary_q_equals_matrix_fraction_q():
             b = O.get_ssm_stationary(sde, t[:, None], R)
             assert float((a.Qs - b.Qs).abs().max()) <= 1e-12 * float(sde.P0.abs().max())
             assert float((a.Fs - b.Fs).abs().max()) == 0.0
+
+
+def test_numba_sequential_kf_ks_matches_the_parallel_restatement():
+    """oracle/seq_numba.py (numba restatement of pssgp/kalman/sequential.py:11-73, the 1-core CPU baseline of
+    bench.py) against the torch restatement of the parallel path: kf == pkf, ks == pks."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import seq_numba
+    from util import make_problem, rel_err
+    for name, T in (("matern52", 300), ("m32+m52", 120)):
+        t, y, cov, ssm = make_problem(name, T, seed=3)
+        P0, Fs, Qs, H, R = [np.ascontiguousarray(x.numpy()) for x in ssm]
+        fms, fPs, sms, sPs, ll = seq_numba.kfs(P0, Fs, Qs, H, R, y)
+        with torch.no_grad():
+            rfm, rfP, rll = O.pkf(ssm, y[:, None], True, max_parallel=T)
+            rsm, rsP = O.pks(ssm, rfm, rfP, max_parallel=T)
+        assert rel_err(fms, rfm) < 1e-11 and rel_err(fPs, rfP) < 1e-11
+        assert abs(ll - float(rll)) < 1e-11 * abs(float(rll))
+        assert rel_err(sms, rsm) < 1e-10 and rel_err(sPs, rsP) < 1e-10
