@@ -412,7 +412,281 @@ template <int MT> MDEV Mat<MT> msub(const Mat<MT>& a, const Mat<MT>& b) {
     return o;
 }
 
-template <int D> constexpr int frag_nslot() { return D <= 8 ? 4 : 3; }
+// ================================================================================================
+// Traits: how a d x d matrix / a d vector is held by one warp.  The kernels below are written once against this
+// interface.  Std<D>: MT x MT tiles of 8 x 8 (any D).  Bord9: D = 9 as an 8 x 8 core tile + border column + border row +
+// corner — the 16 x 16 padding of the tile form wastes 3/4 of the DMMA work at D = 9 (BASELINE configs[4]).
+// ================================================================================================
+template <int D_> struct Std {
+    static constexpr int D = D_, MT = FGeo<D>::MT, DD = D * D;
+    static constexpr int MSZ = FGeo<D>::MSZ;   // doubles per matrix in a ring slot
+    static constexpr int VSZ = FGeo<D>::DP;    // doubles per vector in a ring slot
+    using M = Mat<MT>;
+    using VR = VecR<MT>;
+    using VP = VecP<MT>;
+    using Op = typename InOp<MT>::type;
+    using Cp = CpPlan<D, MT>;
+    using St = StPlan<D, MT>;
+    MDEV static M zero() { M m; mzero(m); return m; }
+    MDEV static M identity(int r, int c) { return identity_d<D, MT>(r, c); }
+    MDEV static VR vzero() { VR v;
+#pragma unroll
+        for (int t = 0; t < MT; ++t) v.v[t] = 0.0;
+        return v; }
+    MDEV static Op in_op(const double* slot, bool tr, int r, int c) { return InOp<MT>::make(slot, tr, r, c); }
+    MDEV static M ld_mat(const double* slot, int r, int c) { return frag::ld_mat<MT>(slot, r, c); }
+    MDEV static M ld_sym(const double* slot, int r, int c) { return frag::ld_sym<MT>(slot, r, c); }
+    MDEV static VR ld_vr(const double* v, int r) { return frag::ld_vr<MT>(v, r); }
+    MDEV static VP ld_vp(const double* v, int c) { return frag::ld_vp<MT>(v, c); }
+    MDEV static void issue_vec(int lane, double* dst, const double* src) { frag::issue_vec<D>(lane, dst, src); }
+    MDEV static void zero_vec(int lane, double* dst) { if (lane < D) dst[lane] = 0.0; }
+    MDEV static M gld_mat(const double* src, int r, int c) { return frag::gld_mat<D, MT>(src, r, c); }
+    MDEV static VR gld_vr(const double* src, int r) { return frag::gld_vr<D, MT>(src, r); }
+    MDEV static VP gld_vp(const double* src, int c) { return frag::gld_vp<D, MT>(src, c); }
+    template <bool TRANS = false> MDEV static void gst_mat(double* dst, const M& m, double scale, const St& sp, int, int) {
+        frag::gst_mat<D, MT, TRANS>(dst, m, scale, sp);
+    }
+    MDEV static void gst_vr(double* dst, const VR& v, int r, int c) { frag::gst_vr<D, MT>(dst, v, r, c); }
+    template <class XO, class SO> MDEV static void mmT(M& acc, const XO& X, const SO& S, int) { frag::mmT<MT, D>(acc, X, S); }
+    template <class XO, class SO> MDEV static M mulT(const XO& X, const SO& S, int) { return frag::mulT<MT, D>(X, S); }
+    // yP (the y vectors in VP layout) is only needed by the bordered form
+    template <int NQ> MDEV static void rank_update(M& acc, const VR (&x)[NQ], const VR (&y)[NQ], const VP (&)[NQ], int c) {
+        frag::rank_update<MT, NQ>(acc, x, y, c);
+    }
+    MDEV static VP vp_for_rank(const VR&, int) { return VP{}; }   // not needed: no shuffles spent
+    template <class MO> MDEV static VR mv(const MO& Mx, const VP& v) { return frag::mv<MT>(Mx, v); }
+    MDEV static VP vr2vp(const VR& x, int c) { return frag::vr2vp<MT>(x, c); }
+    MDEV static void dots2(const VR& x0, const VR& y0, const VR& x1, const VR& y1, int lane, int c, double& o0, double& o1) {
+        frag::dots2<MT>(x0, y0, x1, y1, lane, c, o0, o1);
+    }
+    MDEV static void dots4(const VR* const (&x)[4], const VR* const (&y)[4], int lane, int c, double (&out)[4]) {
+        frag::dots4<MT>(x, y, lane, c, out);
+    }
+    MDEV static VR vscale(double a, const VR& x) { return frag::vscale(a, x); }
+    MDEV static VR vaxpy(double a, const VR& x, const VR& y) { return frag::vaxpy(a, x, y); }
+    MDEV static VR vlin3(double a, const VR& x, double b, const VR& y, double cc, const VR& z) {
+        VR o;
+#pragma unroll
+        for (int t = 0; t < MT; ++t) o.v[t] = a * x.v[t] + b * y.v[t] + cc * z.v[t];
+        return o;
+    }
+    MDEV static void madd(M& a, const M& b) {
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) { a.v[i][j][0] += b.v[i][j][0]; a.v[i][j][1] += b.v[i][j][1]; }
+    }
+    // X - m with X an input operand
+    MDEV static M op_minus(const Op& X, const M& m) {
+        M o;
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+                o.v[i][j][0] = oget<MT>(X, i, j, 0) - m.v[i][j][0];
+                o.v[i][j][1] = oget<MT>(X, i, j, 1) - m.v[i][j][1];
+            }
+        return o;
+    }
+};
+
+// ---- D = 9: 8 x 8 core + border -------------------------------------------------------------------------------
+struct BM { double c[2]; double col; double row[2]; double cor; };  // core CF | M[r][8] | M[8][2c+s] | M[8][8]
+struct BVR { double v, e; };      // x[r] | x[8]
+struct BVP { double v[2], e; };   // x[2c+s] | x[8]
+
+MDEV double red_c(double x) {  // sum over the four lanes of a row (result on all of them)
+    x += __shfl_xor_sync(FULL, x, 1);
+    x += __shfl_xor_sync(FULL, x, 2);
+    return x;
+}
+
+struct Bord9 {
+    static constexpr int D = 9, DD = 81;
+    static constexpr int MSZ = 88;   // slot: core 64 (row-major 8 x 8) | col 8 | row 8 | corner (+ pad)
+    static constexpr int VSZ = 10;   // slot: x[0..8] (+ pad)
+    using M = BM;
+    using VR = BVR;
+    using VP = BVP;
+    using Op = BM;
+    struct Cp {
+        int soff[3], doff[3];
+        MDEV void init(int lane) {
+#pragma unroll
+            for (int q = 0; q < 3; ++q) {
+                const int idx = lane + 32 * q;
+                const int i = idx / 9, j = idx - i * 9;
+                soff[q] = idx;
+                doff[q] = (i < 8 && j < 8) ? i * 8 + j : (i < 8 ? 64 + i : (j < 8 ? 72 + j : 80));
+            }
+        }
+        MDEV void issue(int lane, double* dst, const double* src) const {
+#pragma unroll
+            for (int q = 0; q < 3; ++q)
+                if (q < 2 || lane + 64 < 81) cp8(dst + doff[q], src + soff[q]);
+        }
+    };
+    struct St { MDEV void init(int, int) {} };
+    MDEV static M zero() { return BM{{0.0, 0.0}, 0.0, {0.0, 0.0}, 0.0}; }
+    MDEV static M identity(int r, int c) {
+        BM m = zero();
+        if (r == 2 * c) m.c[0] = 1.0;
+        if (r == 2 * c + 1) m.c[1] = 1.0;
+        m.cor = 1.0;
+        return m;
+    }
+    MDEV static VR vzero() { return BVR{0.0, 0.0}; }
+    MDEV static M ld_mat(const double* sl, int r, int c) {
+        BM m;
+        const double2 a = *reinterpret_cast<const double2*>(sl + r * 8 + 2 * c);
+        const double2 b = *reinterpret_cast<const double2*>(sl + 72 + 2 * c);
+        m.c[0] = a.x; m.c[1] = a.y;
+        m.col = sl[64 + r];
+        m.row[0] = b.x; m.row[1] = b.y;
+        m.cor = sl[80];
+        return m;
+    }
+    MDEV static M ld_matT(const double* sl, int r, int c) {
+        BM m;
+        m.c[0] = sl[(2 * c) * 8 + r];
+        m.c[1] = sl[(2 * c + 1) * 8 + r];
+        m.col = sl[72 + r];
+        const double2 b = *reinterpret_cast<const double2*>(sl + 64 + 2 * c);
+        m.row[0] = b.x; m.row[1] = b.y;
+        m.cor = sl[80];
+        return m;
+    }
+    MDEV static Op in_op(const double* slot, bool tr, int r, int c) { return tr ? ld_matT(slot, r, c) : ld_mat(slot, r, c); }
+    MDEV static M ld_sym(const double* sl, int r, int c) {
+        BM a = ld_mat(sl, r, c);
+        const BM t = ld_matT(sl, r, c);
+        a.c[0] = 0.5 * (a.c[0] + t.c[0]); a.c[1] = 0.5 * (a.c[1] + t.c[1]);
+        a.col = 0.5 * (a.col + t.col);
+        a.row[0] = 0.5 * (a.row[0] + t.row[0]); a.row[1] = 0.5 * (a.row[1] + t.row[1]);
+        return a;
+    }
+    MDEV static VR ld_vr(const double* v, int r) { return BVR{v[r], v[8]}; }
+    MDEV static VP ld_vp(const double* v, int c) {
+        const double2 a = *reinterpret_cast<const double2*>(v + 2 * c);
+        return BVP{{a.x, a.y}, v[8]};
+    }
+    MDEV static void issue_vec(int lane, double* dst, const double* src) { if (lane < 9) cp8(dst + lane, src + lane); }
+    MDEV static void zero_vec(int lane, double* dst) { if (lane < 9) dst[lane] = 0.0; }
+    MDEV static M gld_mat(const double* src, int r, int c) {
+        BM m;
+        m.c[0] = src[r * 9 + 2 * c]; m.c[1] = src[r * 9 + 2 * c + 1];
+        m.col = src[r * 9 + 8];
+        m.row[0] = src[72 + 2 * c]; m.row[1] = src[72 + 2 * c + 1];
+        m.cor = src[80];
+        return m;
+    }
+    MDEV static VR gld_vr(const double* src, int r) { return src != nullptr ? BVR{src[r], src[8]} : BVR{0.0, 0.0}; }
+    MDEV static VP gld_vp(const double* src, int c) {
+        return src != nullptr ? BVP{{src[2 * c], src[2 * c + 1]}, src[8]} : BVP{{0.0, 0.0}, 0.0};
+    }
+    template <bool TRANS = false> MDEV static void gst_mat(double* dst, const M& m, double scale, const St&, int r, int c) {
+        if (TRANS) {
+            dst[(2 * c) * 9 + r] = scale * m.c[0];
+            dst[(2 * c + 1) * 9 + r] = scale * m.c[1];
+            if (c == 0) dst[72 + r] = scale * m.col;
+            if (r == 0) { dst[(2 * c) * 9 + 8] = scale * m.row[0]; dst[(2 * c + 1) * 9 + 8] = scale * m.row[1]; }
+        } else {
+            __stcs(dst + r * 9 + 2 * c, scale * m.c[0]);
+            __stcs(dst + r * 9 + 2 * c + 1, scale * m.c[1]);
+            if (c == 0) __stcs(dst + r * 9 + 8, scale * m.col);
+            if (r == 0) { __stcs(dst + 72 + 2 * c, scale * m.row[0]); __stcs(dst + 72 + 2 * c + 1, scale * m.row[1]); }
+        }
+        if (r == 0 && c == 0) dst[80] = scale * m.cor;
+    }
+    MDEV static void gst_vr(double* dst, const VR& v, int r, int c) {
+        if (c == 0) dst[r] = v.v;
+        if (r == 0 && c == 0) dst[8] = v.e;
+    }
+    // acc += X S^T
+    MDEV static void mmT(M& acc, const M& X, const M& S, int c) {
+        dmma(acc.c, X.c[0], S.c[0]);
+        dmma(acc.c, X.c[1], S.c[1]);
+        dmma(acc.c, c == 0 ? X.col : 0.0, c == 0 ? S.col : 0.0);
+        const double pc = red_c(fma(X.c[0], S.row[0], X.c[1] * S.row[1]));      // sum_k X[r][k] S[8][k]
+        const double pr = red_c(fma(S.c[0], X.row[0], S.c[1] * X.row[1]));      // sum_k X[8][k] S[n][k], n = r
+        const double pz = red_c(fma(X.row[0], S.row[0], X.row[1] * S.row[1]));  // sum_k X[8][k] S[8][k]
+        acc.col += fma(X.col, S.cor, pc);
+        const double zr = fma(X.cor, S.col, pr);                                // Z[8][n] at lane (n, .)
+        acc.row[0] += __shfl_sync(FULL, zr, (2 * c) * 4);
+        acc.row[1] += __shfl_sync(FULL, zr, (2 * c + 1) * 4);
+        acc.cor += fma(X.cor, S.cor, pz);
+    }
+    MDEV static M mulT(const M& X, const M& S, int c) {
+        BM acc = zero();
+        mmT(acc, X, S, c);
+        return acc;
+    }
+    template <int NQ> MDEV static void rank_update(M& acc, const VR (&x)[NQ], const VR (&y)[NQ], const VP (&yP)[NQ], int c) {
+        double a = 0.0, b = 0.0;
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            a = (c == q) ? x[q].v : a;
+            b = (c == q) ? y[q].v : b;
+            acc.col = fma(x[q].v, y[q].e, acc.col);
+            acc.row[0] = fma(x[q].e, yP[q].v[0], acc.row[0]);
+            acc.row[1] = fma(x[q].e, yP[q].v[1], acc.row[1]);
+            acc.cor = fma(x[q].e, y[q].e, acc.cor);
+        }
+        dmma(acc.c, a, b);
+    }
+    MDEV static VP vp_for_rank(const VR& x, int c) { return vr2vp(x, c); }
+    MDEV static VR mv(const M& Mx, const VP& v) {
+        BVR y;
+        y.v = fma(Mx.col, v.e, red_c(fma(Mx.c[0], v.v[0], Mx.c[1] * v.v[1])));
+        y.e = fma(Mx.cor, v.e, red_c(fma(Mx.row[0], v.v[0], Mx.row[1] * v.v[1])));
+        return y;
+    }
+    MDEV static VP vr2vp(const VR& x, int c) {
+        BVP y;
+        y.v[0] = __shfl_sync(FULL, x.v, (2 * c) * 4);
+        y.v[1] = __shfl_sync(FULL, x.v, (2 * c + 1) * 4);
+        y.e = x.e;
+        return y;
+    }
+    MDEV static void dots2(const VR& x0, const VR& y0, const VR& x1, const VR& y1, int lane, int c, double& o0, double& o1) {
+        double p = (c & 1) ? x1.v * y1.v : x0.v * y0.v;
+        p += __shfl_xor_sync(FULL, p, 4);
+        p += __shfl_xor_sync(FULL, p, 8);
+        p += __shfl_xor_sync(FULL, p, 16);
+        o0 = fma(x0.e, y0.e, __shfl_sync(FULL, p, lane & ~3));
+        o1 = fma(x1.e, y1.e, __shfl_sync(FULL, p, (lane & ~3) | 1));
+    }
+    MDEV static void dots4(const VR* const (&x)[4], const VR* const (&y)[4], int lane, int c, double (&out)[4]) {
+        double p = 0.0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) p = (c == q) ? x[q]->v * y[q]->v : p;
+        p += __shfl_xor_sync(FULL, p, 4);
+        p += __shfl_xor_sync(FULL, p, 8);
+        p += __shfl_xor_sync(FULL, p, 16);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[q] = fma(x[q]->e, y[q]->e, __shfl_sync(FULL, p, (lane & ~3) | q));
+    }
+    MDEV static VR vscale(double a, const VR& x) { return BVR{a * x.v, a * x.e}; }
+    MDEV static VR vaxpy(double a, const VR& x, const VR& y) { return BVR{fma(a, x.v, y.v), fma(a, x.e, y.e)}; }
+    MDEV static VR vlin3(double a, const VR& x, double b, const VR& y, double cc, const VR& z) {
+        return BVR{a * x.v + b * y.v + cc * z.v, a * x.e + b * y.e + cc * z.e};
+    }
+    MDEV static void madd(M& a, const M& b) {
+        a.c[0] += b.c[0]; a.c[1] += b.c[1]; a.col += b.col; a.row[0] += b.row[0]; a.row[1] += b.row[1]; a.cor += b.cor;
+    }
+    MDEV static M op_minus(const Op& X, const M& m) {
+        return BM{{X.c[0] - m.c[0], X.c[1] - m.c[1]}, X.col - m.col, {X.row[0] - m.row[0], X.row[1] - m.row[1]}, X.cor - m.cor};
+    }
+};
+
+#ifndef PSSGP_NO_BORDERED
+template <int D> struct TraitsFor { using type = Std<D>; };
+template <> struct TraitsFor<9> { using type = Bord9; };
+#else
+template <int D> struct TraitsFor { using type = Std<D>; };
+#endif
+
+template <int D> constexpr int frag_nslot() { return D <= 9 ? 4 : 3; }
 // warps per CTA: as many as the ring slots of a CTA fit in shared memory, at most `cap` (the launch bound; the option
 // "mid_warps" lowers it at run time)
 template <int D> constexpr int frag_warps(int slot_doubles, int cap) {
@@ -422,15 +696,16 @@ template <int D> constexpr int frag_warps(int slot_doubles, int cap) {
 #ifndef PSSGP_FRAG_CAP_SMALL
 #define PSSGP_FRAG_CAP_SMALL 24
 #endif
+template <int D> constexpr int frag_cap(int big) { return (D <= 8) ? PSSGP_FRAG_CAP_SMALL : (D == 9 ? 16 : big); }
 
 // ------------------------------------------------------------------------------------------------
-// K1: chunk aggregates of the filter.  Tracks At = A^T, C, J (CF), b, eta (VR).
+// K1: chunk aggregates of the filter.  Tracks At = A^T, C, J, b, eta.
 // ------------------------------------------------------------------------------------------------
 template <int D> struct FK1 {
-    using G = FGeo<D>;
+    using TR = typename TraitsFor<D>::type;
     static constexpr int NSLOT = frag_nslot<D>();
-    static constexpr int SLOT = 2 * G::MSZ;  // F | Q
-    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? PSSGP_FRAG_CAP_SMALL : 12);
+    static constexpr int SLOT = 2 * TR::MSZ;  // F | Q
+    static constexpr int WPC = frag_warps<D>(SLOT, frag_cap<D>(12));
     static constexpr size_t WARP_SMEM = (size_t)NSLOT * SLOT * 8;
     static constexpr size_t SMEM = (size_t)WPC * WARP_SMEM;
 };
@@ -438,8 +713,11 @@ template <int D> struct FK1 {
 template <int D>
 __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, int L, long nchunks, double* __restrict__ aggs) {
     using K = FK1<D>;
-    using G = typename K::G;
-    constexpr int MT = G::MT, MSZ = G::MSZ, NSLOT = K::NSLOT, DD = G::DD;
+    using TR = typename K::TR;
+    using M = typename TR::M;
+    using VR = typename TR::VR;
+    using VP = typename TR::VP;
+    constexpr int MSZ = TR::MSZ, NSLOT = K::NSLOT, DD = D * D;
     extern __shared__ __align__(16) double smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
     const long chunk = (long)blockIdx.x * (blockDim.x >> 5) + wid;
@@ -451,9 +729,9 @@ __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, 
     const long k_hi = (k_lo + L < p.n) ? k_lo + L : p.n;
     const int nrows = (int)(k_hi - k_lo);
     constexpr int PD = NSLOT - 1;
-    CpPlan<D, MT> cp;
+    typename TR::Cp cp;
     cp.init(lane);
-    StPlan<D, MT> sp;
+    typename TR::St sp;
     sp.init(r, c);
     auto issue = [&](int i) {
         if (i < nrows) {
@@ -465,15 +743,11 @@ __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, 
     };
 #pragma unroll 1
     for (int i = 0; i < PD; ++i) issue(i);
-    const VecP<MT> hP = gld_vp<D, MT>(p.H, c);
-    const VecR<MT> hR = gld_vr<D, MT>(p.H, r);
+    const VP hP = TR::gld_vp(p.H, c);
+    const VR hR = TR::gld_vr(p.H, r);
     const double Rv = p.R[0];
-    Mat<MT> At = identity_d<D, MT>(r, c), C, J;
-    mzero(C);
-    mzero(J);
-    VecR<MT> b, eta;
-#pragma unroll
-    for (int t = 0; t < MT; ++t) b.v[t] = eta.v[t] = 0.0;
+    M At = TR::identity(r, c), C = TR::zero(), J = TR::zero();
+    VR b = TR::vzero(), eta = TR::vzero();
     double ynext = p.y[k_lo];
 #pragma unroll 1
     for (int i = 0; i < nrows; ++i) {
@@ -486,46 +760,50 @@ __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, 
         const double* sl = ring + (i % NSLOT) * K::SLOT;
         // the first step of the global series is an update without propagation (parallel.py:24-30)
         if (!(k == 0 && p.first_special)) {
-            const auto F = in_op<MT>(sl, false, r, c);
-            Mat<MT> Cn = ld_sym<MT>(sl + MSZ, r, c);
-            At = mulT<MT, D>(At, F);                   // (F A)^T = A^T F^T
+            const auto F = TR::in_op(sl, false, r, c);
+            M Cn = TR::ld_sym(sl + MSZ, r, c);
+            At = TR::mulT(At, F, c);                   // (F A)^T = A^T F^T
             {
-                const Mat<MT> T2 = mulT<MT, D>(F, C);  // F C   (C symmetric)
-                mmT<MT, D>(Cn, T2, F);                 // F C F^T + Q
+                const M T2 = TR::mulT(F, C, c);        // F C   (C symmetric)
+                TR::mmT(Cn, T2, F, c);                 // F C F^T + Q
             }
             C = Cn;
-            b = mv(F, vr2vp(b, c));
+            b = TR::mv(F, TR::vr2vp(b, c));
         }
         const bool obs = !isnan(yk);
-        const VecR<MT> u = mv(C, hP);
-        const VecR<MT> w = mv(At, hP);      // A^T h
+        const VR u = TR::mv(C, hP);
+        const VR w = TR::mv(At, hP);      // A^T h
         double hu, hb;
-        dots2<MT>(hR, u, hR, b, lane, c, hu, hb);
+        TR::dots2(hR, u, hR, b, lane, c, hu, hb);
         const double is = obs ? 1.0 / (Rv + hu) : 0.0;
         const double eis = obs ? (yk - hb) * is : 0.0;
+        const VP uP = TR::vp_for_rank(u, c), wP = TR::vp_for_rank(w, c);
         {
-            const VecR<MT> x1[1] = {vscale(is, w)}, y1[1] = {w};
-            rank_update<MT, 1>(J, x1, y1, c);   // J += w w^T / s
+            const VR x1[1] = {TR::vscale(is, w)}, y1[1] = {w};
+            const VP p1[1] = {wP};
+            TR::template rank_update<1>(J, x1, y1, p1, c);   // J += w w^T / s
         }
         {
-            const VecR<MT> x1[1] = {vscale(-is, w)}, y1[1] = {u};
-            rank_update<MT, 1>(At, x1, y1, c);  // A -= u w^T / s
+            const VR x1[1] = {TR::vscale(-is, w)}, y1[1] = {u};
+            const VP p1[1] = {uP};
+            TR::template rank_update<1>(At, x1, y1, p1, c);  // A -= u w^T / s
         }
         {
-            const VecR<MT> x1[1] = {vscale(-is, u)}, y1[1] = {u};
-            rank_update<MT, 1>(C, x1, y1, c);   // C -= u u^T / s
+            const VR x1[1] = {TR::vscale(-is, u)}, y1[1] = {u};
+            const VP p1[1] = {uP};
+            TR::template rank_update<1>(C, x1, y1, p1, c);   // C -= u u^T / s
         }
-        eta = vaxpy(eis, w, eta);
-        b = vaxpy(eis, u, b);
+        eta = TR::vaxpy(eis, w, eta);
+        b = TR::vaxpy(eis, u, b);
         __syncwarp();  // every lane has read the slot: it may be refilled
     }
     cp_wait<0>();
     double* out = aggs + chunk * (3 * DD + 2 * D);
-    gst_mat<D, MT, true>(out, At, 1.0, sp);
-    gst_mat<D, MT>(out + DD, C, 1.0, sp);
-    gst_mat<D, MT>(out + 2 * DD, J, 1.0, sp);
-    gst_vr<D, MT>(out + 3 * DD, b, r, c);
-    gst_vr<D, MT>(out + 3 * DD + D, eta, r, c);
+    TR::template gst_mat<true>(out, At, 1.0, sp, r, c);
+    TR::template gst_mat<false>(out + DD, C, 1.0, sp, r, c);
+    TR::template gst_mat<false>(out + 2 * DD, J, 1.0, sp, r, c);
+    TR::gst_vr(out + 3 * DD, b, r, c);
+    TR::gst_vr(out + 3 * DD + D, eta, r, c);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -533,11 +811,11 @@ __global__ void __launch_bounds__(FK1<D>::WPC * 32) fk1_filter_reduce(Params p, 
 // (tracked as Abt = Abar^T, Ba, Bm, a).  STORED: filtered moments are read instead of recomputed.
 // ------------------------------------------------------------------------------------------------
 template <int D, bool REV, bool STORED> struct FK2 {
-    using G = FGeo<D>;
+    using TR = typename TraitsFor<D>::type;
     static constexpr int NSLOT = frag_nslot<D>();
     static constexpr int NM = 2 + (STORED ? 1 : 0);  // F | Q | P_{k-1}
-    static constexpr int SLOT = NM * G::MSZ + (STORED ? G::DP : 0);
-    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? PSSGP_FRAG_CAP_SMALL : 12);
+    static constexpr int SLOT = NM * TR::MSZ + (STORED ? TR::VSZ : 0);
+    static constexpr int WPC = frag_warps<D>(SLOT, frag_cap<D>(12));
     static constexpr size_t WARP_SMEM = (size_t)NSLOT * SLOT * 8;
     static constexpr size_t SMEM = (size_t)WPC * WARP_SMEM;
 };
@@ -547,8 +825,11 @@ __global__ void __launch_bounds__(FK2<D, REV, STORED>::WPC * 32)
 fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, double* __restrict__ part,
             double* __restrict__ raggs) {
     using K = FK2<D, REV, STORED>;
-    using G = typename K::G;
-    constexpr int MT = G::MT, MSZ = G::MSZ, NSLOT = K::NSLOT, DD = G::DD;
+    using TR = typename K::TR;
+    using M = typename TR::M;
+    using VR = typename TR::VR;
+    using VP = typename TR::VP;
+    constexpr int MSZ = TR::MSZ, NSLOT = K::NSLOT, DD = D * D;
     constexpr int O_P = 2 * MSZ, O_M = 3 * MSZ;
     extern __shared__ __align__(16) double smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
@@ -561,9 +842,9 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
     const long k_hi = (k_lo + L < p.n) ? k_lo + L : p.n;
     const int nrows = (int)(k_hi - k_lo);
     constexpr int PD = NSLOT - 1;
-    CpPlan<D, MT> cp;
+    typename TR::Cp cp;
     cp.init(lane);
-    StPlan<D, MT> sp;
+    typename TR::St sp;
     sp.init(r, c);
     auto issue = [&](int i) {
         if (i < nrows) {
@@ -573,38 +854,27 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
             cp.issue(lane, sl + MSZ, p.Qs + k * DD);
             if constexpr (STORED) {
                 cp.issue(lane, sl + O_P, k > 0 ? p.fPs_in + (k - 1) * DD : p.P0);
-                if (k > 0) issue_vec<D>(lane, sl + O_M, p.fms_in + (k - 1) * D);
-                else if (p.m0 != nullptr) issue_vec<D>(lane, sl + O_M, p.m0);
-                else if (lane < D) sl[O_M + lane] = 0.0;
+                if (k > 0) TR::issue_vec(lane, sl + O_M, p.fms_in + (k - 1) * D);
+                else if (p.m0 != nullptr) TR::issue_vec(lane, sl + O_M, p.m0);
+                else TR::zero_vec(lane, sl + O_M);
             }
         }
         cp_commit();
     };
 #pragma unroll 1
     for (int i = 0; i < PD; ++i) issue(i);
-    const VecP<MT> hP = gld_vp<D, MT>(p.H, c);
-    const VecR<MT> hR = gld_vr<D, MT>(p.H, r);
+    const VP hP = TR::gld_vp(p.H, c);
+    const VR hR = TR::gld_vr(p.H, r);
     const double Rv = p.R[0];
-    Mat<MT> P;
-    VecR<MT> m;
+    M P = TR::zero();
+    VR m = TR::vzero();
     if constexpr (!STORED) {
         const double* st = fstates + chunk * (D + DD);
-        m = gld_vr<D, MT>(st, r);
-        P = gld_mat<D, MT>(st + D, r, c);
-    } else {
-        mzero(P);
-#pragma unroll
-        for (int t = 0; t < MT; ++t) m.v[t] = 0.0;
+        m = TR::gld_vr(st, r);
+        P = TR::gld_mat(st + D, r, c);
     }
-    Mat<MT> Abt, Ba, Bm;
-    VecR<MT> av;
-    if constexpr (REV) {
-        Abt = identity_d<D, MT>(r, c);
-        mzero(Ba);
-        mzero(Bm);
-#pragma unroll
-        for (int t = 0; t < MT; ++t) av.v[t] = 0.0;
-    }
+    M Abt = TR::identity(r, c), Ba = TR::zero(), Bm = TR::zero();
+    VR av = TR::vzero();
     double ynext = p.y[k_lo];
     double quad = 0.0;
     int nobs = 0;
@@ -622,20 +892,20 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
         if (i + 1 < nrows) ynext = p.y[k + 1];
         const bool obs = !isnan(yk);
         const double* sl = ring + (i % NSLOT) * K::SLOT;
-        const auto F = in_op<MT>(sl, false, r, c);
+        const auto F = TR::in_op(sl, false, r, c);
         if constexpr (STORED) {
-            P = ld_mat<MT>(sl + O_P, r, c);
-            m = ld_vr<MT>(sl + O_M, r);
+            P = TR::ld_mat(sl + O_P, r, c);
+            m = TR::ld_vr(sl + O_M, r);
         }
-        Mat<MT> Pp = ld_sym<MT>(sl + MSZ, r, c);
+        M Pp = TR::ld_sym(sl + MSZ, r, c);
         {
-            const Mat<MT> T1 = mulT<MT, D>(F, P);  // F P (P symmetric)
-            mmT<MT, D>(Pp, T1, F);                 // F P F^T + Q
+            const M T1 = TR::mulT(F, P, c);  // F P (P symmetric)
+            TR::mmT(Pp, T1, F, c);           // F P F^T + Q
         }
-        VecR<MT> mp = mv(F, vr2vp(m, c));
-        VecR<MT> u = mv(Pp, hP);
+        VR mp = TR::mv(F, TR::vr2vp(m, c));
+        VR u = TR::mv(Pp, hP);
         double hu, hm;
-        dots2<MT>(hR, u, hR, mp, lane, c, hu, hm);
+        TR::dots2(hR, u, hR, mp, lane, c, hu, hm);
         double s = Rv + hu;
         double e = obs ? yk - hm : 0.0;
         if constexpr (!STORED) {
@@ -649,45 +919,51 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
             // parallel.py:24-30: the first update is made on (m0, P0) directly, without prediction
             Pp = P;
             mp = m;
-            u = mv(Pp, hP);
-            dots2<MT>(hR, u, hR, mp, lane, c, hu, hm);
+            u = TR::mv(Pp, hP);
+            TR::dots2(hR, u, hR, mp, lane, c, hu, hm);
             s = Rv + hu;
             e = obs ? yk - hm : 0.0;
         }
         const double is = obs ? 1.0 / s : 0.0;
         const double eis = e * is;
+        const VP uP = TR::vp_for_rank(u, c);
         if constexpr (!STORED) {
             P = Pp;
             {
-                const VecR<MT> x1[1] = {vscale(-is, u)}, y1[1] = {u};
-                rank_update<MT, 1>(P, x1, y1, c);
+                const VR x1[1] = {TR::vscale(-is, u)}, y1[1] = {u};
+                const VP p1[1] = {uP};
+                TR::template rank_update<1>(P, x1, y1, p1, c);
             }
-            m = vaxpy(eis, u, mp);
-            gst_mat<D, MT>(p.fPs + k * DD, P, 1.0, sp);
-            gst_vr<D, MT>(p.fms + k * D, m, r, c);
+            m = TR::vaxpy(eis, u, mp);
+            TR::template gst_mat<false>(p.fPs + k * DD, P, 1.0, sp, r, c);
+            TR::gst_vr(p.fms + k * D, m, r, c);
         }
         if constexpr (REV) {
             // append step k on the later side of the chunk's reverse aggregate (nothing for the global first step)
-            const auto Ft = in_op<MT>(sl, true, r, c);
-            const VecR<MT> w = mv(Ft, hP);                 // F^T h
-            const VecR<MT> t = mv(Abt, vr2vp(w, c));       // Abar_old^T w
+            const auto Ft = TR::in_op(sl, true, r, c);
+            const VR w = TR::mv(Ft, hP);                    // F^T h
+            const VR t = TR::mv(Abt, TR::vr2vp(w, c));      // Abar_old^T w
             const double isr = first ? 0.0 : is, eisr = first ? 0.0 : eis;
-            if (!first) Abt = mulT<MT, D>(Abt, F);                // (F Abar_old)^T
+            if (!first) Abt = TR::mulT(Abt, F, c);          // (F Abar_old)^T
+            const VP tP = TR::vp_for_rank(t, c), aP = TR::vp_for_rank(av, c);
             {
-                const VecR<MT> x1[1] = {vscale(-isr, t)}, y1[1] = {u};
-                rank_update<MT, 1>(Abt, x1, y1, c);        // Abar = F Abar_old - u t^T / s
+                const VR x1[1] = {TR::vscale(-isr, t)}, y1[1] = {u};
+                const VP p1[1] = {uP};
+                TR::template rank_update<1>(Abt, x1, y1, p1, c);  // Abar = F Abar_old - u t^T / s
             }
             const double beta = 0.5 * (eisr * eisr - isr);
             {
-                const VecR<MT> x3[3] = {vscale(beta, t), vscale(0.5 * eisr, t), vscale(0.5 * eisr, av)};
-                const VecR<MT> y3[3] = {t, av, t};
-                rank_update<MT, 3>(Ba, x3, y3, c);
+                const VR x3[3] = {TR::vscale(beta, t), TR::vscale(0.5 * eisr, t), TR::vscale(0.5 * eisr, av)};
+                const VR y3[3] = {t, av, t};
+                const VP p3[3] = {tP, aP, tP};
+                TR::template rank_update<3>(Ba, x3, y3, p3, c);
             }
             {
-                const VecR<MT> x1[1] = {vscale(isr, t)}, y1[1] = {t};
-                rank_update<MT, 1>(Bm, x1, y1, c);
+                const VR x1[1] = {TR::vscale(isr, t)}, y1[1] = {t};
+                const VP p1[1] = {tP};
+                TR::template rank_update<1>(Bm, x1, y1, p1, c);
             }
-            av = vaxpy(eisr, t, av);
+            av = TR::vaxpy(eisr, t, av);
         }
         __syncwarp();
     };
@@ -706,10 +982,10 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
     }
     if constexpr (REV) {
         double* out = raggs + (nchunks - 1 - chunk) * (3 * DD + D);
-        gst_mat<D, MT, true>(out, Abt, 1.0, sp);
-        gst_mat<D, MT>(out + DD, Ba, 1.0, sp);
-        gst_mat<D, MT>(out + 2 * DD, Bm, 1.0, sp);
-        gst_vr<D, MT>(out + 3 * DD, av, r, c);
+        TR::template gst_mat<true>(out, Abt, 1.0, sp, r, c);
+        TR::template gst_mat<false>(out + DD, Ba, 1.0, sp, r, c);
+        TR::template gst_mat<false>(out + 2 * DD, Bm, 1.0, sp, r, c);
+        TR::gst_vr(out + 3 * DD, av, r, c);
     }
 }
 
@@ -717,10 +993,10 @@ fk2_forward(Params p, int L, long nchunks, const double* __restrict__ fstates, d
 // K3: reverse pass — smoothed moments (SMOOTH) and / or gradient of the log-likelihood (ADJ).
 // ------------------------------------------------------------------------------------------------
 template <int D, bool SMOOTH, bool ADJ> struct FK3 {
-    using G = FGeo<D>;
+    using TR = typename TraitsFor<D>::type;
     static constexpr int NSLOT = frag_nslot<D>() < 3 ? 3 : frag_nslot<D>();
-    static constexpr int SLOT = 3 * G::MSZ + G::DP;  // F | Q | fP | fm
-    static constexpr int WPC = frag_warps<D>(SLOT, D <= 8 ? PSSGP_FRAG_CAP_SMALL : 10);
+    static constexpr int SLOT = 3 * TR::MSZ + TR::VSZ;  // F | Q | fP | fm
+    static constexpr int WPC = frag_warps<D>(SLOT, frag_cap<D>(10));
     static constexpr size_t WARP_SMEM = (size_t)NSLOT * SLOT * 8;
     static constexpr size_t SMEM = (size_t)WPC * WARP_SMEM;
 };
@@ -729,8 +1005,11 @@ template <int D, bool SMOOTH, bool ADJ>
 __global__ void __launch_bounds__(FK3<D, SMOOTH, ADJ>::WPC * 32)
 fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, double* __restrict__ part) {
     using K = FK3<D, SMOOTH, ADJ>;
-    using G = typename K::G;
-    constexpr int MT = G::MT, MSZ = G::MSZ, NSLOT = K::NSLOT, DD = G::DD;
+    using TR = typename K::TR;
+    using M = typename TR::M;
+    using VR = typename TR::VR;
+    using VP = typename TR::VP;
+    constexpr int MSZ = TR::MSZ, NSLOT = K::NSLOT, DD = D * D;
     constexpr int O_P = 2 * MSZ, O_M = 3 * MSZ;
     extern __shared__ __align__(16) double smem[];
     const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31, r = lane >> 2, c = lane & 3;
@@ -743,9 +1022,9 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
     const long k_hi = (k_lo + L < p.n) ? k_lo + L : p.n;
     const int nrows = (int)(k_hi - k_lo);
     constexpr int PD = NSLOT - 1;
-    CpPlan<D, MT> cp;
+    typename TR::Cp cp;
     cp.init(lane);
-    StPlan<D, MT> sp;
+    typename TR::St sp;
     sp.init(r, c);
     auto slot = [&](long row) { return ring + (int)((row + 8L * NSLOT) % NSLOT) * K::SLOT; };
     auto issue = [&](int j) {
@@ -758,27 +1037,25 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
             }
             if (row >= 0) {
                 cp.issue(lane, sl + O_P, p.fPs_in + row * DD);
-                issue_vec<D>(lane, sl + O_M, p.fms_in + row * D);
+                TR::issue_vec(lane, sl + O_M, p.fms_in + row * D);
             } else {
                 cp.issue(lane, sl + O_P, p.P0);
-                if (p.m0 != nullptr) issue_vec<D>(lane, sl + O_M, p.m0);
-                else if (lane < D) sl[O_M + lane] = 0.0;
+                if (p.m0 != nullptr) TR::issue_vec(lane, sl + O_M, p.m0);
+                else TR::zero_vec(lane, sl + O_M);
             }
         }
         cp_commit();
     };
 #pragma unroll 1
     for (int j = 0; j < PD; ++j) issue(j);
-    const VecP<MT> hP = gld_vp<D, MT>(p.H, c);
-    const VecR<MT> hR = gld_vr<D, MT>(p.H, r);
+    const VP hP = TR::gld_vp(p.H, c);
+    const VR hR = TR::gld_vr(p.H, r);
     const double Rv = p.R[0];
     const double gl = ADJ ? p.g[0] : 1.0;
     const double* st = rstates + (nchunks - 1 - chunk) * (2 * DD + 2 * D);
-    VecR<MT> dm = gld_vr<D, MT>(st, r), lam = gld_vr<D, MT>(st + D, r);
-    Mat<MT> dP = gld_mat<D, MT>(st + 2 * D, r, c), Lam = gld_mat<D, MT>(st + 2 * D + DD, r, c);
-    VecR<MT> dHacc;
-#pragma unroll
-    for (int t = 0; t < MT; ++t) dHacc.v[t] = 0.0;
+    VR dm = TR::gld_vr(st, r), lam = TR::gld_vr(st + D, r);
+    M dP = TR::gld_mat(st + 2 * D, r, c), Lam = TR::gld_mat(st + 2 * D + DD, r, c);
+    VR dHacc = TR::vzero();
     double dRacc = 0.0;
     double ynext = p.y[k_hi - 1];
     // one visited row; FIRST (compile-time) = step 0 of the global series, peeled out of the steady-state loop
@@ -795,35 +1072,29 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
         const double* slp = slot(k - 1);
         if constexpr (SMOOTH) {
             // sm_k = m_k - P_k lam_k ; sP_k = P_k - P_k Lam_k P_k   (state entering from above)
-            const auto Pk = in_op<MT>(sl + O_P, false, r, c);
-            const Mat<MT> Zt = mulT<MT, D>(Pk, Lam);  // P_k Lam = (Lam P_k)^T
-            Mat<MT> PZ = mulT<MT, D>(Pk, Zt);         // P_k (Lam P_k)
-#pragma unroll
-            for (int a = 0; a < MT; ++a)
-#pragma unroll
-                for (int b2 = 0; b2 < MT; ++b2) {
-                    PZ.v[a][b2][0] = oget<MT>(Pk, a, b2, 0) - PZ.v[a][b2][0];
-                    PZ.v[a][b2][1] = oget<MT>(Pk, a, b2, 1) - PZ.v[a][b2][1];
-                }
-            gst_mat<D, MT>(p.sPs + k * DD, PZ, 1.0, sp);
-            const VecR<MT> v1 = mv(Pk, vr2vp(lam, c));
-            const VecR<MT> mk = ld_vr<MT>(sl + O_M, r);
-            gst_vr<D, MT>(p.sms + k * D, vaxpy(-1.0, v1, mk), r, c);
+            const auto Pk = TR::in_op(sl + O_P, false, r, c);
+            const M Zt = TR::mulT(Pk, Lam, c);  // P_k Lam = (Lam P_k)^T
+            const M PZ = TR::mulT(Pk, Zt, c);   // P_k (Lam P_k)
+            TR::template gst_mat<false>(p.sPs + k * DD, TR::op_minus(Pk, PZ), 1.0, sp, r, c);
+            const VR v1 = TR::mv(Pk, TR::vr2vp(lam, c));
+            const VR mk = TR::ld_vr(sl + O_M, r);
+            TR::gst_vr(p.sms + k * D, TR::vaxpy(-1.0, v1, mk), r, c);
         }
         // forward quantities of step k
-        const auto F = in_op<MT>(sl, false, r, c);
-        const auto Ft = in_op<MT>(sl, true, r, c);
-        const auto Pprev = in_op<MT>(slp + O_P, false, r, c);
-        const VecR<MT> mprev = ld_vr<MT>(slp + O_M, r);
-        Mat<MT> Pp = ld_sym<MT>(sl + MSZ, r, c);
+        const auto F = TR::in_op(sl, false, r, c);
+        const auto Ft = TR::in_op(sl, true, r, c);
+        const auto Pprev = TR::in_op(slp + O_P, false, r, c);
+        const VR mprev = TR::ld_vr(slp + O_M, r);
+        M Pp = TR::ld_sym(sl + MSZ, r, c);
         {
-            const Mat<MT> T1 = mulT<MT, D>(F, Pprev);
-            mmT<MT, D>(Pp, T1, F);
+            const M T1 = TR::mulT(F, Pprev, c);
+            TR::mmT(Pp, T1, F, c);
         }
-        const VecR<MT> mp = mv(F, ld_vp<MT>(slp + O_M, c));
-        VecR<MT> u = mv(Pp, hP);
+        const VP mprevP = TR::ld_vp(slp + O_M, c);
+        const VR mp = TR::mv(F, mprevP);
+        VR u = TR::mv(Pp, hP);
         double hu, hm;
-        dots2<MT>(hR, u, hR, mp, lane, c, hu, hm);
+        TR::dots2(hR, u, hR, mp, lane, c, hu, hm);
         const double s = Rv + hu;
         const double rr = obs ? yk - hm : 0.0;
         if constexpr (first) {
@@ -836,57 +1107,51 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
                     sbar0 = 0.5 * (rr * rr * is * is - is);
                     rbar0 = -rr * is;
                     dRacc += sbar0;
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) dHacc.v[t] += 2.0 * sbar0 * u.v[t] - mp.v[t] * rbar0;
+                    dHacc = TR::vlin3(1.0, dHacc, 2.0 * sbar0, u, -rbar0, mp);
                 }
-                Mat<MT> dPp0;
-                mzero(dPp0);
+                M dPp0 = TR::zero();
                 {
-                    const VecR<MT> x1[1] = {vscale(sbar0, hR)}, y1[1] = {hR};
-                    rank_update<MT, 1>(dPp0, x1, y1, c);
+                    const VR x1[1] = {TR::vscale(sbar0, hR)}, y1[1] = {hR};
+                    const VP p1[1] = {hP};
+                    TR::template rank_update<1>(dPp0, x1, y1, p1, c);
                 }
-                const VecR<MT> dmp0 = vscale(-rbar0, hR);
-                gst_mat<D, MT>(p.dQs + k * DD, dPp0, gl, sp);
-                const Mat<MT> X = mulT<MT, D>(dPp0, Ft);   // dPp0 F
-                const Mat<MT> Xt = mulT<MT, D>(Ft, dPp0);  // F^T dPp0
-                Mat<MT> Y = mulT<MT, D>(X, Pprev);
+                const VR dmp0 = TR::vscale(-rbar0, hR);
+                TR::template gst_mat<false>(p.dQs + k * DD, dPp0, gl, sp, r, c);
+                const M X = TR::mulT(dPp0, Ft, c);   // dPp0 F
+                const M Xt = TR::mulT(Ft, dPp0, c);  // F^T dPp0
+                M Y = TR::mulT(X, Pprev, c);
                 {
-                    const VecR<MT> x1[1] = {vscale(0.5, dmp0)}, y1[1] = {mprev};
-                    rank_update<MT, 1>(Y, x1, y1, c);
+                    const VR x1[1] = {TR::vscale(0.5, dmp0)}, y1[1] = {mprev};
+                    const VP p1[1] = {mprevP};
+                    TR::template rank_update<1>(Y, x1, y1, p1, c);
                 }
-                gst_mat<D, MT>(p.dFs + k * DD, Y, 2.0 * gl, sp);
-                Mat<MT> dP0 = mulT<MT, D>(Xt, Ft);  // F^T dPp0 F
+                TR::template gst_mat<false>(p.dFs + k * DD, Y, 2.0 * gl, sp, r, c);
+                M dP0 = TR::mulT(Xt, Ft, c);  // F^T dPp0 F
                 // adjoint of the update on (m0, P0)
-                u = mv(Pprev, hP);
+                u = TR::mv(Pprev, hP);
                 double hu0, hm0;
-                dots2<MT>(hR, u, hR, mprev, lane, c, hu0, hm0);
+                TR::dots2(hR, u, hR, mprev, lane, c, hu0, hm0);
                 const double s0 = Rv + hu0, r0 = yk - hm0;
                 if (obs) {
-                    const VecR<MT> Pu = mv(dP, vr2vp(u, c));
+                    const VR Pu = TR::mv(dP, TR::vr2vp(u, c));
                     double udm, uPu;
-                    dots2<MT>(u, dm, u, Pu, lane, c, udm, uPu);
+                    TR::dots2(u, dm, u, Pu, lane, c, udm, uPu);
                     const double is0 = 1.0 / s0;
                     const double rbar = udm * is0;
                     const double sbar = (-udm * r0 + uPu) * is0 * is0;
-                    VecR<MT> ut;
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) ut.v[t] = dm.v[t] * r0 * is0 - 2.0 * Pu.v[t] * is0 + sbar * hR.v[t];
-                    const VecR<MT> Pput = mv(Pprev, vr2vp(ut, c));
+                    const VR ut = TR::vlin3(r0 * is0, dm, -2.0 * is0, Pu, sbar, hR);
+                    const VP utP = TR::vr2vp(ut, c);
+                    const VR Pput = TR::mv(Pprev, utP);
                     dRacc += sbar;
-#pragma unroll
-                    for (int t = 0; t < MT; ++t) dHacc.v[t] += sbar * u.v[t] + Pput.v[t] - mprev.v[t] * rbar;
-                    const VecR<MT> x2[2] = {vscale(0.5, ut), vscale(0.5, hR)}, y2[2] = {hR, ut};
-                    rank_update<MT, 2>(dP, x2, y2, c);
+                    dHacc = TR::vaxpy(sbar, u, dHacc);
+                    dHacc = TR::vlin3(1.0, dHacc, 1.0, Pput, -rbar, mprev);
+                    const VR x2[2] = {TR::vscale(0.5, ut), TR::vscale(0.5, hR)}, y2[2] = {hR, ut};
+                    const VP p2[2] = {hP, utP};
+                    TR::template rank_update<2>(dP, x2, y2, p2, c);
                 }
                 if (p.dP0 != nullptr) {
-#pragma unroll
-                    for (int a = 0; a < MT; ++a)
-#pragma unroll
-                        for (int b2 = 0; b2 < MT; ++b2) {
-                            dP0.v[a][b2][0] += dP.v[a][b2][0];
-                            dP0.v[a][b2][1] += dP.v[a][b2][1];
-                        }
-                    gst_mat<D, MT>(p.dP0, dP0, gl, sp);
+                    TR::madd(dP0, dP);
+                    TR::template gst_mat<false>(p.dP0, dP0, gl, sp, r, c);
                 }
             }
             __syncwarp();
@@ -894,59 +1159,59 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
         }
         // measurement part (all terms vanish with is = 0 when nothing is observed)
         const double is = obs ? 1.0 / s : 0.0;
-        const VecP<MT> uP = vr2vp(u, c);
-        VecR<MT> Pu = u, gv = u;
-        if constexpr (ADJ) Pu = mv(dP, uP);
-        if constexpr (SMOOTH) gv = mv(Lam, uP);
+        const VP uP = TR::vr2vp(u, c);
+        VR Pu = u, gv = u;
+        if constexpr (ADJ) Pu = TR::mv(dP, uP);
+        if constexpr (SMOOTH) gv = TR::mv(Lam, uP);
         double dv[4];
         {
-            const VecR<MT>* const xa[4] = {&u, &u, &u, &u};
-            const VecR<MT>* const xb[4] = {&dm, &Pu, &lam, &gv};
-            dots4<MT>(xa, xb, lane, c, dv);
+            const VR* const xa[4] = {&u, &u, &u, &u};
+            const VR* const xb[4] = {&dm, &Pu, &lam, &gv};
+            TR::dots4(xa, xb, lane, c, dv);
         }
         const double udm = ADJ ? dv[0] : 0.0, uPu = ADJ ? dv[1] : 0.0, ulam = SMOOTH ? dv[2] : 0.0,
                      alpha = SMOOTH ? dv[3] : 0.0;
         const double rbar = (udm - rr) * is;
         const double sbar = (-udm * rr + uPu) * is * is + 0.5 * (rr * rr * is * is - is);
-        VecR<MT> dmp = dm, lt = lam;
+        VR dmp = dm, lt = lam;
         if constexpr (ADJ) {
-            VecR<MT> ut;
-#pragma unroll
-            for (int t = 0; t < MT; ++t) {
-                ut.v[t] = dm.v[t] * rr * is - 2.0 * Pu.v[t] * is + sbar * hR.v[t];
-                dmp.v[t] = dm.v[t] - hR.v[t] * rbar;
-            }
-            const VecR<MT> Pput = mv(Pp, vr2vp(ut, c));
+            const VR ut = TR::vlin3(rr * is, dm, -2.0 * is, Pu, sbar, hR);
+            dmp = TR::vaxpy(-rbar, hR, dm);
+            const VP utP = TR::vr2vp(ut, c);
+            const VR Pput = TR::mv(Pp, utP);
             dRacc += sbar;
-#pragma unroll
-            for (int t = 0; t < MT; ++t) dHacc.v[t] += sbar * u.v[t] + Pput.v[t] - mp.v[t] * rbar;
-            const VecR<MT> x2[2] = {vscale(0.5, ut), vscale(0.5, hR)}, y2[2] = {hR, ut};
-            rank_update<MT, 2>(dP, x2, y2, c);  // dPp = dP + sym(ut h^T)
-            gst_mat<D, MT>(p.dQs + k * DD, dP, gl, sp);
-            const Mat<MT> X = mulT<MT, D>(dP, Ft);     // dPp F
-            const Mat<MT> Xt = mulT<MT, D>(Ft, dP);    // F^T dPp
-            Mat<MT> Y = mulT<MT, D>(X, Pprev);         // dPp F P_{k-1}
+            dHacc = TR::vaxpy(sbar, u, dHacc);
+            dHacc = TR::vlin3(1.0, dHacc, 1.0, Pput, -rbar, mp);
             {
-                const VecR<MT> x1[1] = {vscale(0.5, dmp)}, y1[1] = {mprev};
-                rank_update<MT, 1>(Y, x1, y1, c);
+                const VR x2[2] = {TR::vscale(0.5, ut), TR::vscale(0.5, hR)}, y2[2] = {hR, ut};
+                const VP p2[2] = {hP, utP};
+                TR::template rank_update<2>(dP, x2, y2, p2, c);  // dPp = dP + sym(ut h^T)
             }
-            gst_mat<D, MT>(p.dFs + k * DD, Y, 2.0 * gl, sp);
-            dP = mulT<MT, D>(Xt, Ft);                  // F^T dPp F
-            dm = mv(Ft, vr2vp(dmp, c));         // F^T dmp
+            TR::template gst_mat<false>(p.dQs + k * DD, dP, gl, sp, r, c);
+            const M X = TR::mulT(dP, Ft, c);     // dPp F
+            const M Xt = TR::mulT(Ft, dP, c);    // F^T dPp
+            M Y = TR::mulT(X, Pprev, c);         // dPp F P_{k-1}
+            {
+                const VR x1[1] = {TR::vscale(0.5, dmp)}, y1[1] = {mprev};
+                const VP p1[1] = {mprevP};
+                TR::template rank_update<1>(Y, x1, y1, p1, c);
+            }
+            TR::template gst_mat<false>(p.dFs + k * DD, Y, 2.0 * gl, sp, r, c);
+            dP = TR::mulT(Xt, Ft, c);            // F^T dPp F
+            dm = TR::mv(Ft, TR::vr2vp(dmp, c));  // F^T dmp
         }
         if constexpr (SMOOTH) {
             const double cm = is + alpha * is * is;
-            VecR<MT> xv;
-#pragma unroll
-            for (int t = 0; t < MT; ++t) {
-                lt.v[t] = lam.v[t] - hR.v[t] * (ulam + rr) * is;
-                xv.v[t] = -gv.v[t] * is + 0.5 * cm * hR.v[t];
+            lt = TR::vaxpy(-(ulam + rr) * is, hR, lam);
+            const VR xv = TR::vlin3(-is, gv, 0.5 * cm, hR, 0.0, hR);
+            {
+                const VR x2[2] = {hR, xv}, y2[2] = {xv, hR};
+                const VP p2[2] = {TR::vp_for_rank(xv, c), hP};
+                TR::template rank_update<2>(Lam, x2, y2, p2, c);  // Lt = Lam - (h g^T + g h^T)/s + h h^T (1/s + alpha/s^2)
             }
-            const VecR<MT> x2[2] = {hR, xv}, y2[2] = {xv, hR};
-            rank_update<MT, 2>(Lam, x2, y2, c);  // Lt = Lam - (h g^T + g h^T)/s + h h^T (1/s + alpha/s^2)
-            const Mat<MT> X2t = mulT<MT, D>(Ft, Lam);   // F^T Lt
-            Lam = mulT<MT, D>(X2t, Ft);                 // F^T Lt F
-            lam = mv(Ft, vr2vp(lt, c));
+            const M X2t = TR::mulT(Ft, Lam, c);   // F^T Lt
+            Lam = TR::mulT(X2t, Ft, c);           // F^T Lt F
+            lam = TR::mv(Ft, TR::vr2vp(lt, c));
         }
         __syncwarp();
     };
@@ -957,11 +1222,7 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
     cp_wait<0>();
     if constexpr (ADJ) {
         if (lane == 0) part[chunk * (1 + D)] = dRacc;
-        if (c == 0) {
-#pragma unroll
-            for (int t = 0; t < MT; ++t)
-                if (8 * t + r < D) part[chunk * (1 + D) + 1 + 8 * t + r] = dHacc.v[t];
-        }
+        TR::gst_vr(part + chunk * (1 + D) + 1, dHacc, r, c);
     }
 }
 

@@ -25,7 +25,7 @@ template <int D> constexpr bool has_frag() { return D <= 24; }
 static thread_local int g_mid_warps = 0;  // option "mid_warps" of the handle in use (0 = compile-time default)
 // measured (scripts/sweep_mid_warps.py, N = 1e6): d = 6 gains up to the 24 warps that fit; d = 9 / d = 16 are fastest with 8
 static int cap_warps(int wpc) {
-    const int lim = g_mid_warps > 0 ? g_mid_warps : (MID_D > 8 ? 8 : 1000);
+    const int lim = g_mid_warps > 0 ? g_mid_warps : (MID_D > 9 ? 8 : 1000);
     return lim < wpc ? lim : wpc;
 }
 
