@@ -693,10 +693,13 @@ template <int D> constexpr int frag_warps(int slot_doubles, int cap) {
     const int fit = (200 * 1024) / (frag_nslot<D>() * slot_doubles * 8);
     return fit > cap ? cap : (fit < 1 ? 1 : fit);
 }
+#ifndef PSSGP_FRAG_CAP_D9
+#define PSSGP_FRAG_CAP_D9 16
+#endif
 #ifndef PSSGP_FRAG_CAP_SMALL
 #define PSSGP_FRAG_CAP_SMALL 24
 #endif
-template <int D> constexpr int frag_cap(int big) { return (D <= 8) ? PSSGP_FRAG_CAP_SMALL : (D == 9 ? 16 : big); }
+template <int D> constexpr int frag_cap(int big) { return (D <= 8) ? PSSGP_FRAG_CAP_SMALL : (D == 9 ? PSSGP_FRAG_CAP_D9 : big); }
 
 // ------------------------------------------------------------------------------------------------
 // K1: chunk aggregates of the filter.  Tracks At = A^T, C, J, b, eta.
