@@ -97,6 +97,10 @@ def extra_configs(world):
             baseline_config=3, kern=lambda K: K.Periodic(K.SquaredExponential(5.0, 1.0), period=1.0, order=5) * K.Matern32(0.1, 50.0),
             noise=0.05, series=make_series_weekly, n_total=1_000_000, scaling="single-gpu",
             what="Periodic(SE(5,1), period 1, order 5) x Matern32(0.1, 50) (CO2-shaped, d = 24), N = 1e6, FP64, 1 GPU"),
+        "qp5_n1e6_fp32": dict(
+            baseline_config=3, kern=lambda K: K.Periodic(K.SquaredExponential(5.0, 1.0), period=1.0, order=5) * K.Matern32(0.1, 50.0),
+            noise=0.05, series=make_series_weekly, n_total=1_000_000, scaling="single-gpu", dtype="f32",
+            what="the same in the FP32 opt-in mode (FP32 storage at the C ABI, FP64 arithmetic in the DMMA kernels)"),
         "m52rbf6_n1p25e7_per_gpu": dict(
             baseline_config=4, kern=lambda K: K.Matern52(1.0, 1.0) + K.RBF(1.0, 1.0, order=6, balancing_iter=5), noise=NOISE,
             series=make_series, n_total=12_500_000 * world, scaling="weak",
@@ -245,6 +249,8 @@ def shard_lgssm(cfg, world, rank, dev, torch, kernels, ops):
     dts = t_dev - torch.cat([torch.tensor([t_prev], dtype=torch.float64, device=dev), t_dev[:-1]])
     y_dev = torch.as_tensor(y_host[lo:hi]).to(dev)
     Fs, Qs = ops.discretise(F, Pinf, dts)
+    if cfg.get("dtype") == "f32":
+        Pinf, Fs, Qs, H, R, y_dev = (x.float().contiguous() for x in (Pinf, Fs, Qs, H, R, y_dev))
     return n, Pinf, Fs, Qs, H, R, y_dev, (t_host, y_host)
 
 
@@ -271,7 +277,8 @@ def run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels,
         return {"skipped": "single-GPU configuration: measured at n_gpus = 1"}
     n, Pinf, Fs, Qs, H, R, y_dev, _ = shard_lgssm(cfg, world, rank, dev, torch, kernels, ops)
     d = Fs.shape[1]
-    g_ll = torch.ones(1, dtype=torch.float64, device=dev)
+    g_ll = torch.ones(1, dtype=Fs.dtype, device=dev)
+    esz = Fs.element_size()
     shard = pdist.TimeShard(rank, world, dist, exchange=xchg) if world > 1 else None
 
     def step():
@@ -289,12 +296,12 @@ def run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels,
     h.set_option("timing", 0)
     del out
     n_total = n * world
-    alg = 8 * (12 * d * d + 4 * d + 2)
+    alg = esz * (12 * d * d + 4 * d + 2)
     gbs = alg * n_total / (ms * 1e-3) / 1e9
     flops = 30.0 * d ** 3  # useful flops of this implementation per time step: 15 d x d products (K1 3, K2 3, K3 9)
     tfl = flops * n_total / (ms * 1e-3) / 1e12
     entry = {
-        "baseline_config": cfg["baseline_config"], "workload": cfg["what"], "state_dim": d, "dtype": "f64",
+        "baseline_config": cfg["baseline_config"], "workload": cfg["what"], "state_dim": d, "dtype": "f64" if esz == 8 else "f32 storage / f64 arithmetic",
         "n_total": n_total, "n_per_gpu": n, "n_gpus": world, "scaling": cfg["scaling"], "steps": K, "warmup": W,
         "ms_per_step": ms, "value": n_total / (ms * 1e-3), "unit": UNIT,
         "roofline": {"bound": "hbm" if d <= 9 else "fp64", "alg_bytes_per_timestep": alg, "achieved_gbs": gbs,

@@ -437,6 +437,11 @@ int pssgp_pkfs_grad(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0
                                        (const double*)R, (const double*)y, (const double*)g_ll, (double*)fms, (double*)fPs,
                                        (double*)ll, (double*)sms, (double*)sPs, (double*)dP0, (double*)dFs, (double*)dQs,
                                        (double*)dH, (double*)dR, st);
+    if (dtype == PSSGP_F32 && mid::supported(d) && !h->force_generic)
+        return mid::f32_pkfs_grad(h, n, d, (const float*)P0, (const float*)Fs, (const float*)Qs, (const float*)H,
+                                  (const float*)R, (const float*)y, (const float*)g_ll, (float*)fms, (float*)fPs, (float*)ll,
+                                  (float*)sms, (float*)sPs, (float*)dP0, (float*)dFs, (float*)dQs, (float*)dH, (float*)dR,
+                                  false, st);
     // generic state dimension (or no common partition): the three scans one after the other
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;
     if (sms != nullptr)
@@ -542,6 +547,10 @@ int pssgp_pkfs(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, con
         return mid::pkfs_grad_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
                                        (const double*)R, (const double*)y, nullptr, (double*)fms, (double*)fPs, (double*)ll,
                                        (double*)sms, (double*)sPs, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+    if (!proj && dtype == PSSGP_F32 && mid::supported(d) && !h->force_generic)
+        return mid::f32_pkfs_grad(h, n, d, (const float*)P0, (const float*)Fs, (const float*)Qs, (const float*)H,
+                                  (const float*)R, (const float*)y, nullptr, (float*)fms, (float*)fPs, (float*)ll, (float*)sms,
+                                  (float*)sPs, nullptr, nullptr, nullptr, nullptr, nullptr, false, st);
     if (proj) return set_err(PSSGP_ERR_UNSUPPORTED, "pkfs: projected output is implemented for the fused d <= 4 path only "
                                                     "(d = %d): pass sms / sPs", d);
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;

@@ -405,6 +405,11 @@ int pkf_generic(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, co
         return mid::pkf_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
                                  (const double*)R, (const double*)y, (const double*)m0, first_special, (double*)fms,
                                  (double*)fPs, (double*)ll, (double*)final_state, (double*)summary, st);
+    if (dtype == PSSGP_F32 && mid::supported(d) && !h->force_generic && m0 == nullptr && first_special &&
+        final_state == nullptr && summary == nullptr)
+        return mid::f32_pkfs_grad(h, n, d, (const float*)P0, (const float*)Fs, (const float*)Qs, (const float*)H,
+                                  (const float*)R, (const float*)y, nullptr, (float*)fms, (float*)fPs, (float*)ll, nullptr,
+                                  nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, true, st);
     if (dtype == PSSGP_F64)
         return pkf_generic_t<double>(h, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, final_state, summary, st);
     return pkf_generic_t<float>(h, n, d, P0, Fs, Qs, H, R, y, m0, first_special, fms, fPs, ll, final_state, summary, st);

@@ -39,6 +39,11 @@ template <int D>
 int rev_fold(pssgp_handle* h, const double* summaries, int count, int64_t stride, double* state_out, cudaStream_t st);
 
 bool supported(int d);
+// FP32 storage, FP64 arithmetic (mid_f32.cu)
+int f32_pkfs_grad(pssgp_handle* h, int64_t n, int d, const float* P0, const float* Fs, const float* Qs, const float* H,
+                  const float* R, const float* y, const float* g_ll, float* fms, float* fPs, float* ll, float* sms,
+                  float* sPs, float* dP0, float* dFs, float* dQs, float* dH, float* dR, bool filter_only,
+                  cudaStream_t st);
 int shard_forward_dispatch(int d, pssgp_handle* h, int64_t n, const double* P0, const double* Fs, const double* Qs,
                            const double* H, const double* R, const double* y, const double* m0, int first_special,
                            double* fms, double* fPs, double* ll, double* rev_summary, cudaStream_t st);

@@ -85,3 +85,35 @@ def test_fused_step_chunk_invariance(name, tol, chunk, smem):
     if smem and name == "qp5":
         pytest.skip("d > 16 always runs the shared-memory family")
     check(name, tol, 1200, seed=9, chunk=chunk, smem=smem)
+
+
+@pytest.mark.parametrize("name,tol", [("rbf6", 2e-6), ("m52+rbf6", 2e-6), ("qp3", 2e-5), ("qp5", 2e-4)])
+def test_fp32_storage_mode(name, tol):
+    """FP32 opt-in mode at 5 <= d <= 32 = FP32 storage at the C ABI, FP64 arithmetic (csrc/mid_f32.cu): on inputs that
+    are exactly representable in FP32 the results equal the oracle's up to the FP32 rounding of the outputs."""
+    pkg()
+    from pssgp_b200 import ops
+    T = 1500
+    span = 40.0 if name.startswith("qp") else 4.0
+    t, y, cov, ssm = make_problem(name, T, seed=21, span=span)
+    ssm = ssm._replace(Qs=sym(ssm.Qs))
+    ssm32 = type(ssm)(*[x.float().double() for x in ssm])
+    ssm32 = ssm32._replace(Qs=sym(ssm32.Qs), P0=sym(ssm32.P0))
+    y32 = torch.as_tensor(y).float().double().numpy()
+    g = 1.0
+    rfm, rfP, rll, rsm, rsP, (gP0, gFs, gQs, gH, gR) = oracle_all(ssm32, y32, T, g)
+    to = lambda x: x.detach().to(device=DEV, dtype=torch.float32).contiguous()
+    P0, Fs, Qs, H, R = to(ssm32.P0), to(ssm32.Fs), to(ssm32.Qs), to(ssm32.H).reshape(-1), to(ssm32.R).reshape(-1)
+    yd = torch.as_tensor(y32).to(device=DEV, dtype=torch.float32)
+    (fms, fPs, ll), (sms, sPs), (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(P0, Fs, Qs, H, R, yd,
+                                                                     torch.tensor([g], dtype=torch.float32, device=DEV))
+    assert fms.dtype == torch.float32 and dFs.dtype == torch.float32
+    c = lambda x: x.double().cpu()
+    assert rel_err(c(fms), rfm) < tol and rel_err(c(fPs), rfP) < tol
+    assert abs(float(ll) - float(rll)) <= tol * max(1.0, abs(float(rll)))
+    assert rel_err(c(sms), rsm) < tol and rel_err(c(sPs), rsP) < tol
+    assert rel_err(c(dFs), gFs) < tol and rel_err(c(dQs), sym(gQs)) < tol
+    f2, fP2, ll2, s2, sP2 = ops.pkfs(P0, Fs, Qs, H, R, yd, want_ll=True)
+    assert rel_err(c(s2), rsm) < tol and rel_err(c(sP2), rsP) < tol
+    f3, fP3, ll3, _ = ops.pkf(P0, Fs, Qs, H, R, yd)
+    assert rel_err(c(f3), rfm) < tol and abs(float(ll3) - float(rll)) <= tol * max(1.0, abs(float(rll)))
