@@ -275,7 +275,21 @@ def run_extra_config(name, cfg, world, rank, dev, dist, barrier, torch, kernels,
                      with_cpu, xchg=None):
     if cfg["scaling"] == "single-gpu" and world > 1:
         return {"skipped": "single-GPU configuration: measured at n_gpus = 1"}
-    n, Pinf, Fs, Qs, H, R, y_dev, _ = shard_lgssm(cfg, world, rank, dev, torch, kernels, ops)
+    # set-up (allocations, discretisation) first; the ranks then agree that everybody is ready before any collective
+    # or peer exchange of the timed steps is issued (a rank that failed here must not leave the others waiting)
+    setup_err = None
+    try:
+        n, Pinf, Fs, Qs, H, R, y_dev, _ = shard_lgssm(cfg, world, rank, dev, torch, kernels, ops)
+        torch.cuda.synchronize()
+    except Exception as e:
+        setup_err = repr(e)
+    if dist is not None:
+        ok = torch.tensor([0.0 if setup_err else 1.0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok) == 0.0:
+            return {"error": setup_err or "set-up failed on another rank"}
+    elif setup_err:
+        return {"error": setup_err}
     d = Fs.shape[1]
     g_ll = torch.ones(1, dtype=Fs.dtype, device=dev)
     esz = Fs.element_size()
