@@ -117,3 +117,44 @@ def test_fp32_storage_mode(name, tol):
     assert rel_err(c(s2), rsm) < tol and rel_err(c(sP2), rsP) < tol
     f3, fP3, ll3, _ = ops.pkf(P0, Fs, Qs, H, R, yd)
     assert rel_err(c(f3), rfm) < tol and abs(float(ll3) - float(rll)) <= tol * max(1.0, abs(float(rll)))
+
+
+def _random_lgssm(d, T, seed):
+    """A stable random LGSSM of state dimension d (not tied to a covariance function): covers every compiled
+    instantiation of the warp-level path, including exact multiples of the 8 x 8 tile and the shared-memory family."""
+    g = torch.Generator().manual_seed(seed)
+    A = torch.randn(d, d, dtype=torch.float64, generator=g) / (2.0 * d ** 0.5)
+    F0 = torch.linalg.matrix_exp(A - 0.6 * torch.eye(d, dtype=torch.float64))
+    dts = 0.5 + torch.rand(T, dtype=torch.float64, generator=g)
+    Fs = torch.stack([torch.linalg.matrix_power(F0, 1) * (0.9 + 0.1 * float(x)) for x in dts])
+    B = torch.randn(T, d, d, dtype=torch.float64, generator=g) / d ** 0.5
+    Qs = 0.05 * (B @ B.transpose(-1, -2)) + 0.01 * torch.eye(d, dtype=torch.float64)
+    B0 = torch.randn(d, d, dtype=torch.float64, generator=g) / d ** 0.5
+    P0 = B0 @ B0.T + 0.1 * torch.eye(d, dtype=torch.float64)
+    H = torch.randn(d, dtype=torch.float64, generator=g)
+    R = torch.tensor([0.3], dtype=torch.float64)
+    y = torch.randn(T, dtype=torch.float64, generator=g)
+    y[torch.rand(T, generator=g) < 0.1] = float("nan")
+    return P0, Fs, Qs, H, R, y
+
+
+@pytest.mark.parametrize("d", [5, 7, 8, 10, 12, 13, 15, 16, 17, 20, 23, 24, 25, 28, 31, 32])
+def test_every_dimension_against_the_cta_cooperative_path(d):
+    """Warp-level DMMA path (fragment family d <= 24, shared-memory family above, bordered form at d = 9 is covered by
+    the kernel cases) against the independent CTA-cooperative kernels of generic.cu (option force_generic: RTS element
+    smoother, separate adjoint scan), which the oracle tests validate: 1e-9 on every output of the fused step."""
+    pkg()
+    from pssgp_b200 import _lib, ops
+    T = 257
+    P0, Fs, Qs, H, R, y = (x.to(DEV).contiguous() for x in _random_lgssm(d, T, seed=100 + d))
+    g = torch.tensor([1.2], dtype=torch.float64, device=DEV)
+    h = _lib.handle(0)
+    h.set_option("force_generic", 1)
+    try:
+        (rfm, rfP, rll), (rsm, rsP), (rdP0, rdF, rdQ, rdH, rdR) = ops.pkfs_grad(P0, Fs, Qs, H, R, y, g)
+    finally:
+        h.set_option("force_generic", 0)
+    (fm, fP, ll), (sm, sP), (dP0, dF, dQ, dH, dR) = ops.pkfs_grad(P0, Fs, Qs, H, R, y, g)
+    tol = 1e-9
+    for a, b in ((fm, rfm), (fP, rfP), (ll, rll), (sm, rsm), (sP, rsP), (dP0, rdP0), (dF, rdF), (dQ, rdQ), (dH, rdH), (dR, rdR)):
+        assert rel_err(a.cpu(), b.cpu()) < tol
