@@ -239,6 +239,29 @@ int pssgp_peer_exchange(pssgp_handle* h, const void* msg, int64_t nvals, void* c
                         void* seq_counter, void* err_counter, void* stream);
 
 /*
+ * Sequential Kalman filter for `batch` independent series.  Replaces pssgp/kalman/sequential.py:11-47 (kf): per step
+ * predict (mp = F m, Pp = sym(F P F^T + Q)), skip the update where y is NaN, else update with the scalar
+ * observation and add log N(y; H mp, H Pp H^T + R) to the log-likelihood; m0 = 0 as in the reference.
+ * y [batch,n]; lgssm_batched = 0: ONE LGSSM (P0 [d,d], Fs,Qs [n,d,d], H [d], R [1]) shared by all series,
+ * != 0: one per series (P0 [batch,d,d], Fs,Qs [batch,n,d,d], H [batch,d], R [batch]).  d <= 32.
+ * Outputs: fms [batch,n,d], fPs [batch,n,d,d]; mps, Pps (predicted moments, same shapes; both or neither: the
+ * reference's return_predicted); ll [batch] or NULL.  The parallel axis is the batch: one thread per series for
+ * d <= 4, one warp per series above.
+ */
+int pssgp_kf(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, int lgssm_batched,
+             const void* P0, const void* Fs, const void* Qs, const void* H, const void* R, const void* y,
+             void* fms, void* fPs, void* mps, void* Pps, void* ll, void* stream);
+/*
+ * Sequential RTS smoother.  Replaces pssgp/kalman/sequential.py:50-68 (ks): backwards from the last filtered state,
+ * C = P_k F_{k+1}^T Pp_{k+1}^-1 (Cholesky), sm_k = m_k + C (sm_{k+1} - mp_{k+1}),
+ * sP_k = sym(P_k + C (sP_{k+1} - Pp_{k+1}) C^T).  Inputs as produced by pssgp_kf; sms [batch,n,d], sPs [batch,n,d,d].
+ * A predicted covariance that is not positive definite gives NaNs from that step on (the reference raises).
+ */
+int pssgp_ks(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, int lgssm_batched,
+             const void* Fs, const void* fms, const void* fPs, const void* mps, const void* Pps,
+             void* sms, void* sPs, void* stream);
+
+/*
  * Adjoint of pssgp_discretise: (dFs, dQs) -> (dF, dPinf).  dF, dPinf: [d,d].
  */
 int pssgp_discretise_backward(pssgp_handle* h, int dtype, int64_t n, int d,

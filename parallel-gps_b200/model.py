@@ -22,7 +22,7 @@ class _LogLikelihood(torch.autograd.Function):
     """ll(F, Pinf, H, R; dts, y) with P0 = Pinf (kernels/base.py:47)."""
 
     @staticmethod
-    def forward(ctx, F, Pinf, H, R, dts, y):
+    def forward(ctx, F, Pinf, H, R, dts, y, sequential=False):
         device, dtype = dts.device, dts.dtype
         # the d x d SDE goes to the device as ONE pinned, asynchronous copy (four pageable copies would each
         # synchronise the host with the stream)
@@ -34,7 +34,16 @@ class _LogLikelihood(torch.autograd.Function):
         Hd, Rd = pd[2 * d * d:2 * d * d + d], pd[2 * d * d + d:2 * d * d + d + 1]
         Fs, Qs = ops.discretise(Fd, Pd, dts)
         ctx.host = (F.device, F.dtype, tuple(H.shape), tuple(R.shape))
-        if any(ctx.needs_input_grad[:4]):
+        if sequential:
+            # parallel=False (model.py:74-77): the sequential Kalman filter (C ABI pssgp_kf); the gradient comes from
+            # the adjoint scan on its filtered moments (the gradient is a function of (Fs, Qs, y, fms, fPs) only)
+            fms, fPs, ll, _, _ = ops.kf(Pd, Fs, Qs, Hd, Rd, y)
+            if any(ctx.needs_input_grad[:4]):
+                one = torch.ones(1, dtype=dtype, device=device)
+                dP0, dFs, dQs, dH, dR = ops.pkf_backward(Pd, Fs, Qs, Hd, Rd, y, fms, fPs, one)
+                dF, dPinf = ops.discretise_backward(Fd, Pd, dts, Fs, dFs, dQs)
+                ctx.save_for_backward(dF, dPinf + dP0, dH, dR)
+        elif any(ctx.needs_input_grad[:4]):
             # training step: the fused filter + adjoint call (C ABI pssgp_pkfs_grad without smoother) with unit upstream
             # gradient, then the discretisation adjoint; backward() only scales (the gradient is linear in g).  One pass
             # over (Fs, Qs, y) fewer than pkf followed by pkf_backward, and nothing of size N is kept for backward.
@@ -56,7 +65,7 @@ class _LogLikelihood(torch.autograd.Function):
         packed = packed * g.detach().to(device=hdev, dtype=hdt)
         gF, gP = packed[:d * d].reshape(d, d), packed[d * d:2 * d * d].reshape(d, d)
         gH, gR = packed[2 * d * d:2 * d * d + d].reshape(hshape), packed[2 * d * d + d:].reshape(rshape)
-        return gF, gP, gH, gR, None, None
+        return gF, gP, gH, gR, None, None, None
 
 
 def _merge_sorted_idx(a, b, *args):
@@ -89,20 +98,14 @@ def _merge_sorted(a, b, *args):
 
 
 class StateSpaceGP:
-    """model.py:58-117.  Both ``parallel`` values run the temporally-parallel CUDA path: the reference's sequential
-    ``kf`` / ``ks`` (pssgp/kalman/sequential.py, selected there by ``parallel=False``) compute the same quantities to
-    rounding and exist here only as the test comparator (oracle/).  ``parallel=False`` therefore warns once instead of
-    silently pretending to be sequential.  ``max_parallel`` (depth cap of TFP's recursion) is accepted and unused."""
-
-    _warned_sequential = False
+    """model.py:58-117.  ``parallel=True`` runs the temporally-parallel scan kernels (pkf / pkfs, model.py:78-84);
+    ``parallel=False`` — the reference's default — runs the sequential Kalman filter and RTS smoother (kf / kfs,
+    model.py:73-77; C ABI ``pssgp_kf`` / ``pssgp_ks``): one GPU thread or warp walks the series, which is the
+    comparator, not the fast path (≈ 0.3 µs per step).  ``max_parallel`` (depth cap of TFP's recursion) is accepted
+    and unused."""
 
     def __init__(self, data, kernel, noise_variance=1.0, parallel=False, max_parallel=10000, device=None):
         A.require_cuda()
-        if not parallel and not StateSpaceGP._warned_sequential:
-            import warnings
-            warnings.warn("pssgp_b200.StateSpaceGP(parallel=False): there is no sequential CUDA mode; the parallel-scan "
-                          "kernels are used (identical results to rounding)", stacklevel=2)
-            StateSpaceGP._warned_sequential = True
         self.noise_variance = Parameter(noise_variance, name="noise_variance")
         self.kernel = kernel
         self.parallel = parallel
@@ -172,7 +175,7 @@ class StateSpaceGP:
         sde = self.kernel.get_sde()
         R = self.noise_variance.value.reshape(1, 1)
         dts = time_steps(ts, 0., ts.dtype, ts.device)
-        return _LogLikelihood.apply(sde.F, sde.P0, sde.H, R, dts, Y.reshape(-1))
+        return _LogLikelihood.apply(sde.F, sde.P0, sde.H, R, dts, Y.reshape(-1), not self.parallel)
 
     def predict_f(self, Xnew, full_cov=False, full_output_cov=False, out=None):
         """model.py:92-111: merge query times as NaN observations, filter + smooth, project with H.
@@ -189,7 +192,14 @@ class StateSpaceGP:
             ssm = self._make_model(all_ts[:, None])
             Hd, Rd = ssm.H.reshape(-1).contiguous(), ssm.R.reshape(-1).contiguous()
             yv = all_ys.reshape(-1).contiguous()
-            if ops.has_projection(ssm.Fs.shape[1], dtype):
+            if not self.parallel:
+                # model.py:76-77: kfs = sequential filter (with predicted moments) + sequential RTS smoother
+                fms, fPs, _, mps, Pps = ops.kf(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, want_ll=False, want_predicted=True)
+                sms, sPs = ops.ks(ssm.Fs, fms, fPs, mps, Pps)
+                rm, rP = sms.index_select(0, q_idx), sPs.index_select(0, q_idx)
+                mean = rm @ Hd.reshape(-1, 1)
+                var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)
+            elif ops.has_projection(ssm.Fs.shape[1], dtype):
                 # fused filter + smoother that emits only (H m, H P H^T) of every smoothed state
                 proj = ops.pkfs(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, project=True)[3]
                 # rows of the queries (the reference's boolean_mask, model.py:107-108).  The (mean, var) pairs are

@@ -114,6 +114,37 @@ def pkfs(P0, Fs, Qs, H, R, y, want_ll=False, project=False):
     return fms, fPs, ll, sms, sPs
 
 
+def kf(P0, Fs, Qs, H, R, y, want_ll=True, want_predicted=False):
+    """C ABI: pssgp_kf (sequential Kalman filter).  y [n] or [batch,n]; the LGSSM is shared by the series when Fs is
+    [n,d,d] and per series when it is [batch,n,d,d].  -> fms, fPs, ll[batch] or None, mps, Pps (or None, None)."""
+    batched_y = y.dim() == 2
+    batch = y.shape[0] if batched_y else 1
+    lg = Fs.dim() == 4
+    n, d = Fs.shape[-3], Fs.shape[-1]
+    kw = dict(dtype=Fs.dtype, device=Fs.device)
+    lead = (batch,) if batched_y else ()
+    fms, fPs = torch.empty(lead + (n, d), **kw), torch.empty(lead + (n, d, d), **kw)
+    mps = torch.empty(lead + (n, d), **kw) if want_predicted else None
+    Pps = torch.empty(lead + (n, d, d), **kw) if want_predicted else None
+    ll = torch.empty((batch,), **kw) if want_ll else None
+    _lib.check(_lib.lib().pssgp_kf(_h(Fs).ptr, A.dtype_code(Fs), batch, n, d, 1 if lg else 0, A.ptr(P0), A.ptr(Fs),
+                                  A.ptr(Qs), A.ptr(H), A.ptr(R), A.ptr(y), A.ptr(fms), A.ptr(fPs), A.ptr(mps),
+                                  A.ptr(Pps), A.ptr(ll), A.stream_ptr(Fs.device)))
+    return fms, fPs, ll, mps, Pps
+
+
+def ks(Fs, fms, fPs, mps, Pps):
+    """C ABI: pssgp_ks (sequential RTS smoother) on the outputs of kf(want_predicted=True). -> sms, sPs."""
+    batched = fms.dim() == 3
+    batch = fms.shape[0] if batched else 1
+    n, d = fms.shape[-2], fms.shape[-1]
+    sms, sPs = torch.empty_like(fms), torch.empty_like(fPs)
+    _lib.check(_lib.lib().pssgp_ks(_h(Fs).ptr, A.dtype_code(Fs), batch, n, d, 1 if Fs.dim() == 4 else 0, A.ptr(Fs),
+                                  A.ptr(fms), A.ptr(fPs), A.ptr(mps), A.ptr(Pps), A.ptr(sms), A.ptr(sPs),
+                                  A.stream_ptr(Fs.device)))
+    return sms, sPs
+
+
 def has_projection(d, dtype):
     """pssgp_pkfs can emit (H m, H P H^T) of the smoothed states directly (fused d <= 4 kernels with a common
     partition: every d <= 3, and d = 4 in FP32)."""
