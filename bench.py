@@ -610,9 +610,33 @@ def main():
                "api": "StateSpaceGP.data= (pinned t, y) ; maximum_log_likelihood_objective + autograd.grad ; "
                       "predict_f(N pinned queries, out=pinned mean/var)"}
     else:
-        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-               "note": "model-level e2e is measured at n_gpus=1"}
+        # time-sharded: every rank holds ITS shard of the series in pinned host memory; one step = H2D of the shard,
+        # discretise, sharded filter + smoother + gradient (exchanges over NVLink), gradient pulled back to the SDE,
+        # D2H of (ll, gradient) and of the posterior mean / variance at the shard's times (dist.TimeShard.series_step)
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        t_pin, y_pin = pin(t_host[lo:hi]), pin(y_host[lo:hi])
+        mean_pin = torch.empty(n, dtype=torch.float64).pin_memory()
+        var_pin = torch.empty(n, dtype=torch.float64).pin_memory()
 
+        def e2e_step():
+            return shard.series_step(F, Pinf, H, R, t_pin, y_pin, t_prev, out=(mean_pin, var_pin))
+
+        for _ in range(W):
+            r = e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            r = e2e_step()
+        barrier()
+        dt_t = torch.tensor([(time.perf_counter() - t0) / K], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt_t, op=dist.ReduceOp.MAX)
+        dt = float(dt_t)
+        e2e = {"value": n * world / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * 2 * n * world),
+               "d2h_bytes_per_step": int((8 * 2 * n + 8 * (2 + 2 * d * d + d)) * world), "ms_per_step": dt * 1e3,
+               "api": "dist.TimeShard.series_step: per rank pinned (t, y) shard -> device, discretise, sharded filter + "
+                      "smoother + gradient, -> host (ll, dF, dPinf, dH, dR) + pinned posterior mean/var of the shard; "
+                      "bytes are totals over the ranks, time is the max over ranks",
+               "finite": bool(torch.isfinite(r[0][0]))}
     # ---- the other BASELINE configurations + the sharded-vs-unsharded check (all ranks take part) ----------
     peaks_all = {}
     try:

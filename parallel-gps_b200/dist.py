@@ -246,3 +246,40 @@ class TimeShard:
         fms, fPs, ll = self.filter(P0, Fs, Qs, H, R, y, reduce_ll=False, with_reverse_summaries=True)
         o = self.smoother_and_grad(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=ll)
         return o["ll"], o["sms"], o["sPs"], (o["dP0"], o["dFs"], o["dQs"], o["dH"], o["dR"])
+
+    def series_step(self, F, Pinf, H, R, ts, ys, t_prev, out=None):
+        """One training + smoothing step of a time-sharded series from HOST buffers: this rank's shard of the sampling
+        times ``ts`` [n] and observations ``ys`` [n] (host tensors, pinned for full PCIe speed; ``t_prev`` = the last
+        time of the previous shard, 0 for the first: kernels/base.py:31-33) goes to the device, is discretised
+        (kernels/base.py:29-47), filtered, smoothed and differentiated (filter_smoother_grad), the gradient is pulled
+        back through the discretisation and summed over the shards.
+        Returns (ll, dF[d,d], dPinf[d,d], dH[d], dR[1]) — global, host tensors — and the posterior mean / variance of
+        the latent function at this shard's times, (H sm_k, H sP_k H^T), as host tensors [n] (written into
+        ``out=(mean, var)`` when given: pinned buffers make the read-back asynchronous at full speed)."""
+        from . import _arrays as A
+        ops = self.ops
+        dev, dtype = F.device, F.dtype
+        t_dev = A.to_device(ts, dtype, dev, "shard_ts").reshape(-1)
+        y_dev = A.to_device(ys, dtype, dev, "shard_ys").reshape(-1)
+        prev = torch.empty_like(t_dev)
+        prev[1:] = t_dev[:-1]
+        prev[0] = float(t_prev)
+        dts = t_dev - prev
+        d = F.shape[0]
+        Fs, Qs = ops.discretise(F, Pinf, dts)
+        one = torch.ones(1, dtype=dtype, device=dev)
+        Hd, Rd = H.reshape(-1).contiguous(), R.reshape(-1).contiguous()
+        ll, sms, sPs, (dP0, dFs, dQs, dH, dR) = self.filter_smoother_grad(Pinf, Fs, Qs, Hd, Rd, y_dev, one)
+        dF, dPinf = ops.discretise_backward(F, Pinf, dts, Fs, dFs, dQs)
+        red = self._all_reduce(torch.cat([dF.reshape(-1), dPinf.reshape(-1)]))
+        # P0 = Pinf (kernels/base.py:47): its gradient joins dPinf
+        small = torch.cat([ll.reshape(-1), red[:d * d], red[d * d:] + dP0.reshape(-1), dH.reshape(-1), dR.reshape(-1)])
+        mean = sms @ Hd
+        var = torch.einsum("i,kij,j->k", Hd, sPs, Hd)
+        if out is not None:
+            mean_h, var_h = A.to_host_into(mean, out[0]), A.to_host_into(var, out[1])
+        else:
+            mean_h, var_h = mean.cpu(), var.cpu()
+        sh = small.cpu()
+        return (sh[0], sh[1:1 + d * d].reshape(d, d), sh[1 + d * d:1 + 2 * d * d].reshape(d, d),
+                sh[1 + 2 * d * d:1 + 2 * d * d + d], sh[1 + 2 * d * d + d:]), (mean_h, var_h)

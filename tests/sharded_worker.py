@@ -54,6 +54,31 @@ def main():
     ok = (rel_err(fms.cpu(), rfm[lo:hi]) < 1e-9 and rel_err(fPs.cpu(), rfP[lo:hi]) < 1e-9
           and abs(float(ll) - float(rll)) <= 1e-9 * abs(float(rll))
           and rel_err(o["sms"].cpu(), rsm[lo:hi]) < 1e-9 and rel_err(o["sPs"].cpu(), rsP[lo:hi]) < 1e-9)
+    if backend in ("nccl", "peer"):
+        # host-buffer step (TimeShard.series_step): ll, gradient w.r.t. the SDE and the posterior of the latent function
+        # against the oracle differentiated through its own discretisation (stationary-Q form, like the CUDA path)
+        with torch.no_grad():
+            sde = cov.get_sde()
+        Fo, Po, Ho, Ro = [x.clone().requires_grad_(True) for x in (sde.F, sde.P0, sde.H, ssm.R)]
+        ossm = O.get_ssm_stationary(sde._replace(F=Fo, P0=Po, H=Ho), t[:, None], Ro)
+        ofm, ofP, oll = O.pkf(ossm, y[:, None], True)
+        gF, gP, gH, gR = torch.autograd.grad(oll, (Fo, Po, Ho, Ro))
+        with torch.no_grad():
+            osm, osP = O.pks(ossm, ofm.detach(), ofP.detach())
+            omean = (osm @ sde.H.reshape(-1))[lo:hi]
+            ovar = torch.einsum("i,kij,j->k", sde.H.reshape(-1), osP, sde.H.reshape(-1))[lo:hi]
+        pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        t_prev = 0.0 if lo == 0 else float(t[lo - 1])
+        for _ in range(2):
+            (ll_s, dF, dPinf, dH, dR), (mean, var) = sh.series_step(to(sde.F), to(sde.P0), to(sde.H), R, pin(t[lo:hi]),
+                                                                    pin(y[lo:hi]), t_prev)
+        errs = {"ll": abs(float(ll_s) - float(oll)) / abs(float(oll)), "dF": rel_err(dF, gF), "dPinf": rel_err(dPinf, 0.5 * (gP + gP.T)),  # gradient w.r.t. a symmetric matrix: symmetric part
+               
+                "dH": rel_err(dH, gH.reshape(-1)), "dR": rel_err(dR, gR.reshape(-1)), "mean": rel_err(mean, omean),
+                "var": rel_err(var, ovar)}
+        if max(errs.values()) >= 1e-8 or errs["ll"] > 1e-9:
+            print(f"[rank {rank}] series_step errors: {errs}", file=sys.stderr)
+            ok = False
     flag = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
