@@ -239,6 +239,32 @@ int pssgp_peer_exchange(pssgp_handle* h, const void* msg, int64_t nvals, void* c
                         void* seq_counter, void* err_counter, void* stream);
 
 /*
+ * HOST routines (host pointers, float64): native batched construction of the LTI SDE of a covariance function for
+ * `batch` hyper-parameter settings.  Replaces, per setting, get_sde of the Matern family
+ * (pssgp/kernels/matern/common.py:26-52, matern12.py:18-23, matern32.py:20-28, matern52.py:21-25), RBF
+ * (rbf.py:14-101), Periodic (periodic.py:18-81), SDESum (kernels/base.py:151-183), SDEProduct (:199-244), balance_ss
+ * (math_utils.py:10-81) and solve_lyap_vec (math_utils.py:84-120).
+ * spec (int32): [balancing iterations of Sum/Product, n_terms, then per term: n_factors, then per factor:
+ *   type (0 Matern12, 1 Matern32, 2 Matern52, 3 RBF, 4 Periodic over a squared-exponential), order (RBF / Periodic),
+ *   balancing iterations of the factor].  The kernel is the SUM of the terms, each term the PRODUCT of its factors.
+ * params [batch, params_stride]: per factor in spec order (variance, lengthscale[, period for Periodic]).
+ * Outputs: F [batch,d,d] (balanced drift), Pinf [batch,d,d] (stationary covariance = P0), H [batch,d].
+ * nthreads: host threads over the settings (0 = all).
+ */
+int pssgp_sde_dim(const int32_t* spec, int spec_len, int* d_out, int* nparams_out);
+int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const double* params, int64_t params_stride,
+                    double* F, double* Pinf, double* H, int nthreads);
+/*
+ * Log-likelihood of ONE series under `batch` hyper-parameter settings (BASELINE configs[4]b, the grid search the
+ * reference runs as a Python loop over models): per setting discretise (kernels/base.py:29-47) + pkf with
+ * log-likelihood (kalman/parallel.py:121-152), all enqueued on `stream` from this one call; the LGSSM of a setting
+ * lives in the handle's workspace and is never returned.  F, Pinf [batch,d,d], H [batch,d], R [batch] (device, as
+ * uploaded from pssgp_sde_batch); dts, y [n]; ll [batch].
+ */
+int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
+                      const void* H, const void* R, const void* dts, const void* y, void* ll, void* stream);
+
+/*
  * Sequential Kalman filter for `batch` independent series.  Replaces pssgp/kalman/sequential.py:11-47 (kf): per step
  * predict (mp = F m, Pp = sym(F P F^T + Q)), skip the update where y is NaN, else update with the scalar
  * observation and add log N(y; H mp, H Pp H^T + R) to the log-likelihood; m0 = 0 as in the reference.

@@ -480,9 +480,18 @@ def block_diag(arrs):
     return torch.block_diag(*arrs)
 
 
+def _flatten(kernels, cls):
+    """gpflow.kernels.Combination._set_kernels (gpflow 2.2.1, reached through kernels/base.py:113-127): nested
+    combinations of the SAME type are flattened into one list, so (a + b) + c is one three-term sum."""
+    out = []
+    for k in kernels:
+        out.extend(k.kernels if type(k) is cls else [k])
+    return out
+
+
 class SDESum(SDEKernel):
     def __init__(self, kernels):
-        self.kernels = list(kernels)
+        self.kernels = _flatten(kernels, SDESum)
 
     @property
     def trainable_variables(self):
@@ -505,7 +514,7 @@ class SDESum(SDEKernel):
 
 class SDEProduct(SDEKernel):
     def __init__(self, kernels):
-        self.kernels = list(kernels)
+        self.kernels = _flatten(kernels, SDEProduct)
 
     @property
     def trainable_variables(self):

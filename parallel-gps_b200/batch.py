@@ -10,6 +10,7 @@ only), i.e. ``StateSpaceGP.maximum_log_likelihood_objective`` without the autogr
 import torch
 
 from . import _arrays as A
+from . import _lib
 from . import config as pssgp_config
 from . import ops
 from .kernels.base import time_steps
@@ -20,13 +21,44 @@ def shard_indices(n_settings, rank=0, world=1):
     return list(range(int(rank), int(n_settings), int(world)))
 
 
+def _native_grid(make_kernel, settings, noise_variance, dts, ys, dtype, device):
+    """Settings whose kernels share one structure inside the native grammar (kernels/native.py): ONE host call builds
+    every SDE (C ABI pssgp_sde_batch, all host threads), one copy uploads them, ONE call enqueues discretise + filter
+    + log-likelihood of every setting (pssgp_grid_loglik).  None when the structure is outside the grammar."""
+    import numpy as np
+    from .kernels import native
+    spec0, rows, nvs = None, [], []
+    for setting in settings:
+        setting = setting if isinstance(setting, (tuple, list)) else (setting,)
+        r = native.native_spec(make_kernel(*setting))
+        if r is None or (spec0 is not None and r[0] != spec0):
+            return None
+        spec0 = r[0]
+        rows.append(r[1])
+        nvs.append(float(noise_variance(*setting)) if callable(noise_variance) else float(noise_variance))
+    F, Pinf, H = native.sde_batch(spec0, np.asarray(rows))
+    B, d = F.shape[0], F.shape[1]
+    packed = np.concatenate([F.reshape(-1), Pinf.reshape(-1), H.reshape(-1), np.asarray(nvs)])
+    pd = A.to_device(packed, dtype, device, "grid_sde")
+    Fd, Pd = pd[:B * d * d], pd[B * d * d:2 * B * d * d]
+    Hd, Rd = pd[2 * B * d * d:2 * B * d * d + B * d], pd[2 * B * d * d + B * d:]
+    ll = torch.empty((B,), dtype=dtype, device=device)
+    h = _lib.handle(device.index)
+    _lib.check(_lib.lib().pssgp_grid_loglik(h.ptr, A.dtype_code(ll), B, dts.numel(), d, A.ptr(Fd), A.ptr(Pd), A.ptr(Hd),
+                                           A.ptr(Rd), A.ptr(dts), A.ptr(ys), A.ptr(ll), A.stream_ptr(device)))
+    return ll
+
+
 def grid_log_likelihood(make_kernel, settings, data, noise_variance, rank=0, world=1, dist=None, group=None,
-                        device=None):
+                        device=None, native=True):
     """ll[i] = log p(y | kernel = make_kernel(*settings[i]), noise_variance) for every i.
 
     ``make_kernel(*setting)`` returns an SDE kernel (pssgp_b200.kernels); ``noise_variance`` is a float or a
     callable of the setting.  ``data = (ts[T,1], ys[T,1])`` host or device.  With ``world > 1`` (one process per
     GPU) the grid is split across ranks and ``dist.all_gather_into_tensor`` assembles the result on every rank.
+    ``native=True`` (default): kernels inside the native grammar (sums of products of Matern / RBF / Periodic) take
+    the batched path — SDEs of all settings from one C++ call, all GPU work enqueued from one C call; other kernels,
+    or ``native=False``, build each SDE with the Python host layer and make one discretise + pkf call per setting.
     Returns a float64 CPU tensor of shape [len(settings)].
     """
     A.require_cuda()
@@ -39,6 +71,11 @@ def grid_log_likelihood(make_kernel, settings, data, noise_variance, rank=0, wor
     per = (n + world - 1) // world
     mine = shard_indices(n, rank, world)
     local = torch.full((per,), float("nan"), dtype=torch.float64, device=device)
+    if native and mine:
+        ll = _native_grid(make_kernel, [settings[i] for i in mine], noise_variance, dts, ys, dtype, device)
+        if ll is not None:
+            local[:len(mine)] = ll.to(torch.float64)
+            mine = []
     with torch.no_grad():
         for slot, i in enumerate(mine):
             setting = settings[i]

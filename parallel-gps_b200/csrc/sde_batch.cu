@@ -1,0 +1,510 @@
+// C ABI: pssgp_sde_dim, pssgp_sde_batch, pssgp_grid_loglik (see include/pssgp_b200.h).
+//
+// Native batched construction of the LTI SDE of a covariance function for B hyper-parameter settings at once — what
+// the reference does one setting at a time in Python/TF with a numba + host round trip: get_sde of the Matern family
+// (pssgp/kernels/matern/common.py:26-52, matern12.py:18-23, matern32.py:20-28, matern52.py:21-25), RBF
+// (rbf.py:14-61, 78-101), Periodic (periodic.py:18-81), sums (kernels/base.py:151-183) and products (:199-244),
+// balance_ss (math_utils.py:10-81) and solve_lyap_vec (math_utils.py:84-120).  Host code (a d x d problem per setting,
+// microseconds each), spread over the host threads; the time-parallel work of every setting then runs on the GPU
+// through pssgp_grid_loglik: discretise + filter + log-likelihood per setting, enqueued back to back from ONE call.
+#include "../../include/pssgp_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <array>
+#include <complex>
+#include <thread>
+#include <vector>
+
+#include "scan_run.cuh"
+#include "workspace.h"
+
+namespace pssgp {
+namespace sde {
+
+typedef std::vector<double> Mat;  // dense row-major
+
+struct Sde {
+    int d = 0, r = 0;      // state dimension, noise dimension
+    Mat P0, F, L, H, Q;    // P0 [d,d], F [d,d], L [d,r], H [d], Q [r,r]
+};
+
+static Mat eye(int n) {
+    Mat I((size_t)n * n, 0.0);
+    for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = 1.0;
+    return I;
+}
+// C[m,n] = A[m,k] B[k,n]
+static Mat matmul(const Mat& A, const Mat& B, int m, int k, int n) {
+    Mat C((size_t)m * n, 0.0);
+    for (int i = 0; i < m; ++i)
+        for (int p = 0; p < k; ++p) {
+            const double a = A[(size_t)i * k + p];
+            if (a == 0.0) continue;
+            for (int j = 0; j < n; ++j) C[(size_t)i * n + j] += a * B[(size_t)p * n + j];
+        }
+    return C;
+}
+static Mat transpose(const Mat& A, int m, int n) {
+    Mat T((size_t)m * n);
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) T[(size_t)j * m + i] = A[(size_t)i * n + j];
+    return T;
+}
+// kron(A[ma,na], B[mb,nb])
+static Mat kron(const Mat& A, int ma, int na, const Mat& B, int mb, int nb) {
+    Mat K((size_t)ma * mb * na * nb, 0.0);
+    const size_t ld = (size_t)na * nb;
+    for (int i = 0; i < ma; ++i)
+        for (int j = 0; j < na; ++j) {
+            const double a = A[(size_t)i * na + j];
+            if (a == 0.0) continue;
+            for (int p = 0; p < mb; ++p)
+                for (int q = 0; q < nb; ++q) K[((size_t)i * mb + p) * ld + (size_t)j * nb + q] = a * B[(size_t)p * nb + q];
+        }
+    return K;
+}
+// L Q L^T  ([d,d])
+static Mat lqlt(const Sde& s) {
+    Mat LQ = matmul(s.L, s.Q, s.d, s.r, s.r);
+    return matmul(LQ, transpose(s.L, s.d, s.r), s.d, s.r, s.d);
+}
+
+// Solve A x = b in place (A [n,n] destroyed, b -> x), Gaussian elimination with partial pivoting; zero multipliers
+// are skipped (the Kronecker-sum systems below are mostly zeros).  Returns false for a singular matrix.
+static bool solve_inplace(Mat& A, Mat& b, int n) {
+    for (int c = 0; c < n; ++c) {
+        int piv = c;
+        double best = fabs(A[(size_t)c * n + c]);
+        for (int r = c + 1; r < n; ++r) {
+            const double v = fabs(A[(size_t)r * n + c]);
+            if (v > best) best = v, piv = r;
+        }
+        if (!(best > 0.0)) return false;
+        if (piv != c) {
+            for (int j = c; j < n; ++j) std::swap(A[(size_t)c * n + j], A[(size_t)piv * n + j]);
+            std::swap(b[c], b[piv]);
+        }
+        const double inv = 1.0 / A[(size_t)c * n + c];
+        for (int r = c + 1; r < n; ++r) {
+            const double f = A[(size_t)r * n + c] * inv;
+            if (f == 0.0) continue;
+            double* rr = &A[(size_t)r * n];
+            const double* rc = &A[(size_t)c * n];
+            for (int j = c + 1; j < n; ++j) rr[j] -= f * rc[j];
+            b[r] -= f * b[c];
+        }
+    }
+    for (int c = n - 1; c >= 0; --c) {
+        double v = b[c];
+        const double* rc = &A[(size_t)c * n];
+        for (int j = c + 1; j < n; ++j) v -= rc[j] * b[j];
+        b[c] = v / rc[c];
+    }
+    return true;
+}
+
+// math_utils.py:84-120: F P + P F^T + L Q L^T = 0 through the d^2 x d^2 Kronecker system, P = -sym(solution)
+static bool solve_lyap_vec(const Sde& s, Mat& P) {
+    const int d = s.d, n = d * d;
+    Mat I = eye(d);
+    Mat op = kron(I, d, d, s.F, d, d);
+    Mat op2 = kron(s.F, d, d, I, d, d);
+    for (size_t i = 0; i < op.size(); ++i) op[i] += op2[i];
+    Mat rhs = lqlt(s);
+    if (!solve_inplace(op, rhs, n)) return false;
+    P.assign((size_t)n, 0.0);
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) P[(size_t)i * d + j] = -0.5 * (rhs[(size_t)i * d + j] + rhs[(size_t)j * d + i]);
+    return true;
+}
+
+// math_utils.py:32-81 (balance_ss) with the scaling of math_utils.py:10-29 (pssgp_balance_ss, host_utils.cu)
+static void balance_ss(Sde& s, int n_iter) {
+    const int d = s.d;
+    std::vector<double> dv(d);
+    pssgp_balance_ss(s.F.data(), d, n_iter, dv.data());
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < d; ++j) s.F[(size_t)i * d + j] = s.F[(size_t)i * d + j] * dv[j] / dv[i];
+    double t3 = 0.0, t4 = 0.0;
+    for (int i = 0; i < d; ++i)
+        for (int j = 0; j < s.r; ++j) {
+            s.L[(size_t)i * s.r + j] /= dv[i];
+            t3 = std::max(t3, fabs(s.L[(size_t)i * s.r + j]));
+        }
+    for (int i = 0; i < d; ++i) {
+        s.H[i] *= dv[i];
+        t4 = std::max(t4, fabs(s.H[i]));
+    }
+    for (auto& v : s.L) v /= t3;
+    for (auto& v : s.H) v /= t4;
+    for (auto& v : s.Q) v *= (t3 * t3) * (t4 * t4);
+}
+
+static double factorial(int n) {
+    double f = 1.0;
+    for (int i = 2; i <= n; ++i) f *= i;
+    return f;
+}
+static double binom(int n, int k) {
+    if (k < 0 || k > n) return 0.0;
+    double b = 1.0;
+    for (int i = 1; i <= k; ++i) b = b * (n - k + i) / i;
+    return floor(b + 0.5);
+}
+
+// matern/common.py:26-52
+static Sde matern_companion(int d, double variance, double ell) {
+    Sde s;
+    s.d = d, s.r = 1;
+    const double lam = sqrt(2.0 * d - 1.0) / ell;
+    s.F.assign((size_t)d * d, 0.0);
+    for (int i = 0; i + 1 < d; ++i) s.F[(size_t)i * d + i + 1] = 1.0;
+    for (int k = 0; k < d; ++k) s.F[(size_t)(d - 1) * d + k] = -binom(d, k) * pow(lam, d - k);
+    s.L.assign(d, 0.0);
+    s.L[d - 1] = 1.0;
+    s.H.assign(d, 0.0);
+    s.H[0] = 1.0;
+    s.Q.assign(1, pow(2.0 * lam, 2 * d - 1) * variance * factorial(d - 1) * factorial(d - 1) / factorial(2 * d - 2));
+    return s;
+}
+
+// Roots of g(z) = sum_k a[k] z^k (degree m, real coefficients) by the Aberth-Ehrlich iteration.
+static std::vector<std::complex<double>> poly_roots(const std::vector<double>& a) {
+    typedef std::complex<double> C;
+    const int m = (int)a.size() - 1;
+    std::vector<C> z(m);
+    const double radius = pow(fabs(a[0] / a[m]), 1.0 / m);
+    for (int j = 0; j < m; ++j) z[j] = std::polar(radius, 2.0 * M_PI * j / m + 0.4);
+    for (int it = 0; it < 2000; ++it) {
+        double worst = 0.0;
+        for (int j = 0; j < m; ++j) {
+            C p = a[m], dp = 0.0;
+            for (int k = m - 1; k >= 0; --k) {
+                dp = dp * z[j] + p;
+                p = p * z[j] + a[k];
+            }
+            const C newton = p / dp;
+            C rep = 0.0;
+            for (int l = 0; l < m; ++l)
+                if (l != j) rep += 1.0 / (z[j] - z[l]);
+            const C step = newton / (1.0 - newton * rep);
+            z[j] -= step;
+            worst = std::max(worst, std::abs(step) / std::max(std::abs(z[j]), 1e-300));
+        }
+        if (worst < 1e-16) break;
+    }
+    return z;
+}
+
+// rbf.py:14-61.  The denominator polynomial is the order-`order` Taylor polynomial of exp(-s^2/2): even in s, so
+// its roots are the square roots of the roots of g(z) = sum_k (-z/2)^k / k!; the stable half gives the drift.
+static void rbf_unscaled(int order, Mat& F, double& gain, double& q) {
+    typedef std::complex<double> C;
+    std::vector<double> a(order + 1);
+    for (int k = 0; k <= order; ++k) a[k] = pow(-0.5, k) / factorial(k);
+    std::vector<C> zr = poly_roots(a);
+    std::vector<C> stable;
+    for (const C& z : zr) {
+        C s = std::sqrt(z);
+        if (s.real() > 0.0) s = -s;
+        stable.push_back(s);
+    }
+    // conjugate pairs next to each other, then the monic polynomial prod (s - r_j), highest power first
+    std::sort(stable.begin(), stable.end(), [](const C& x, const C& y) {
+        if (x.real() != y.real()) return x.real() < y.real();
+        return x.imag() < y.imag();
+    });
+    std::vector<C> poly(1, C(1.0));
+    for (const C& r : stable) {
+        std::vector<C> np(poly.size() + 1, C(0.0));
+        for (size_t i = 0; i < poly.size(); ++i) {
+            np[i] += poly[i];
+            np[i + 1] -= poly[i] * r;
+        }
+        poly.swap(np);
+    }
+    const int n = order;
+    std::vector<double> denom(n + 1);
+    for (int i = 0; i <= n; ++i) denom[i] = poly[i].real();
+    // rbf.py:40-43: normalise the constant term to one, the gain is the inverse leading coefficient, monic again
+    const double c0 = denom[n];
+    for (auto& v : denom) v /= c0;
+    gain = 1.0 / denom[0];
+    const double lead = denom[0];
+    for (auto& v : denom) v /= lead;
+    F.assign((size_t)n * n, 0.0);
+    for (int i = 0; i + 1 < n; ++i) F[(size_t)i * n + i + 1] = 1.0;
+    for (int j = 0; j < n; ++j) F[(size_t)(n - 1) * n + j] = -denom[n - j];
+    q = sqrt(2.0 * M_PI);  // rbf.py:24: sqrt(2 pi) / coeffs[-1], the constant Taylor coefficient being 1
+}
+
+enum { K_MATERN12 = 0, K_MATERN32 = 1, K_MATERN52 = 2, K_RBF = 3, K_PERIODIC = 4 };
+
+static int base_dim(int type, int order) {
+    switch (type) {
+        case K_MATERN12: return 1;
+        case K_MATERN32: return 2;
+        case K_MATERN52: return 3;
+        case K_RBF: return order;
+        case K_PERIODIC: return 2 * (order + 1);
+    }
+    return -1;
+}
+static int base_nparams(int type) { return type == K_PERIODIC ? 3 : 2; }
+
+struct RbfCache {  // the unscaled RBF SDE depends on the order only: computed once per call, shared by the settings
+    int order = -1;
+    Mat F;
+    double gain = 0.0, q = 0.0;
+};
+
+// one base kernel; p = (variance, lengthscale[, period])
+static bool base_sde(int type, int order, int bal_iter, const double* p, const std::vector<RbfCache>& rbf, Sde& s) {
+    const double variance = p[0], ell = p[1];
+    switch (type) {
+        case K_MATERN12: {  // matern12.py:18-23
+            s = matern_companion(1, variance, ell);
+            s.P0.assign(1, variance);
+            return true;
+        }
+        case K_MATERN32: {  // matern32.py:20-28
+            s = matern_companion(2, variance, ell);
+            const double lam = sqrt(3.0) / ell;
+            s.P0 = {variance, 0.0, 0.0, lam * lam * variance};
+            return true;
+        }
+        case K_MATERN52: {  // matern52.py:21-25
+            s = matern_companion(3, variance, ell);
+            balance_ss(s, bal_iter);
+            return solve_lyap_vec(s, s.P0);
+        }
+        case K_RBF: {  // rbf.py:78-101
+            const RbfCache* c = nullptr;
+            for (const auto& e : rbf)
+                if (e.order == order) c = &e;
+            if (!c) return false;
+            const int n = order;
+            s.d = n, s.r = 1;
+            s.F = c->F;
+            for (int j = 0; j < n; ++j) s.F[(size_t)(n - 1) * n + j] /= pow(ell, n - j);
+            s.L.assign(n, 0.0);
+            s.L[n - 1] = 1.0;
+            s.H.assign(n, 0.0);
+            s.H[0] = c->gain / pow(ell, n);
+            s.Q.assign(1, variance * ell * c->q);
+            balance_ss(s, bal_iter);
+            return solve_lyap_vec(s, s.P0);
+        }
+        case K_PERIODIC: {  // periodic.py:18-81
+            const int N = order, dim = 2 * (N + 1);
+            const double w0 = 2.0 * M_PI / p[2], l2 = 2.0 * ell;  // periodic.py:57: lengthscale x 2
+            s.d = dim, s.r = dim;
+            s.F.assign((size_t)dim * dim, 0.0);
+            for (int j = 0; j <= N; ++j) {
+                s.F[(size_t)(2 * j) * dim + 2 * j + 1] = -w0 * j;
+                s.F[(size_t)(2 * j + 1) * dim + 2 * j] = w0 * j;
+            }
+            s.L = eye(dim);
+            s.Q.assign((size_t)dim * dim, 0.0);
+            s.P0.assign((size_t)dim * dim, 0.0);
+            const double il2 = 1.0 / (l2 * l2);
+            for (int J = 0; J <= N; ++J) {
+                double q2 = 0.0;  // sum over K of b(K,J) l^-2K / K! exp(-l^-2) 2^-K variance
+                for (int K = J; K <= N; K += 2) {
+                    const double b = 2.0 * binom(K, (K - J) / 2) / (J == 0 ? 2.0 : 1.0);
+                    q2 += b * pow(il2, K) / factorial(K) * exp(-il2) * pow(2.0, -K) * variance;
+                }
+                s.P0[(size_t)(2 * J) * dim + 2 * J] = q2;
+                s.P0[(size_t)(2 * J + 1) * dim + 2 * J + 1] = q2;
+            }
+            s.H.assign(dim, 0.0);
+            for (int j = 0; j <= N; ++j) s.H[2 * j] = 1.0;
+            return true;
+        }
+    }
+    return false;
+}
+
+// kernels/base.py:199-220 (Kronecker-sum drift, product diffusion and stationary covariance of two factors)
+static Sde product2(const Sde& a, const Sde& b) {
+    Sde s;
+    s.d = a.d * b.d, s.r = s.d;
+    Mat Ia = eye(a.d), Ib = eye(b.d);
+    s.F = kron(a.F, a.d, a.d, Ib, b.d, b.d);
+    Mat t = kron(Ia, a.d, a.d, b.F, b.d, b.d);
+    for (size_t i = 0; i < t.size(); ++i) s.F[i] += t[i];
+    Mat g1 = lqlt(a), g2 = lqlt(b);
+    s.Q = kron(g1, a.d, a.d, b.P0, b.d, b.d);
+    t = kron(a.P0, a.d, a.d, g2, b.d, b.d);
+    for (size_t i = 0; i < t.size(); ++i) s.Q[i] += t[i];
+    s.H = kron(a.H, 1, a.d, b.H, 1, b.d);
+    s.P0 = kron(a.P0, a.d, a.d, b.P0, b.d, b.d);
+    s.L = eye(s.d);
+    return s;
+}
+
+// spec: [combine_balancing_iter, n_terms, {n_factors, {type, order, balancing_iter} x n_factors} x n_terms]
+struct Spec {
+    int comb_iter = 0;
+    std::vector<std::vector<std::array<int, 3>>> terms;
+    int d = 0, nparams = 0;
+};
+
+static bool parse_spec(const int32_t* spec, int len, Spec& out) {
+    if (!spec || len < 2) return false;
+    int pos = 0;
+    out.comb_iter = spec[pos++];
+    const int nt = spec[pos++];
+    if (nt < 1 || out.comb_iter < 0) return false;
+    out.d = 0, out.nparams = 0;
+    for (int t = 0; t < nt; ++t) {
+        if (pos >= len) return false;
+        const int nf = spec[pos++];
+        if (nf < 1 || pos + 3 * nf > len) return false;
+        std::vector<std::array<int, 3>> fs;
+        int td = 1;
+        for (int f = 0; f < nf; ++f) {
+            std::array<int, 3> e = {spec[pos], spec[pos + 1], spec[pos + 2]};
+            pos += 3;
+            const int bd = base_dim(e[0], e[1]);
+            if (bd < 1 || e[2] < 0) return false;
+            td *= bd;
+            out.nparams += base_nparams(e[0]);
+            fs.push_back(e);
+        }
+        out.d += td;
+        out.terms.push_back(fs);
+    }
+    return pos == len;
+}
+
+static bool build_one(const Spec& sp, const std::vector<RbfCache>& rbf, const double* params, Sde& out) {
+    std::vector<Sde> terms;
+    const double* p = params;
+    for (const auto& fs : sp.terms) {
+        Sde term;
+        for (size_t f = 0; f < fs.size(); ++f) {
+            Sde b;
+            if (!base_sde(fs[f][0], fs[f][1], fs[f][2], p, rbf, b)) return false;
+            p += base_nparams(fs[f][0]);
+            term = f == 0 ? b : product2(term, b);
+        }
+        if (fs.size() > 1) {  // kernels/base.py:236-244: the product is balanced and its Pinf solved again
+            balance_ss(term, sp.comb_iter);
+            if (!solve_lyap_vec(term, term.P0)) return false;
+        }
+        terms.push_back(std::move(term));
+    }
+    if (terms.size() == 1) {
+        out = std::move(terms[0]);
+        return true;
+    }
+    // kernels/base.py:151-183: block-diagonal sum, balanced, Pinf solved for the whole system
+    Sde s;
+    for (const auto& t : terms) s.d += t.d, s.r += t.r;
+    s.F.assign((size_t)s.d * s.d, 0.0);
+    s.L.assign((size_t)s.d * s.r, 0.0);
+    s.Q.assign((size_t)s.r * s.r, 0.0);
+    s.H.assign(s.d, 0.0);
+    int od = 0, orr = 0;
+    for (const auto& t : terms) {
+        for (int i = 0; i < t.d; ++i) {
+            for (int j = 0; j < t.d; ++j) s.F[(size_t)(od + i) * s.d + od + j] = t.F[(size_t)i * t.d + j];
+            for (int j = 0; j < t.r; ++j) s.L[(size_t)(od + i) * s.r + orr + j] = t.L[(size_t)i * t.r + j];
+            s.H[od + i] = t.H[i];
+        }
+        for (int i = 0; i < t.r; ++i)
+            for (int j = 0; j < t.r; ++j) s.Q[(size_t)(orr + i) * s.r + orr + j] = t.Q[(size_t)i * t.r + j];
+        od += t.d, orr += t.r;
+    }
+    balance_ss(s, sp.comb_iter);
+    if (!solve_lyap_vec(s, s.P0)) return false;
+    out = std::move(s);
+    return true;
+}
+
+}  // namespace sde
+}  // namespace pssgp
+
+using namespace pssgp;
+
+extern "C" {
+
+int pssgp_sde_dim(const int32_t* spec, int spec_len, int* d_out, int* nparams_out) {
+    sde::Spec sp;
+    if (!sde::parse_spec(spec, spec_len, sp)) return set_err(PSSGP_ERR_INVALID, "sde: malformed kernel spec");
+    if (d_out) *d_out = sp.d;
+    if (nparams_out) *nparams_out = sp.nparams;
+    return PSSGP_OK;
+}
+
+int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const double* params, int64_t params_stride,
+                    double* F, double* Pinf, double* H, int nthreads) {
+    sde::Spec sp;
+    if (!sde::parse_spec(spec, spec_len, sp)) return set_err(PSSGP_ERR_INVALID, "sde: malformed kernel spec");
+    if (batch < 1 || !params || !F || !Pinf || !H || params_stride < sp.nparams)
+        return set_err(PSSGP_ERR_INVALID, "sde_batch: bad argument");
+    std::vector<sde::RbfCache> rbf;
+    for (const auto& fs : sp.terms)
+        for (const auto& f : fs)
+            if (f[0] == sde::K_RBF && std::none_of(rbf.begin(), rbf.end(), [&](const sde::RbfCache& c) { return c.order == f[1]; })) {
+                sde::RbfCache c;
+                c.order = f[1];
+                sde::rbf_unscaled(c.order, c.F, c.gain, c.q);
+                rbf.push_back(c);
+            }
+    const int d = sp.d;
+    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 64), batch));
+    std::vector<int> failed(nt, 0);
+    auto work = [&](int tid) {
+        for (int64_t b = tid; b < batch; b += nt) {
+            sde::Sde s;
+            if (!sde::build_one(sp, rbf, params + b * params_stride, s) || s.d != d) {
+                failed[tid] = 1;
+                continue;
+            }
+            std::copy(s.F.begin(), s.F.end(), F + b * d * d);
+            std::copy(s.P0.begin(), s.P0.end(), Pinf + b * d * d);
+            std::copy(s.H.begin(), s.H.end(), H + b * d);
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (int f : failed)
+        if (f) return set_err(PSSGP_ERR_INVALID, "sde_batch: singular Lyapunov system or unsupported kernel in a setting");
+    return PSSGP_OK;
+}
+
+int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
+                      const void* H, const void* R, const void* dts, const void* y, void* ll, void* stream) {
+    int rc = check_common(h, dtype, n, d);
+    if (rc) return rc;
+    if (batch < 1 || !F || !Pinf || !H || !R || !dts || !y || !ll) return set_err(PSSGP_ERR_INVALID, "grid_loglik: bad argument");
+    const size_t es = dtype == PSSGP_F64 ? 8 : 4;
+    const size_t nm = (size_t)n * d * d * es, nv = (size_t)n * d * es;
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    if ((rc = ws_reserve(h, WS_GRID, 3 * up(nm) + up(nv)))) return rc;
+    char* base = (char*)h->buf[WS_GRID];
+    void *Fs = base, *Qs = base + up(nm), *fPs = base + 2 * up(nm), *fms = base + 3 * up(nm);
+    for (int64_t b = 0; b < batch; ++b) {
+        const char* Fb = (const char*)F + (size_t)b * d * d * es;
+        const char* Pb = (const char*)Pinf + (size_t)b * d * d * es;
+        if ((rc = pssgp_discretise(h, dtype, n, d, Fb, Pb, dts, Fs, Qs, stream))) return rc;
+        if ((rc = pssgp_pkf(h, dtype, n, d, Pb, Fs, Qs, (const char*)H + (size_t)b * d * es, (const char*)R + (size_t)b * es, y,
+                            nullptr, 1, fms, fPs, (char*)ll + (size_t)b * es, nullptr, stream)))
+            return rc;
+    }
+    return PSSGP_OK;
+}
+
+}  // extern "C"

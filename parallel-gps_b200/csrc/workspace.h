@@ -5,7 +5,7 @@
 
 // chunk-aggregate slots exist once per scan kind (filter / smoother / adjoint) so that several
 // *_summary calls can be pending at the same time.
-enum { WS_LANE = 0, WS_WAGG = 3, WS_WEXCL = 6, WS_WSTATE = 9, WS_PART, WS_MISC, WS_GEN0, WS_GEN1, WS_GEN2, WS_GEN3, WS_WSTATE_S, WS_WPREFIX, WS_WPREFIX1, WS_WPREFIX2, WS_F32, WS_COUNT };
+enum { WS_LANE = 0, WS_WAGG = 3, WS_WEXCL = 6, WS_WSTATE = 9, WS_PART, WS_MISC, WS_GEN0, WS_GEN1, WS_GEN2, WS_GEN3, WS_WSTATE_S, WS_WPREFIX, WS_WPREFIX1, WS_WPREFIX2, WS_F32, WS_GRID, WS_COUNT };
 enum { KIND_FILTER = 0, KIND_SMOOTHER = 1, KIND_ADJOINT = 2 };
 
 struct pssgp_handle {
