@@ -358,7 +358,8 @@ def run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, W):
     return {"baseline_config": 4, "workload": "grid log-likelihood, 32 x 32 settings of Matern52 + RBF6 (d = 9), N = 1e5, "
                                               "batch-sharded over n_gpus", "settings": len(settings), "n": n,
             "seconds": dt, "value": len(settings) / dt, "unit": "settings/s", "timesteps_per_s": len(settings) * n / dt,
-            "n_gpus": world, "finite": bool(torch.isfinite(ll).all()), "ll_max": float(ll.max()),
+            "n_gpus": world, "path": "native batched SDE (pssgp_sde_batch, host C++) + one pssgp_grid_loglik call per rank "
+            "(4 concurrent settings)", "finite": bool(torch.isfinite(ll).all()), "ll_max": float(ll.max()),
             "argmax_setting": [float(x) for x in settings[int(ll.argmax())]]}
 
 

@@ -485,6 +485,24 @@ int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const doub
     return PSSGP_OK;
 }
 
+// Settings are independent: they are dealt out to kGridLanes concurrent lanes (child handle = own workspace, own
+// stream), so that the latency-bound aggregate hierarchy of one setting overlaps the SM-filling kernels of the others.
+static int grid_lanes_init(pssgp_handle* h, int lanes) {
+    cudaError_t e = cudaSuccess;
+    if (!h->fork_event) e = cudaEventCreateWithFlags((cudaEvent_t*)&h->fork_event, cudaEventDisableTiming);
+    for (int i = 0; i < lanes && e == cudaSuccess; ++i) {
+        if (!h->lane[i]) {
+            int rc = pssgp_create(&h->lane[i], h->device);
+            if (rc) return rc;
+        }
+        if (!h->lane_stream[i]) e = cudaStreamCreateWithFlags((cudaStream_t*)&h->lane_stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess && !h->lane_event[i])
+            e = cudaEventCreateWithFlags((cudaEvent_t*)&h->lane_event[i], cudaEventDisableTiming);
+    }
+    if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "grid_loglik: %s", cudaGetErrorString(e));
+    return PSSGP_OK;
+}
+
 int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
                       const void* H, const void* R, const void* dts, const void* y, void* ll, void* stream) {
     int rc = check_common(h, dtype, n, d);
@@ -493,17 +511,41 @@ int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int 
     const size_t es = dtype == PSSGP_F64 ? 8 : 4;
     const size_t nm = (size_t)n * d * d * es, nv = (size_t)n * d * es;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
-    if ((rc = ws_reserve(h, WS_GRID, 3 * up(nm) + up(nv)))) return rc;
-    char* base = (char*)h->buf[WS_GRID];
-    void *Fs = base, *Qs = base + up(nm), *fPs = base + 2 * up(nm), *fms = base + 3 * up(nm);
+    // per-kernel timing (option "timing") brackets launches with events on ONE stream: a single lane then
+    const int lanes = h->timing ? 1 : (int)std::min<int64_t>(h->grid_lanes > 0 ? h->grid_lanes : 4, std::min<int64_t>(batch, 4));
+    if (lanes > 1 && (rc = grid_lanes_init(h, lanes))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (lanes > 1) {
+        cudaEventRecord((cudaEvent_t)h->fork_event, st);
+        for (int i = 0; i < lanes; ++i) cudaStreamWaitEvent((cudaStream_t)h->lane_stream[i], (cudaEvent_t)h->fork_event, 0);
+    }
     for (int64_t b = 0; b < batch; ++b) {
+        const int l = (int)(b % lanes);
+        pssgp_handle* hl = lanes > 1 ? h->lane[l] : h;
+        void* sl = lanes > 1 ? h->lane_stream[l] : stream;
+        if (lanes > 1) {
+            hl->chunk_opt = h->chunk_opt, hl->mid_warps = h->mid_warps, hl->mid_smem = h->mid_smem;
+            hl->force_generic = h->force_generic, hl->pdl = h->pdl;
+        }
+        if ((rc = ws_reserve(hl, WS_GRID, 3 * up(nm) + up(nv)))) return rc;
+        char* base = (char*)hl->buf[WS_GRID];
+        void *Fs = base, *Qs = base + up(nm), *fPs = base + 2 * up(nm), *fms = base + 3 * up(nm);
         const char* Fb = (const char*)F + (size_t)b * d * d * es;
         const char* Pb = (const char*)Pinf + (size_t)b * d * d * es;
-        if ((rc = pssgp_discretise(h, dtype, n, d, Fb, Pb, dts, Fs, Qs, stream))) return rc;
-        if ((rc = pssgp_pkf(h, dtype, n, d, Pb, Fs, Qs, (const char*)H + (size_t)b * d * es, (const char*)R + (size_t)b * es, y,
-                            nullptr, 1, fms, fPs, (char*)ll + (size_t)b * es, nullptr, stream)))
+        const int64_t l0 = hl->launches;
+        if ((rc = pssgp_discretise(hl, dtype, n, d, Fb, Pb, dts, Fs, Qs, sl))) return rc;
+        if ((rc = pssgp_pkf(hl, dtype, n, d, Pb, Fs, Qs, (const char*)H + (size_t)b * d * es, (const char*)R + (size_t)b * es, y,
+                            nullptr, 1, fms, fPs, (char*)ll + (size_t)b * es, nullptr, sl)))
             return rc;
+        if (lanes > 1) h->launches += hl->launches - l0;
     }
+    if (lanes > 1)
+        for (int i = 0; i < lanes; ++i) {
+            cudaEventRecord((cudaEvent_t)h->lane_event[i], (cudaStream_t)h->lane_stream[i]);
+            cudaStreamWaitEvent(st, (cudaEvent_t)h->lane_event[i], 0);
+        }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "grid_loglik: %s", cudaGetErrorString(e));
     return PSSGP_OK;
 }
 
