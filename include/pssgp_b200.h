@@ -251,6 +251,10 @@ int pssgp_peer_exchange(pssgp_handle* h, const void* msg, int64_t nvals, void* c
  * Outputs: F [batch,d,d] (balanced drift), Pinf [batch,d,d] (stationary covariance = P0), H [batch,d].
  * nthreads: host threads over the settings (0 = all).
  */
+/* HOST routine: X [d,d] with F X + X F^T = G (float64, row-major), the d^2 x d^2 Kronecker solve inside
+ * solve_lyap_vec (pssgp/kernels/math_utils.py:108-118; Pinf = -sym(X) for G = L Q L^T).  The same routine with F^T is
+ * its adjoint (kernels/math_utils.py of this package). */
+int pssgp_lyap_solve(const void* F, const void* G, int d, void* X);
 int pssgp_sde_dim(const int32_t* spec, int spec_len, int* d_out, int* nparams_out);
 int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const double* params, int64_t params_stride,
                     double* F, double* Pinf, double* H, int nthreads);

@@ -36,11 +36,35 @@ def balance_ss(F, L, H, q, n_iter=5):
     return F, L, H, q
 
 
+def _lyap(F, G):
+    """X with F X + X F^T = G: compiled host routine (C ABI pssgp_lyap_solve), numpy float64 in and out."""
+    Fh = np.ascontiguousarray(F, dtype=np.float64)
+    Gh = np.ascontiguousarray(G, dtype=np.float64)
+    X = np.empty_like(Fh)
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.lib().pssgp_lyap_solve(vp(Fh), vp(Gh), int(Fh.shape[0]), vp(X)))
+    return X
+
+
+class _LyapSolve(torch.autograd.Function):
+    """X = Lyap(F, G), F X + X F^T = G.  The adjoint is the same solve with F^T: with S from F^T S + S F = gX,
+    gG = S and gF = -(S X^T + S^T X) — instead of differentiating through a d^2 x d^2 dense solve and two Kronecker
+    products."""
+
+    @staticmethod
+    def forward(ctx, F, G):
+        X = torch.as_tensor(_lyap(F.detach().numpy(), G.detach().numpy()), dtype=F.dtype)
+        ctx.save_for_backward(F.detach(), X)
+        return X
+
+    @staticmethod
+    def backward(ctx, gX):
+        F, X = ctx.saved_tensors
+        S = torch.as_tensor(_lyap(F.numpy().T, gX.detach().numpy()), dtype=F.dtype)
+        return -(S @ X.T + S.T @ X), S
+
+
 def solve_lyap_vec(F, L, Q):
-    """math_utils.py:84-120:  F P + P F^T + L Q L^T = 0  through the d^2 x d^2 Kronecker system."""
-    dim = F.shape[0]
-    eye = torch.eye(dim, dtype=F.dtype)
-    op = torch.kron(eye, F) + torch.kron(F, eye)
-    rhs = (L @ (Q @ L.T)).reshape(-1, 1)
-    Pinf = torch.linalg.solve(op, rhs).reshape(dim, dim)
-    return -0.5 * (Pinf + Pinf.T)
+    """math_utils.py:84-120:  F P + P F^T + L Q L^T = 0  through the d^2 x d^2 Kronecker system, P = -sym(X)."""
+    X = _LyapSolve.apply(F, L @ (Q @ L.T))
+    return -0.5 * (X + X.T)

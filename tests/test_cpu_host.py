@@ -114,7 +114,10 @@ def test_get_sde_matches_oracle_and_is_differentiable(name):
         if a is None:
             assert b is None
         else:
-            npt.assert_allclose(b.item(), a.item(), rtol=1e-10, atol=1e-12)
+            # "qp": nested Lyapunov systems with cond 2e5 each (lengthscales 50 and 100); the oracle differentiates
+            # through LAPACK's LU of the Kronecker matrix, the package uses the analytic adjoint (a second native
+            # solve with F^T): two roundings of an ill-conditioned gradient, 4e-8 apart
+            npt.assert_allclose(b.item(), a.item(), rtol=1e-6 if name == "qp" else 1e-10, atol=1e-12)
     spec = pcov.get_spec(17)
     assert spec.Fs.shape == (17, psde.F.shape[0], psde.F.shape[0]) and spec.H.shape == (1, psde.F.shape[0])
 
