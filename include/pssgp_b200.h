@@ -251,6 +251,18 @@ int pssgp_peer_exchange(pssgp_handle* h, const void* msg, int64_t nvals, void* c
  * Outputs: F [batch,d,d] (balanced drift), Pinf [batch,d,d] (stationary covariance = P0), H [batch,d].
  * nthreads: host threads over the settings (0 = all).
  */
+/*
+ * Data preparation of predict_f.  Replaces pssgp/model.py:15-55 (_merge_sorted), :99 (NaN observations at the query
+ * times) and the time differencing of kernels/base.py:31-35: ts, ys [n] (sorted training times, observations),
+ * q [K] (sorted query times), t0 = time before the first step (the reference's t0 = 0).
+ * Outputs: t_all, y_all, dts [n+K] (merged times; observations with NaN at the queries; dts[k] = t_all[k] -
+ * t_all[k-1], dts[0] = t_all[0] - t0) and q_idx [K] (int64: rows of the queries in the merged arrays — the
+ * reference's boolean mask).  Ties between a training and a query time put the element of the SHORTER array first,
+ * like the reference's scatter.
+ */
+int pssgp_merge_queries(pssgp_handle* h, int dtype, int64_t n, int64_t K, const void* ts, const void* ys, const void* q,
+                        double t0, void* t_all, void* y_all, void* dts, void* q_idx, void* stream);
+
 /* HOST routine: X [d,d] with F X + X F^T = G (float64, row-major), the d^2 x d^2 Kronecker solve inside
  * solve_lyap_vec (pssgp/kernels/math_utils.py:108-118; Pinf = -sym(X) for G = L Q L^T).  The same routine with F^T is
  * its adjoint (kernels/math_utils.py of this package). */

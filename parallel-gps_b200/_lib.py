@@ -52,6 +52,7 @@ SIGNATURES = {
                                    _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_peer_exchange": (_int, [_vp, _vp, _i64, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _int, _int, _i64, _i64, _i64,
                                    _vp, _vp, _vp]),
+    "pssgp_merge_queries": (_int, [_vp, _int, _i64, _i64, _vp, _vp, _vp, ctypes.c_double, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_lyap_solve": (_int, [_vp, _vp, _int, _vp]),
     "pssgp_sde_dim": (_int, [_vp, _int, _vp, _vp]),
     "pssgp_sde_batch": (_int, [_vp, _int, _i64, _vp, _i64, _vp, _vp, _vp, _int]),

@@ -13,6 +13,7 @@
 #include "../../include/pssgp_b200.h"
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 
 #include "coop.cuh"
 #include "workspace.h"
@@ -400,6 +401,9 @@ __global__ void discretise_bwd_final_kernel(const T* __restrict__ coefT, const T
     }
 }
 
+int discretise_frag_f64(pssgp_handle* h, int64_t n, int d, const double* coef, const double* Pinf, const double* dts,
+                        double* Fs, double* Qs, cudaStream_t st);
+
 constexpr size_t coef_count(int deg, int d) { return 8 + (size_t)(deg + 1) * d * d; }
 
 template <typename T>
@@ -513,88 +517,99 @@ __global__ void discretise_generic_kernel(const T* __restrict__ coef, const T* _
     }
 }
 
-// part[cta][p*dd + idx]: p = 0 -> dPinf, p >= 1 -> W_p.  Each CTA accumulates into its own slice.
-template <typename T>
-__global__ void discretise_bwd_generic_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, int d,
+// part[cta][p*dd + e]: p = 0 -> dPinf, p >= 1 -> W_p.  ONE THREAD PER MATRIX ELEMENT (i, j): its DEG + 1 moment
+// accumulators live in registers for the whole grid-stride loop and are written once at the end; matrices sit in shared
+// memory with an odd leading dimension, and every product reads one operand as a row broadcast and the other along
+// consecutive columns (no bank conflicts, no integer division inside the loop).
+template <typename T, int MAXNT>
+__global__ void __launch_bounds__(MAXNT)
+discretise_bwd_generic_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, int d,
                                               const T* __restrict__ dts, long n, const T* __restrict__ Fs,
                                               const T* __restrict__ dFs, const T* __restrict__ dQs,
                                               T* __restrict__ part) {
     constexpr int DEG = Taylor<T>::DEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int dd = d * d;
+    const int dd = d * d, LD = d | 1, MS = d * LD;
     T* A = (T*)smem_raw;   // A_k
-    T* dA = A + dd;
-    T* dQ = dA + dd;
-    T* T1 = dQ + dd;
-    T* T2 = T1 + dd;
-    T* P = T2 + dd;
-    T* Ah = P + dd;
-    Coop c{(int)threadIdx.x, (int)blockDim.x};
-    const int NOUT = (DEG + 1) * dd;
-    T* mine = part + (size_t)blockIdx.x * NOUT;
-    for (int o = c.tid; o < NOUT; o += c.nt) mine[o] = T(0);
-    for (int idx = c.tid; idx < dd; idx += c.nt) {
-        const int i = idx / d, j = idx - i * d;
-        P[idx] = T(0.5) * (Pinf[idx] + Pinf[j * d + i]);
-    }
+    T* dA = A + MS;
+    T* dQ = dA + MS;
+    T* T1 = dQ + MS;
+    T* T2 = T1 + MS;
+    T* P = T2 + MS;
+    T* Ah = P + MS;
+    const int e = threadIdx.x;
+    const bool on = e < dd;
+    const int i = on ? e / d : 0, j = on ? e - i * d : 0;
+    const int ij = i * LD + j, eT = j * d + i;
+    T acc[DEG + 1];
+#pragma unroll
+    for (int p = 0; p <= DEG; ++p) acc[p] = T(0);
+    if (on) P[ij] = T(0.5) * (Pinf[e] + Pinf[eT]);
     const T normF = coef[0];
     const T* C = coef + 8;
-    c.sync();
+    __syncthreads();
     for (long k = blockIdx.x; k < n; k += gridDim.x) {
         const T dt = dts[k];
         T x;
         const int s = pick_squarings<T>(normF * t_abs(dt), x);
         if (dt < T(0)) x = -x;
-        for (int idx = c.tid; idx < dd; idx += c.nt) {
-            const int i = idx / d, j = idx - i * d;
-            A[idx] = Fs[k * dd + idx];
-            dA[idx] = dFs[k * dd + idx];
-            dQ[idx] = T(0.5) * (dQs[k * dd + idx] + dQs[k * dd + j * d + i]);
+        T dq = T(0), da = T(0);
+        if (on) {
+            A[ij] = Fs[k * dd + e];
+            da = dFs[k * dd + e];
+            dq = T(0.5) * (dQs[k * dd + e] + dQs[k * dd + eT]);
+            dQ[ij] = dq;
         }
-        c.sync();
-        co_mm(c, d, d, d, dQ, d, 1, A, d, 1, T1, d, (const T*)nullptr, T(1));   // dQ A
-        c.sync();
-        co_mm(c, d, d, d, T1, d, 1, P, d, 1, dA, d, dA, T(-2));                 // dA -= 2 dQ A P
-        for (int idx = c.tid; idx < dd; idx += c.nt) {
-            const int i = idx / d, j = idx - i * d;
-            T a1 = dQ[idx];
-            for (int kk = 0; kk < d; ++kk) a1 = fma(-A[kk * d + i], T1[kk * d + j], a1);
-            mine[idx] += a1;                                                     // dPinf += dQ - A^T dQ A
+        __syncthreads();
+        if (on) {  // T1 = dQ A
+            T a1 = T(0);
+            for (int kk = 0; kk < d; ++kk) a1 = fma(dQ[i * LD + kk], A[kk * LD + j], a1);
+            T1[ij] = a1;
         }
-        c.sync();
-        if (s > 0) {
-            for (int idx = c.tid; idx < dd; idx += c.nt) {
-                T a = C[(size_t)DEG * dd + idx];
-                for (int p = DEG - 1; p >= 0; --p) a = fma(a, x, C[(size_t)p * dd + idx]);
-                Ah[idx] = a;
+        __syncthreads();
+        if (on) {
+            T a1 = T(0), a2 = T(0);
+            for (int kk = 0; kk < d; ++kk) {
+                a1 = fma(T1[i * LD + kk], P[kk * LD + j], a1);   // (dQ A P)_ij
+                a2 = fma(A[kk * LD + i], T1[kk * LD + j], a2);   // (A^T dQ A)_ij
             }
-            c.sync();
-            for (int i = s - 1; i >= 0; --i) {
-                // A_i = Ah^(2^i) by i squarings (recomputed: no per-level storage)
-                T* cur = T1;
-                T* nxt = T2;
-                co_copy(c, dd, Ah, cur);
-                c.sync();
-                for (int q = 0; q < i; ++q) {
-                    co_mm(c, d, d, d, cur, d, 1, cur, d, 1, nxt, d, (const T*)nullptr, T(1));
-                    c.sync();
-                    T* t = cur;
+            da = fma(T(-2), a1, da);                             // dA -= 2 dQ A P
+            acc[0] += dq - a2;                                   // dPinf += dQ - A^T dQ A
+        }
+        if (s > 0) {  // block-uniform: back-propagate through the squarings A = Ah^(2^s)
+            if (on) {
+                dA[ij] = da;
+                T a = C[(size_t)DEG * dd + e];
+                for (int p = DEG - 1; p >= 0; --p) a = fma(a, x, C[(size_t)p * dd + e]);
+                Ah[ij] = a;
+            }
+            __syncthreads();
+            for (int lvl = s - 1; lvl >= 0; --lvl) {
+                // A_lvl = Ah^(2^lvl) by lvl squarings (recomputed: no per-level storage)
+                const T* cur = Ah;
+                T* nxt = T1;
+                for (int q = 0; q < lvl; ++q) {
+                    if (on) {
+                        T a1 = T(0);
+                        for (int kk = 0; kk < d; ++kk) a1 = fma(cur[i * LD + kk], cur[kk * LD + j], a1);
+                        nxt[ij] = a1;
+                    }
+                    __syncthreads();
                     cur = nxt;
-                    nxt = t;
+                    nxt = (nxt == T1) ? T2 : T1;
                 }
-                // dA_i = A_i^T dA + dA A_i^T   (into nxt, then back to dA)
-                for (int idx = c.tid; idx < dd; idx += c.nt) {
-                    const int r = idx / d, cc = idx - r * d;
+                // dA <- A_lvl^T dA + dA A_lvl^T
+                if (on) {
                     T a1 = T(0);
                     for (int kk = 0; kk < d; ++kk) {
-                        a1 = fma(cur[kk * d + r], dA[kk * d + cc], a1);
-                        a1 = fma(dA[r * d + kk], cur[cc * d + kk], a1);
+                        a1 = fma(cur[kk * LD + i], dA[kk * LD + j], a1);
+                        a1 = fma(dA[i * LD + kk], cur[j * LD + kk], a1);
                     }
-                    nxt[idx] = a1;
+                    da = a1;
                 }
-                c.sync();
-                co_copy(c, dd, nxt, dA);
-                c.sync();
+                __syncthreads();
+                if (on) dA[ij] = da;
+                __syncthreads();
             }
         }
         // moments W_p += x^p dA_h, skipping degrees whose weight x^(p-1)/p! is negligible
@@ -611,17 +626,30 @@ __global__ void discretise_bwd_generic_kernel(const T* __restrict__ coef, const 
                 }
             }
             if (pmax < 1) pmax = 1;
-            for (int idx = c.tid; idx < dd; idx += c.nt) {
-                const T v = dA[idx];
-                T xp = T(1);
-                for (int p = 1; p <= pmax; ++p) {
-                    xp *= x;
-                    mine[(size_t)p * dd + idx] = fma(xp, v, mine[(size_t)p * dd + idx]);
-                }
+            T xp = T(1);
+#pragma unroll
+            for (int p = 1; p <= DEG; ++p) {
+                xp *= x;
+                if (p <= pmax) acc[p] = fma(xp, da, acc[p]);
             }
         }
-        c.sync();
+        __syncthreads();
     }
+    if (on) {
+        T* mine = part + (size_t)blockIdx.x * (DEG + 1) * dd;
+#pragma unroll
+        for (int p = 0; p <= DEG; ++p) mine[(size_t)p * dd + e] = acc[p];
+    }
+}
+
+// out[g][o] = sum of part[b][o] over the partials b = g, g + G, ... (fixed order: deterministic), G = gridDim.y
+template <typename T>
+__global__ void partials_reduce_kernel(const T* __restrict__ part, int nparts, int nout, T* __restrict__ out) {
+    const int o = blockIdx.x * blockDim.x + threadIdx.x;
+    if (o >= nout) return;
+    T s = T(0);
+    for (int b = blockIdx.y; b < nparts; b += gridDim.y) s += part[(size_t)b * nout + o];
+    out[(size_t)blockIdx.y * nout + o] = s;
 }
 
 template <typename T>
@@ -632,8 +660,17 @@ int discretise_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F, co
     if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * cnt * 2))) return rc;
     T* coef;
     if ((rc = setup_coef<T>(h, F, d, 0, &coef, 0, st))) return rc;
-    const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
-    long grid = (long)h->num_sms * 8;
+    if constexpr (sizeof(T) == 8) {
+        // FP64, d <= 32: warp-per-step tensor-core kernel (discretise_frag.cu)
+        if (d <= 32 && !h->force_generic)
+            return discretise_frag_f64(h, n, d, (const double*)coef, (const double*)Pinf, (const double*)dts, (double*)Fs,
+                                       (double*)Qs, st);
+    }
+    int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
+    int per_sm = 8;
+    if (const char* e = getenv("PSSGP_DISC_CTAS")) per_sm = atoi(e);   // tuning aids
+    if (const char* e = getenv("PSSGP_DISC_NT")) nt = atoi(e);
+    long grid = (long)h->num_sms * per_sm;
     if (grid > n) grid = n;
     const size_t sm = sizeof(T) * 3 * d * d;
     if (sm > 48 * 1024) cudaFuncSetAttribute(discretise_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -649,30 +686,49 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
                                 cudaStream_t st) {
     int rc;
     constexpr int DEG = Taylor<T>::DEG;
+    constexpr int kGroups = 16;
     const size_t cnt = coef_count(DEG, d);
     const int NOUT = (DEG + 1) * d * d;
-    long grid = (long)h->num_sms * 2;
+    const int nt = (d * d + 31) / 32 * 32;   // one thread per matrix element
+    if (nt > 1024) return set_err(PSSGP_ERR_UNSUPPORTED, "discretise_backward: d <= 32 (got %d)", d);
+    const size_t sm = sizeof(T) * 7 * d * (d | 1);
+    int per_sm = 2048 / nt;
+    if (per_sm > 16) per_sm = 16;
+    if ((size_t)per_sm * (sm + 1024) > (size_t)200 * 1024) per_sm = (int)((size_t)200 * 1024 / (sm + 1024));
+    if (per_sm < 1) per_sm = 1;
+    if (const char* e = getenv("PSSGP_DISCB_CTAS")) per_sm = atoi(e);  // tuning aid
+    long grid = (long)h->num_sms * per_sm;
     if (grid > n) grid = n;
     if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + 2 * NOUT)))) return rc;
-    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * grid))) return rc;
+    if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * (grid + kGroups)))) return rc;
     T *coef, *coefT;
     if ((rc = setup_coef<T>(h, F, d, 0, &coef, 0, st))) return rc;
     if ((rc = setup_coef<T>(h, F, d, 1, &coefT, cnt, st))) return rc;
     T* W = (T*)h->buf[WS_MISC] + 2 * cnt;
     T* V = W + NOUT;
     T* part = (T*)h->buf[WS_PART];
-    const int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
-    const size_t sm = sizeof(T) * 7 * d * d;
-    if (sm > 48 * 1024)
-        cudaFuncSetAttribute(discretise_bwd_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    PSSGP_LAUNCH(h, "discretise_bwd", st,
-                 (discretise_bwd_generic_kernel<T><<<(unsigned)grid, nt, sm, st>>>(coef, (const T*)Pinf, d, (const T*)dts,
-                                                                                  n, (const T*)Fs, (const T*)dFs,
-                                                                                  (const T*)dQs, part)));
+    T* grouped = part + (size_t)NOUT * grid;
+    // register budget follows the CTA size: 256 threads keep the 19 moment accumulators in registers, the larger
+    // CTAs of d > 16 are compiled for 128 / 64 registers per thread (the accumulators spill to local memory there)
+    auto launch = [&](auto kern) {
+        if (sm > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        PSSGP_LAUNCH(h, "discretise_bwd", st,
+                     (kern<<<(unsigned)grid, nt, sm, st>>>(coef, (const T*)Pinf, d, (const T*)dts, n, (const T*)Fs,
+                                                           (const T*)dFs, (const T*)dQs, part)));
+    };
+    if (nt <= 256)
+        launch(discretise_bwd_generic_kernel<T, 256>);
+    else if (nt <= 512)
+        launch(discretise_bwd_generic_kernel<T, 512>);
+    else
+        launch(discretise_bwd_generic_kernel<T, 1024>);
+    const int groups = grid < kGroups ? (int)grid : kGroups;
+    PSSGP_LAUNCH(h, "discretise_bwd_reduce", st,
+                 (partials_reduce_kernel<T><<<dim3((NOUT + 127) / 128, groups), 128, 0, st>>>(part, (int)grid, NOUT, grouped)));
     PSSGP_LAUNCH(h, "discretise_bwd_final", st,
-                 (discretise_bwd_final_kernel<T><<<1, 1024, 1024 * sizeof(T), st>>>(coefT, part, (int)grid, d, W, V,
+                 (discretise_bwd_final_kernel<T><<<1, 1024, 1024 * sizeof(T), st>>>(coefT, grouped, groups, d, W, V,
                                                                                    (T*)dF, (T*)dPinf)));
-    return check_launch(h, "discretise_backward", 4);
+    return check_launch(h, "discretise_backward", 5);
 }
 
 }  // namespace pssgp

@@ -14,6 +14,7 @@ from . import _arrays as A
 from . import _lib
 from . import config as pssgp_config
 from . import ops
+from .kalman.base import LGSSM
 from .kernels.base import time_steps
 from .params import Parameter
 
@@ -186,12 +187,20 @@ class StateSpaceGP:
         dtype, dev = ts.dtype, ts.device
         Xd = A.to_device(Xnew, dtype, dev, "Xnew").reshape(-1)
         K = Xd.shape[0]
-        nan_ys = torch.full((K, ys.shape[1]), float("nan"), dtype=dtype, device=dev)
-        (all_ts, all_ys), (_, q_idx) = _merge_sorted_idx(ts.reshape(-1), Xd, (ys, nan_ys))
+        if ys.shape[1] != 1:
+            raise ValueError("single-output models only (pssgp/model.py:72)")
         with torch.no_grad():
-            ssm = self._make_model(all_ts[:, None])
-            Hd, Rd = ssm.H.reshape(-1).contiguous(), ssm.R.reshape(-1).contiguous()
-            yv = all_ys.reshape(-1).contiguous()
+            # model.py:95-104 in one C-ABI call: merged grid, NaN observations at the queries, time steps, query rows
+            _, yv, dts, q_idx = ops.merge_queries(ts.reshape(-1).contiguous(), ys.reshape(-1).contiguous(), Xd.contiguous())
+            sde = self._cached_sde()
+            d = sde.F.shape[0]
+            # the d x d SDE goes to the device as ONE pinned asynchronous copy
+            pd = A.to_device(torch.cat([sde.F.reshape(-1), sde.P0.reshape(-1), sde.H.reshape(-1),
+                                        self.noise_variance.value.detach().reshape(-1)]), dtype, dev, "pred_sde")
+            Fd, Pd = pd[:d * d].view(d, d), pd[d * d:2 * d * d].view(d, d)
+            Hd, Rd = pd[2 * d * d:2 * d * d + d], pd[2 * d * d + d:2 * d * d + d + 1]
+            Fs, Qs = ops.discretise(Fd, Pd, dts)
+            ssm = LGSSM(Pd, Fs, Qs, Hd.reshape(1, -1), Rd.reshape(1, 1))
             if not self.parallel:
                 # model.py:76-77: kfs = sequential filter (with predicted moments) + sequential RTS smoother
                 fms, fPs, _, mps, Pps = ops.kf(ssm.P0, ssm.Fs, ssm.Qs, Hd, Rd, yv, want_ll=False, want_predicted=True)

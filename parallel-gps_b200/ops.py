@@ -114,6 +114,19 @@ def pkfs(P0, Fs, Qs, H, R, y, want_ll=False, project=False):
     return fms, fPs, ll, sms, sPs
 
 
+def merge_queries(ts, ys, q, t0=0.0):
+    """C ABI: pssgp_merge_queries.  ts, ys [n], q [K] sorted device vectors.
+    -> t_all, y_all, dts [n+K], q_idx [K] (int64 rows of the queries in the merged arrays)."""
+    n, K = ts.numel(), q.numel()
+    kw = dict(dtype=ts.dtype, device=ts.device)
+    t_all, y_all, dts = torch.empty(n + K, **kw), torch.empty(n + K, **kw), torch.empty(n + K, **kw)
+    q_idx = torch.empty(K, dtype=torch.int64, device=ts.device)
+    _lib.check(_lib.lib().pssgp_merge_queries(_h(ts).ptr, A.dtype_code(ts), n, K, A.ptr(ts), A.ptr(ys), A.ptr(q), float(t0),
+                                             A.ptr(t_all), A.ptr(y_all), A.ptr(dts), A.ptr(q_idx),
+                                             A.stream_ptr(ts.device)))
+    return t_all, y_all, dts, q_idx
+
+
 def kf(P0, Fs, Qs, H, R, y, want_ll=True, want_predicted=False):
     """C ABI: pssgp_kf (sequential Kalman filter).  y [n] or [batch,n]; the LGSSM is shared by the series when Fs is
     [n,d,d] and per series when it is [batch,n,d,d].  -> fms, fPs, ll[batch] or None, mps, Pps (or None, None)."""
