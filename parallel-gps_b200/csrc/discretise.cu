@@ -403,6 +403,9 @@ __global__ void discretise_bwd_final_kernel(const T* __restrict__ coefT, const T
 
 int discretise_frag_f64(pssgp_handle* h, int64_t n, int d, const double* coef, const double* Pinf, const double* dts,
                         double* Fs, double* Qs, cudaStream_t st);
+int discretise_bwd_frag_f64(pssgp_handle* h, int64_t n, int d, const double* coef, const double* Pinf, const double* dts,
+                            const double* Fs, const double* dFs, const double* dQs, double* part, long* grid_out,
+                            int* per_cta, cudaStream_t st);
 
 constexpr size_t coef_count(int deg, int d) { return 8 + (size_t)(deg + 1) * d * d; }
 
@@ -689,6 +692,18 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
     constexpr int kGroups = 16;
     const size_t cnt = coef_count(DEG, d);
     const int NOUT = (DEG + 1) * d * d;
+    // FP64, d <= 24: warp-per-step tensor-core products + thread-per-element moments (discretise_frag.cu)
+    bool frag = false;
+    long fgrid = 0;
+    int per_cta = 1;
+    if constexpr (sizeof(T) == 8) {
+        if (d <= 24 && !h->force_generic) {
+            frag = true;
+            if ((rc = discretise_bwd_frag_f64(h, n, d, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, &fgrid,
+                                              &per_cta, st)))
+                return rc;
+        }
+    }
     const int nt = (d * d + 31) / 32 * 32;   // one thread per matrix element
     if (nt > 1024) return set_err(PSSGP_ERR_UNSUPPORTED, "discretise_backward: d <= 32 (got %d)", d);
     const size_t sm = sizeof(T) * 7 * d * (d | 1);
@@ -699,6 +714,7 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
     if (const char* e = getenv("PSSGP_DISCB_CTAS")) per_sm = atoi(e);  // tuning aid
     long grid = (long)h->num_sms * per_sm;
     if (grid > n) grid = n;
+    if (frag) grid = fgrid * per_cta;   // number of partials
     if ((rc = ws_reserve(h, WS_MISC, sizeof(T) * (cnt * 2 + 2 * NOUT)))) return rc;
     if ((rc = ws_reserve(h, WS_PART, sizeof(T) * (size_t)NOUT * (grid + kGroups)))) return rc;
     T *coef, *coefT;
@@ -708,6 +724,14 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
     T* V = W + NOUT;
     T* part = (T*)h->buf[WS_PART];
     T* grouped = part + (size_t)NOUT * grid;
+    if (frag) {
+        if constexpr (sizeof(T) == 8) {
+            if ((rc = discretise_bwd_frag_f64(h, n, d, (const double*)coef, (const double*)Pinf, (const double*)dts,
+                                              (const double*)Fs, (const double*)dFs, (const double*)dQs, (double*)part, &fgrid,
+                                              &per_cta, st)))
+                return rc;
+        }
+    } else {
     // register budget follows the CTA size: 256 threads keep the 19 moment accumulators in registers, the larger
     // CTAs of d > 16 are compiled for 128 / 64 registers per thread (the accumulators spill to local memory there)
     auto launch = [&](auto kern) {
@@ -722,6 +746,7 @@ int discretise_bwd_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F
         launch(discretise_bwd_generic_kernel<T, 512>);
     else
         launch(discretise_bwd_generic_kernel<T, 1024>);
+    }
     const int groups = grid < kGroups ? (int)grid : kGroups;
     PSSGP_LAUNCH(h, "discretise_bwd_reduce", st,
                  (partials_reduce_kernel<T><<<dim3((NOUT + 127) / 128, groups), 128, 0, st>>>(part, (int)grid, NOUT, grouped)));
