@@ -363,6 +363,44 @@ def run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, W):
             "argmax_setting": [float(x) for x in settings[int(ll.argmax())]]}
 
 
+def run_model_e2e(dev, torch, kernels, K):
+    """End to end through StateSpaceGP with HOST buffers for the d > 4 configurations (N = 1e6): one step = pinned (t, y)
+    to the device, log-likelihood + gradient w.r.t. the hyper-parameters, predict_f at N pinned queries back into pinned
+    memory.  Exercises get_sde (host), pssgp_discretise / _backward, the fused filter + adjoint, merge, filter + smoother."""
+    from pssgp_b200.model import StateSpaceGP
+    out = {}
+    n = 1_000_000
+    t_host, y_host = make_series(n)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    t_pin, y_pin, q_pin = pin(t_host[:, None]), pin(y_host[:, None]), pin((t_host + 0.002)[:, None])
+    mean_pin = torch.empty((n, 1), dtype=torch.float64).pin_memory()
+    var_pin = torch.empty((n, 1), dtype=torch.float64).pin_memory()
+    for name, mk in (("rbf6_d6", lambda: kernels.RBF(1.0, 1.0, order=6, balancing_iter=5)),
+                     ("m52rbf6_d9", lambda: kernels.Matern52(1.0, 1.0) + kernels.RBF(1.0, 1.0, order=6, balancing_iter=5))):
+        model = StateSpaceGP((t_pin, y_pin), mk(), noise_variance=NOISE, parallel=True, max_parallel=2 * n)
+
+        def step():
+            model.data = (t_pin, y_pin)
+            ll = model.maximum_log_likelihood_objective()
+            grads = torch.autograd.grad(ll, model.trainable_variables)
+            model.predict_f(q_pin, out=(mean_pin, var_pin))
+            return float(ll.detach()), [float(g) for g in grads]
+
+        for _ in range(3):
+            r = step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(K):
+            r = step()
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / K
+        out[name] = {"n": n, "ms_per_step": dt * 1e3, "value": n / dt, "unit": UNIT, "finite": bool(np.isfinite(r[0])),
+                     "h2d_bytes_per_step": int(8 * 3 * n), "d2h_bytes_per_step": int(8 * 2 * n)}
+        del model
+        torch.cuda.empty_cache()
+    return out
+
+
 def sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist, xchg=None):
     """Time-sharded step against the unsharded step of the same series (computed on every rank), d = 3 and d = 6."""
     out = {}
@@ -665,6 +703,12 @@ def main():
                 extras["grid_1024"] = run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, Wx)
             except Exception as e:
                 extras["grid_1024"] = {"error": repr(e)}
+        if world == 1 and (not args.only or "model_e2e" in args.only.split(",")):
+            try:
+                extras["model_e2e"] = run_model_e2e(dev, torch, kernels, Kx)
+            except Exception as e:
+                extras["model_e2e"] = {"error": repr(e)}
+                torch.cuda.empty_cache()
         if world > 1:
             try:
                 check = sharded_check(world, rank, dev, dist, torch, kernels, ops, pdist, xchg)

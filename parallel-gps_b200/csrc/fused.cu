@@ -543,16 +543,22 @@ int pssgp_pkfs(pssgp_handle* h, int dtype, int64_t n, int d, const void* P0, con
     cudaStream_t st = (cudaStream_t)stream;
     rc = pkfs_dispatch(h, dtype, n, d, P0, Fs, Qs, H, R, y, fms, fPs, ll, sms, sPs, proj, st);
     if (rc != kNotFused) return rc;
-    if (!proj && dtype == PSSGP_F64 && mid::supported(d) && !h->force_generic)
-        return mid::pkfs_grad_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
-                                       (const double*)R, (const double*)y, nullptr, (double*)fms, (double*)fPs, (double*)ll,
-                                       (double*)sms, (double*)sPs, nullptr, nullptr, nullptr, nullptr, nullptr, st);
+    if (dtype == PSSGP_F64 && mid::supported(d) && !h->force_generic && (!proj || (d <= 24 && !h->mid_smem))) {
+        // proj: the fragment-resident reverse kernel emits (H sm, H sP H^T) per step instead of sms / sPs
+        h->mid_proj = proj;
+        rc = mid::pkfs_grad_dispatch(d, h, n, (const double*)P0, (const double*)Fs, (const double*)Qs, (const double*)H,
+                                     (const double*)R, (const double*)y, nullptr, (double*)fms, (double*)fPs, (double*)ll,
+                                     proj ? nullptr : (double*)sms, proj ? nullptr : (double*)sPs, nullptr, nullptr, nullptr,
+                                     nullptr, nullptr, st);
+        h->mid_proj = nullptr;
+        return rc;
+    }
     if (!proj && dtype == PSSGP_F32 && mid::supported(d) && !h->force_generic)
         return mid::f32_pkfs_grad(h, n, d, (const float*)P0, (const float*)Fs, (const float*)Qs, (const float*)H,
                                   (const float*)R, (const float*)y, nullptr, (float*)fms, (float*)fPs, (float*)ll, (float*)sms,
                                   (float*)sPs, nullptr, nullptr, nullptr, nullptr, nullptr, false, st);
-    if (proj) return set_err(PSSGP_ERR_UNSUPPORTED, "pkfs: projected output is implemented for the fused d <= 4 path only "
-                                                    "(d = %d): pass sms / sPs", d);
+    if (proj) return set_err(PSSGP_ERR_UNSUPPORTED, "pkfs: projected output is implemented for the fused d <= 4 kernels and the "
+                                                    "FP64 fragment-resident kernels (5 <= d <= 24); d = %d: pass sms / sPs", d);
     if ((rc = pssgp_pkf(h, dtype, n, d, P0, Fs, Qs, H, R, y, nullptr, 1, fms, fPs, ll, nullptr, stream))) return rc;
     return pssgp_pks(h, dtype, n, d, Fs, Qs, fms, fPs, 1, nullptr, nullptr, nullptr, sms, sPs, nullptr, stream);
 }

@@ -175,6 +175,7 @@ struct Params {
     const double *Fs, *Qs, *y, *H, *R, *P0, *m0, *g;
     const double *fms_in, *fPs_in;  // filtered moments as inputs (K3; K2 in STORED mode)
     double *fms, *fPs, *sms, *sPs, *dFs, *dQs, *dP0;
+    double* proj;  // fragment K3 only: [n,2] = (H sm_k, H sP_k H^T) instead of sms / sPs (predict_f, model.py:107-111)
     long n;
     int first_special;
 };

@@ -1074,6 +1074,19 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
         const double* sl = slot(k);
         const double* slp = slot(k - 1);
         if constexpr (SMOOTH) {
+          if (p.proj != nullptr) {
+            // projected output only: H sm_k = h.m_k - h.(P_k lam_k),  H sP_k H^T = h.w - w.(Lam_k w) with w = P_k h
+            // (four matrix-vector products instead of the two matrix products below, and 2 values stored instead of d^2 + d)
+            const auto Pk = TR::in_op(sl + O_P, false, r, c);
+            const VR w = TR::mv(Pk, hP);
+            const VR v1 = TR::mv(Pk, TR::vr2vp(lam, c));
+            const VR Lw = TR::mv(Lam, TR::vr2vp(w, c));
+            const VR mk = TR::ld_vr(sl + O_M, r);
+            double hw, wLw, hmk, hv1;
+            TR::dots2(hR, w, w, Lw, lane, c, hw, wLw);
+            TR::dots2(hR, mk, hR, v1, lane, c, hmk, hv1);
+            if (lane == 0) *reinterpret_cast<double2*>(p.proj + 2 * k) = make_double2(hmk - hv1, hw - wLw);
+          } else {
             // sm_k = m_k - P_k lam_k ; sP_k = P_k - P_k Lam_k P_k   (state entering from above)
             const auto Pk = TR::in_op(sl + O_P, false, r, c);
             const M Zt = TR::mulT(Pk, Lam, c);  // P_k Lam = (Lam P_k)^T
@@ -1082,6 +1095,7 @@ fk3_reverse(Params p, int L, long nchunks, const double* __restrict__ rstates, d
             const VR v1 = TR::mv(Pk, TR::vr2vp(lam, c));
             const VR mk = TR::ld_vr(sl + O_M, r);
             TR::gst_vr(p.sms + k * D, TR::vaxpy(-1.0, v1, mk), r, c);
+          }
         }
         // forward quantities of step k
         const auto F = TR::in_op(sl, false, r, c);

@@ -241,11 +241,15 @@ int pkfs_grad(pssgp_handle* h, int64_t n, const double* P0, const double* Fs, co
               double* sPs, double* dP0, double* dFs, double* dQs, double* dH, double* dR, cudaStream_t st) {
     g_mid_warps = h->mid_warps;
     const bool fr = has_frag<D>() && !h->mid_smem;
-    const bool smooth = sms != nullptr, adj = dFs != nullptr;
+    double* proj = (double*)h->mid_proj;   // set by pssgp_pkfs: (H sm, H sP H^T) per step instead of sms / sPs
+    h->mid_proj = nullptr;
+    if (proj != nullptr && !fr)
+        return set_err(PSSGP_ERR_UNSUPPORTED, "pkfs: projected output needs the fragment-resident kernels (d <= 24)");
+    const bool smooth = sms != nullptr || proj != nullptr, adj = dFs != nullptr;
     int rc;
     Params p = base_params(n, P0, Fs, Qs, H, R, y, nullptr, 1);
     p.fms = fms; p.fPs = fPs; p.fms_in = fms; p.fPs_in = fPs; p.g = g_ll;
-    p.sms = sms; p.sPs = sPs; p.dFs = dFs; p.dQs = dQs; p.dP0 = dP0;
+    p.sms = sms; p.sPs = sPs; p.dFs = dFs; p.dQs = dQs; p.dP0 = dP0; p.proj = proj;
     int gpc = k3_groups<D, true, true>(fr);
     if (k2_groups<D, true, false>(fr) < gpc) gpc = k2_groups<D, true, false>(fr);
     if (k1_groups<D>(fr) < gpc) gpc = k1_groups<D>(fr);

@@ -21,6 +21,7 @@ struct pssgp_handle {
     int force_generic;  // option "force_generic": d > 4 runs the CTA-cooperative kernels of generic.cu (tuning / tests)
     int grid_lanes;     // option "grid_lanes": concurrent settings in pssgp_grid_loglik (0 = default 4 = max)
     int fused_reverse;  // option "fused_reverse": pkfs_grad runs smoother + adjoint recursions in one kernel
+    void* mid_proj;     // internal: projected output [n,2] requested by pssgp_pkfs for its next mid::pkfs_grad call
     int64_t launches;
     // chunk aggregates left in the workspace by a *_summary call (time sharding)
     // pending_key = signature (dtype size, d, n, every input pointer, the first/last flags) of the call that built

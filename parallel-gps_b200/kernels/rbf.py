@@ -1,4 +1,5 @@
 """RBF kernel in state-space form: mirrors pssgp/kernels/rbf.py."""
+import functools
 import math
 
 import numpy as np
@@ -10,6 +11,7 @@ from .matern import DT, _Stationary
 from .math_utils import balance_ss, solve_lyap_vec
 
 
+@functools.lru_cache(maxsize=None)
 def _get_unscaled_rbf_sde(order=6):
     """rbf.py:14-61: spectral factorisation of the order-`order` Taylor expansion of exp(w^2/2):
     the stable roots of the denominator polynomial give the companion-form drift."""

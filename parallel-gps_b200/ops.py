@@ -159,9 +159,9 @@ def ks(Fs, fms, fPs, mps, Pps):
 
 
 def has_projection(d, dtype):
-    """pssgp_pkfs can emit (H m, H P H^T) of the smoothed states directly (fused d <= 4 kernels with a common
-    partition: every d <= 3, and d = 4 in FP32)."""
-    return d <= 3 or (d == 4 and dtype == torch.float32)
+    """pssgp_pkfs can emit (H m, H P H^T) of the smoothed states directly: the fused d <= 4 kernels with a common
+    partition (every d <= 3, and d = 4 in FP32) and the FP64 fragment-resident kernels (5 <= d <= 24)."""
+    return d <= 3 or (d == 4 and dtype == torch.float32) or (5 <= d <= 24 and dtype == torch.float64)
 
 
 def pkfs_grad(P0, Fs, Qs, H, R, y, g_ll, want_smoother=True):

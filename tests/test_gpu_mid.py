@@ -158,3 +158,32 @@ def test_every_dimension_against_the_cta_cooperative_path(d):
     tol = 1e-9
     for a, b in ((fm, rfm), (fP, rfP), (ll, rll), (sm, rsm), (sP, rsP), (dP0, rdP0), (dF, rdF), (dQ, rdQ), (dH, rdH), (dR, rdR)):
         assert rel_err(a.cpu(), b.cpu()) < tol
+
+
+@pytest.mark.parametrize("name", ["m32+m52", "rbf6", "m52+rbf6", "qp3", "qp5"])
+def test_projected_smoother_output(name):
+    """pssgp_pkfs with proj (what predict_f keeps, pssgp/model.py:107-111): (H sm_k, H sP_k H^T) straight from the
+    reverse kernel equals the projection of the full smoothed moments and of the oracle's."""
+    pkg()
+    from pssgp_b200 import ops
+    T = 777
+    span = 40.0 if name.startswith("qp") else 4.0
+    t, y, cov, ssm = make_problem(name, T, seed=21, span=span)
+    to = lambda x: x.detach().to(DEV).contiguous()
+    P0, Fs, Qs, H, R = to(ssm.P0), to(ssm.Fs), to(sym(ssm.Qs)), to(ssm.H).reshape(-1), to(ssm.R).reshape(-1)
+    yd = torch.as_tensor(y).to(DEV)
+    d = Fs.shape[1]
+    assert ops.has_projection(d, torch.float64)
+    fms, fPs, ll, proj = ops.pkfs(P0, Fs, Qs, H, R, yd, want_ll=True, project=True)
+    f2, fP2, ll2, sms, sPs = ops.pkfs(P0, Fs, Qs, H, R, yd, want_ll=True)
+    mean = sms @ H
+    var = torch.einsum("i,kij,j->k", H, sPs, H)
+    assert torch.equal(fms, f2) and torch.equal(fPs, fP2) and float(ll) == float(ll2)
+    assert rel_err(proj[:, 0].cpu(), mean.cpu()) < 1e-11 and rel_err(proj[:, 1].cpu(), var.cpu()) < 1e-9
+    with torch.no_grad():
+        rfm, rfP = O.pkf(ssm, y[:, None], max_parallel=T)
+        rsm, rsP = O.pks(ssm, rfm, rfP, max_parallel=T)
+        Ho = ssm.H.reshape(-1)
+        tol = 1e-7 if name.startswith("qp") else 1e-9
+        assert rel_err(proj[:, 0].cpu(), rsm @ Ho) < tol
+        assert rel_err(proj[:, 1].cpu(), torch.einsum("i,kij,j->k", Ho, rsP, Ho)) < tol
