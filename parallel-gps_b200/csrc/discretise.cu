@@ -466,57 +466,72 @@ int discretise_bwd_impl(pssgp_handle* h, int64_t n, const void* F, const void* P
 // ---------------------------------------------------------------------------------------------
 // generic state dimension: one CTA per time step (grid-stride), matrices in shared memory
 // ---------------------------------------------------------------------------------------------
+// One thread per matrix element (i, j); matrices in shared memory with an odd leading dimension, every product reads one
+// operand as a row broadcast and the other along consecutive columns (no bank conflicts, no division in the loop).
+// FP64 with d <= 32 runs discretise_frag.cu instead; this kernel serves FP32 and the option "force_generic".
 template <typename T>
-__global__ void discretise_generic_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, int d,
+__global__ void __launch_bounds__(1024) discretise_generic_kernel(const T* __restrict__ coef, const T* __restrict__ Pinf, int d,
                                           const T* __restrict__ dts, long n, T* __restrict__ Fs, T* __restrict__ Qs) {
     constexpr int DEG = Taylor<T>::DEG;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int dd = d * d;
+    const int dd = d * d, LD = d | 1, MS = d * LD;
     T* A = (T*)smem_raw;
-    T* B = A + dd;
-    T* P = B + dd;
-    Coop c{(int)threadIdx.x, (int)blockDim.x};
-    for (int idx = c.tid; idx < dd; idx += c.nt) {
-        const int i = idx / d, j = idx - i * d;
-        P[idx] = T(0.5) * (Pinf[idx] + Pinf[j * d + i]);
+    T* B = A + MS;
+    T* P = B + MS;
+    const int e = threadIdx.x;
+    const bool on = e < dd;
+    const int i = on ? e / d : 0, j = on ? e - i * d : 0;
+    const int ij = i * LD + j;
+    T pij = T(0);
+    if (on) {
+        pij = T(0.5) * (Pinf[e] + Pinf[j * d + i]);
+        P[ij] = pij;
     }
     const T normF = coef[0];
     const T* C = coef + 8;
-    c.sync();
+    __syncthreads();
     for (long k = blockIdx.x; k < n; k += gridDim.x) {
         const T dt = dts[k];
         T x;
         const int s = pick_squarings<T>(normF * t_abs(dt), x);
         if (dt < T(0)) x = -x;
-        for (int idx = c.tid; idx < dd; idx += c.nt) {
-            T a = C[(size_t)DEG * dd + idx];
-            for (int p = DEG - 1; p >= 0; --p) a = fma(a, x, C[(size_t)p * dd + idx]);
-            A[idx] = a;
+        T a = T(0);
+        if (on) {
+            a = C[(size_t)DEG * dd + e];
+            for (int p = DEG - 1; p >= 0; --p) a = fma(a, x, C[(size_t)p * dd + e]);
+            A[ij] = a;
         }
-        c.sync();
+        __syncthreads();
         T* cur = A;
         T* nxt = B;
-        for (int i = 0; i < s; ++i) {
-            co_mm(c, d, d, d, cur, d, 1, cur, d, 1, nxt, d, (const T*)nullptr, T(1));
-            c.sync();
+        for (int q = 0; q < s; ++q) {
+            if (on) {
+                a = T(0);
+                for (int kk = 0; kk < d; ++kk) a = fma(cur[i * LD + kk], cur[kk * LD + j], a);
+                nxt[ij] = a;
+            }
+            __syncthreads();
             T* t = cur;
             cur = nxt;
             nxt = t;
         }
-        co_copy(c, dd, cur, Fs + k * dd);
-        co_mm(c, d, d, d, cur, d, 1, P, d, 1, nxt, d, (const T*)nullptr, T(1));  // A P
-        c.sync();
-        T* gq = Qs + k * dd;
-        for (int idx = c.tid; idx < dd; idx += c.nt) {
-            const int i = idx / d, j = idx - i * d;
+        if (on) {
+            Fs[k * dd + e] = a;
+            T ap = T(0);   // (A P)_ij
+            for (int kk = 0; kk < d; ++kk) ap = fma(cur[i * LD + kk], P[kk * LD + j], ap);
+            nxt[ij] = ap;
+        }
+        __syncthreads();
+        if (on) {
+            // Q_ij = P_ij - ((A P A^T)_ij + (A P A^T)_ji) / 2
             T a1 = T(0), a2 = T(0);
             for (int kk = 0; kk < d; ++kk) {
-                a1 = fma(nxt[i * d + kk], cur[j * d + kk], a1);
-                a2 = fma(nxt[j * d + kk], cur[i * d + kk], a2);
+                a1 = fma(nxt[i * LD + kk], cur[j * LD + kk], a1);
+                a2 = fma(nxt[j * LD + kk], cur[i * LD + kk], a2);
             }
-            gq[idx] = P[idx] - T(0.5) * (a1 + a2);
+            Qs[k * dd + e] = pij - T(0.5) * (a1 + a2);
         }
-        c.sync();
+        __syncthreads();
     }
 }
 
@@ -669,13 +684,14 @@ int discretise_generic_impl(pssgp_handle* h, int64_t n, int d, const void* F, co
             return discretise_frag_f64(h, n, d, (const double*)coef, (const double*)Pinf, (const double*)dts, (double*)Fs,
                                        (double*)Qs, st);
     }
-    int nt = d <= 8 ? 64 : (d <= 16 ? 128 : 256);
-    int per_sm = 8;
-    if (const char* e = getenv("PSSGP_DISC_CTAS")) per_sm = atoi(e);   // tuning aids
-    if (const char* e = getenv("PSSGP_DISC_NT")) nt = atoi(e);
+    const int nt = (d * d + 31) / 32 * 32;   // one thread per matrix element
+    if (nt > 1024) return set_err(PSSGP_ERR_UNSUPPORTED, "discretise: d <= 32 (got %d)", d);
+    const size_t sm = sizeof(T) * 3 * d * (d | 1);
+    int per_sm = 2048 / nt;
+    if (per_sm > 16) per_sm = 16;
+    if (const char* e = getenv("PSSGP_DISC_CTAS")) per_sm = atoi(e);   // tuning aid
     long grid = (long)h->num_sms * per_sm;
     if (grid > n) grid = n;
-    const size_t sm = sizeof(T) * 3 * d * d;
     if (sm > 48 * 1024) cudaFuncSetAttribute(discretise_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     PSSGP_LAUNCH(h, "discretise", st,
                  (discretise_generic_kernel<T><<<(unsigned)grid, nt, sm, st>>>(coef, (const T*)Pinf, d, (const T*)dts, n,

@@ -162,3 +162,20 @@ def test_model_sequential_mode(kname):
     assert rel_err(m, om) < 1e-8 and rel_err(v, ov) < 1e-8
     assert abs(ll - res[True][0]) < 1e-9 * abs(ll)
     assert rel_err(m, res[True][2]) < 1e-8 and rel_err(v, res[True][3]) < 1e-8
+
+
+def test_long_series_against_numba_port():
+    """One series of 2e5 steps (the comparator use of kf / ks): against the numba restatement of sequential.py
+    (oracle/seq_numba.py, itself pinned to the torch restatement in tests/test_cpu_oracle.py)."""
+    pkg()
+    import seq_numba
+    from pssgp_b200.kalman.sequential import kf, kfs
+    T = 200_000
+    t, y, cov, ssm = make_problem("matern52", T, seed=8, span=800.0)
+    P0, Fs, Qs, H, R = [np.ascontiguousarray(x.detach().numpy()) for x in ssm]
+    rfm, rfP, rmp, rPp, rll = seq_numba.kf(P0, Fs, Qs, H, R, y)
+    rsm, rsP = seq_numba.ks(Fs, rfm, rfP, rmp, rPp)
+    fm, fP, ll = kf((P0, Fs, Qs, H, R), y[:, None], return_loglikelihood=True)
+    assert rel_err(fm, rfm) < 1e-9 and rel_err(fP, rfP) < 1e-9 and abs(float(ll) - float(rll)) < 1e-9 * abs(float(rll))
+    sm, sP = kfs((P0, Fs, Qs, H, R), y[:, None])
+    assert rel_err(sm, rsm) < 1e-8 and rel_err(sP, rsP) < 1e-8
