@@ -663,6 +663,25 @@ def main():
         for _ in range(W):
             r = e2e_step()
         barrier()
+        # the same step as one CUDA graph per rank (H2D of the shard ... D2H of the results): kernels, copies and peer
+        # exchanges replay from one launch; falls back to the eager step if any rank cannot capture
+        e2e_graphed = False
+        if xchg is not None and os.environ.get("PSSGP_GRAPH", "1") == "1":
+            try:
+                replay = shard.capture_series_step(F, Pinf, H, R, t_pin, y_pin, t_prev, (mean_pin, var_pin))
+                okc = torch.tensor([1.0], device=dev)
+            except Exception as e:
+                print(f"[bench] CUDA-graph capture of the series step failed ({e!r}); eager step", file=sys.stderr)
+                okc = torch.tensor([0.0], device=dev)
+            dist.all_reduce(okc, op=dist.ReduceOp.MIN)
+            if float(okc) == 1.0:
+                r_eager = r
+                e2e_step = replay
+                e2e_graphed = True
+                for _ in range(W):
+                    r = e2e_step()
+                barrier()
+                assert abs(float(r[0][0]) - float(r_eager[0][0])) <= 1e-12 * abs(float(r_eager[0][0])), "graph replay differs"
         t0 = time.perf_counter()
         for _ in range(K):
             r = e2e_step()
@@ -675,7 +694,7 @@ def main():
                "api": "dist.TimeShard.series_step: per rank pinned (t, y) shard -> device, discretise, sharded filter + "
                       "smoother + gradient, -> host (ll, dF, dPinf, dH, dR) + pinned posterior mean/var of the shard; "
                       "bytes are totals over the ranks, time is the max over ranks",
-               "finite": bool(torch.isfinite(r[0][0]))}
+               "finite": bool(torch.isfinite(r[0][0])), "cuda_graph": e2e_graphed}
     # ---- the other BASELINE configurations + the sharded-vs-unsharded check (all ranks take part) ----------
     peaks_all = {}
     try:

@@ -247,15 +247,10 @@ class TimeShard:
         o = self.smoother_and_grad(P0, Fs, Qs, H, R, y, fms, fPs, g_ll, ll=ll)
         return o["ll"], o["sms"], o["sPs"], (o["dP0"], o["dFs"], o["dQs"], o["dH"], o["dR"])
 
-    def series_step(self, F, Pinf, H, R, ts, ys, t_prev, out=None):
-        """One training + smoothing step of a time-sharded series from HOST buffers: this rank's shard of the sampling
-        times ``ts`` [n] and observations ``ys`` [n] (host tensors, pinned for full PCIe speed; ``t_prev`` = the last
-        time of the previous shard, 0 for the first: kernels/base.py:31-33) goes to the device, is discretised
-        (kernels/base.py:29-47), filtered, smoothed and differentiated (filter_smoother_grad), the gradient is pulled
-        back through the discretisation and summed over the shards.
-        Returns (ll, dF[d,d], dPinf[d,d], dH[d], dR[1]) — global, host tensors — and the posterior mean / variance of
-        the latent function at this shard's times, (H sm_k, H sP_k H^T), as host tensors [n] (written into
-        ``out=(mean, var)`` when given: pinned buffers make the read-back asynchronous at full speed)."""
+    def _series_enqueue(self, F, Pinf, H, R, ts, ys, t_prev, mean_out, var_out, small_out):
+        """Enqueues one series step on the current stream, host synchronisation free: H2D of the shard, discretise,
+        sharded filter + smoother + gradient, gradient pulled back to the SDE and summed over the shards, D2H of the
+        posterior and of the packed small results [ll | dF | dPinf | dH | dR] into the given host tensors."""
         from . import _arrays as A
         ops = self.ops
         dev, dtype = F.device, F.dtype
@@ -263,7 +258,7 @@ class TimeShard:
         y_dev = A.to_device(ys, dtype, dev, "shard_ys").reshape(-1)
         prev = torch.empty_like(t_dev)
         prev[1:] = t_dev[:-1]
-        prev[0] = float(t_prev)
+        prev[:1].fill_(float(t_prev))   # (a scalar assignment would stage a pageable host copy: not capturable)
         dts = t_dev - prev
         d = F.shape[0]
         Fs, Qs = ops.discretise(F, Pinf, dts)
@@ -276,10 +271,67 @@ class TimeShard:
         small = torch.cat([ll.reshape(-1), red[:d * d], red[d * d:] + dP0.reshape(-1), dH.reshape(-1), dR.reshape(-1)])
         mean = sms @ Hd
         var = torch.einsum("i,kij,j->k", Hd, sPs, Hd)
-        if out is not None:
-            mean_h, var_h = A.to_host_into(mean, out[0]), A.to_host_into(var, out[1])
-        else:
-            mean_h, var_h = mean.cpu(), var.cpu()
-        sh = small.cpu()
-        return (sh[0], sh[1:1 + d * d].reshape(d, d), sh[1 + d * d:1 + 2 * d * d].reshape(d, d),
-                sh[1 + 2 * d * d:1 + 2 * d * d + d], sh[1 + 2 * d * d + d:]), (mean_h, var_h)
+        mean_out.view(-1).copy_(mean, non_blocking=True)
+        var_out.view(-1).copy_(var, non_blocking=True)
+        small_out.copy_(small, non_blocking=True)
+
+    @staticmethod
+    def _series_unpack(small, d, mean_out, var_out):
+        return (small[0], small[1:1 + d * d].reshape(d, d), small[1 + d * d:1 + 2 * d * d].reshape(d, d),
+                small[1 + 2 * d * d:1 + 2 * d * d + d], small[1 + 2 * d * d + d:]), (mean_out, var_out)
+
+    def series_step(self, F, Pinf, H, R, ts, ys, t_prev, out=None):
+        """One training + smoothing step of a time-sharded series from HOST buffers: this rank's shard of the sampling
+        times ``ts`` [n] and observations ``ys`` [n] (host tensors, pinned for full PCIe speed; ``t_prev`` = the last
+        time of the previous shard, 0 for the first: kernels/base.py:31-33) goes to the device, is discretised
+        (kernels/base.py:29-47), filtered, smoothed and differentiated (filter_smoother_grad), the gradient is pulled
+        back through the discretisation and summed over the shards.
+        Returns (ll, dF[d,d], dPinf[d,d], dH[d], dR[1]) — global, host tensors — and the posterior mean / variance of
+        the latent function at this shard's times, (H sm_k, H sP_k H^T), as host tensors [n] (written into
+        ``out=(mean, var)`` when given: pinned buffers make the read-back asynchronous at full speed)."""
+        d, n = F.shape[0], ts.numel()
+        if out is None:
+            out = (torch.empty(n, dtype=F.dtype).pin_memory(), torch.empty(n, dtype=F.dtype).pin_memory())
+        small = self._small_host(2 * d * d + d + 2, F.dtype)
+        self._series_enqueue(F, Pinf, H, R, ts, ys, t_prev, out[0], out[1], small)
+        torch.cuda.current_stream(F.device).synchronize()
+        return self._series_unpack(small.clone(), d, out[0], out[1])
+
+    def _small_host(self, numel, dtype):
+        buf = getattr(self, "_small_pin", None)
+        if buf is None or buf.numel() != numel or buf.dtype != dtype:
+            buf = torch.empty(numel, dtype=dtype).pin_memory()
+            self._small_pin = buf
+        return buf
+
+    def capture_series_step(self, F, Pinf, H, R, ts, ys, t_prev, out, warmup=3):
+        """The series step on FIXED buffers as ONE CUDA graph (for loops that refit the same shard: the hyper-parameter
+        tensors F, Pinf, H, R and the pinned host buffers ts, ys are updated in place between replays; ``t_prev`` is
+        baked in).  Everything between the host-to-device copy of the shard and the device-to-host copy of the results
+        — about forty kernels, memcpys and three peer exchanges — replays from one launch, which takes the per-launch
+        host work off every rank's critical path.  Needs the peer exchange (or a single rank): NCCL collectives are not
+        captured.  Every rank must capture and replay in step.  Returns ``replay() -> same as series_step``."""
+        if self.world > 1 and self.xchg is None:
+            raise RuntimeError("capture_series_step needs TimeShard(exchange=PeerExchange(...))")
+        if not (ts.is_pinned() and ys.is_pinned() and out[0].is_pinned() and out[1].is_pinned()):
+            raise ValueError("capture_series_step: ts, ys and out must be pinned host tensors")
+        dev, d = F.device, F.shape[0]
+        small = torch.empty(2 * d * d + d + 2, dtype=F.dtype).pin_memory()
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):   # workspaces reach their final size outside the capture
+                self._series_enqueue(F, Pinf, H, R, ts, ys, t_prev, out[0], out[1], small)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            self._series_enqueue(F, Pinf, H, R, ts, ys, t_prev, out[0], out[1], small)
+
+        def replay():
+            graph.replay()
+            torch.cuda.current_stream(dev).synchronize()
+            return self._series_unpack(small.clone(), d, out[0], out[1])
+
+        replay.graph = graph
+        return replay

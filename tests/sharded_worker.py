@@ -72,6 +72,15 @@ def main():
         for _ in range(2):
             (ll_s, dF, dPinf, dH, dR), (mean, var) = sh.series_step(to(sde.F), to(sde.P0), to(sde.H), R, pin(t[lo:hi]),
                                                                     pin(y[lo:hi]), t_prev)
+        if backend == "peer":
+            # the same step captured as one CUDA graph and replayed: identical results
+            mp, vp = torch.empty(hi - lo, dtype=torch.float64).pin_memory(), torch.empty(hi - lo, dtype=torch.float64).pin_memory()
+            replay = sh.capture_series_step(to(sde.F), to(sde.P0), to(sde.H), R, pin(t[lo:hi]), pin(y[lo:hi]), t_prev, (mp, vp))
+            for _ in range(3):
+                (ll_g, dF_g, dP_g, dH_g, dR_g), (mean_g, var_g) = replay()
+            if not (float(ll_g) == float(ll_s) and torch.equal(dF_g, dF) and torch.equal(mean_g, mean) and torch.equal(var_g, var)):
+                print(f"[rank {rank}] graph replay differs from the eager series step", file=sys.stderr)
+                ok = False
         errs = {"ll": abs(float(ll_s) - float(oll)) / abs(float(oll)), "dF": rel_err(dF, gF), "dPinf": rel_err(dPinf, 0.5 * (gP + gP.T)),  # gradient w.r.t. a symmetric matrix: symmetric part
                
                 "dH": rel_err(dH, gH.reshape(-1)), "dR": rel_err(dR, gR.reshape(-1)), "mean": rel_err(mean, omean),
