@@ -256,3 +256,15 @@ def test_matern52_closed_form_sde_equals_generic_path():
             assert float((a - b).abs().max()) <= 1e-13 * max(1.0, float(b.abs().max()))
         for a, b in zip(outs[True][1], outs[False][1]):
             assert float((a - b).abs().max()) <= 1e-11 * max(1.0, float(b.abs().max()))
+
+
+def test_toymodels_match_reference_vectors():
+    """pssgp_b200.toymodels against vectors generated from the reference's own pssgp.toymodels (scripts/make_golden.py)."""
+    import os
+    pkg()
+    from pssgp_b200 import toymodels as TM
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "toy_sinusoid_n1000.npz"))
+    t = g["t"]
+    assert np.array_equal(TM.sinu(t), g["ft"]) and np.array_equal(TM.comp_sinu(t), g["comp"]) and np.array_equal(TM.rect(t), g["rect"])
+    assert np.array_equal(TM.obs_noise(TM.sinu(t), 0.1, 0), g["y"])
+    assert np.array_equal(TM.obs_noise(TM.sinu(t), 0.5, 666), g["y_seed666"])
