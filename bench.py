@@ -774,6 +774,14 @@ def main():
                     "frac": achieved / hbm_peak, "traffic": traffic, "alg_bytes_per_launch": alg_bytes.get(dom, 0) * n,
                     "peak_source": peak_src,
                     "share_of_step": ktimes[dom][1] / sum(v[1] for v in ktimes.values())}
+    if e2e is not None and e2e.get("value"):
+        # the north star's compulsory-traffic floor beside the API-boundary roofline: a fully fused path would only read
+        # (t, y) and write the smoothed moments, s (2 + d^2 + d) bytes per step
+        floor_bytes = s * (2 + d * d + d)
+        e2e["compulsory_floor"] = {"bytes_per_timestep": floor_bytes,
+                                   "hbm_floor_ms_per_step": floor_bytes * n / (hbm_peak * 1e9) * 1e3,
+                                   "achieved_gbs_per_gpu": floor_bytes * e2e["value"] / world / 1e9,
+                                   "pcie_bytes_per_step_per_gpu": (e2e["h2d_bytes_per_step"] + e2e["d2h_bytes_per_step"]) // world}
     stage_bytes = s * (12 * d * d + 4 * d + 2)
     step_roof = {"alg_bytes_per_timestep": stage_bytes, "achieved_gbs": stage_bytes * n * world / (ms_dev * 1e-3) / 1e9,
                  "frac_of_hbm_peak": stage_bytes * n * world / (ms_dev * 1e-3) / 1e9 / (hbm_peak * world)}
