@@ -630,10 +630,12 @@ def main():
 
         def e2e_step():
             model.data = (t_pin, y_pin)  # H2D of this step's inputs from pinned memory
+            # queries from pinned memory, posterior mean / variance read back into pinned memory (D2H of the result);
+            # non_blocking: the read-back runs on a copy stream while the training step below computes
+            mean, var = model.predict_f(q_pin, out=(mean_pin, var_pin), non_blocking=True)
             ll = model.maximum_log_likelihood_objective()
             grads = torch.autograd.grad(ll, model.trainable_variables)
-            # queries from pinned memory, posterior mean / variance read back into pinned memory (D2H of the result)
-            mean, var = model.predict_f(q_pin, out=(mean_pin, var_pin))
+            model.synchronize()          # posterior buffers valid
             return float(ll), [float(g) for g in grads], mean, var
 
         for _ in range(W):
@@ -646,8 +648,8 @@ def main():
         dt = (time.perf_counter() - t0) / K
         e2e = {"value": n / dt, "unit": UNIT, "h2d_bytes_per_step": int(8 * 2 * n + 8 * n),
                "d2h_bytes_per_step": int(8 * 2 * n + 8 * 4), "ms_per_step": dt * 1e3,
-               "api": "StateSpaceGP.data= (pinned t, y) ; maximum_log_likelihood_objective + autograd.grad ; "
-                      "predict_f(N pinned queries, out=pinned mean/var)"}
+               "api": "StateSpaceGP.data= (pinned t, y) ; predict_f(N pinned queries, out=pinned mean/var, non_blocking=True) ; "
+                      "maximum_log_likelihood_objective + autograd.grad ; model.synchronize()"}
     else:
         # time-sharded: every rank holds ITS shard of the series in pinned host memory; one step = H2D of the shard,
         # discretise, sharded filter + smoother + gradient (exchanges over NVLink), gradient pulled back to the SDE,

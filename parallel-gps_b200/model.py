@@ -178,11 +178,21 @@ class StateSpaceGP:
         dts = time_steps(ts, 0., ts.dtype, ts.device)
         return _LogLikelihood.apply(sde.F, sde.P0, sde.H, R, dts, Y.reshape(-1), not self.parallel)
 
-    def predict_f(self, Xnew, full_cov=False, full_output_cov=False, out=None):
+    def synchronize(self):
+        """Waits for everything this model has enqueued, including the read-back of ``predict_f(non_blocking=True)``."""
+        torch.cuda.current_stream(self.device).synchronize()
+        side = getattr(self, "_copy_stream", None)
+        if side is not None:
+            side.synchronize()
+
+    def predict_f(self, Xnew, full_cov=False, full_output_cov=False, out=None, non_blocking=False):
         """model.py:92-111: merge query times as NaN observations, filter + smooth, project with H.
         Returns (mean[K,1], var[K,1]) — numpy for host inputs, CUDA tensors for device inputs.
         ``out=(mean_buf, var_buf)``: host torch tensors (pinned for full PCIe speed) that receive the result
-        directly, without the intermediate staging copy of the numpy path; they are returned."""
+        directly, without the intermediate staging copy of the numpy path; they are returned.
+        ``non_blocking=True`` (with ``out``): returns as soon as the work is enqueued; the read-back runs on a copy
+        stream behind the kernels, so whatever the caller enqueues next (a training step) overlaps it.  The buffers
+        are valid after ``model.synchronize()`` (or ``torch.cuda.synchronize()``)."""
         ts, ys = self._data
         dtype, dev = ts.dtype, ts.device
         Xd = A.to_device(Xnew, dtype, dev, "Xnew").reshape(-1)
@@ -223,6 +233,18 @@ class StateSpaceGP:
                 rm, rP = sms.index_select(0, q_idx), sPs.index_select(0, q_idx)
                 mean = rm @ Hd.reshape(-1, 1)
                 var = torch.einsum("i,kij,j->k", Hd, rP, Hd).reshape(-1, 1)
+        if out is not None and non_blocking:
+            cur = torch.cuda.current_stream(dev)
+            side = getattr(self, "_copy_stream", None)
+            if side is None:
+                side = self._copy_stream = torch.cuda.Stream(device=dev)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                out[0].view(mean.shape).copy_(mean, non_blocking=True)
+                out[1].view(var.shape).copy_(var, non_blocking=True)
+            mean.record_stream(side)
+            var.record_stream(side)
+            return out
         if out is not None:
             return A.to_host_into(mean, out[0]), A.to_host_into(var, out[1])
         if A.is_device_tensor(Xnew):

@@ -177,3 +177,27 @@ def test_config0_toy_sinusoid_from_the_golden_fixture():
     np.testing.assert_allclose(float(ll), float(gp_ll), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(mean[:, 0], gp_mean.numpy().reshape(-1), rtol=1e-6, atol=1e-6)
     np.testing.assert_allclose(var[:, 0], gp_var.numpy().reshape(-1), rtol=1e-6, atol=1e-6)
+
+
+def test_predict_f_non_blocking_readback():
+    """predict_f(out=pinned buffers, non_blocking=True) + model.synchronize() gives the same posterior as the blocking
+    call, also when a training step is enqueued in between (the read-back runs on a copy stream)."""
+    pkg()
+    from pssgp_b200 import kernels as PK
+    from pssgp_b200.model import StateSpaceGP
+    rng = np.random.RandomState(7)
+    T = 20_000
+    t = np.sort(rng.uniform(0, 50, T))
+    y = O.obs_noise(O.sinu(t), 0.1, 3)
+    q = np.sort(rng.uniform(0, 50, T))
+    ss = StateSpaceGP((t[:, None], y[:, None]), PK.Matern52(1., .5), 0.1, parallel=True)
+    m0, v0 = ss.predict_f(q[:, None])
+    mp, vp = torch.empty((T, 1), dtype=torch.float64).pin_memory(), torch.empty((T, 1), dtype=torch.float64).pin_memory()
+    for _ in range(3):
+        mp.zero_(); vp.zero_()
+        m1, v1 = ss.predict_f(torch.as_tensor(q[:, None]).pin_memory(), out=(mp, vp), non_blocking=True)
+        ll = ss.maximum_log_likelihood_objective()
+        torch.autograd.grad(ll, ss.trainable_variables)
+        ss.synchronize()
+        assert m1 is mp and v1 is vp
+        assert np.array_equal(mp.numpy(), m0) and np.array_equal(vp.numpy(), v0)
