@@ -51,18 +51,26 @@ class _LogLikelihood(torch.autograd.Function):
             one = torch.ones(1, dtype=dtype, device=device)
             (fms, fPs, ll), _, (dP0, dFs, dQs, dH, dR) = ops.pkfs_grad(Pd, Fs, Qs, Hd, Rd, y, one, want_smoother=False)
             dF, dPinf = ops.discretise_backward(Fd, Pd, dts, Fs, dFs, dQs)
-            ctx.save_for_backward(dF, dPinf + dP0, dH, dR)
+            # ll and the four d x d sized gradients come back in ONE device -> host copy (one synchronisation per
+            # training step; backward() is host arithmetic only)
+            packed = torch.cat([ll.reshape(-1), dF.reshape(-1), (dPinf + dP0).reshape(-1), dH.reshape(-1),
+                                dR.reshape(-1)]).to(device=F.device, dtype=F.dtype)
+            ctx.save_for_backward(packed[1:])
+            return packed[0].clone()
         else:
             fms, fPs, ll, _ = ops.pkf(Pd, Fs, Qs, Hd, Rd, y)
         return ll[0].to(device=F.device, dtype=F.dtype)
 
     @staticmethod
     def backward(ctx, g):
-        dF, dPinf, dH, dR = ctx.saved_tensors
         hdev, hdt, hshape, rshape = ctx.host
-        # one small device -> host copy for the four d x d sized gradients
-        d = dF.shape[0]
-        packed = torch.cat([dF.reshape(-1), dPinf.reshape(-1), dH.reshape(-1), dR.reshape(-1)]).to(device=hdev, dtype=hdt)
+        if len(ctx.saved_tensors) == 1:
+            packed = ctx.saved_tensors[0]          # already on the host (forward's single read-back)
+            d = hshape[-1]
+        else:
+            dF, dPinf, dH, dR = ctx.saved_tensors  # sequential mode: still on the device
+            d = dF.shape[0]
+            packed = torch.cat([dF.reshape(-1), dPinf.reshape(-1), dH.reshape(-1), dR.reshape(-1)]).to(device=hdev, dtype=hdt)
         packed = packed * g.detach().to(device=hdev, dtype=hdt)
         gF, gP = packed[:d * d].reshape(d, d), packed[d * d:2 * d * d].reshape(d, d)
         gH, gR = packed[2 * d * d:2 * d * d + d].reshape(hshape), packed[2 * d * d + d:].reshape(rshape)
