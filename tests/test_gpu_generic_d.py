@@ -92,7 +92,7 @@ def test_backward_vs_autograd(name, tol, T):
 
 
 @pytest.mark.parametrize("name,span", [("rbf6", 4.0), ("rbf6", 4000.0), ("m52+rbf6", 40.0), ("qp3", 40.0), ("qp5", 20.0),
-                                       ("periodic2", 4.0)])
+                                       ("qp6", 20.0), ("qp5", 4000.0), ("periodic2", 4.0)])
 def test_discretise_forward_backward(name, span):
     pkg()
     from pssgp_b200 import ops

@@ -46,6 +46,8 @@ def make_kernel(name):
         return O.Periodic(O.SquaredExponential(5.0, 1.0), period=1.0, order=3) * O.Matern32(0.1, 50.0)
     if name == "qp5":
         return O.Periodic(O.SquaredExponential(5.0, 1.0), period=1.0, order=5) * O.Matern32(0.1, 50.0)
+    if name == "qp6":
+        return O.Periodic(O.SquaredExponential(5.0, 1.0), period=1.0, order=6) * O.Matern32(0.1, 50.0)
     if name == "periodic2":
         return O.Periodic(O.SquaredExponential(1.0, 0.5), period=0.5, order=2)
     raise KeyError(name)
