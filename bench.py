@@ -636,7 +636,7 @@ def main():
             ll = model.maximum_log_likelihood_objective()
             grads = torch.autograd.grad(ll, model.trainable_variables)
             model.synchronize()          # posterior buffers valid
-            return float(ll), [float(g) for g in grads], mean, var
+            return float(ll.detach()), [float(g) for g in grads], mean, var
 
         for _ in range(W):
             r = e2e_step()
