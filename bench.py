@@ -677,13 +677,18 @@ def main():
                 okc = torch.tensor([0.0], device=dev)
             dist.all_reduce(okc, op=dist.ReduceOp.MIN)
             if float(okc) == 1.0:
-                r_eager = r
-                e2e_step = replay
-                e2e_graphed = True
+                r_eager, eager_fn = r, e2e_step
                 for _ in range(W):
-                    r = e2e_step()
+                    r = replay()
                 barrier()
-                assert abs(float(r[0][0]) - float(r_eager[0][0])) <= 1e-12 * abs(float(r_eager[0][0])), "graph replay differs"
+                same = torch.tensor([1.0 if abs(float(r[0][0]) - float(r_eager[0][0])) <= 1e-12 * abs(float(r_eager[0][0]))
+                                     else 0.0], device=dev)
+                dist.all_reduce(same, op=dist.ReduceOp.MIN)
+                if float(same) == 1.0:
+                    e2e_step, e2e_graphed = replay, True
+                else:   # never seen; the eager step is the reference behaviour
+                    print("[bench] graph replay of the series step differs from the eager step; eager step", file=sys.stderr)
+                    e2e_step = eager_fn
         t0 = time.perf_counter()
         for _ in range(K):
             r = e2e_step()
