@@ -124,3 +124,29 @@ def test_discretise_forward_backward(name, span):
     dF, dP = ops.discretise_backward(Fd, Pd, dtd, Fs, dFs.to(DEV), dQs.to(DEV))
     assert rel_err(dF.cpu(), gF) < 1e-10
     assert rel_err(dP.cpu(), sym(gP)) < 1e-10
+
+
+@pytest.mark.parametrize("name", ["rbf6", "m52+rbf6", "qp3", "qp5", "qp6"])
+@pytest.mark.parametrize("n", [1, 2, 13])
+def test_discretise_tiny_series(name, n):
+    """Fewer time steps than warps in one CTA (the warp-per-step kernels' boundary handling), zero and negative steps."""
+    pkg()
+    from pssgp_b200 import ops
+    cov = make_problem(name, 4, seed=1)[2]
+    with torch.no_grad():
+        sde = cov.get_sde()
+    F = sde.F.clone().requires_grad_(True)
+    Pinf = sde.P0.clone().requires_grad_(True)
+    dts = torch.tensor([0.0, 0.013, -0.02, 0.5, 0.001, 0.07, 0.0, 0.2, 0.011, 0.3, 0.05, 0.09, 0.04], dtype=torch.float64)[:n]
+    Fs_ref = torch.linalg.matrix_exp(dts.reshape(-1, 1, 1) * F.unsqueeze(0))
+    Qs_ref = sym(Pinf.unsqueeze(0) - Fs_ref @ Pinf.unsqueeze(0) @ Fs_ref.transpose(1, 2))
+    gen = torch.Generator().manual_seed(n)
+    dFs = torch.randn(Fs_ref.shape, dtype=torch.float64, generator=gen)
+    dQs = sym(torch.randn(Qs_ref.shape, dtype=torch.float64, generator=gen))
+    gF, gP = torch.autograd.grad((Fs_ref * dFs).sum() + (Qs_ref * dQs).sum(), (F, Pinf))
+    Fd, Pd, dtd = F.detach().to(DEV).contiguous(), Pinf.detach().to(DEV).contiguous(), dts.to(DEV)
+    Fs, Qs = ops.discretise(Fd, Pd, dtd)
+    assert rel_err(Fs.cpu(), Fs_ref.detach()) < 1e-12
+    assert float((Qs.cpu() - Qs_ref.detach()).abs().max()) < 1e-12 * float(Pinf.detach().abs().max())
+    dF, dP = ops.discretise_backward(Fd, Pd, dtd, Fs, dFs.to(DEV), dQs.to(DEV))
+    assert rel_err(dF.cpu(), gF) < 1e-10 and rel_err(dP.cpu(), sym(gP)) < 1e-10
