@@ -42,7 +42,10 @@ int pssgp_destroy(pssgp_handle* h);
 /* Options: "chunk" = time steps per thread-chunk (0 = heuristic); "timing" = 1 brackets every
  * kernel launch with CUDA events on its stream (read back with pssgp_timing_report);
  * "fused_reverse" = 1 makes pssgp_pkfs_grad run the smoother and adjoint recursions in one kernel;
- * "pdl" = 0 turns off programmatic dependent launch between the kernels of pssgp_pkfs_grad (default 1). */
+ * "pdl" = 0 turns off programmatic dependent launch between the kernels of pssgp_pkfs_grad (default 1);
+ * "grid_lanes" = settings in flight in pssgp_grid_loglik (0 = default 4, at most 4); tuning / test switches:
+ * "mid_warps" (warps per CTA of the 5 <= d <= 24 kernels), "mid_smem" = 1 (shared-memory tile kernels also for
+ * d <= 24), "force_generic" = 1 (CTA-cooperative kernels for d > 4, element-per-thread discretisation). */
 int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value);
 /* Number of kernels launched through this handle since creation (bench.py's gpu_launches). */
 int64_t pssgp_launch_count(const pssgp_handle* h);
