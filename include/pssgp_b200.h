@@ -273,6 +273,12 @@ int pssgp_lyap_solve(const void* F, const void* G, int d, void* X);
 int pssgp_sde_dim(const int32_t* spec, int spec_len, int* d_out, int* nparams_out);
 int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const double* params, int64_t params_stride,
                     double* F, double* Pinf, double* H, int nthreads);
+/* The same with the Jacobians w.r.t. the hyper-parameters (forward-mode dual numbers through the whole construction,
+ * balancing vector held constant like the reference's tf.numpy_function, math_utils.py:68): dF, dPinf
+ * [batch, nparams, d, d], dH [batch, nparams, d] = derivatives w.r.t. params[:, q] (the CONSTRAINED values: variance,
+ * lengthscale, period).  Replaces TF autodiff through get_sde; at most 16 hyper-parameters. */
+int pssgp_sde_batch_jac(const int32_t* spec, int spec_len, int64_t batch, const double* params, int64_t params_stride,
+                        double* F, double* Pinf, double* H, double* dF, double* dPinf, double* dH, int nthreads);
 /*
  * Log-likelihood of ONE series under `batch` hyper-parameter settings (BASELINE configs[4]b, the grid search the
  * reference runs as a Python loop over models): per setting discretise (kernels/base.py:29-47) + pkf with

@@ -10,6 +10,12 @@ _DEFAULT_FLOAT = torch.float64
 FAST_MATERN_SDE = True
 
 
+# Training path of StateSpaceGP: (F, Pinf, H) and their hyper-parameter Jacobians from the native builder
+# (kernels/native.py, C ABI pssgp_sde_batch_jac) instead of torch autograd through the Python get_sde, for every kernel
+# inside the native grammar (sums of products of Matern / RBF / Periodic).  Same values and gradients to rounding.
+NATIVE_SDE = True
+
+
 def set_number_balancing_steps(n_balancing_steps):
     """pssgp/config.py:9-16."""
     global NUMBER_OF_BALANCING_STEPS

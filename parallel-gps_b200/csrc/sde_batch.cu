@@ -16,6 +16,7 @@
 #include <algorithm>
 #include <array>
 #include <complex>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -25,67 +26,129 @@
 namespace pssgp {
 namespace sde {
 
-typedef std::vector<double> Mat;  // dense row-major
-
-struct Sde {
-    int d = 0, r = 0;      // state dimension, noise dimension
-    Mat P0, F, L, H, Q;    // P0 [d,d], F [d,d], L [d,r], H [d], Q [r,r]
+// ---- scalar types: double, or a forward-mode dual number carrying the derivatives w.r.t. NP hyper-parameters -----
+template <int NP> struct Dual {
+    double v;
+    double g[NP];
+    Dual() : v(0.0) { for (int i = 0; i < NP; ++i) g[i] = 0.0; }
+    Dual(double x) : v(x) { for (int i = 0; i < NP; ++i) g[i] = 0.0; }
 };
+inline double val(double x) { return x; }
+template <int NP> inline double val(const Dual<NP>& x) { return x.v; }
+inline bool is_zero(double x) { return x == 0.0; }
+template <int NP> inline bool is_zero(const Dual<NP>& x) {
+    if (x.v != 0.0) return false;
+    for (int i = 0; i < NP; ++i)
+        if (x.g[i] != 0.0) return false;
+    return true;
+}
+#define SDE_DUAL_BIN(OP, VEXPR, GEXPR)                                                            \
+    template <int NP> inline Dual<NP> operator OP(const Dual<NP>& a, const Dual<NP>& b) {        \
+        Dual<NP> r;                                                                               \
+        r.v = VEXPR;                                                                              \
+        for (int i = 0; i < NP; ++i) r.g[i] = GEXPR;                                              \
+        return r;                                                                                 \
+    }                                                                                             \
+    template <int NP> inline Dual<NP> operator OP(const Dual<NP>& a, double b) { return a OP Dual<NP>(b); } \
+    template <int NP> inline Dual<NP> operator OP(double a, const Dual<NP>& b) { return Dual<NP>(a) OP b; }
+SDE_DUAL_BIN(+, a.v + b.v, a.g[i] + b.g[i])
+SDE_DUAL_BIN(-, a.v - b.v, a.g[i] - b.g[i])
+SDE_DUAL_BIN(*, a.v * b.v, a.g[i] * b.v + a.v * b.g[i])
+SDE_DUAL_BIN(/, a.v / b.v, (a.g[i] - (a.v / b.v) * b.g[i]) / b.v)
+#undef SDE_DUAL_BIN
+template <int NP> inline Dual<NP> operator-(const Dual<NP>& a) { return Dual<NP>(0.0) - a; }
+template <int NP, class B> inline Dual<NP>& operator+=(Dual<NP>& a, const B& b) { a = a + b; return a; }
+template <int NP, class B> inline Dual<NP>& operator-=(Dual<NP>& a, const B& b) { a = a - b; return a; }
+template <int NP, class B> inline Dual<NP>& operator*=(Dual<NP>& a, const B& b) { a = a * b; return a; }
+template <int NP, class B> inline Dual<NP>& operator/=(Dual<NP>& a, const B& b) { a = a / b; return a; }
+inline double s_sqrt(double x) { return sqrt(x); }
+inline double s_exp(double x) { return exp(x); }
+inline double s_abs(double x) { return fabs(x); }
+inline double s_powi(double x, int k) { return pow(x, k); }
+template <int NP> inline Dual<NP> s_sqrt(const Dual<NP>& x) {
+    Dual<NP> r(sqrt(x.v));
+    for (int i = 0; i < NP; ++i) r.g[i] = 0.5 * x.g[i] / r.v;
+    return r;
+}
+template <int NP> inline Dual<NP> s_exp(const Dual<NP>& x) {
+    Dual<NP> r(exp(x.v));
+    for (int i = 0; i < NP; ++i) r.g[i] = r.v * x.g[i];
+    return r;
+}
+template <int NP> inline Dual<NP> s_abs(const Dual<NP>& x) { return x.v < 0.0 ? -x : x; }
+template <int NP> inline Dual<NP> s_powi(const Dual<NP>& x, int k) {
+    Dual<NP> r(pow(x.v, k));
+    const double dv = k == 0 ? 0.0 : k * pow(x.v, k - 1);
+    for (int i = 0; i < NP; ++i) r.g[i] = dv * x.g[i];
+    return r;
+}
 
-static Mat eye(int n) {
-    Mat I((size_t)n * n, 0.0);
-    for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = 1.0;
+template <class S> using MatT = std::vector<S>;  // dense row-major
+typedef MatT<double> Mat;
+
+template <class S> struct SdeT {
+    int d = 0, r = 0;           // state dimension, noise dimension
+    MatT<S> P0, F, L, H, Q;     // P0 [d,d], F [d,d], L [d,r], H [d], Q [r,r]
+};
+typedef SdeT<double> Sde;
+
+template <class S> static MatT<S> eye(int n) {
+    MatT<S> I((size_t)n * n, S(0.0));
+    for (int i = 0; i < n; ++i) I[(size_t)i * n + i] = S(1.0);
     return I;
 }
 // C[m,n] = A[m,k] B[k,n]
-static Mat matmul(const Mat& A, const Mat& B, int m, int k, int n) {
-    Mat C((size_t)m * n, 0.0);
+template <class S> static MatT<S> matmul(const MatT<S>& A, const MatT<S>& B, int m, int k, int n) {
+    MatT<S> C((size_t)m * n, S(0.0));
     for (int i = 0; i < m; ++i)
         for (int p = 0; p < k; ++p) {
-            const double a = A[(size_t)i * k + p];
-            if (a == 0.0) continue;
+            const S a = A[(size_t)i * k + p];
+            if (is_zero(a)) continue;
             for (int j = 0; j < n; ++j) C[(size_t)i * n + j] += a * B[(size_t)p * n + j];
         }
     return C;
 }
-static Mat transpose(const Mat& A, int m, int n) {
-    Mat T((size_t)m * n);
+template <class S> static MatT<S> transpose(const MatT<S>& A, int m, int n) {
+    MatT<S> T((size_t)m * n);
     for (int i = 0; i < m; ++i)
         for (int j = 0; j < n; ++j) T[(size_t)j * m + i] = A[(size_t)i * n + j];
     return T;
 }
 // kron(A[ma,na], B[mb,nb])
-static Mat kron(const Mat& A, int ma, int na, const Mat& B, int mb, int nb) {
-    Mat K((size_t)ma * mb * na * nb, 0.0);
+template <class S> static MatT<S> kron(const MatT<S>& A, int ma, int na, const MatT<S>& B, int mb, int nb) {
+    MatT<S> K((size_t)ma * mb * na * nb, S(0.0));
     const size_t ld = (size_t)na * nb;
     for (int i = 0; i < ma; ++i)
         for (int j = 0; j < na; ++j) {
-            const double a = A[(size_t)i * na + j];
-            if (a == 0.0) continue;
+            const S a = A[(size_t)i * na + j];
+            if (is_zero(a)) continue;
             for (int p = 0; p < mb; ++p)
                 for (int q = 0; q < nb; ++q) K[((size_t)i * mb + p) * ld + (size_t)j * nb + q] = a * B[(size_t)p * nb + q];
         }
     return K;
 }
 // L Q L^T  ([d,d])
-static Mat lqlt(const Sde& s) {
-    Mat LQ = matmul(s.L, s.Q, s.d, s.r, s.r);
-    return matmul(LQ, transpose(s.L, s.d, s.r), s.d, s.r, s.d);
+template <class S> static MatT<S> lqlt(const SdeT<S>& s) {
+    MatT<S> LQ = matmul<S>(s.L, s.Q, s.d, s.r, s.r);
+    return matmul<S>(LQ, transpose<S>(s.L, s.d, s.r), s.d, s.r, s.d);
 }
 
-// Solve A x = b in place (A [n,n] destroyed, b -> x), Gaussian elimination with partial pivoting; zero multipliers
-// are skipped (the Kronecker-sum systems below are mostly zeros).  Returns false for a singular matrix.
-// The row update is the hot loop (d^6 / 3 flops for a dense drift): compiled for AVX2 + FMA where the host has it.
+// The row update is the hot loop of the elimination (n^3 / 3 flops): compiled for AVX2 + FMA where the host has it.
 __attribute__((target_clones("avx2,fma", "default"))) static void row_axpy(double* __restrict__ rr, const double* __restrict__ rc,
                                                                             double f, int lo, int n) {
     for (int j = lo; j < n; ++j) rr[j] -= f * rc[j];
 }
-static bool solve_inplace(Mat& A, Mat& b, int n) {
+template <int NP> static void row_axpy(Dual<NP>* rr, const Dual<NP>* rc, const Dual<NP>& f, int lo, int n) {
+    for (int j = lo; j < n; ++j) rr[j] -= f * rc[j];
+}
+// Solve A x = b in place (A [n,n] destroyed, b -> x), Gaussian elimination with partial pivoting (on the values); zero
+// multipliers are skipped (the Lyapunov systems below are mostly zeros).  Returns false for a singular matrix.
+template <class S> static bool solve_inplace(MatT<S>& A, MatT<S>& b, int n) {
     for (int c = 0; c < n; ++c) {
         int piv = c;
-        double best = fabs(A[(size_t)c * n + c]);
+        double best = fabs(val(A[(size_t)c * n + c]));
         for (int r = c + 1; r < n; ++r) {
-            const double v = fabs(A[(size_t)r * n + c]);
+            const double v = fabs(val(A[(size_t)r * n + c]));
             if (v > best) best = v, piv = r;
         }
         if (!(best > 0.0)) return false;
@@ -93,17 +156,17 @@ static bool solve_inplace(Mat& A, Mat& b, int n) {
             for (int j = c; j < n; ++j) std::swap(A[(size_t)c * n + j], A[(size_t)piv * n + j]);
             std::swap(b[c], b[piv]);
         }
-        const double inv = 1.0 / A[(size_t)c * n + c];
+        const S inv = S(1.0) / A[(size_t)c * n + c];
         for (int r = c + 1; r < n; ++r) {
-            const double f = A[(size_t)r * n + c] * inv;
-            if (f == 0.0) continue;
+            const S f = A[(size_t)r * n + c] * inv;
+            if (is_zero(f)) continue;
             row_axpy(&A[(size_t)r * n], &A[(size_t)c * n], f, c + 1, n);
             b[r] -= f * b[c];
         }
     }
     for (int c = n - 1; c >= 0; --c) {
-        double v = b[c];
-        const double* rc = &A[(size_t)c * n];
+        S v = b[c];
+        const S* rc = &A[(size_t)c * n];
         for (int j = c + 1; j < n; ++j) v -= rc[j] * b[j];
         b[c] = v / rc[c];
     }
@@ -113,70 +176,74 @@ static bool solve_inplace(Mat& A, Mat& b, int n) {
 // X with F X + X F^T = G (math_utils.py:108-118 solves the d^2 x d^2 Kronecker system kron(I,F) + kron(F,I)).
 // For a symmetric right-hand side the solution is symmetric, and the system is assembled directly in the
 // d(d+1)/2 unknowns of its lower triangle: the same equations, about 8x fewer elimination flops.
-static bool lyap_solve(const Mat& F, const Mat& G, int d, Mat& X) {
+template <class S> static bool lyap_solve(const MatT<S>& F, const MatT<S>& G, int d, MatT<S>& X) {
     double gmax = 0.0, asym = 0.0;
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < d; ++j) {
-            gmax = std::max(gmax, fabs(G[(size_t)i * d + j]));
-            asym = std::max(asym, fabs(G[(size_t)i * d + j] - G[(size_t)j * d + i]));
+            gmax = std::max(gmax, fabs(val(G[(size_t)i * d + j])));
+            asym = std::max(asym, fabs(val(G[(size_t)i * d + j]) - val(G[(size_t)j * d + i])));
         }
-    X.assign((size_t)d * d, 0.0);
+    X.assign((size_t)d * d, S(0.0));
     if (asym <= 1e-14 * gmax) {
         const int m = d * (d + 1) / 2;
         auto idx = [](int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; };
-        Mat op((size_t)m * m, 0.0), rhs((size_t)m);
+        MatT<S> op((size_t)m * m, S(0.0)), rhs((size_t)m);
         for (int i = 0; i < d; ++i)
             for (int j = 0; j <= i; ++j) {
-                double* row = &op[(size_t)idx(i, j) * m];
+                S* row = &op[(size_t)idx(i, j) * m];
                 for (int k = 0; k < d; ++k) {
                     row[idx(k, j)] += F[(size_t)i * d + k];  // (F X)_ij
                     row[idx(i, k)] += F[(size_t)j * d + k];  // (X F^T)_ij
                 }
                 rhs[idx(i, j)] = 0.5 * (G[(size_t)i * d + j] + G[(size_t)j * d + i]);
             }
-        if (!solve_inplace(op, rhs, m)) return false;
+        if (!solve_inplace<S>(op, rhs, m)) return false;
         for (int i = 0; i < d; ++i)
             for (int j = 0; j < d; ++j) X[(size_t)i * d + j] = rhs[idx(i, j)];
         return true;
     }
-    Mat I = eye(d);
-    Mat op = kron(I, d, d, F, d, d);
-    Mat op2 = kron(F, d, d, I, d, d);
+    MatT<S> I = eye<S>(d);
+    MatT<S> op = kron<S>(I, d, d, F, d, d);
+    MatT<S> op2 = kron<S>(F, d, d, I, d, d);
     for (size_t i = 0; i < op.size(); ++i) op[i] += op2[i];
-    Mat rhs = G;
-    if (!solve_inplace(op, rhs, d * d)) return false;
+    MatT<S> rhs = G;
+    if (!solve_inplace<S>(op, rhs, d * d)) return false;
     X = rhs;
     return true;
 }
 
 // math_utils.py:84-120: F P + P F^T + L Q L^T = 0, P = -sym(X)
-static bool solve_lyap_vec(const Sde& s, Mat& P) {
+template <class S> static bool solve_lyap_vec(const SdeT<S>& s, MatT<S>& P) {
     const int d = s.d;
-    Mat X;
-    if (!lyap_solve(s.F, lqlt(s), d, X)) return false;
-    P.assign((size_t)d * d, 0.0);
+    MatT<S> X;
+    if (!lyap_solve<S>(s.F, lqlt<S>(s), d, X)) return false;
+    P.assign((size_t)d * d, S(0.0));
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < d; ++j) P[(size_t)i * d + j] = -0.5 * (X[(size_t)i * d + j] + X[(size_t)j * d + i]);
     return true;
 }
 
-// math_utils.py:32-81 (balance_ss) with the scaling of math_utils.py:10-29 (pssgp_balance_ss, host_utils.cu)
-static void balance_ss(Sde& s, int n_iter) {
+// math_utils.py:32-81 (balance_ss) with the scaling of math_utils.py:10-29 (pssgp_balance_ss, host_utils.cu).  The
+// scaling vector is computed from the VALUES of F and is a constant w.r.t. differentiation, as in the reference
+// (it crosses tf.numpy_function, math_utils.py:68); the two max-abs normalisations differentiate through their argmax.
+template <class S> static void balance_ss(SdeT<S>& s, int n_iter) {
     const int d = s.d;
-    std::vector<double> dv(d);
-    pssgp_balance_ss(s.F.data(), d, n_iter, dv.data());
+    std::vector<double> dv(d), Fv((size_t)d * d);
+    for (size_t i = 0; i < Fv.size(); ++i) Fv[i] = val(s.F[i]);
+    pssgp_balance_ss(Fv.data(), d, n_iter, dv.data());
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < d; ++j) s.F[(size_t)i * d + j] = s.F[(size_t)i * d + j] * dv[j] / dv[i];
-    double t3 = 0.0, t4 = 0.0;
+    size_t a3 = 0, a4 = 0;
     for (int i = 0; i < d; ++i)
         for (int j = 0; j < s.r; ++j) {
             s.L[(size_t)i * s.r + j] /= dv[i];
-            t3 = std::max(t3, fabs(s.L[(size_t)i * s.r + j]));
+            if (fabs(val(s.L[(size_t)i * s.r + j])) > fabs(val(s.L[a3]))) a3 = (size_t)i * s.r + j;
         }
     for (int i = 0; i < d; ++i) {
         s.H[i] *= dv[i];
-        t4 = std::max(t4, fabs(s.H[i]));
+        if (fabs(val(s.H[i])) > fabs(val(s.H[a4]))) a4 = i;
     }
+    const S t3 = s_abs(s.L[a3]), t4 = s_abs(s.H[a4]);
     for (auto& v : s.L) v /= t3;
     for (auto& v : s.H) v /= t4;
     for (auto& v : s.Q) v *= (t3 * t3) * (t4 * t4);
@@ -195,18 +262,18 @@ static double binom(int n, int k) {
 }
 
 // matern/common.py:26-52
-static Sde matern_companion(int d, double variance, double ell) {
-    Sde s;
+template <class S> static SdeT<S> matern_companion(int d, const S& variance, const S& ell) {
+    SdeT<S> s;
     s.d = d, s.r = 1;
-    const double lam = sqrt(2.0 * d - 1.0) / ell;
-    s.F.assign((size_t)d * d, 0.0);
-    for (int i = 0; i + 1 < d; ++i) s.F[(size_t)i * d + i + 1] = 1.0;
-    for (int k = 0; k < d; ++k) s.F[(size_t)(d - 1) * d + k] = -binom(d, k) * pow(lam, d - k);
-    s.L.assign(d, 0.0);
-    s.L[d - 1] = 1.0;
-    s.H.assign(d, 0.0);
-    s.H[0] = 1.0;
-    s.Q.assign(1, pow(2.0 * lam, 2 * d - 1) * variance * factorial(d - 1) * factorial(d - 1) / factorial(2 * d - 2));
+    const S lam = sqrt(2.0 * d - 1.0) / ell;
+    s.F.assign((size_t)d * d, S(0.0));
+    for (int i = 0; i + 1 < d; ++i) s.F[(size_t)i * d + i + 1] = S(1.0);
+    for (int k = 0; k < d; ++k) s.F[(size_t)(d - 1) * d + k] = -binom(d, k) * s_powi(lam, d - k);
+    s.L.assign(d, S(0.0));
+    s.L[d - 1] = S(1.0);
+    s.H.assign(d, S(0.0));
+    s.H[0] = S(1.0);
+    s.Q.assign(1, s_powi(2.0 * lam, 2 * d - 1) * variance * factorial(d - 1) * factorial(d - 1) / factorial(2 * d - 2));
     return s;
 }
 
@@ -240,6 +307,7 @@ static std::vector<std::complex<double>> poly_roots(const std::vector<double>& a
 
 // rbf.py:14-61.  The denominator polynomial is the order-`order` Taylor polynomial of exp(-s^2/2): even in s, so
 // its roots are the square roots of the roots of g(z) = sum_k (-z/2)^k / k!; the stable half gives the drift.
+// Independent of the hyper-parameters (plain doubles).
 static void rbf_unscaled(int order, Mat& F, double& gain, double& q) {
     typedef std::complex<double> C;
     std::vector<double> a(order + 1);
@@ -301,24 +369,25 @@ struct RbfCache {  // the unscaled RBF SDE depends on the order only: computed o
 };
 
 // one base kernel; p = (variance, lengthscale[, period])
-static bool base_sde(int type, int order, int bal_iter, const double* p, const std::vector<RbfCache>& rbf, Sde& s) {
-    const double variance = p[0], ell = p[1];
+template <class S>
+static bool base_sde(int type, int order, int bal_iter, const S* p, const std::vector<RbfCache>& rbf, SdeT<S>& s) {
+    const S variance = p[0], ell = p[1];
     switch (type) {
         case K_MATERN12: {  // matern12.py:18-23
-            s = matern_companion(1, variance, ell);
+            s = matern_companion<S>(1, variance, ell);
             s.P0.assign(1, variance);
             return true;
         }
         case K_MATERN32: {  // matern32.py:20-28
-            s = matern_companion(2, variance, ell);
-            const double lam = sqrt(3.0) / ell;
-            s.P0 = {variance, 0.0, 0.0, lam * lam * variance};
+            s = matern_companion<S>(2, variance, ell);
+            const S lam = sqrt(3.0) / ell;
+            s.P0 = {variance, S(0.0), S(0.0), lam * lam * variance};
             return true;
         }
         case K_MATERN52: {  // matern52.py:21-25
-            s = matern_companion(3, variance, ell);
-            balance_ss(s, bal_iter);
-            return solve_lyap_vec(s, s.P0);
+            s = matern_companion<S>(3, variance, ell);
+            balance_ss<S>(s, bal_iter);
+            return solve_lyap_vec<S>(s, s.P0);
         }
         case K_RBF: {  // rbf.py:78-101
             const RbfCache* c = nullptr;
@@ -327,40 +396,41 @@ static bool base_sde(int type, int order, int bal_iter, const double* p, const s
             if (!c) return false;
             const int n = order;
             s.d = n, s.r = 1;
-            s.F = c->F;
-            for (int j = 0; j < n; ++j) s.F[(size_t)(n - 1) * n + j] /= pow(ell, n - j);
-            s.L.assign(n, 0.0);
-            s.L[n - 1] = 1.0;
-            s.H.assign(n, 0.0);
-            s.H[0] = c->gain / pow(ell, n);
+            s.F.assign((size_t)n * n, S(0.0));
+            for (size_t i = 0; i < s.F.size(); ++i) s.F[i] = S(c->F[i]);
+            for (int j = 0; j < n; ++j) s.F[(size_t)(n - 1) * n + j] /= s_powi(ell, n - j);
+            s.L.assign(n, S(0.0));
+            s.L[n - 1] = S(1.0);
+            s.H.assign(n, S(0.0));
+            s.H[0] = c->gain / s_powi(ell, n);
             s.Q.assign(1, variance * ell * c->q);
-            balance_ss(s, bal_iter);
-            return solve_lyap_vec(s, s.P0);
+            balance_ss<S>(s, bal_iter);
+            return solve_lyap_vec<S>(s, s.P0);
         }
         case K_PERIODIC: {  // periodic.py:18-81
             const int N = order, dim = 2 * (N + 1);
-            const double w0 = 2.0 * M_PI / p[2], l2 = 2.0 * ell;  // periodic.py:57: lengthscale x 2
+            const S w0 = 2.0 * M_PI / p[2], l2 = 2.0 * ell;  // periodic.py:57: lengthscale x 2
             s.d = dim, s.r = dim;
-            s.F.assign((size_t)dim * dim, 0.0);
+            s.F.assign((size_t)dim * dim, S(0.0));
             for (int j = 0; j <= N; ++j) {
-                s.F[(size_t)(2 * j) * dim + 2 * j + 1] = -w0 * j;
-                s.F[(size_t)(2 * j + 1) * dim + 2 * j] = w0 * j;
+                s.F[(size_t)(2 * j) * dim + 2 * j + 1] = -w0 * (double)j;
+                s.F[(size_t)(2 * j + 1) * dim + 2 * j] = w0 * (double)j;
             }
-            s.L = eye(dim);
-            s.Q.assign((size_t)dim * dim, 0.0);
-            s.P0.assign((size_t)dim * dim, 0.0);
-            const double il2 = 1.0 / (l2 * l2);
+            s.L = eye<S>(dim);
+            s.Q.assign((size_t)dim * dim, S(0.0));
+            s.P0.assign((size_t)dim * dim, S(0.0));
+            const S il2 = 1.0 / (l2 * l2);
             for (int J = 0; J <= N; ++J) {
-                double q2 = 0.0;  // sum over K of b(K,J) l^-2K / K! exp(-l^-2) 2^-K variance
+                S q2(0.0);  // sum over K of b(K,J) l^-2K / K! exp(-l^-2) 2^-K variance
                 for (int K = J; K <= N; K += 2) {
                     const double b = 2.0 * binom(K, (K - J) / 2) / (J == 0 ? 2.0 : 1.0);
-                    q2 += b * pow(il2, K) / factorial(K) * exp(-il2) * pow(2.0, -K) * variance;
+                    q2 += b * s_powi(il2, K) / factorial(K) * s_exp(-il2) * pow(2.0, -K) * variance;
                 }
                 s.P0[(size_t)(2 * J) * dim + 2 * J] = q2;
                 s.P0[(size_t)(2 * J + 1) * dim + 2 * J + 1] = q2;
             }
-            s.H.assign(dim, 0.0);
-            for (int j = 0; j <= N; ++j) s.H[2 * j] = 1.0;
+            s.H.assign(dim, S(0.0));
+            for (int j = 0; j <= N; ++j) s.H[2 * j] = S(1.0);
             return true;
         }
     }
@@ -368,20 +438,20 @@ static bool base_sde(int type, int order, int bal_iter, const double* p, const s
 }
 
 // kernels/base.py:199-220 (Kronecker-sum drift, product diffusion and stationary covariance of two factors)
-static Sde product2(const Sde& a, const Sde& b) {
-    Sde s;
+template <class S> static SdeT<S> product2(const SdeT<S>& a, const SdeT<S>& b) {
+    SdeT<S> s;
     s.d = a.d * b.d, s.r = s.d;
-    Mat Ia = eye(a.d), Ib = eye(b.d);
-    s.F = kron(a.F, a.d, a.d, Ib, b.d, b.d);
-    Mat t = kron(Ia, a.d, a.d, b.F, b.d, b.d);
+    MatT<S> Ia = eye<S>(a.d), Ib = eye<S>(b.d);
+    s.F = kron<S>(a.F, a.d, a.d, Ib, b.d, b.d);
+    MatT<S> t = kron<S>(Ia, a.d, a.d, b.F, b.d, b.d);
     for (size_t i = 0; i < t.size(); ++i) s.F[i] += t[i];
-    Mat g1 = lqlt(a), g2 = lqlt(b);
-    s.Q = kron(g1, a.d, a.d, b.P0, b.d, b.d);
-    t = kron(a.P0, a.d, a.d, g2, b.d, b.d);
+    MatT<S> g1 = lqlt<S>(a), g2 = lqlt<S>(b);
+    s.Q = kron<S>(g1, a.d, a.d, b.P0, b.d, b.d);
+    t = kron<S>(a.P0, a.d, a.d, g2, b.d, b.d);
     for (size_t i = 0; i < t.size(); ++i) s.Q[i] += t[i];
-    s.H = kron(a.H, 1, a.d, b.H, 1, b.d);
-    s.P0 = kron(a.P0, a.d, a.d, b.P0, b.d, b.d);
-    s.L = eye(s.d);
+    s.H = kron<S>(a.H, 1, a.d, b.H, 1, b.d);
+    s.P0 = kron<S>(a.P0, a.d, a.d, b.P0, b.d, b.d);
+    s.L = eye<S>(s.d);
     return s;
 }
 
@@ -420,20 +490,21 @@ static bool parse_spec(const int32_t* spec, int len, Spec& out) {
     return pos == len;
 }
 
-static bool build_one(const Spec& sp, const std::vector<RbfCache>& rbf, const double* params, Sde& out) {
-    std::vector<Sde> terms;
-    const double* p = params;
+template <class S>
+static bool build_one(const Spec& sp, const std::vector<RbfCache>& rbf, const S* params, SdeT<S>& out) {
+    std::vector<SdeT<S>> terms;
+    const S* p = params;
     for (const auto& fs : sp.terms) {
-        Sde term;
+        SdeT<S> term;
         for (size_t f = 0; f < fs.size(); ++f) {
-            Sde b;
-            if (!base_sde(fs[f][0], fs[f][1], fs[f][2], p, rbf, b)) return false;
+            SdeT<S> b;
+            if (!base_sde<S>(fs[f][0], fs[f][1], fs[f][2], p, rbf, b)) return false;
             p += base_nparams(fs[f][0]);
-            term = f == 0 ? b : product2(term, b);
+            term = f == 0 ? b : product2<S>(term, b);
         }
         if (fs.size() > 1) {  // kernels/base.py:236-244: the product is balanced and its Pinf solved again
-            balance_ss(term, sp.comb_iter);
-            if (!solve_lyap_vec(term, term.P0)) return false;
+            balance_ss<S>(term, sp.comb_iter);
+            if (!solve_lyap_vec<S>(term, term.P0)) return false;
         }
         terms.push_back(std::move(term));
     }
@@ -442,12 +513,12 @@ static bool build_one(const Spec& sp, const std::vector<RbfCache>& rbf, const do
         return true;
     }
     // kernels/base.py:151-183: block-diagonal sum, balanced, Pinf solved for the whole system
-    Sde s;
+    SdeT<S> s;
     for (const auto& t : terms) s.d += t.d, s.r += t.r;
-    s.F.assign((size_t)s.d * s.d, 0.0);
-    s.L.assign((size_t)s.d * s.r, 0.0);
-    s.Q.assign((size_t)s.r * s.r, 0.0);
-    s.H.assign(s.d, 0.0);
+    s.F.assign((size_t)s.d * s.d, S(0.0));
+    s.L.assign((size_t)s.d * s.r, S(0.0));
+    s.Q.assign((size_t)s.r * s.r, S(0.0));
+    s.H.assign(s.d, S(0.0));
     int od = 0, orr = 0;
     for (const auto& t : terms) {
         for (int i = 0; i < t.d; ++i) {
@@ -459,9 +530,59 @@ static bool build_one(const Spec& sp, const std::vector<RbfCache>& rbf, const do
             for (int j = 0; j < t.r; ++j) s.Q[(size_t)(orr + i) * s.r + orr + j] = t.Q[(size_t)i * t.r + j];
         od += t.d, orr += t.r;
     }
-    balance_ss(s, sp.comb_iter);
-    if (!solve_lyap_vec(s, s.P0)) return false;
+    balance_ss<S>(s, sp.comb_iter);
+    if (!solve_lyap_vec<S>(s, s.P0)) return false;
     out = std::move(s);
+    return true;
+}
+
+// the tables are functions of the order only: computed once per process (the root iteration costs ~2 ms)
+static std::vector<RbfCache> rbf_tables(const Spec& sp) {
+    static std::mutex mu;
+    static std::vector<RbfCache> known;
+    std::lock_guard<std::mutex> lock(mu);
+    std::vector<RbfCache> rbf;
+    for (const auto& fs : sp.terms)
+        for (const auto& f : fs)
+            if (f[0] == K_RBF && std::none_of(rbf.begin(), rbf.end(), [&](const RbfCache& c) { return c.order == f[1]; })) {
+                auto it = std::find_if(known.begin(), known.end(), [&](const RbfCache& c) { return c.order == f[1]; });
+                if (it == known.end()) {
+                    RbfCache c;
+                    c.order = f[1];
+                    rbf_unscaled(c.order, c.F, c.gain, c.q);
+                    known.push_back(c);
+                    it = known.end() - 1;
+                }
+                rbf.push_back(*it);
+            }
+    return rbf;
+}
+
+// values and Jacobians w.r.t. the NP >= nparams hyper-parameters of one setting (forward mode: one dual build)
+template <int NP>
+static bool build_jac(const Spec& sp, const std::vector<RbfCache>& rbf, const double* params, double* F, double* Pinf,
+                      double* H, double* dF, double* dPinf, double* dH) {
+    typedef Dual<NP> S;
+    std::vector<S> p(sp.nparams);
+    for (int i = 0; i < sp.nparams; ++i) {
+        p[i] = S(params[i]);
+        p[i].g[i] = 1.0;
+    }
+    SdeT<S> s;
+    if (!build_one<S>(sp, rbf, p.data(), s) || s.d != sp.d) return false;
+    const int d = sp.d, dd = d * d;
+    for (int e = 0; e < dd; ++e) {
+        F[e] = s.F[e].v;
+        Pinf[e] = s.P0[e].v;
+        for (int q = 0; q < sp.nparams; ++q) {
+            dF[(size_t)q * dd + e] = s.F[e].g[q];
+            dPinf[(size_t)q * dd + e] = s.P0[e].g[q];
+        }
+    }
+    for (int e = 0; e < d; ++e) {
+        H[e] = s.H[e].v;
+        for (int q = 0; q < sp.nparams; ++q) dH[(size_t)q * d + e] = s.H[e].g[q];
+    }
     return true;
 }
 
@@ -484,7 +605,7 @@ int pssgp_lyap_solve(const void* F, const void* G, int d, void* X) {
     if (!F || !G || !X || d < 1) return set_err(PSSGP_ERR_INVALID, "lyap_solve: bad argument");
     const double *Fp = (const double*)F, *Gp = (const double*)G;
     sde::Mat Fm(Fp, Fp + (size_t)d * d), Gm(Gp, Gp + (size_t)d * d), Xm;
-    if (!sde::lyap_solve(Fm, Gm, d, Xm))
+    if (!sde::lyap_solve<double>(Fm, Gm, d, Xm))
         return set_err(PSSGP_ERR_INVALID, "lyap_solve: singular system (F and -F share an eigenvalue)");
     std::copy(Xm.begin(), Xm.end(), (double*)X);
     return PSSGP_OK;
@@ -496,15 +617,7 @@ int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const doub
     if (!sde::parse_spec(spec, spec_len, sp)) return set_err(PSSGP_ERR_INVALID, "sde: malformed kernel spec");
     if (batch < 1 || !params || !F || !Pinf || !H || params_stride < sp.nparams)
         return set_err(PSSGP_ERR_INVALID, "sde_batch: bad argument");
-    std::vector<sde::RbfCache> rbf;
-    for (const auto& fs : sp.terms)
-        for (const auto& f : fs)
-            if (f[0] == sde::K_RBF && std::none_of(rbf.begin(), rbf.end(), [&](const sde::RbfCache& c) { return c.order == f[1]; })) {
-                sde::RbfCache c;
-                c.order = f[1];
-                sde::rbf_unscaled(c.order, c.F, c.gain, c.q);
-                rbf.push_back(c);
-            }
+    const std::vector<sde::RbfCache> rbf = sde::rbf_tables(sp);
     const int d = sp.d;
     int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
     nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 64), batch));
@@ -512,7 +625,7 @@ int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const doub
     auto work = [&](int tid) {
         for (int64_t b = tid; b < batch; b += nt) {
             sde::Sde s;
-            if (!sde::build_one(sp, rbf, params + b * params_stride, s) || s.d != d) {
+            if (!sde::build_one<double>(sp, rbf, params + b * params_stride, s) || s.d != d) {
                 failed[tid] = 1;
                 continue;
             }
@@ -530,6 +643,42 @@ int pssgp_sde_batch(const int32_t* spec, int spec_len, int64_t batch, const doub
     }
     for (int f : failed)
         if (f) return set_err(PSSGP_ERR_INVALID, "sde_batch: singular Lyapunov system or unsupported kernel in a setting");
+    return PSSGP_OK;
+}
+
+int pssgp_sde_batch_jac(const int32_t* spec, int spec_len, int64_t batch, const double* params, int64_t params_stride,
+                        double* F, double* Pinf, double* H, double* dF, double* dPinf, double* dH, int nthreads) {
+    sde::Spec sp;
+    if (!sde::parse_spec(spec, spec_len, sp)) return set_err(PSSGP_ERR_INVALID, "sde: malformed kernel spec");
+    if (batch < 1 || !params || !F || !Pinf || !H || !dF || !dPinf || !dH || params_stride < sp.nparams)
+        return set_err(PSSGP_ERR_INVALID, "sde_batch_jac: bad argument");
+    if (sp.nparams > 16) return set_err(PSSGP_ERR_UNSUPPORTED, "sde_batch_jac: at most 16 hyper-parameters (got %d)", sp.nparams);
+    const std::vector<sde::RbfCache> rbf = sde::rbf_tables(sp);
+    const int d = sp.d, np = sp.nparams;
+    int nt = nthreads > 0 ? nthreads : (int)std::thread::hardware_concurrency();
+    nt = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(nt, 64), batch));
+    std::vector<int> failed(nt, 0);
+    auto work = [&](int tid) {
+        for (int64_t b = tid; b < batch; b += nt) {
+            const double* pb = params + b * params_stride;
+            double *Fb = F + b * d * d, *Pb = Pinf + b * d * d, *Hb = H + b * d;
+            double *dFb = dF + b * np * d * d, *dPb = dPinf + b * np * d * d, *dHb = dH + b * np * d;
+            bool ok;
+            if (np <= 4) ok = sde::build_jac<4>(sp, rbf, pb, Fb, Pb, Hb, dFb, dPb, dHb);
+            else if (np <= 8) ok = sde::build_jac<8>(sp, rbf, pb, Fb, Pb, Hb, dFb, dPb, dHb);
+            else ok = sde::build_jac<16>(sp, rbf, pb, Fb, Pb, Hb, dFb, dPb, dHb);
+            if (!ok) failed[tid] = 1;
+        }
+    };
+    if (nt == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; ++t) th.emplace_back(work, t);
+        for (auto& t : th) t.join();
+    }
+    for (int f : failed)
+        if (f) return set_err(PSSGP_ERR_INVALID, "sde_batch_jac: singular Lyapunov system or unsupported kernel in a setting");
     return PSSGP_OK;
 }
 

@@ -8,6 +8,7 @@ the integer spec of include/pssgp_b200.h plus its hyper-parameter vector; ``sde_
 import ctypes
 
 import numpy as np
+import torch
 
 from .. import _lib
 from .. import config as pssgp_config
@@ -34,6 +35,24 @@ def _base(kernel):
         b = kernel.base_kernel
         return [PERIODIC, int(kernel._order), 0], [f(b.variance), f(b.lengthscales), f(kernel.period)]
     return None
+
+
+def _base_parameters(kernel):
+    """The Parameter objects of a base kernel in the order of its hyper-parameter row."""
+    if isinstance(kernel, Periodic):
+        return [kernel.base_kernel.variance, kernel.base_kernel.lengthscales, kernel.period]
+    return [kernel.variance, kernel.lengthscales]
+
+
+def native_parameters(kernel):
+    """Parameter objects in the order of native_spec(kernel)[1] (None outside the native grammar)."""
+    if native_spec(kernel) is None:
+        return None
+    out = []
+    for t in (kernel.kernels if isinstance(kernel, SDESum) else [kernel]):
+        for f in (t.kernels if isinstance(t, SDEProduct) else [t]):
+            out += _base_parameters(f)
+    return out
 
 
 def _term(kernel):
@@ -84,3 +103,52 @@ def sde_batch(spec, params, nthreads=0):
     _lib.check(_lib.lib().pssgp_sde_batch(vp(arr), int(arr.size), B, vp(params), npar, vp(F), vp(Pinf), vp(H),
                                          int(nthreads)))
     return F, Pinf, H
+
+
+def sde_batch_jac(spec, params, nthreads=0):
+    """sde_batch plus the Jacobians w.r.t. the (constrained) hyper-parameters: C ABI pssgp_sde_batch_jac.
+    -> F, Pinf [B,d,d], H [B,d], dF, dPinf [B,P,d,d], dH [B,P,d]."""
+    arr = np.ascontiguousarray(spec, dtype=np.int32)
+    d, npar = sde_dim(arr)
+    params = np.ascontiguousarray(np.atleast_2d(np.asarray(params, dtype=np.float64)))
+    if params.shape[1] != npar:
+        raise ValueError(f"params must be [B,{npar}] for this spec, got {params.shape}")
+    B = params.shape[0]
+    F, Pinf, H = np.empty((B, d, d)), np.empty((B, d, d)), np.empty((B, d))
+    dF, dPinf, dH = np.empty((B, npar, d, d)), np.empty((B, npar, d, d)), np.empty((B, npar, d))
+    vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    _lib.check(_lib.lib().pssgp_sde_batch_jac(vp(arr), int(arr.size), B, vp(params), npar, vp(F), vp(Pinf), vp(H), vp(dF),
+                                             vp(dPinf), vp(dH), int(nthreads)))
+    return F, Pinf, H, dF, dPinf, dH
+
+
+class NativeSDE(torch.autograd.Function):
+    """(F, Pinf, H) of a kernel structure as a differentiable function of its constrained hyper-parameters: forward and
+    Jacobian come from ONE call of the native builder (forward-mode duals through balancing, Lyapunov solves and
+    Kronecker products); backward contracts the upstream gradients with the stored Jacobians.  Replaces torch autograd
+    through the Python get_sde on the training path (``config.NATIVE_SDE``)."""
+
+    @staticmethod
+    def forward(ctx, spec, *params):
+        row = [float(p.detach()) for p in params]
+        F, Pinf, H, dF, dPinf, dH = sde_batch_jac(list(spec), [row])
+        ctx.jac = (dF[0], dPinf[0], dH[0])
+        dt = params[0].dtype
+        tt = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+        return tt(F[0]), tt(Pinf[0]), tt(H[0]).reshape(1, -1)
+
+    @staticmethod
+    def backward(ctx, gF, gP, gH):
+        dF, dPinf, dH = ctx.jac
+        z = lambda g, like: np.zeros(like.shape[1:]) if g is None else g.detach().cpu().numpy().reshape(like.shape[1:])
+        gF, gP, gH = z(gF, dF), z(gP, dPinf), z(gH, dH)
+        grads = (dF * gF).sum(axis=(1, 2)) + (dPinf * gP).sum(axis=(1, 2)) + (dH * gH).sum(axis=1)
+        return (None,) + tuple(torch.tensor(float(g), dtype=torch.float64) for g in grads)
+
+
+def native_sde(kernel):
+    """(F, Pinf, H) through NativeSDE, or None when the kernel is outside the native grammar."""
+    r = native_spec(kernel)
+    if r is None:
+        return None
+    return NativeSDE.apply(tuple(r[0]), *[p.value for p in native_parameters(kernel)])

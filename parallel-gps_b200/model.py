@@ -181,10 +181,16 @@ class StateSpaceGP:
     def maximum_log_likelihood_objective(self):
         """model.py:113-117; differentiable w.r.t. trainable_variables."""
         ts, Y = self._data
-        sde = self.kernel.get_sde()
+        sde3 = None
+        if pssgp_config.NATIVE_SDE:
+            from .kernels import native
+            sde3 = native.native_sde(self.kernel)      # None outside the native grammar
+        if sde3 is None:
+            sde = self.kernel.get_sde()
+            sde3 = (sde.F, sde.P0, sde.H)
         R = self.noise_variance.value.reshape(1, 1)
         dts = time_steps(ts, 0., ts.dtype, ts.device)
-        return _LogLikelihood.apply(sde.F, sde.P0, sde.H, R, dts, Y.reshape(-1), not self.parallel)
+        return _LogLikelihood.apply(sde3[0], sde3[1], sde3[2], R, dts, Y.reshape(-1), not self.parallel)
 
     def synchronize(self):
         """Waits for everything this model has enqueued, including the read-back of ``predict_f(non_blocking=True)``."""

@@ -116,3 +116,38 @@ def test_native_lyapunov_solve_and_adjoint(d):
     X = _lyap(F.detach().numpy(), G)
     Fn = F.detach().numpy()
     assert np.max(np.abs(Fn @ X + X @ Fn.T - G)) < 1e-12 * max(1.0, np.max(np.abs(X)))
+
+
+@pytest.mark.parametrize("name", ["m12", "m32", "m52", "rbf6", "periodic4", "m52+rbf6", "m32xm52", "qp3", "m32+m32xm32+qp2"])
+def test_native_sde_jacobian_matches_autograd(name):
+    """pssgp_sde_batch_jac (forward-mode duals in C++) and the differentiable wrapper kernels.native.NativeSDE against
+    torch autograd through the package's Python get_sde (itself pinned to the oracle in test_cpu_host.py)."""
+    cases, PK = _cases()
+    from pssgp_b200 import config as cfg
+    from pssgp_b200.kernels import native
+    mk, npar, _ = cases[name]
+    rng = np.random.RandomState(3 + len(name))
+    P = rng.uniform(0.4, 2.0, size=npar)
+    old = cfg.FAST_MATERN_SDE
+    cfg.FAST_MATERN_SDE = False
+    try:
+        k = mk(PK, *P)
+        sde = k.get_sde()
+        gen = torch.Generator().manual_seed(1)
+        W1 = torch.randn(sde.F.shape, dtype=torch.float64, generator=gen)
+        W2 = torch.randn(sde.P0.shape, dtype=torch.float64, generator=gen)
+        W3 = torch.randn(sde.H.shape, dtype=torch.float64, generator=gen)
+        ps = native.native_parameters(k)
+        ref = torch.autograd.grad((sde.F * W1).sum() + (sde.P0 * W2).sum() + (sde.H * W3).sum(),
+                                  [p.unconstrained_variable for p in ps], allow_unused=True)
+        F, Pinf, H = native.native_sde(k)
+        assert _rel(F.detach().numpy(), sde.F.detach()) < 1e-12 and _rel(Pinf.detach().numpy(), sde.P0.detach()) < 1e-12
+        got = torch.autograd.grad((F * W1).sum() + (Pinf * W2).sum() + (H * W3).sum(),
+                                  [p.unconstrained_variable for p in ps], allow_unused=True)
+    finally:
+        cfg.FAST_MATERN_SDE = old
+    scale = max(abs(float(g)) for g in ref if g is not None)
+    for a, b in zip(got, ref):
+        a = 0.0 if a is None else float(a)
+        b = 0.0 if b is None else float(b)
+        assert abs(a - b) <= 1e-10 * scale
