@@ -288,6 +288,14 @@ int pssgp_sde_batch_jac(const int32_t* spec, int spec_len, int64_t batch, const 
  */
 int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
                       const void* H, const void* R, const void* dts, const void* y, void* ll, void* stream);
+/* The same with the gradient of every log-likelihood w.r.t. the SDE of its setting (per setting: discretise, fused
+ * filter + adjoint = pssgp_pkfs_grad without smoother, pssgp_discretise_backward): dF, dPinf [batch,d,d] (through the
+ * discretisation), dP0 [batch,d,d] (through the initial covariance; P0 = Pinf, so the total is dPinf + dP0), dH
+ * [batch,d], dR [batch].  Contracted with the Jacobians of pssgp_sde_batch_jac this is the hyper-parameter gradient of
+ * a whole batch of settings (gradient-based search, many MCMC chains) from one call. */
+int pssgp_grid_loglik_grad(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
+                           const void* H, const void* R, const void* dts, const void* y, void* ll, void* dF, void* dPinf,
+                           void* dP0, void* dH, void* dR, void* stream);
 
 /*
  * Sequential Kalman filter for `batch` independent series.  Replaces pssgp/kalman/sequential.py:11-47 (kf): per step

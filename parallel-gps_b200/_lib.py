@@ -58,6 +58,8 @@ SIGNATURES = {
     "pssgp_sde_batch": (_int, [_vp, _int, _i64, _vp, _i64, _vp, _vp, _vp, _int]),
     "pssgp_sde_batch_jac": (_int, [_vp, _int, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _int]),
     "pssgp_grid_loglik": (_int, [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "pssgp_grid_loglik_grad": (_int, [_vp, _int, _i64, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp]),
     "pssgp_kf": (_int, [_vp, _int, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_ks": (_int, [_vp, _int, _i64, _i64, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "pssgp_discretise_backward": (_int, [_vp, _int, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -700,14 +700,18 @@ static int grid_lanes_init(pssgp_handle* h, int lanes) {
     return PSSGP_OK;
 }
 
-int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
-                      const void* H, const void* R, const void* dts, const void* y, void* ll, void* stream) {
+static int grid_impl(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
+                     const void* H, const void* R, const void* dts, const void* y, void* ll, void* dF, void* dPinf,
+                     void* dP0, void* dH, void* dR, void* stream) {
     int rc = check_common(h, dtype, n, d);
     if (rc) return rc;
-    if (batch < 1 || !F || !Pinf || !H || !R || !dts || !y || !ll) return set_err(PSSGP_ERR_INVALID, "grid_loglik: bad argument");
+    const bool grad = dF != nullptr;
+    if (batch < 1 || !F || !Pinf || !H || !R || !dts || !y || !ll || (grad && (!dPinf || !dP0 || !dH || !dR)))
+        return set_err(PSSGP_ERR_INVALID, "grid_loglik: bad argument");
     const size_t es = dtype == PSSGP_F64 ? 8 : 4;
     const size_t nm = (size_t)n * d * d * es, nv = (size_t)n * d * es;
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    const size_t need = (grad ? 5 : 3) * up(nm) + up(nv) + 256;
     // per-kernel timing (option "timing") brackets launches with events on ONE stream: a single lane then
     const int lanes = h->timing ? 1 : (int)std::min<int64_t>(h->grid_lanes > 0 ? h->grid_lanes : 4, std::min<int64_t>(batch, 4));
     if (lanes > 1 && (rc = grid_lanes_init(h, lanes))) return rc;
@@ -716,6 +720,8 @@ int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int 
         cudaEventRecord((cudaEvent_t)h->fork_event, st);
         for (int i = 0; i < lanes; ++i) cudaStreamWaitEvent((cudaStream_t)h->lane_stream[i], (cudaEvent_t)h->fork_event, 0);
     }
+    static const double one64 = 1.0;   // static: the asynchronous copies below may read them after this call returns
+    static const float one32 = 1.0f;
     for (int64_t b = 0; b < batch; ++b) {
         const int l = (int)(b % lanes);
         pssgp_handle* hl = lanes > 1 ? h->lane[l] : h;
@@ -724,16 +730,34 @@ int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int 
             hl->chunk_opt = h->chunk_opt, hl->mid_warps = h->mid_warps, hl->mid_smem = h->mid_smem;
             hl->force_generic = h->force_generic, hl->pdl = h->pdl;
         }
-        if ((rc = ws_reserve(hl, WS_GRID, 3 * up(nm) + up(nv)))) return rc;
+        if ((rc = ws_reserve(hl, WS_GRID, need))) return rc;
         char* base = (char*)hl->buf[WS_GRID];
-        void *Fs = base, *Qs = base + up(nm), *fPs = base + 2 * up(nm), *fms = base + 3 * up(nm);
+        void* g_ll = base;   // device scalar 1 (upstream gradient of the log-likelihood), then the per-setting arrays
+        char* arr = base + 256;
+        void *Fs = arr, *Qs = arr + up(nm), *fPs = arr + 2 * up(nm), *fms = arr + 3 * up(nm);
+        void *dFs = arr + 3 * up(nm) + up(nv), *dQs = arr + 4 * up(nm) + up(nv);
+        if (grad && b < lanes) {   // first setting of this lane in this call
+            cudaError_t e = cudaMemcpyAsync(g_ll, dtype == PSSGP_F64 ? (const void*)&one64 : (const void*)&one32, es,
+                                            cudaMemcpyHostToDevice, (cudaStream_t)sl);
+            if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "grid_loglik: %s", cudaGetErrorString(e));
+        }
         const char* Fb = (const char*)F + (size_t)b * d * d * es;
         const char* Pb = (const char*)Pinf + (size_t)b * d * d * es;
+        const char* Hb = (const char*)H + (size_t)b * d * es;
+        const char* Rb = (const char*)R + (size_t)b * es;
         const int64_t l0 = hl->launches;
         if ((rc = pssgp_discretise(hl, dtype, n, d, Fb, Pb, dts, Fs, Qs, sl))) return rc;
-        if ((rc = pssgp_pkf(hl, dtype, n, d, Pb, Fs, Qs, (const char*)H + (size_t)b * d * es, (const char*)R + (size_t)b * es, y,
-                            nullptr, 1, fms, fPs, (char*)ll + (size_t)b * es, nullptr, sl)))
-            return rc;
+        if (!grad) {
+            rc = pssgp_pkf(hl, dtype, n, d, Pb, Fs, Qs, Hb, Rb, y, nullptr, 1, fms, fPs, (char*)ll + (size_t)b * es, nullptr, sl);
+        } else {
+            rc = pssgp_pkfs_grad(hl, dtype, n, d, Pb, Fs, Qs, Hb, Rb, y, g_ll, fms, fPs, (char*)ll + (size_t)b * es, nullptr,
+                                 nullptr, (char*)dP0 + (size_t)b * d * d * es, dFs, dQs, (char*)dH + (size_t)b * d * es,
+                                 (char*)dR + (size_t)b * es, sl);
+            if (!rc)
+                rc = pssgp_discretise_backward(hl, dtype, n, d, Fb, Pb, dts, Fs, dFs, dQs, (char*)dF + (size_t)b * d * d * es,
+                                               (char*)dPinf + (size_t)b * d * d * es, sl);
+        }
+        if (rc) return rc;
         if (lanes > 1) h->launches += hl->launches - l0;
     }
     if (lanes > 1)
@@ -744,6 +768,18 @@ int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return set_err(PSSGP_ERR_CUDA, "grid_loglik: %s", cudaGetErrorString(e));
     return PSSGP_OK;
+}
+
+int pssgp_grid_loglik(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
+                      const void* H, const void* R, const void* dts, const void* y, void* ll, void* stream) {
+    return grid_impl(h, dtype, batch, n, d, F, Pinf, H, R, dts, y, ll, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+}
+
+int pssgp_grid_loglik_grad(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d, const void* F, const void* Pinf,
+                           const void* H, const void* R, const void* dts, const void* y, void* ll, void* dF, void* dPinf,
+                           void* dP0, void* dH, void* dR, void* stream) {
+    if (!dF) return set_err(PSSGP_ERR_INVALID, "grid_loglik_grad: null gradient output");
+    return grid_impl(h, dtype, batch, n, d, F, Pinf, H, R, dts, y, ll, dF, dPinf, dP0, dH, dR, stream);
 }
 
 }  // extern "C"

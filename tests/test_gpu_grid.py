@@ -67,3 +67,35 @@ def test_grid_noise_callable_and_fallback_for_nested_kernels():
     nested = lambda a, b: (PK.Matern32(1.0, float(a)) + PK.Matern52(1.0, float(b))) * PK.Matern32(1.0, 1.0)
     ll2 = batch.grid_log_likelihood(nested, [(0.5, 1.0), (1.0, 2.0)], data, 0.1)
     assert bool(torch.isfinite(ll2).all())
+
+
+@pytest.mark.parametrize("name", ["m52+rbf6", "matern32", "qp2"])
+def test_grid_gradient_matches_model_autograd(name):
+    """grid_log_likelihood(with_grad=True): per setting the gradient w.r.t. the constrained kernel hyper-parameters and
+    the noise variance equals the one StateSpaceGP + autograd gives for that setting (itself pinned to the oracle)."""
+    pkg()
+    from pssgp_b200 import batch, kernels as PK
+    from pssgp_b200.kernels import native
+    from pssgp_b200.model import StateSpaceGP
+    mk, _ = CASES[name]
+    T = 500
+    t, y = _series(T, seed=2)
+    settings = [(0.4, 0.7), (1.1, 0.5), (0.8, 1.6), (2.0, 0.9), (0.6, 0.6)]
+    data = (t[:, None], y[:, None])
+    ll, dparams, dnoise = batch.grid_log_likelihood(lambda a, b: mk(PK, a, b), settings, data, 0.1, with_grad=True)
+    ll_only = batch.grid_log_likelihood(lambda a, b: mk(PK, a, b), settings, data, 0.1)
+    assert torch.allclose(ll, ll_only, rtol=1e-12, atol=0)
+    for i, (a, b) in enumerate(settings):
+        k = mk(PK, a, b)
+        model = StateSpaceGP(data, k, noise_variance=0.1, parallel=True)
+        val = model.maximum_log_likelihood_objective()
+        ps = native.native_parameters(k)
+        g = torch.autograd.grad(val, [p.unconstrained_variable for p in ps] + [model.noise_variance.unconstrained_variable],
+                                allow_unused=True)
+        # d / d constrained = (d / d unconstrained) / sigmoid(unconstrained)
+        con = [0.0 if gi is None else float(gi) / float(torch.sigmoid(p.unconstrained_variable.detach()))
+               for gi, p in zip(g, ps + [model.noise_variance])]
+        scale = max(abs(c) for c in con)
+        assert abs(float(ll[i]) - float(val)) <= 1e-10 * abs(float(val))
+        np.testing.assert_allclose(dparams[i].numpy(), con[:-1], rtol=1e-7, atol=1e-9 * scale)
+        assert abs(float(dnoise[i]) - con[-1]) <= 1e-7 * abs(con[-1]) + 1e-9 * scale
