@@ -355,7 +355,29 @@ def run_grid_config(world, rank, dev, dist, barrier, torch, kernels, ops, W):
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt)
-    return {"baseline_config": 4, "workload": "grid log-likelihood, 32 x 32 settings of Matern52 + RBF6 (d = 9), N = 1e5, "
+    # the same with the hyper-parameter gradient of every setting (pssgp_grid_loglik_grad + native Jacobians), on the first
+    # 256 settings
+    grad_info = None
+    try:
+        sub = settings[:256]
+        batch.grid_log_likelihood(mk, sub[:8 * world], data, NOISE, rank=rank, world=world, dist=dist, device=dev, with_grad=True)
+        barrier()
+        t1 = time.perf_counter()
+        llg, dpar, dnz = batch.grid_log_likelihood(mk, sub, data, NOISE, rank=rank, world=world, dist=dist, device=dev,
+                                                   with_grad=True)
+        barrier()
+        dtg = time.perf_counter() - t1
+        if dist is not None:
+            tg = torch.tensor([dtg], dtype=torch.float64, device=dev)
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+            dtg = float(tg)
+        grad_info = {"settings": len(sub), "seconds": dtg, "value": len(sub) / dtg, "unit": "settings/s",
+                     "finite": bool(torch.isfinite(dpar).all() and torch.isfinite(dnz).all()),
+                     "ll_matches": bool(torch.allclose(llg, ll[:len(sub)], rtol=1e-10, atol=0))}
+    except Exception as e:
+        grad_info = {"error": repr(e)}
+    return {"with_gradient": grad_info,
+            "baseline_config": 4, "workload": "grid log-likelihood, 32 x 32 settings of Matern52 + RBF6 (d = 9), N = 1e5, "
                                               "batch-sharded over n_gpus", "settings": len(settings), "n": n,
             "seconds": dt, "value": len(settings) / dt, "unit": "settings/s", "timesteps_per_s": len(settings) * n / dt,
             "n_gpus": world, "path": "native batched SDE (pssgp_sde_batch, host C++) + one pssgp_grid_loglik call per rank "
