@@ -12,6 +12,8 @@ producer).
     pkf_ll_grad(ctx, g_ll)                       -> (dP0, dFs, dQs, dH, dR) capsules  (TF autodiff in the reference)
     pkfs(P0, Fs, Qs, H, R, y)                    -> (sms, sPs) capsules               parallel.py:199-201
     get_ssm(F, Pinf, dts)                        -> (Fs, Qs) capsules                 pssgp/kernels/base.py:29-47
+    kf_ll(P0, Fs, Qs, H, R, y)                   -> (fms, fPs, ll) capsules, ctx      pssgp/kalman/sequential.py:11-47
+    kfs(P0, Fs, Qs, H, R, y)                     -> (sms, sPs) capsules               sequential.py:71-73
 """
 import torch
 from torch.utils.dlpack import to_dlpack
@@ -52,6 +54,23 @@ def pkfs(P0, Fs, Qs, H, R, y):
     P0, Fs, Qs, H, R, y = (_view(v) for v in (P0, Fs, Qs, H, R, y))
     out = ops.pkfs(P0, Fs, Qs, H.reshape(-1), R.reshape(-1), y.reshape(-1))
     return to_dlpack(out[3]), to_dlpack(out[4])
+
+
+def kf_ll(P0, Fs, Qs, H, R, y):
+    """Sequential filter + log-likelihood (StateSpaceGP(parallel=False), model.py:73-75); the ctx is the one of pkf_ll:
+    pkf_ll_grad gives the gradient (it is a function of the filtered moments, whichever filter produced them)."""
+    P0, Fs, Qs, H, R, y = (_view(v) for v in (P0, Fs, Qs, H, R, y))
+    fms, fPs, ll, _, _ = ops.kf(P0, Fs, Qs, H.reshape(-1), R.reshape(-1), y.reshape(-1))
+    ctx = (P0, Fs, Qs, H, R, y, fms, fPs)
+    return (to_dlpack(fms), to_dlpack(fPs), to_dlpack(ll)), ctx
+
+
+def kfs(P0, Fs, Qs, H, R, y):
+    """Sequential filter + RTS smoother (model.py:76-77)."""
+    P0, Fs, Qs, H, R, y = (_view(v) for v in (P0, Fs, Qs, H, R, y))
+    fms, fPs, _, mps, Pps = ops.kf(P0, Fs, Qs, H.reshape(-1), R.reshape(-1), y.reshape(-1), want_ll=False, want_predicted=True)
+    sms, sPs = ops.ks(Fs, fms, fPs, mps, Pps)
+    return to_dlpack(sms), to_dlpack(sPs)
 
 
 def make_tf_ops():

@@ -79,6 +79,13 @@ def test_capsule_level_binding_matches_oracle(name):
     assert abs(float(grads[4]) - float(gR)) < 1e-9 * abs(float(gR))
     sm, sP = (from_dlpack(c) for c in B.pkfs(*caps()))
     assert rel_err(sm.cpu(), rsm) < 1e-9 and rel_err(sP.cpu(), rsP) < 1e-9
+    # the sequential filter / smoother through the same boundary (StateSpaceGP(parallel=False) of the reference)
+    (k_fm, k_fP, k_ll), kctx = B.kf_ll(*caps())
+    assert rel_err(from_dlpack(k_fm).cpu(), rfm.detach()) < 1e-9 and abs(float(from_dlpack(k_ll)) - float(rll)) < 1e-9 * abs(float(rll))
+    kgrads = [from_dlpack(c) for c in B.pkf_ll_grad(kctx, to_dlpack(torch.tensor([g], dtype=torch.float64, device=DEV)))]
+    assert rel_err(kgrads[1].cpu(), gFs) < 1e-8 and rel_err(kgrads[2].cpu(), sym(gQs)) < 1e-8
+    ksm, ksP = (from_dlpack(c) for c in B.kfs(*caps()))
+    assert rel_err(ksm.cpu(), rsm) < 1e-8 and rel_err(ksP.cpu(), rsP) < 1e-8
     # discretisation through the same boundary
     with torch.no_grad():
         sde = cov.get_sde()
