@@ -43,7 +43,7 @@ int pssgp_destroy(pssgp_handle* h);
  * kernel launch with CUDA events on its stream (read back with pssgp_timing_report);
  * "fused_reverse" = 1 makes pssgp_pkfs_grad run the smoother and adjoint recursions in one kernel;
  * "pdl" = 0 turns off programmatic dependent launch between the kernels of pssgp_pkfs_grad (default 1);
- * "grid_lanes" = settings in flight in pssgp_grid_loglik (0 = default 4, at most 4); tuning / test switches:
+ * "grid_lanes" = settings in flight in pssgp_grid_loglik (0 = default 4, at most 8: measured +2 % at 8); tuning / test switches:
  * "mid_warps" (warps per CTA of the 5 <= d <= 24 kernels), "mid_smem" = 1 (shared-memory tile kernels also for
  * d <= 24), "force_generic" = 1 (CTA-cooperative kernels for d > 4, element-per-thread discretisation). */
 int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value);

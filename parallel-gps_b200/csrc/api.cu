@@ -148,7 +148,7 @@ int pssgp_destroy(pssgp_handle* h) {
     }
     free(h->recs);
     if (h->ticket) cudaFree(h->ticket);
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 8; ++i) {
         if (h->lane[i]) pssgp_destroy(h->lane[i]);
         if (h->lane_stream[i]) cudaStreamDestroy((cudaStream_t)h->lane_stream[i]);
         if (h->lane_event[i]) cudaEventDestroy((cudaEvent_t)h->lane_event[i]);
@@ -174,7 +174,7 @@ int pssgp_set_option(pssgp_handle* h, const char* name, int64_t value) {
         return PSSGP_OK;
     }
     if (strcmp(name, "grid_lanes") == 0) {
-        if (value < 0 || value > 4) return set_err(PSSGP_ERR_INVALID, "grid_lanes out of range (0..4)");
+        if (value < 0 || value > 8) return set_err(PSSGP_ERR_INVALID, "grid_lanes out of range (0..8)");
         h->grid_lanes = (int)value;
         return PSSGP_OK;
     }

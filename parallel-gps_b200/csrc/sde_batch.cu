@@ -713,7 +713,7 @@ static int grid_impl(pssgp_handle* h, int dtype, int64_t batch, int64_t n, int d
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     const size_t need = (grad ? 5 : 3) * up(nm) + up(nv) + 256;
     // per-kernel timing (option "timing") brackets launches with events on ONE stream: a single lane then
-    const int lanes = h->timing ? 1 : (int)std::min<int64_t>(h->grid_lanes > 0 ? h->grid_lanes : 4, std::min<int64_t>(batch, 4));
+    const int lanes = h->timing ? 1 : (int)std::min<int64_t>(h->grid_lanes > 0 ? h->grid_lanes : 4, std::min<int64_t>(batch, 8));
     if (lanes > 1 && (rc = grid_lanes_init(h, lanes))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (lanes > 1) {

@@ -19,7 +19,7 @@ struct pssgp_handle {
     int mid_warps;      // option "mid_warps": cap on the warps per CTA of the fragment-resident d > 4 kernels (0 = default)
     int mid_smem;       // option "mid_smem": 5 <= d <= 16 runs the shared-memory tile kernels instead of the fragment-resident ones
     int force_generic;  // option "force_generic": d > 4 runs the CTA-cooperative kernels of generic.cu (tuning / tests)
-    int grid_lanes;     // option "grid_lanes": concurrent settings in pssgp_grid_loglik (0 = default 4 = max)
+    int grid_lanes;     // option "grid_lanes": concurrent settings in pssgp_grid_loglik (0 = default 4, at most 8)
     int fused_reverse;  // option "fused_reverse": pkfs_grad runs smoother + adjoint recursions in one kernel
     void* mid_proj;     // internal: projected output [n,2] requested by pssgp_pkfs for its next mid::pkfs_grad call
     int64_t launches;
@@ -41,9 +41,9 @@ struct pssgp_handle {
     void* fold_state_out;  // kind 0 only: where the folded state entering the shard is written
     // optional per-kernel CUDA-event timing (option "timing" = 1)
     // pssgp_grid_loglik: child handles (own workspace), streams and events of the concurrent lanes, created lazily
-    pssgp_handle* lane[4];
-    void* lane_stream[4];
-    void* lane_event[4];
+    pssgp_handle* lane[8];
+    void* lane_stream[8];
+    void* lane_event[8];
     void* fork_event;
     int timing;
     int n_rec, cap_rec;
