@@ -23,15 +23,16 @@ MATERN12, MATERN32, MATERN52, RBF_T, PERIODIC = range(5)
 def _base(kernel):
     """-> ([type, order, balancing_iter], [hyper-parameters]) of a base kernel, None for anything else."""
     f = lambda p: float(p.value.detach())
-    if isinstance(kernel, Matern12):
+    # exact types only: a subclass may override get_sde, and then the native construction would not be its SDE
+    if type(kernel) is Matern12:
         return [MATERN12, 0, 0], [f(kernel.variance), f(kernel.lengthscales)]
-    if isinstance(kernel, Matern32):
+    if type(kernel) is Matern32:
         return [MATERN32, 0, 0], [f(kernel.variance), f(kernel.lengthscales)]
-    if isinstance(kernel, Matern52):
+    if type(kernel) is Matern52:
         return [MATERN52, 0, int(kernel._balancing_iter)], [f(kernel.variance), f(kernel.lengthscales)]
-    if isinstance(kernel, RBF):
+    if type(kernel) is RBF:
         return [RBF_T, int(kernel._order), int(kernel._balancing_iter)], [f(kernel.variance), f(kernel.lengthscales)]
-    if isinstance(kernel, Periodic):
+    if type(kernel) is Periodic:
         b = kernel.base_kernel
         return [PERIODIC, int(kernel._order), 0], [f(b.variance), f(b.lengthscales), f(kernel.period)]
     return None
@@ -39,7 +40,7 @@ def _base(kernel):
 
 def _base_parameters(kernel):
     """The Parameter objects of a base kernel in the order of its hyper-parameter row."""
-    if isinstance(kernel, Periodic):
+    if type(kernel) is Periodic:
         return [kernel.base_kernel.variance, kernel.base_kernel.lengthscales, kernel.period]
     return [kernel.variance, kernel.lengthscales]
 
@@ -49,14 +50,14 @@ def native_parameters(kernel):
     if native_spec(kernel) is None:
         return None
     out = []
-    for t in (kernel.kernels if isinstance(kernel, SDESum) else [kernel]):
-        for f in (t.kernels if isinstance(t, SDEProduct) else [t]):
+    for t in (kernel.kernels if type(kernel) is SDESum else [kernel]):
+        for f in (t.kernels if type(t) is SDEProduct else [t]):
             out += _base_parameters(f)
     return out
 
 
 def _term(kernel):
-    factors = kernel.kernels if isinstance(kernel, SDEProduct) else [kernel]
+    factors = kernel.kernels if type(kernel) is SDEProduct else [kernel]
     spec, params = [len(factors)], []
     for k in factors:
         b = _base(k)
@@ -70,7 +71,7 @@ def _term(kernel):
 def native_spec(kernel):
     """(spec: list of int, params: list of float) of ``kernel`` or None when its structure is outside the native
     grammar (sum of products of base kernels)."""
-    terms = kernel.kernels if isinstance(kernel, SDESum) else [kernel]
+    terms = kernel.kernels if type(kernel) is SDESum else [kernel]
     spec, params = [int(pssgp_config.NUMBER_OF_BALANCING_STEPS), len(terms)], []
     for t in terms:
         r = _term(t)

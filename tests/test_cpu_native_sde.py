@@ -151,3 +151,16 @@ def test_native_sde_jacobian_matches_autograd(name):
         a = 0.0 if a is None else float(a)
         b = 0.0 if b is None else float(b)
         assert abs(a - b) <= 1e-10 * scale
+
+
+def test_native_spec_ignores_subclasses():
+    """A user subclass may override get_sde: only the exact kernel classes take the native construction."""
+    cases, PK = _cases()
+    from pssgp_b200.kernels import native
+
+    class MyMatern(PK.Matern32):
+        pass
+
+    assert native.native_spec(MyMatern(1., 1.)) is None
+    assert native.native_spec(PK.Matern32(1., 1.) + MyMatern(1., 1.)) is None
+    assert native.native_sde(MyMatern(1., 1.)) is None
